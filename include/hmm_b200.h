@@ -1,0 +1,111 @@
+/*
+ * hmm_b200.h -- C ABI of the B200-native HMM inference engine (libhmm_b200.so).
+ *
+ * This is the drop-in boundary for pytorch_hmm's hot path.  The reference has no FFI (it is pure Python on
+ * torch); each entry point below names the reference routine whose arithmetic it replaces (paths relative to
+ * the reference repository root), and pytorch_hmm_b200/*.py binds them with ctypes behind the reference's
+ * class API.  INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain C types only: device pointers, sizes, a CUDA stream passed as void* (cudaStream_t), no torch types;
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; tensors are dense row-major fp32;
+ *   - no allocation, no ownership transfer, no host synchronisation, no global mutable state: safe to call
+ *     from several host threads on different streams; work is enqueued on `stream` and the call returns;
+ *   - return 0 on success, <0 on error (HMMB200_E*); hmmb200_last_error() gives the thread's last message;
+ *   - there is NO CPU fallback: on a machine without an sm_100 device every compute call returns
+ *     HMMB200_ENODEVICE.
+ */
+#ifndef HMM_B200_H
+#define HMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMMB200_ABI_VERSION 1
+
+#define HMMB200_OK            0
+#define HMMB200_EINVAL       -1   /* bad argument (null pointer, non-positive size, ...)            */
+#define HMMB200_EUNSUPPORTED -2   /* shape outside what this entry point covers (e.g. K > 32)        */
+#define HMMB200_ELAUNCH      -3   /* CUDA reported an error at launch                                */
+#define HMMB200_EWORKSPACE   -4   /* workspace too small (see the *_workspace_bytes query)           */
+#define HMMB200_ENODEVICE    -5   /* no CUDA device of compute capability 10.x                       */
+
+/* How an emission tensor `emis[B,T,K]` is to be read by the recursions. */
+#define HMMB200_EMIS_LOG            0  /* log b_t(k) as is (NeuralHMM-style log emissions; mixture_gaussian.py:312-324)      */
+#define HMMB200_EMIS_PROB_FLOOR     1  /* probabilities: log b = log(p + eps)             (hmm.py:86, :152)                   */
+#define HMMB200_EMIS_LOG_NORM_FLOOR 2  /* log-lik l: log b = log(exp(l - max_k l) + eps)  (per-frame      */
+                                       /*   max-normalised probabilities fed to HMMPyTorch)                                   */
+#define HMMB200_EMIS_LOG_EXP_FLOOR  3  /* log-lik l: log b = log(exp(l) + eps)            (hmm_layer.py:336-337 then hmm.py:86) */
+
+int         hmmb200_abi_version(void);
+const char *hmmb200_last_error(void);
+/* 0 if device `ordinal` (or the current device when ordinal < 0) is compute capability 10.x. */
+int         hmmb200_device_check(int ordinal);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Emission: diagonal-Gaussian / GMM log-likelihood.
+ *   replaces  MixtureGaussianHMMLayer.get_observation_log_probs   pytorch_hmm/mixture_gaussian.py:157-214
+ *             GaussianHMMLayer._compute_gaussian_log_probs        pytorch_hmm/hmm_layer.py:270-323 ('diag')
+ *             HSMMLayer.get_observation_log_probs                 pytorch_hmm/hsmm.py:181-206
+ *
+ * hmmb200_gmm_pack_f32 turns the layer parameters into the kernel's packed form (once per parameter update):
+ *   means, log_vars : [K, C, D]   variance = exp(log_var_scale * log_vars)  (1 for log_vars, 2 for log_scales)
+ *   log_weights     : [K, C] log mixture weights, or NULL for a single Gaussian per state (C must be 1)
+ *   packed          : hmmb200_gmm_packed_floats(K, C, D) floats
+ * hmmb200_gmm_emission_f32:
+ *   x [n_frames, D] -> logb [n_frames, K];   logb_k = own_lse_c( log w_kc + log N(x | mu_kc, var_kc) ),
+ *   where own_lse is the reference's private logsumexp (max, log(clamp(sum, 1e-8)) + max).
+ * --------------------------------------------------------------------------------------------------------- */
+size_t hmmb200_gmm_packed_floats(int K, int C, int D);
+int    hmmb200_gmm_pack_f32(const float *means, const float *log_vars, float log_var_scale,
+                            const float *log_weights, int K, int C, int D, float *packed, void *stream);
+int    hmmb200_gmm_emission_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
+                                float *logb, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Forward-backward (small K: K <= 32).
+ *   replaces  HMMPyTorch.forward_backward / compute_likelihood    pytorch_hmm/hmm.py:66-130, :186-211
+ *
+ *   emis [B,T,K] read according to emis_mode / floor_eps (see HMMB200_EMIS_*).
+ *   trans_prob [K,K], init_prob [K]: the EFFECTIVE probabilities exp(log_P), exp(log_p0), i.e. P + 1e-8 and
+ *     p0 + 1e-8 for HMMPyTorch (hmm.py:42,55).  The recursion runs in scaled-probability space.
+ *   outputs (any may be NULL): gamma [B,T,K] posterior (hmm.py:120-126); fwd_prob, bwd_prob [B,T,K] =
+ *     exp(log alpha), exp(log beta) as the reference returns them (hmm.py:127-128; they underflow to 0);
+ *     log_alpha, log_beta [B,T,K]; loglik [B] = logsumexp_k log alpha_{T-1} (the true value; the reference's
+ *     saturating compute_likelihood is derived from fwd_prob on the host).
+ *   add_rowmax: for EMIS_LOG_NORM_FLOOR, also add sum_t max_k l_t back into loglik (0 = reference behaviour).
+ *   workspace: hmmb200_fb_workspace_bytes(B, T, K) bytes of device scratch.
+ * --------------------------------------------------------------------------------------------------------- */
+size_t hmmb200_fb_workspace_bytes(int B, int T, int K);
+int    hmmb200_forward_backward_f32(const float *emis, int emis_mode, float floor_eps, int add_rowmax,
+                                    const float *trans_prob, const float *init_prob, int B, int T, int K,
+                                    float *gamma, float *fwd_prob, float *bwd_prob,
+                                    float *log_alpha, float *log_beta, float *loglik,
+                                    void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Viterbi (small K: K <= 32), packed uint8 backpointers, on-device traceback.
+ *   replaces  HMMPyTorch.viterbi_decode                           pytorch_hmm/hmm.py:132-184
+ *             MixtureGaussianHMMLayer._viterbi_decode             pytorch_hmm/mixture_gaussian.py:290-338
+ *
+ *   delta_0 = log_init + log b_0;  (m, psi_t[j]) = max_i(delta_{t-1}[i] + log_trans[i][j]) with the LOWEST i on
+ *   ties;  delta_t = m + log b_t (two fp32 roundings in that order);  s_{T-1} = first argmax; s_t = psi_{t+1}[s_{t+1}].
+ *   With emis_mode == HMMB200_EMIS_LOG the result is bit-identical to the reference given the same fp32 inputs.
+ *   outputs (NULL allowed except states): delta [B,T,K]; psi [B,T,K] uint8 (psi_0 = 0); states [B,T] int64;
+ *     score [B] = max_k delta_{T-1}.
+ *   workspace: hmmb200_viterbi_workspace_bytes(B, T, K) bytes (0 when the backpointers fit in shared memory).
+ * --------------------------------------------------------------------------------------------------------- */
+size_t hmmb200_viterbi_workspace_bytes(int B, int T, int K);
+int    hmmb200_viterbi_f32(const float *emis, int emis_mode, float floor_eps,
+                           const float *log_trans, const float *log_init, int B, int T, int K,
+                           float *delta, uint8_t *psi, int64_t *states, float *score,
+                           void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMM_B200_H */

@@ -1,0 +1,32 @@
+// common.cuh -- shared helpers for libhmm_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/hmm_b200.h"
+
+#define HMMB200_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace hmmb200 {
+
+// Thread-local last-error string (no global mutable state shared between host threads).
+char *last_error_buf();
+int set_error(int code, const char *fmt, ...);
+
+// Called after every launch: converts a launch error into HMMB200_ELAUNCH without synchronising.
+int check_launch(const char *what);
+
+// 0 when the current device is compute capability 10.x (cached per device ordinal).
+int require_sm100();
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+// Smallest power of two >= k, clamped to [4, 32]: lanes per sequence in the small-K recursions.
+inline int group_lanes(int K) { int g = 4; while (g < K) g <<= 1; return g; }
+// Number of broadcast slots (multiple of 4, >= K).
+inline int pad4(int K) { return (K + 3) & ~3; }
+
+}  // namespace hmmb200

@@ -1,0 +1,118 @@
+"""MixtureGaussianHMMLayer -- drop-in for pytorch_hmm/mixture_gaussian.py on the sm_100a kernels.
+
+Parameter names (`transition_logits` / buffer `transition_matrix`, `mixture_weights_logits`, `means`, `log_vars`)
+and initialisation follow the reference (mixture_gaussian.py:58-105).  forward() = GMM emission kernel + Viterbi
+kernel on the RAW log-emissions with a uniform prior -log K and log(clamp(softmax(logits), 1e-8)) transitions
+(mixture_gaussian.py:312, :357).  Covariance types: 'diag', 'tied' and 'spherical' run on the diagonal kernel
+(the latter two are broadcast special cases); 'full' is outside the north-star path and raises.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Optional, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+
+
+class MixtureGaussianHMMLayer(nn.Module):
+    def __init__(self, num_states: int, feature_dim: int, num_components: int = 3, covariance_type: str = "diag",
+                 learnable_transitions: bool = True, max_sequence_length: int = 10000):
+        super().__init__()
+        self.num_states, self.feature_dim, self.num_components = num_states, feature_dim, num_components
+        self.covariance_type = covariance_type
+        self.learnable_transitions = learnable_transitions
+        self.max_sequence_length = max_sequence_length
+        self.eps = 1e-8
+        self.log_eps = math.log(self.eps)
+        S, Cn, D = num_states, num_components, feature_dim
+        if learnable_transitions:
+            self.transition_logits = nn.Parameter(torch.randn(S, S) * 0.1)
+        else:
+            self.register_buffer("transition_matrix", self._create_left_to_right_matrix())
+        self.mixture_weights_logits = nn.Parameter(torch.randn(S, Cn) * 0.1)
+        self.means = nn.Parameter(torch.randn(S, Cn, D) * math.sqrt(2.0 / D))
+        if covariance_type == "diag":
+            self.log_vars = nn.Parameter(torch.zeros(S, Cn, D))
+        elif covariance_type == "tied":
+            self.log_vars = nn.Parameter(torch.zeros(D))
+        elif covariance_type == "spherical":
+            self.log_vars = nn.Parameter(torch.zeros(S, Cn))
+        elif covariance_type == "full":
+            raise NotImplementedError("covariance_type='full' is outside the B200 hot path (diag/tied/spherical only)")
+        else:
+            raise ValueError(f"Unknown covariance_type: {covariance_type}")
+
+    def _create_left_to_right_matrix(self) -> torch.Tensor:
+        S = self.num_states
+        P = torch.zeros(S, S)
+        i = torch.arange(S - 1)
+        P[i, i], P[i, i + 1] = 0.8, 0.2
+        P[S - 1, S - 1] = 1.0
+        return P
+
+    def get_transition_matrix(self) -> torch.Tensor:
+        if self.learnable_transitions:
+            return F.softmax(self.transition_logits, dim=-1)
+        return self.transition_matrix
+
+    def _safe_log(self, x: torch.Tensor) -> torch.Tensor:
+        return torch.log(torch.clamp(x, min=self.eps))
+
+    def _diag_log_vars(self) -> torch.Tensor:
+        S, Cn, D = self.num_states, self.num_components, self.feature_dim
+        if self.covariance_type == "tied":
+            return self.log_vars.view(1, 1, D).expand(S, Cn, D)
+        if self.covariance_type == "spherical":
+            return self.log_vars.unsqueeze(-1).expand(S, Cn, D)
+        return self.log_vars
+
+    def _packed(self) -> torch.Tensor:
+        logw = self._safe_log(F.softmax(self.mixture_weights_logits, dim=-1))       # mixture_gaussian.py:178-179
+        return ops.gmm_pack(self.means, self._diag_log_vars(), 1.0, logw)
+
+    def get_observation_log_probs(self, observations: torch.Tensor) -> torch.Tensor:
+        """(B,T,D) -> (B,T,S) log-likelihood under each state's GMM (mixture_gaussian.py:157-198)."""
+        if observations.shape[1] > self.max_sequence_length:
+            warnings.warn(f"Sequence length {observations.shape[1]} exceeds recommended maximum "
+                          f"{self.max_sequence_length}. Consider chunked processing.")
+        dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
+        out = ops.gmm_emission(observations.detach().to(dev), self._packed(), self.num_states, self.num_components,
+                               self.feature_dim)
+        return out if observations.device == out.device else out.to(observations.device)
+
+    def _viterbi_decode(self, obs_log_probs: torch.Tensor, log_transitions: torch.Tensor
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(B,T,S) raw log-emissions -> (states int64 (B,T), final_scores (B,))  (mixture_gaussian.py:290-338)."""
+        dev = ops.require_cuda(obs_log_probs.device if obs_log_probs.is_cuda else None)
+        S = obs_log_probs.shape[-1]
+        prior = torch.full((S,), -math.log(S), dtype=torch.float32, device=dev)
+        r = ops.viterbi(obs_log_probs.detach().to(dev), ops.EMIS_LOG, log_transitions.detach().to(dev), prior,
+                        want_delta=False, want_score=True)
+        st, sc = r["states"], r["score"]
+        if obs_log_probs.device != st.device:
+            st, sc = st.to(obs_log_probs.device), sc.to(obs_log_probs.device)
+        return st, sc
+
+    def forward(self, observations: torch.Tensor, return_log_probs: bool = False
+                ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
+        logb = ops.gmm_emission(observations.detach().to(dev), self._packed(), self.num_states, self.num_components,
+                                self.feature_dim)
+        log_trans = self._safe_log(self.get_transition_matrix())                     # mixture_gaussian.py:357
+        states, scores = self._viterbi_decode(logb, log_trans)
+        if observations.device != states.device:
+            states, scores = states.to(observations.device), scores.to(observations.device)
+        return (states, scores) if return_log_probs else (states, None)
+
+    def get_model_info(self) -> dict:
+        total = sum(p.numel() for p in self.parameters())
+        return {"num_states": self.num_states, "feature_dim": self.feature_dim, "num_components": self.num_components,
+                "covariance_type": self.covariance_type, "learnable_transitions": self.learnable_transitions,
+                "total_parameters": total,
+                "trainable_parameters": sum(p.numel() for p in self.parameters() if p.requires_grad),
+                "memory_efficient": True, "max_sequence_length": self.max_sequence_length}

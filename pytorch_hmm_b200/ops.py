@@ -1,0 +1,149 @@
+"""Tensor-level wrappers over the C ABI (include/hmm_b200.h).  torch is used for device memory and streams only.
+
+Every function takes CUDA tensors and enqueues work on torch's current stream of the tensor's device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+EMIS_LOG = 0
+EMIS_PROB_FLOOR = 1
+EMIS_LOG_NORM_FLOOR = 2
+EMIS_LOG_EXP_FLOOR = 3
+
+EPS = 1e-8
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(dev: torch.device):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {_lib.last_error()}")
+
+
+def require_cuda(device=None) -> torch.device:
+    """The engine is CUDA-only.  Resolves the compute device or raises -- there is no CPU fallback."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("pytorch_hmm_b200 needs a CUDA device (B200 / sm_100a); it has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(f"compute device must be CUDA, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _f32c(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# emission
+# ------------------------------------------------------------------------------------------------------
+def gmm_pack(means: torch.Tensor, log_vars: torch.Tensor, log_var_scale: float,
+             log_weights: Optional[torch.Tensor]) -> torch.Tensor:
+    """means/log_vars [K,C,D] (or [K,D]), log_weights [K,C] or None -> packed parameter buffer (device)."""
+    dev = require_cuda(means.device if means.is_cuda else None)
+    if means.dim() == 2:
+        means, log_vars = means.unsqueeze(1), log_vars.unsqueeze(1)
+    K, Cn, D = means.shape
+    means, log_vars = _f32c(means.detach(), dev), _f32c(log_vars.detach(), dev)
+    lw = None if log_weights is None else _f32c(log_weights.detach(), dev)
+    lib = _lib.load()
+    n = lib.hmmb200_gmm_packed_floats(K, Cn, D)
+    packed = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_gmm_pack_f32(_p(means), _p(log_vars), float(log_var_scale), _p(lw), K, Cn, D,
+                                        _p(packed), _stream(dev)), "hmmb200_gmm_pack_f32")
+    return packed
+
+
+def gmm_emission(x: torch.Tensor, packed: torch.Tensor, K: int, Cn: int, D: int,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [..., D] (CUDA) -> log b [..., K]."""
+    dev = packed.device
+    x = _f32c(x, dev)
+    if x.shape[-1] != D:
+        raise ValueError(f"feature dim {x.shape[-1]} != {D}")
+    n = x.numel() // D
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (K,), dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_gmm_emission_f32(_p(x), _p(packed), n, K, Cn, D, _p(out), _stream(dev)),
+               "hmmb200_gmm_emission_f32")
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+# recursions
+# ------------------------------------------------------------------------------------------------------
+def forward_backward(emis: torch.Tensor, mode: int, trans_prob: torch.Tensor, init_prob: torch.Tensor,
+                     eps: float = EPS, add_rowmax: bool = False, want=("gamma", "fwd", "bwd"),
+                     out: Optional[dict] = None) -> dict:
+    """emis [B,T,K] CUDA fp32.  Returns a dict with the requested tensors among
+    gamma, fwd, bwd, log_alpha, log_beta (each [B,T,K]) and always 'loglik' [B]."""
+    dev = require_cuda(emis.device)
+    emis = _f32c(emis, dev)
+    B, T, K = emis.shape
+    trans_prob, init_prob = _f32c(trans_prob, dev), _f32c(init_prob, dev)
+    lib = _lib.load()
+    res = {} if out is None else out
+    for name in ("gamma", "fwd", "bwd", "log_alpha", "log_beta"):
+        if name in want and name not in res:
+            res[name] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    if "loglik" not in res:
+        res["loglik"] = torch.empty(B, dtype=torch.float32, device=dev)
+    ws_bytes = lib.hmmb200_fb_workspace_bytes(B, T, K)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_forward_backward_f32(
+            _p(emis), int(mode), float(eps), int(bool(add_rowmax)), _p(trans_prob), _p(init_prob), B, T, K,
+            _p(res.get("gamma")), _p(res.get("fwd")), _p(res.get("bwd")), _p(res.get("log_alpha")),
+            _p(res.get("log_beta")), _p(res["loglik"]), _p(ws), ws_bytes, _stream(dev)),
+            "hmmb200_forward_backward_f32")
+    return res
+
+
+def viterbi(emis: torch.Tensor, mode: int, log_trans: torch.Tensor, log_init: torch.Tensor, eps: float = EPS,
+            want_delta: bool = True, want_psi: bool = False, want_score: bool = True,
+            out: Optional[dict] = None) -> dict:
+    """emis [B,T,K] CUDA fp32 -> dict(states int64 [B,T], delta [B,T,K], psi uint8 [B,T,K], score [B])."""
+    dev = require_cuda(emis.device)
+    emis = _f32c(emis, dev)
+    B, T, K = emis.shape
+    log_trans, log_init = _f32c(log_trans, dev), _f32c(log_init, dev)
+    lib = _lib.load()
+    res = {} if out is None else out
+    if "states" not in res:
+        res["states"] = torch.empty(B, T, dtype=torch.int64, device=dev)
+    if want_delta and "delta" not in res:
+        res["delta"] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    if want_psi and "psi" not in res:
+        res["psi"] = torch.empty(B, T, K, dtype=torch.uint8, device=dev)
+    if want_score and "score" not in res:
+        res["score"] = torch.empty(B, dtype=torch.float32, device=dev)
+    ws_bytes = lib.hmmb200_viterbi_workspace_bytes(B, T, K)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_viterbi_f32(_p(emis), int(mode), float(eps), _p(log_trans), _p(log_init), B, T, K,
+                                       _p(res.get("delta")), _p(res.get("psi")), _p(res["states"]),
+                                       _p(res.get("score")), _p(ws), ws_bytes, _stream(dev)),
+               "hmmb200_viterbi_f32")
+    return res

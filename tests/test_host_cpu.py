@@ -1,0 +1,99 @@
+"""CPU tests (-m "not gpu"): host-side logic of the drop-in classes, and that the C-ABI library loads and exports
+every symbol include/hmm_b200.h declares.  No compute call is made (there is no GPU here and no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_hmm_b200 as hm
+from pytorch_hmm_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "hmm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(hmmb200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    path = build.build_library()
+    assert os.path.exists(path)
+    lib = ctypes.CDLL(path)
+    names = _declared_symbols()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/hmm_b200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert _lib.load().hmmb200_abi_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_fails_loudly():
+    lib = _lib.load()
+    assert lib.hmmb200_device_check(-1) == -5                       # HMMB200_ENODEVICE
+    assert b"no CUDA device" in lib.hmmb200_last_error()
+    hmm = hm.HMMPyTorch(torch.eye(3) + 0.1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hmm.forward_backward(torch.rand(2, 4, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        hm.MixtureGaussianHMMLayer(3, 4)(torch.randn(1, 5, 4))
+
+
+def test_size_queries_need_no_device():
+    lib = _lib.load()
+    assert lib.hmmb200_gmm_packed_floats(12, 4, 80) == 80 * 24 * 4 + 48
+    assert lib.hmmb200_fb_workspace_bytes(256, 2000, 12) >= 256 * 2000 * (2 * 12 + 2) * 4
+    assert lib.hmmb200_viterbi_workspace_bytes(256, 2000, 12) == 0          # backpointers fit in shared memory
+    assert lib.hmmb200_viterbi_workspace_bytes(2, 9000, 16) == 2 * 9000 * 16
+
+
+def test_hmm_init_matches_reference(golden):
+    g = golden("core")
+    for tag in "abcde":
+        p0 = torch.from_numpy(g[f"{tag}_p0"]) if f"{tag}_p0" in g.files else None
+        h = hm.HMMPyTorch(torch.from_numpy(g[f"{tag}_P"]), p0)
+        assert np.array_equal(h.log_P.numpy(), g[f"{tag}_log_P"])
+        assert np.array_equal(h.log_p0.numpy(), g[f"{tag}_log_p0"])
+    with pytest.raises(ValueError):
+        hm.HMM(torch.ones(2, 3))
+    with pytest.raises(ValueError):
+        hm.HMM(torch.ones(3, 3), torch.ones(4))
+    h = hm.HMM(np.ones((3, 3), np.float32))                                  # numpy input accepted (hmm.py:24-25)
+    assert h.K == 3
+
+
+def test_transition_builders_match_reference(golden):
+    g = golden("core")
+    assert np.array_equal(hm.create_left_to_right_matrix(10, 0.7).numpy(), g["b_P"])
+    assert np.array_equal(hm.create_transition_matrix(6, "ergodic").numpy(), g["c_P"])
+    assert np.array_equal(hm.create_transition_matrix(5, "left_to_right_skip").numpy(), g["d_P"])
+    P = hm.create_transition_matrix(4, "circular")
+    assert torch.allclose(P.sum(1), torch.ones(4))
+    with pytest.raises(ValueError):
+        hm.create_transition_matrix(4, "nope")
+
+
+def test_layer_parameter_names_and_state_dict_compat(golden):
+    hl = hm.HMMLayer(7)
+    assert set(hl.state_dict()) == {"log_transition_logits", "log_initial_logits"}
+    assert set(hm.HMMLayer(5, learnable_transitions=False).state_dict()) == {"transition_matrix", "log_initial_logits"}
+    gl = hm.GaussianHMMLayer(4, 6)
+    assert set(gl.state_dict()) == {"means", "log_scales", "hmm_layer.log_transition_logits", "hmm_layer.log_initial_logits"}
+    mg = hm.MixtureGaussianHMMLayer(12, 80, num_components=4)
+    assert set(mg.state_dict()) == {"transition_logits", "mixture_weights_logits", "means", "log_vars"}
+    assert mg.means.shape == (12, 4, 80) and mg.log_vars.shape == (12, 4, 80)
+    g = golden("gaussian")
+    hl.load_state_dict({"log_transition_logits": torch.from_numpy(g["hl_log_transition_logits"]),
+                        "log_initial_logits": torch.from_numpy(g["hl_log_initial_logits"])})
+    assert torch.allclose(hl.get_transition_matrix().sum(1), torch.ones(7), atol=1e-6)
+    fixed = hm.MixtureGaussianHMMLayer(4, 3, learnable_transitions=False)
+    assert fixed.get_transition_matrix()[0, 0].item() == pytest.approx(0.8)
+    with pytest.raises(ValueError):
+        hm.MixtureGaussianHMMLayer(4, 3, covariance_type="bogus")
+    with pytest.raises(ValueError):
+        hm.GaussianHMMLayer(4, 3, covariance_type="bogus")
