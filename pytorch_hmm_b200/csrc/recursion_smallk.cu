@@ -1,62 +1,180 @@
-// recursion_smallk.cu -- small-K (K <= 32) HMM recursions for sm_100a.
+// recursion_smallk.cu -- small-K (K <= 32) HMM recursions for sm_100a, warp-specialised.
 //
-//   fb_sweep_kernel     forward and backward sweeps (two independent roles of one launch), scaled-probability
-//                       space, G lanes per sequence, transition column/row in registers, warp shuffles.
+//   fb_sweep_kernel     forward and backward sweeps (blockIdx.y = direction), scaled-probability space.
 //                       Replaces the per-time-step ATen launches of pytorch_hmm/hmm.py:95-117.
 //   fb_combine_kernel   posterior / exp(log alpha) / exp(log beta) from the two scaled sweeps (hmm.py:120-128).
-//   viterbi_kernel      max-plus recursion with packed uint8 backpointers in shared memory and a
-//                       chunk-parallel on-device traceback (hmm.py:159-178; mixture_gaussian.py:312-336).
+//   viterbi_kernel      max-plus recursion, packed uint8 backpointers in shared memory, chunk-parallel on-device
+//                       traceback (hmm.py:159-178; mixture_gaussian.py:312-336).
 //
-// Lane layout: a warp carries NS = 32/G sequences; lane (sub, j) owns state j of sequence `sub`.
-// Every step broadcasts the K previous values with K shuffles and reduces in registers; nothing on the
-// per-step critical path touches memory (emissions are prefetched a block of U frames ahead).
+// The time recursion is a latency problem (T dependent steps), so each CTA splits roles:
+//   * ONE consumer warp carries the dependent chain and nothing else.  A warp holds NS = 32/G sequences; lane
+//     (sub, j) owns state j of sequence `sub` and keeps its column (or row) of the transition matrix in registers.
+//     Per step it reads the previous K-vector back from a shared-memory ring with K/4 broadcast LDS.128, does K
+//     FMAs (or K add + max), one multiply/add with the emission term and one STS.  No global access, no
+//     transcendental, no integer division on the chain.
+//   * helper warps stream emissions from HBM a chunk of CH frames ahead, convert them to what the consumer needs
+//     (floor, max-normalise, exp) into a shared-memory ring, and trail behind the consumer draining its results to
+//     HBM with coalesced stores; for Viterbi they also recompute the backpointers from the stored delta vectors
+//     (same fp32 adds -> bit-identical), which takes the arg-max off the chain entirely.
+//   * hand-off is two named barriers per ring buffer (FULL: helpers -> consumer, DONE: consumer -> helpers).
+// Scaling: the forward/backward vectors are renormalised every step by a power of two taken from the exponent of the
+// previous step's largest entry (one REDUX; exact; integer exponent bookkeeping), so alpha = a * 2^ksum * exp(sum m).
+// A lone warp issues roughly one instruction every ~4-5 cycles on a dependent chain, so the consumer's instruction
+// count IS its latency: packed fp32x2 FMAs/adds, 3-input max, no per-step branches, 4x unrolled (fits the L0 I-cache).
 #include "common.cuh"
 
 namespace hmmb200 {
 
-// ----------------------------------------------------------------------------------------------------------
-// emission -> per-frame scaled probability b~ and the log-scale m that was divided out
-// ----------------------------------------------------------------------------------------------------------
-template <int G>
-__device__ __forceinline__ float group_max(float v) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o, G));
-    return v;
-}
-template <int G>
-__device__ __forceinline__ float group_sum(float v) {
-#pragma unroll
-    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o, G);
-    return v;
-}
+constexpr int CH = 64;          // frames per pipeline chunk
+constexpr int NB = 2;           // ring buffers
+constexpr int BT_PITCH = 33;    // floats per frame row of the emission ring (32 lanes + 1 pad)
+constexpr int MAXNS = 8;        // sequences per warp at G = 4
+constexpr int MR_BUFS = 2 * NB; // log-scale ring depth: loaders run up to NB chunks ahead of the drainer's read
+constexpr int BAR_FULL = 1;     // named barriers BAR_FULL + b, BAR_DONE + b  (0 is __syncthreads)
+constexpr int BAR_DONE = 1 + NB;
 
-template <int G>
-__device__ __forceinline__ void emis_to_scaled(int mode, float eps, float e, bool lane_ok, float &bt, float &m) {
-    if (mode == HMMB200_EMIS_PROB_FLOOR) {
-        m = 0.f;
-        bt = lane_ok ? e + eps : 0.f;
-    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
-        m = 0.f;
-        bt = lane_ok ? __expf(e) + eps : 0.f;
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// Blackwell packed fp32 pairs (one issue slot for two IEEE round-to-nearest operations) and 3-input max.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// exact maximum of N values as a 3-ary tree (order-independent, so bit-identical to any other order)
+template <int N>
+__device__ __forceinline__ float max_tree(float (&x)[N]) {
+    if constexpr (N == 1) {
+        return x[0];
+    } else if constexpr (N == 2) {
+        return fmaxf(x[0], x[1]);
     } else {
-        float ev = lane_ok ? e : -INFINITY;
-        m = group_max<G>(ev);
-        if (!(m > -INFINITY)) m = 0.f;                 // all states impossible: keep the frame finite
-        float b = lane_ok ? __expf(ev - m) : 0.f;
-        if (mode == HMMB200_EMIS_LOG_NORM_FLOOR && lane_ok) b += eps;
-        bt = b;
+        constexpr int M = (N + 2) / 3;
+        float y[M];
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            if (3 * i + 2 < N) y[i] = fmax3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
+            else if (3 * i + 1 < N) y[i] = fmaxf(x[3 * i], x[3 * i + 1]);
+            else y[i] = x[3 * i];
+        }
+        return max_tree<M>(y);
     }
 }
 
-// The log-emission the Viterbi recursion adds (fp32, same formula as the reference for each input kind).
-template <int G>
-__device__ __forceinline__ float emis_to_log(int mode, float eps, float e, bool lane_ok) {
-    if (mode == HMMB200_EMIS_LOG) return e;
-    if (mode == HMMB200_EMIS_PROB_FLOOR) return logf(e + eps);
-    if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) return logf(expf(e) + eps);
-    float ev = lane_ok ? e : -INFINITY;
-    float m = group_max<G>(ev);
-    return logf(expf(e - m) + eps);
+// ----------------------------------------------------------------------------------------------------------
+// per-frame emission transforms (helper side; one lane holds the K values of one frame)
+// ----------------------------------------------------------------------------------------------------------
+// scaled-probability form for forward/backward: b~ and the log-scale m divided out of the frame
+template <int KP>
+__device__ __forceinline__ void row_to_scaled(int mode, float eps, int K, float (&e)[KP], float &m) {
+    m = 0.f;
+    if (mode == HMMB200_EMIS_PROB_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? e[k] + eps : 0.f;
+    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? expf(e[k]) + eps : 0.f;
+    } else {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) if (k < K) mx = fmaxf(mx, e[k]);
+        if (!(mx > -INFINITY)) mx = 0.f;                     // all states impossible: keep the frame finite
+        const float add = (mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? expf(e[k] - mx) + add : 0.f;
+        m = mx;
+    }
+}
+
+// log form for Viterbi (fp32, the reference's formula for each input kind)
+template <int KP>
+__device__ __forceinline__ void row_to_log(int mode, float eps, int K, float (&e)[KP]) {
+    if (mode == HMMB200_EMIS_LOG) return;
+    if (mode == HMMB200_EMIS_PROB_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? logf(e[k] + eps) : 0.f;
+    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? logf(expf(e[k]) + eps) : 0.f;
+    } else {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) if (k < K) mx = fmaxf(mx, e[k]);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? logf(expf(e[k] - mx) + eps) : 0.f;
+    }
+}
+
+// Loader-warp loop: stream this CTA's NS sequences from HBM one chunk (CH frames) ahead of the consumer, transform each
+// frame (scaled-probability form for forward/backward, log form for Viterbi) and publish the per-lane values in bt[b]
+// (and the per-frame log-scale in mraw[b]).  NL loader warps split the frames; lane (sub, q) of loader `lw` handles
+// FL = CH/G/NL consecutive frames of sequence `sub`.  Raw values for chunk c+1 are already in flight (registers)
+// while chunk c is converted, so no HBM latency is exposed.
+template <int G, int KP, int DIR, bool SCALED, int NL>
+__device__ __forceinline__ void loader_loop(const float *emis, int mode, float eps, int B, int T, int K, int lw,
+                                            float *bt, float *mraw, int n_bar) {
+    constexpr int NS = 32 / G, FPL = CH / G, FL = FPL / NL;
+    static_assert(FPL % NL == 0 && FL >= 1, "loader split");
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, q = lane % G;
+    const int seq = blockIdx.x * NS + sub;
+    const bool seq_ok = seq < B;
+    const int nch = (T + CH - 1) / CH;
+    const int u_base = q * FPL + lw * FL;
+
+    float cur[FL][KP], nxt[FL][KP];
+    auto fetch = [&](int c, float (&dst)[FL][KP]) {
+#pragma unroll
+        for (int i = 0; i < FL; ++i) {
+            const int n = c * CH + u_base + i;
+            const bool ok = seq_ok && n < T;
+            const int f = (DIR == 0) ? n : T - 1 - n;
+            const float *row = emis + ((size_t)(ok ? seq : 0) * T + (ok ? f : 0)) * K;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) dst[i][k] = (ok && k < K) ? __ldg(row + k) : 0.f;
+        }
+    };
+    fetch(0, cur);
+    for (int c = 0; c < nch; ++c) {
+        const int b = c % NB;
+        if (c + 1 < nch) fetch(c + 1, nxt);
+        if (c >= NB) bar_sync(BAR_DONE + b, n_bar);          // consumer is done reading bt[b] (chunk c - NB)
+        float *btb = bt + (size_t)b * CH * BT_PITCH;
+#pragma unroll
+        for (int i = 0; i < FL; ++i) {
+            const int u = u_base + i;
+            const bool ok = seq_ok && (c * CH + u) < T;
+            float m = 0.f;
+            if (SCALED) row_to_scaled<KP>(mode, eps, K, cur[i], m);
+            else row_to_log<KP>(mode, eps, K, cur[i]);
+            float *dst = btb + u * BT_PITCH + sub * G;
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                float v = 0.f;
+                if (k < KP) v = (ok && k < K) ? cur[i][k] : 0.f;
+                dst[k] = v;
+            }
+            if (SCALED) mraw[((size_t)(c % MR_BUFS) * CH + u) * MAXNS + sub] = ok ? m : 0.f;
+        }
+        bar_arrive(BAR_FULL + b, n_bar);
+#pragma unroll
+        for (int i = 0; i < FL; ++i)
+#pragma unroll
+            for (int k = 0; k < KP; ++k) cur[i][k] = nxt[i][k];
+    }
+    for (int c = max(0, nch - NB); c < nch; ++c) bar_sync(BAR_DONE + (c % NB), n_bar);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -75,130 +193,218 @@ struct FbParams {
     float *loglik;        // [B] or null
 };
 
-// One sweep over one warp's sequences.  DIR 0: alpha_t(j) = (sum_i alpha_{t-1}(i) P(i,j)) b_t(j)   (hmm.py:98-101)
-//                                       DIR 1: beta_t(i)  = sum_j P(i,j) b_{t+1}(j) beta_{t+1}(j)   (hmm.py:113-117)
-// Both are the same register recursion  w <- (sum_i shfl(w,i) * M[i]) * b~ * r  on w = alpha (DIR 0) or
-// w = beta .* b~ (DIR 1), with M the column (DIR 0) or row (DIR 1) of P owned by the lane.  r is a lagged
-// normaliser 1/sum(w) from the previous step, so it never sits on the dependent chain; its log is
-// accumulated (in double) into the per-frame log-scale.
-template <int G, int KP, int DIR>
-__device__ __forceinline__ void fb_sweep(const FbParams &p) {
+constexpr int FB_NL = 2;                                   // loader warps
+constexpr int FB_ND = 1;                                   // drainer warps
+constexpr int FB_THREADS = 32 * (1 + FB_NL + FB_ND);
+constexpr size_t FB_SMEM_BT = (size_t)NB * CH * BT_PITCH * sizeof(float);
+constexpr size_t FB_SMEM_WR = (size_t)NB * CH * 32 * sizeof(float);
+constexpr size_t FB_SMEM_ER = (size_t)NB * CH * MAXNS * sizeof(int);
+constexpr size_t FB_SMEM_MR = (size_t)MR_BUFS * CH * MAXNS * sizeof(float);
+constexpr size_t FB_SMEM_BYTES = FB_SMEM_MR + FB_SMEM_BT + 2 * FB_SMEM_WR + FB_SMEM_ER;
+
+// DIR 0: alpha_t(j) = (sum_i alpha_{t-1}(i) P(i,j)) b_t(j)                         (hmm.py:98-101)
+// DIR 1: beta_t(i)  = sum_j P(i,j) b_{t+1}(j) beta_{t+1}(j)                         (hmm.py:113-117)
+// Both are  w <- (sum_i w_prev(i) * M[i]) * b~ * r  on w = alpha (DIR 0) or w = beta .* b~ (DIR 1), M = the lane's
+// column (DIR 0) / row (DIR 1) of P, r = 2^-k from the previous step's sum.
+template <int G, int KP, int DIR, bool PAD>
+__device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, float *wr, float *br, int *er) {
     constexpr int NS = 32 / G;
-    constexpr int U = 16;
     const int lane = threadIdx.x & 31;
     const int sub = lane / G, j = lane % G;
     const int seq = blockIdx.x * NS + sub;
     const int K = p.K, T = p.T;
-    const bool seq_ok = seq < p.B;
-    const bool lane_ok = seq_ok && j < K;
-    const int seq_c = seq_ok ? seq : p.B - 1;
-    const int j_c = j < K ? j : K - 1;
-    const int mode = p.mode;
-    const float eps = p.eps;
-    const bool add_m = (mode == HMMB200_EMIS_LOG) || (mode == HMMB200_EMIS_LOG_NORM_FLOOR && p.add_rowmax);
+    const bool lane_ok = seq < p.B && j < K;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
+    // PAD (K < G): the last lane of each group owns no state; it publishes the running exponent in its ring slot,
+    // so the bookkeeping costs no extra store.  Otherwise lane 0 writes it to the `er` ring.
+    const bool pad_lane = PAD && (j == G - 1);
 
-    float M[KP];
+    float2 M2[KP / 2];
 #pragma unroll
-    for (int i = 0; i < KP; ++i) {
-        float v = 0.f;
-        if (lane_ok && i < K) v = (DIR == 0) ? __ldg(p.trans + i * K + j) : __ldg(p.trans + j * K + i);
-        M[i] = v;
+    for (int i = 0; i < KP / 2; ++i) {
+        float v0 = 0.f, v1 = 0.f;
+        if (lane_ok && 2 * i < K) v0 = (DIR == 0) ? __ldg(p.trans + (2 * i) * K + j) : __ldg(p.trans + j * K + 2 * i);
+        if (lane_ok && 2 * i + 1 < K) v1 = (DIR == 0) ? __ldg(p.trans + (2 * i + 1) * K + j) : __ldg(p.trans + j * K + 2 * i + 1);
+        M2[i] = make_float2(v0, v1);
     }
-    const float *ep = p.emis + (size_t)seq_c * T * K + j_c;
-    float *out = ((DIR == 0) ? p.ws_a : p.ws_b) + (size_t)seq_c * T * K + j_c;
-    float *outL = ((DIR == 0) ? p.ws_la : p.ws_lb) + (size_t)seq_c * T;
+    const float pi = (DIR == 0 && lane_ok) ? __ldg(p.init + j) : 0.f;
 
-    // ---- step 0 -------------------------------------------------------------------------------------
-    float w, bt0, m0;
-    double L;
-    float m_carry = 0.f;   // DIR 1: log-scale of the frame consumed by the previous step
-    {
-        const int f0 = (DIR == 0) ? 0 : T - 1;
-        float e0 = __ldg(ep + (size_t)f0 * K);
-        emis_to_scaled<G>(mode, eps, e0, lane_ok, bt0, m0);
-        if (DIR == 0) {
-            float pi = lane_ok ? __ldg(p.init + j) : 0.f;
-            w = pi * bt0;
-            L = add_m ? (double)m0 : 0.0;
-            if (lane_ok) out[(size_t)f0 * K] = w;
-        } else {
-            w = bt0;
-            L = 0.0;
-            m_carry = add_m ? m0 : 0.f;
-            if (lane_ok) out[(size_t)f0 * K] = 1.0f;
-        }
-        if (seq_ok && j == 0) outL[f0] = (float)L;
-    }
-
-    // ---- steps 1 .. T-1, emissions prefetched one block (U frames) ahead ---------------------------------
     float r_cur = 1.f;
-    float eb[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        int n = 1 + u;
-        int f = (DIR == 0) ? n : T - 1 - n;
-        eb[u] = (n < T) ? __ldg(ep + (size_t)f * K) : 0.f;
-    }
-    for (int n0 = 1; n0 < T; n0 += U) {
-        float en[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            int n = n0 + U + u;
-            int f = (DIR == 0) ? n : T - 1 - n;
-            en[u] = (n < T) ? __ldg(ep + (size_t)f * K) : 0.f;
-        }
-        float bt[U], mt[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) emis_to_scaled<G>(mode, eps, eb[u], lane_ok, bt[u], mt[u]);
+    int k_cur = 0, ksum = 0;
+    const float4 *prev = reinterpret_cast<const float4 *>(wr + sub * G);
+    float *wp = wr, *bp2 = br;
+    int *ep = er;
 
+    // one time step: w <- (sum_i prev[i] * M[i]) * (b~ * r) ; the pad lane carries (float)ksum instead
+    auto step = [&](int u, float bqv) {
+        float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int n = n0 + u;
-            if (n < T) {
-                const int f = (DIR == 0) ? n : T - 1 - n;
-                float v[KP];
-#pragma unroll
-                for (int i = 0; i < KP; ++i) v[i] = __shfl_sync(FULL_MASK, w, i, G);
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-                for (int i = 0; i < KP; i += 4) {
-                    a0 = fmaf(v[i + 0], M[i + 0], a0); s0 += v[i + 0];
-                    a1 = fmaf(v[i + 1], M[i + 1], a1); s1 += v[i + 1];
-                    a2 = fmaf(v[i + 2], M[i + 2], a2); s2 += v[i + 2];
-                    a3 = fmaf(v[i + 3], M[i + 3], a3); s3 += v[i + 3];
-                }
-                const float acc = (a0 + a1) + (a2 + a3);
-                const float S = (s0 + s1) + (s2 + s3);
-                const float mb = bt[u] * r_cur;              // ready long before acc
-                w = acc * mb;
-                const float lr = __logf(r_cur);
-                if (DIR == 0) {
-                    L += (double)(add_m ? mt[u] : 0.f) - (double)lr;
-                    if (lane_ok) out[(size_t)f * K] = w;
-                } else {
-                    L += (double)m_carry - (double)lr;
-                    m_carry = add_m ? mt[u] : 0.f;
-                    if (lane_ok) out[(size_t)f * K] = acc * r_cur;
-                }
-                if (seq_ok && j == 0) outL[f] = (float)L;
-                r_cur = (S > 1e-30f && S < 1e30f) ? __fdividef(1.f, S) : 1.f;   // used by the NEXT step
-            }
+        for (int i4 = 0; i4 < KP / 4; ++i4) {
+            const float4 t = prev[i4];
+            acc_a = ffma2(make_float2(t.x, t.y), M2[2 * i4], acc_a);
+            acc_b = ffma2(make_float2(t.z, t.w), M2[2 * i4 + 1], acc_b);
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) eb[u] = en[u];
-    }
+        const float2 s2 = fadd2(acc_a, acc_b);
+        const float acc = s2.x + s2.y;
+        const float mb = bqv * r_cur;
+        ksum += k_cur;
+        const float padf = pad_lane ? (float)ksum : 0.f;
+        const float w = fmaf(acc, mb, padf);
+        if (DIR == 1) bp2[u * 32] = acc * r_cur;
+        wp[u * 32] = w;
+        if (!PAD && j == 0) ep[u * MAXNS] = ksum;
+        // next step's power-of-two normaliser: exponent of the group's largest entry (one REDUX, off the chain)
+        const unsigned mx = __reduce_max_sync(gmask, lane_ok ? __float_as_uint(w) : 0u);
+        const unsigned eb = mx >> 23;
+        k_cur = (int)eb - 127;
+        r_cur = __uint_as_float((254u - eb) << 23);
+        prev = reinterpret_cast<const float4 *>(wp + u * 32 - j);
+        __syncwarp();
+    };
 
-    if (DIR == 0 && p.loglik != nullptr) {
-        float tot = group_sum<G>(lane_ok ? w : 0.f);
-        if (seq_ok && j == 0) p.loglik[seq] = (float)(L + (double)logf(tot));
+    const int nch = (T + CH - 1) / CH;
+    for (int c = 0; c < nch; ++c) {
+        const int b = c % NB;
+        bar_sync(BAR_FULL + b, FB_THREADS);
+        const int nf = min(CH, T - c * CH);
+        const float *btb = bt + (size_t)b * CH * BT_PITCH + lane;
+        wp = wr + (size_t)b * CH * 32 + lane;
+        bp2 = br + (size_t)b * CH * 32 + lane;
+        ep = er + (size_t)b * CH * MAXNS + sub;
+        int u = 0;
+        if (c == 0) {
+            // step 0: alpha_0 = p0 .* b_0 (hmm.py:92)  /  beta_{T-1} = 1 (hmm.py:107)
+            const float b0 = btb[0];
+            const float w = (DIR == 0) ? pi * b0 : (lane_ok ? b0 : 0.f);
+            if (DIR == 1) bp2[0] = lane_ok ? 1.f : 0.f;
+            wp[0] = w;                                       // pad lane: ksum = 0
+            if (!PAD && j == 0) ep[0] = 0;
+            const unsigned mx = __reduce_max_sync(gmask, lane_ok ? __float_as_uint(w) : 0u);
+            const unsigned eb = mx >> 23;
+            k_cur = (int)eb - 127;
+            r_cur = __uint_as_float((254u - eb) << 23);
+            prev = reinterpret_cast<const float4 *>(wp - j);
+            __syncwarp();
+            u = 1;
+        }
+        for (; u + 4 <= nf; u += 4) {
+            float bq[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) bq[i] = btb[(u + i) * BT_PITCH];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) step(u + i, bq[i]);
+        }
+        for (; u < nf; ++u) step(u, btb[u * BT_PITCH]);
+        bar_arrive(BAR_DONE + b, FB_THREADS);
     }
 }
 
+// Drainer warp: trails the consumer by NB chunks; copies the scaled vectors from the ring to HBM with coalesced
+// stores and turns the exponent / log-scale bookkeeping into the per-frame log scale la (alpha = a * exp(la)).
+template <int G, int KP, int DIR, bool PAD>
+__device__ __forceinline__ void fb_drainer(const FbParams &p, const float *wr, const float *br, const int *er,
+                                           const float *mraw) {
+    constexpr int NS = 32 / G;
+    static_assert(CH == 64, "the log-scale scan assumes two frames per lane");
+    const int lane = threadIdx.x & 31;
+    const int K = p.K, T = p.T, B = p.B;
+    const bool add_m = (p.mode == HMMB200_EMIS_LOG) || (p.mode == HMMB200_EMIS_LOG_NORM_FLOOR && p.add_rowmax);
+    const int nch = (T + CH - 1) / CH;
+    float *ws = (DIR == 0) ? p.ws_a : p.ws_b;
+    float *wsl = (DIR == 0) ? p.ws_la : p.ws_lb;
+    const float *src_ring = (DIR == 0) ? wr : br;
+    double carry[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) carry[s] = 0.0;
+    // running exponent published by the consumer: pad slot of the w ring (PAD) or the er ring
+    auto ksum_at = [&](int b, int u, int s) -> double {
+        return PAD ? (double)wr[((size_t)b * CH + u) * 32 + s * G + (G - 1)] : (double)er[((size_t)b * CH + u) * MAXNS + s];
+    };
+
+    auto drain = [&](int c, int b) {
+        const int nf = min(CH, T - c * CH);
+        const int n_lo = c * CH;
+        const int f_lo = (DIR == 0) ? n_lo : T - n_lo - nf;          // lowest frame index of the chunk
+        constexpr int R = 32 / G;                                    // frame rows covered per warp iteration
+        const int rr = lane / G, k = lane % G;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int sq = blockIdx.x * NS + s;
+            if (sq < B) {
+                const float *src = src_ring + (size_t)b * CH * 32 + s * G;
+                float *dst = ws + ((size_t)sq * T + f_lo) * K;
+                for (int fl0 = 0; fl0 < nf; fl0 += R) {
+                    const int fl = fl0 + rr;
+                    if (fl < nf && k < K) {
+                        const int u = (DIR == 0) ? fl : nf - 1 - fl;
+                        dst[(size_t)fl * K + k] = src[u * 32 + k];
+                    }
+                }
+                // log scale: prefix of the per-frame m (inclusive for alpha, exclusive for beta) + ln2 * exponent
+                const int u0 = 2 * lane, u1 = 2 * lane + 1;
+                const double m0 = add_m ? (double)mraw[((size_t)(c % MR_BUFS) * CH + u0) * MAXNS + s] : 0.0;
+                const double m1 = add_m ? (double)mraw[((size_t)(c % MR_BUFS) * CH + u1) * MAXNS + s] : 0.0;
+                double x = m0 + m1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double y = __shfl_up_sync(FULL_MASK, x, o);
+                    if (lane >= o) x += y;
+                }
+                const double pre0 = carry[s] + (x - m1);             // inclusive prefix at u0
+                const double pre1 = carry[s] + x;                    // inclusive prefix at u1
+                carry[s] += __shfl_sync(FULL_MASK, x, 31);
+                const double l0 = ((DIR == 0) ? pre0 : pre0 - m0) + 0.69314718055994530942 * ksum_at(b, u0, s);
+                const double l1 = ((DIR == 0) ? pre1 : pre1 - m1) + 0.69314718055994530942 * ksum_at(b, u1, s);
+                float *dl = wsl + (size_t)sq * T;
+                if (u0 < nf) dl[(DIR == 0) ? n_lo + u0 : T - 1 - (n_lo + u0)] = (float)l0;
+                if (u1 < nf) dl[(DIR == 0) ? n_lo + u1 : T - 1 - (n_lo + u1)] = (float)l1;
+                if (DIR == 0 && p.loglik != nullptr && c == nch - 1) {
+                    const int ul = (T - 1) - n_lo;                   // last frame: loglik = la + log(sum_k a)
+                    if (u0 == ul || u1 == ul) {
+                        const float *v = wr + ((size_t)b * CH + ul) * 32 + s * G;
+                        float tot = 0.f;
+                        for (int kk = 0; kk < K; ++kk) tot += v[kk];
+                        p.loglik[sq] = (float)(((u0 == ul) ? l0 : l1) + (double)logf(tot));
+                    }
+                }
+            }
+        }
+    };
+
+    for (int c = 0; c < nch; ++c) {
+        const int b = c % NB;
+        if (c >= NB) {
+            bar_sync(BAR_DONE + b, FB_THREADS);
+            drain(c - NB, b);
+        }
+        bar_arrive(BAR_FULL + b, FB_THREADS);                        // ring buffer b drained: consumer may overwrite it
+    }
+    for (int c = max(0, nch - NB); c < nch; ++c) {
+        const int b = c % NB;
+        bar_sync(BAR_DONE + b, FB_THREADS);
+        drain(c, b);
+    }
+}
+
+template <int G, int KP, int DIR, bool PAD>
+__device__ __forceinline__ void fb_roles(const FbParams &p, uint8_t *smem) {
+    float *mraw = reinterpret_cast<float *>(smem);
+    float *bt = reinterpret_cast<float *>(smem + FB_SMEM_MR);
+    float *wr = reinterpret_cast<float *>(smem + FB_SMEM_MR + FB_SMEM_BT);
+    float *br = reinterpret_cast<float *>(smem + FB_SMEM_MR + FB_SMEM_BT + FB_SMEM_WR);
+    int *er = reinterpret_cast<int *>(smem + FB_SMEM_MR + FB_SMEM_BT + 2 * FB_SMEM_WR);
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) fb_consumer<G, KP, DIR, PAD>(p, bt, wr, br, er);
+    else if (warp <= FB_NL) loader_loop<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, warp - 1, bt, mraw, FB_THREADS);
+    else fb_drainer<G, KP, DIR, PAD>(p, wr, br, er, mraw);
+}
+
 template <int G, int KP>
-__global__ void __launch_bounds__(32) fb_sweep_kernel(FbParams p) {
-    if (blockIdx.y == 0) fb_sweep<G, KP, 0>(p);
-    else fb_sweep<G, KP, 1>(p);
+__global__ void __launch_bounds__(FB_THREADS) fb_sweep_kernel(FbParams p) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    const bool pad = p.K < G;
+    if (blockIdx.y == 0) { if (pad) fb_roles<G, KP, 0, true>(p, smem); else fb_roles<G, KP, 0, false>(p, smem); }
+    else { if (pad) fb_roles<G, KP, 1, true>(p, smem); else fb_roles<G, KP, 1, false>(p, smem); }
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -272,105 +478,160 @@ struct VitParams {
     int n_chunks;        // ceil((T-1)/L)
 };
 
-constexpr int VIT_THREADS = 128;
+constexpr int VIT_NL = 2;                                  // loader warps
+constexpr int VIT_ND = 3;                                  // drainer warps (delta store + backpointers)
+constexpr int VIT_THREADS = 32 * (1 + VIT_NL + VIT_ND);
+constexpr size_t VIT_SMEM_BT = (size_t)NB * CH * BT_PITCH * sizeof(float);
+constexpr size_t VIT_SMEM_DR = (size_t)NB * CH * 32 * sizeof(float);
+constexpr size_t VIT_SMEM_CARRY = 2 * 32 * sizeof(float);
+constexpr size_t VIT_SMEM_PIPE = VIT_SMEM_BT + VIT_SMEM_DR + VIT_SMEM_CARRY;
 
 // Shared-memory layout (bytes), NS sequences per CTA:
-//   [psi: NS*T*G if psi_in_smem][st: NS*T][exit: NS*n_chunks*G][entry: NS*n_chunks][final: NS ints + NS floats]
+//   [bt ring][delta ring][carry][psi: NS*T*G if psi_in_smem][st: NS*T][exit: NS*n_chunks*G][entry: NS*n_chunks][final]
 template <int G, int KP>
 __global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
     constexpr int NS = 32 / G;
-    constexpr int U = 16;
     extern __shared__ __align__(16) uint8_t smem[];
-    const int K = p.K, T = p.T;
+    const int K = p.K, T = p.T, B = p.B;
     const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
     const int seq_base = blockIdx.x * NS;
 
-    uint8_t *psi_s = smem;
-    size_t off = p.psi_in_smem ? (size_t)NS * T * G : 0;
+    float *bt = reinterpret_cast<float *>(smem);
+    float *dr = reinterpret_cast<float *>(smem + VIT_SMEM_BT);
+    float *carry = reinterpret_cast<float *>(smem + VIT_SMEM_BT + VIT_SMEM_DR);
+    uint8_t *psi_s = smem + VIT_SMEM_PIPE;
+    size_t off = VIT_SMEM_PIPE + (p.psi_in_smem ? (size_t)NS * T * G : 0);
     uint8_t *st_s = smem + off;            off += (size_t)NS * T;
     uint8_t *exit_s = smem + off;          off += (size_t)NS * p.n_chunks * G;
     uint8_t *entry_s = smem + off;         off += (size_t)NS * p.n_chunks;
     off = (off + 15) & ~(size_t)15;
     int *final_s = reinterpret_cast<int *>(smem + off);
 
-    // ---------------- recursion: warp 0 ----------------------------------------------------------------
-    if (tid < 32) {
-        const int lane = tid;
-        const int sub = lane / G, j = lane % G;
-        const int seq = seq_base + sub;
-        const bool seq_ok = seq < p.B;
-        const bool lane_ok = seq_ok && j < K;
-        const int seq_c = seq_ok ? seq : p.B - 1;
-        const int j_c = j < K ? j : K - 1;
-        const int mode = p.mode;
-        const float eps = p.eps;
+    const int sub = lane / G, j = lane % G;
+    const int seq = seq_base + sub;
+    const bool seq_ok = seq < B;
+    const bool lane_ok = seq_ok && j < K;
+    const int nch = (T + CH - 1) / CH;
 
-        float M[KP];
+    // every warp keeps the lane's transition column: the consumer for the recursion, the helpers for psi.
+    // Lanes that own no state hold -inf, so their delta stays -inf without any select on the chain.
+    float2 M2[KP / 2];
 #pragma unroll
-        for (int i = 0; i < KP; ++i) M[i] = (lane_ok && i < K) ? __ldg(p.log_trans + i * K + j) : -INFINITY;
-
-        const float *ep = p.emis + (size_t)seq_c * T * K + j_c;
-        float *dout = p.delta ? p.delta + (size_t)seq_c * T * K + j_c : nullptr;
-        uint8_t *pout = p.psi_out ? p.psi_out + (size_t)seq_c * T * K + j_c : nullptr;
-        uint8_t *pst = p.psi_in_smem ? psi_s + (size_t)sub * T * G + j : p.psi_ws + (size_t)seq_c * T * G + j;
-
-        float d;
-        {
-            float e0 = emis_to_log<G>(mode, eps, __ldg(ep), lane_ok);
-            d = lane_ok ? __fadd_rn(__ldg(p.log_init + j), e0) : -INFINITY;
-            if (lane_ok && dout) dout[0] = d;
-            if (lane_ok && pout) pout[0] = 0;
-            if (seq_ok || p.psi_in_smem) pst[0] = 0;
+    for (int i = 0; i < KP / 2; ++i) {
+        const float v0 = (lane_ok && 2 * i < K) ? __ldg(p.log_trans + (2 * i) * K + j) : -INFINITY;
+        const float v1 = (lane_ok && 2 * i + 1 < K) ? __ldg(p.log_trans + (2 * i + 1) * K + j) : -INFINITY;
+        M2[i] = make_float2(v0, v1);
+    }
+    // c[i] = delta_prev[i] + logP[i][j] as packed IEEE adds (bit-identical to scalar adds)
+    auto candidates = [&](const float4 *pv, float (&cv)[KP]) {
+#pragma unroll
+        for (int i4 = 0; i4 < KP / 4; ++i4) {
+            const float4 t = pv[i4];
+            const float2 lo = fadd2(make_float2(t.x, t.y), M2[2 * i4]);
+            const float2 hi = fadd2(make_float2(t.z, t.w), M2[2 * i4 + 1]);
+            cv[4 * i4 + 0] = lo.x; cv[4 * i4 + 1] = lo.y; cv[4 * i4 + 2] = hi.x; cv[4 * i4 + 3] = hi.y;
         }
-        float eb[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) eb[u] = (1 + u < T) ? __ldg(ep + (size_t)(1 + u) * K) : 0.f;
-        for (int t0 = 1; t0 < T; t0 += U) {
-            float en[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) en[u] = (t0 + U + u < T) ? __ldg(ep + (size_t)(t0 + U + u) * K) : 0.f;
-            float le[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) le[u] = emis_to_log<G>(mode, eps, eb[u], lane_ok);
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int t = t0 + u;
-                if (t < T) {
-                    float c[KP];
-#pragma unroll
-                    for (int i = 0; i < KP; ++i) c[i] = __fadd_rn(__shfl_sync(FULL_MASK, d, i, G), M[i]);
-                    // exact max (order-independent), then the lowest index attaining it (torch.max tie rule)
-                    float m4[KP / 4];
-#pragma unroll
-                    for (int i = 0; i < KP; i += 4) m4[i / 4] = fmaxf(fmaxf(c[i], c[i + 1]), fmaxf(c[i + 2], c[i + 3]));
-                    float best = m4[0];
-#pragma unroll
-                    for (int q = 1; q < KP / 4; ++q) best = fmaxf(best, m4[q]);
-                    d = __fadd_rn(best, le[u]);
-                    int arg = 0;
-#pragma unroll
-                    for (int i = KP - 1; i >= 0; --i) arg = (c[i] == best) ? i : arg;
-                    if (!lane_ok) d = -INFINITY;
-                    if (lane_ok && dout) dout[(size_t)t * K] = d;
-                    if (lane_ok && pout) pout[(size_t)t * K] = (uint8_t)arg;
-                    if (seq_ok || p.psi_in_smem) pst[(size_t)t * G] = (uint8_t)arg;
-                }
+    };
+
+    if (warp == 0) {
+        // ---------------- consumer: delta_t(j) = max_i(delta_{t-1}(i) + logP(i,j)) + log b_t(j) --------------
+        const float li = lane_ok ? __ldg(p.log_init + j) : -INFINITY;
+        float d = -INFINITY;
+        const float4 *prev = reinterpret_cast<const float4 *>(dr + sub * G);
+        float *dp = dr;
+        auto step = [&](int u, float eqv) {
+            float cv[KP];
+            candidates(prev, cv);
+            d = __fadd_rn(max_tree<KP>(cv), eqv);
+            dp[u * 32] = d;
+            prev = reinterpret_cast<const float4 *>(dp + u * 32 - j);
+            __syncwarp();
+        };
+        for (int c = 0; c < nch; ++c) {
+            const int b = c % NB;
+            bar_sync(BAR_FULL + b, VIT_THREADS);
+            const int nf = min(CH, T - c * CH);
+            const float *btb = bt + (size_t)b * CH * BT_PITCH + lane;
+            dp = dr + (size_t)b * CH * 32 + lane;
+            int u = 0;
+            if (c == 0) {
+                d = __fadd_rn(li, btb[0]);                  // delta_0 = log_p0 + log b_0 (hmm.py:159)
+                dp[0] = d;
+                prev = reinterpret_cast<const float4 *>(dp - j);
+                __syncwarp();
+                u = 1;
             }
+            for (; u + 4 <= nf; u += 4) {
+                float eq[4];
 #pragma unroll
-            for (int u = 0; u < U; ++u) eb[u] = en[u];
+                for (int i = 0; i < 4; ++i) eq[i] = btb[(u + i) * BT_PITCH];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) step(u + i, eq[i]);
+            }
+            for (; u < nf; ++u) step(u, btb[u * BT_PITCH]);
+            bar_arrive(BAR_DONE + b, VIT_THREADS);
         }
         // final state: first index of the maximum (hmm.py:174)
         float bv = lane_ok ? d : -INFINITY;
         int bi = j;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(FULL_MASK, bv, o, G);
-            int oi = __shfl_xor_sync(FULL_MASK, bi, o, G);
+            const float ov = __shfl_xor_sync(FULL_MASK, bv, o, G);
+            const int oi = __shfl_xor_sync(FULL_MASK, bi, o, G);
             if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
         }
         if (j == 0) {
             final_s[sub] = (bi < K) ? bi : 0;
             if (seq_ok && p.score) p.score[seq] = bv;
+        }
+    } else if (warp <= VIT_NL) {
+        // ---------------- loaders: emission feed -----------------------------------------------------------
+        loader_loop<G, KP, 0, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, warp - 1, bt, nullptr, VIT_THREADS);
+    } else {
+        // ---------------- drainers: delta store and backpointers, NB chunks behind the consumer ------------
+        const int hw = warp - 1 - VIT_NL;
+        const int seq_c = seq_ok ? seq : B - 1;
+        auto drain = [&](int c, int b) {
+            const int nf = min(CH, T - c * CH);
+            const float *drb = dr + (size_t)b * CH * 32;
+            for (int u = hw; u < nf; u += VIT_ND) {
+                const int n = c * CH + u;
+                const float dv = drb[u * 32 + lane];
+                if (lane_ok && p.delta) p.delta[((size_t)seq * T + n) * K + j] = dv;
+                int arg = 0;
+                if (n > 0) {
+                    const float4 *pv = reinterpret_cast<const float4 *>(
+                        (u > 0) ? (drb + (u - 1) * 32 + sub * G) : (carry + ((c - 1) & 1) * 32 + sub * G));
+                    float cv[KP], cw[KP];
+                    candidates(pv, cv);
+#pragma unroll
+                    for (int i = 0; i < KP; ++i) cw[i] = cv[i];
+                    const float best = max_tree<KP>(cw);
+                    // lowest index attaining the maximum (torch.max tie rule, hmm.py:167)
+                    unsigned eqm = 0u;
+#pragma unroll
+                    for (int i = 0; i < KP; ++i) eqm |= (cv[i] == best) ? (1u << i) : 0u;
+                    arg = eqm ? (__ffs(eqm) - 1) : 0;
+                }
+                if (lane_ok && p.psi_out) p.psi_out[((size_t)seq * T + n) * K + j] = (uint8_t)arg;
+                if (p.psi_in_smem) psi_s[((size_t)sub * T + n) * G + j] = (uint8_t)arg;
+                else if (seq_ok) p.psi_ws[((size_t)seq_c * T + n) * G + j] = (uint8_t)arg;
+                if (u == nf - 1) carry[(c & 1) * 32 + lane] = dv;
+            }
+        };
+        for (int c = 0; c < nch; ++c) {
+            const int b = c % NB;
+            if (c >= NB) {
+                bar_sync(BAR_DONE + b, VIT_THREADS);
+                drain(c - NB, b);
+            }
+            bar_arrive(BAR_FULL + b, VIT_THREADS);              // ring buffer b drained: consumer may overwrite it
+        }
+        for (int c = max(0, nch - NB); c < nch; ++c) {
+            const int b = c % NB;
+            bar_sync(BAR_DONE + b, VIT_THREADS);
+            drain(c, b);
         }
         if (!p.psi_in_smem) __threadfence_block();
     }
@@ -380,17 +641,17 @@ __global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
     // chunk c covers t in [1 + c*L, min(T-1, (c+1)*L)]; following psi from its top frame to its bottom frame
     // maps the state at t_hi to the state at t_lo - 1.
     const int L = p.chunk, nC = p.n_chunks;
-    auto psi_at = [&](int sub, int seq_c, int t, int s) -> int {
-        return p.psi_in_smem ? psi_s[((size_t)sub * T + t) * G + s] : p.psi_ws[((size_t)seq_c * T + t) * G + s];
+    auto psi_at = [&](int s_sub, int s_seq, int t, int s) -> int {
+        return p.psi_in_smem ? psi_s[((size_t)s_sub * T + t) * G + s] : p.psi_ws[((size_t)s_seq * T + t) * G + s];
     };
     // phase A: exit state for every (sequence, chunk, entry state)
     for (int task = tid; task < NS * nC * K; task += VIT_THREADS) {
-        const int e = task % K, c = (task / K) % nC, sub = task / (K * nC);
-        const int seq_c = min(seq_base + sub, p.B - 1);
+        const int e = task % K, c = (task / K) % nC, s_sub = task / (K * nC);
+        const int s_seq = min(seq_base + s_sub, B - 1);
         const int t_lo = 1 + c * L, t_hi = min(T - 1, t_lo + L - 1);
         int s = e;
-        for (int t = t_hi; t >= t_lo; --t) s = psi_at(sub, seq_c, t, s);
-        exit_s[((size_t)sub * nC + c) * G + e] = (uint8_t)s;
+        for (int t = t_hi; t >= t_lo; --t) s = psi_at(s_sub, s_seq, t, s);
+        exit_s[((size_t)s_sub * nC + c) * G + e] = (uint8_t)s;
     }
     __syncthreads();
     // phase B: the true entry state of every chunk (serial over chunks, one thread per sequence)
@@ -405,21 +666,21 @@ __global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
     __syncthreads();
     // phase C: re-walk every chunk from its true entry state, recording the path
     for (int task = tid; task < NS * nC; task += VIT_THREADS) {
-        const int c = task % nC, sub = task / nC;
-        const int seq_c = min(seq_base + sub, p.B - 1);
+        const int c = task % nC, s_sub = task / nC;
+        const int s_seq = min(seq_base + s_sub, B - 1);
         const int t_lo = 1 + c * L, t_hi = min(T - 1, t_lo + L - 1);
-        int s = entry_s[(size_t)sub * nC + c];
+        int s = entry_s[(size_t)s_sub * nC + c];
         for (int t = t_hi; t >= t_lo; --t) {
-            s = psi_at(sub, seq_c, t, s);
-            st_s[(size_t)sub * T + (t - 1)] = (uint8_t)s;
+            s = psi_at(s_sub, s_seq, t, s);
+            st_s[(size_t)s_sub * T + (t - 1)] = (uint8_t)s;
         }
     }
     __syncthreads();
     // phase D: coalesced int64 store
     for (int i = tid; i < NS * T; i += VIT_THREADS) {
-        const int sub = i / T, t = i % T;
-        const int seq = seq_base + sub;
-        if (seq < p.B) p.states[(size_t)seq * T + t] = (int64_t)st_s[i];
+        const int s_sub = i / T, t = i % T;
+        const int s_seq = seq_base + s_sub;
+        if (s_seq < B) p.states[(size_t)s_seq * T + t] = (int64_t)st_s[i];
     }
 }
 
@@ -429,15 +690,17 @@ __global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
 template <int G, int KP>
 static int launch_fb(const FbParams &p, cudaStream_t s) {
     constexpr int NS = 32 / G;
+    cudaError_t e = cudaFuncSetAttribute(fb_sweep_kernel<G, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "fb smem opt-in: %s", cudaGetErrorString(e));
     dim3 grid((p.B + NS - 1) / NS, 2);
-    fb_sweep_kernel<G, KP><<<grid, 32, 0, s>>>(p);
+    fb_sweep_kernel<G, KP><<<grid, FB_THREADS, FB_SMEM_BYTES, s>>>(p);
     return check_launch("fb_sweep_kernel");
 }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static size_t vit_smem_bytes(int NS, int T, int G, int nC, bool psi_in_smem) {
-    size_t off = psi_in_smem ? (size_t)NS * T * G : 0;
+    size_t off = VIT_SMEM_PIPE + (psi_in_smem ? (size_t)NS * T * G : 0);
     off += (size_t)NS * T + (size_t)NS * nC * G + (size_t)NS * nC;
     off = (off + 15) & ~(size_t)15;
     return off + NS * sizeof(int) * 2;
