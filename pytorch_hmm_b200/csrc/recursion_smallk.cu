@@ -214,9 +214,9 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
     const int seq = blockIdx.x * NS + sub;
     const int K = p.K, T = p.T;
     const bool lane_ok = seq < p.B && j < K;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sub * G));
-    // PAD (K < G): the last lane of each group owns no state; it publishes the running exponent in its ring slot,
-    // so the bookkeeping costs no extra store.  Otherwise lane 0 writes it to the `er` ring.
+    // PAD (KP < G): the last lane of each group owns no state and its ring slot is never read back by the recursion;
+    // it publishes the running exponent there, so the bookkeeping costs no extra store.  Otherwise lane 0 writes
+    // it to the `er` ring.
     const bool pad_lane = PAD && (j == G - 1);
 
     float2 M2[KP / 2];
@@ -235,14 +235,25 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
     float *wp = wr, *bp2 = br;
     int *ep = er;
 
+    // Power-of-two normaliser r = 2^-k for the NEXT step, from the exponent of the largest entry (exact scaling,
+    // integer bookkeeping).  One sequence per warp: a single REDUX over the new vector.  Several sequences per warp:
+    // a REDUX with per-group masks takes a slow divergent path, so each lane instead reduces the previous vector it
+    // has just read back (3-input max tree, no cross-lane traffic; one more step of lag, which is harmless).
+    auto set_scale = [&](unsigned mx) {
+        const unsigned eb = mx >> 23;
+        k_cur = (int)eb - 127;
+        r_cur = __uint_as_float((254u - eb) << 23);
+    };
     // one time step: w <- (sum_i prev[i] * M[i]) * (b~ * r) ; the pad lane carries (float)ksum instead
     auto step = [&](int u, float bqv) {
         float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
+        float v[KP];
 #pragma unroll
         for (int i4 = 0; i4 < KP / 4; ++i4) {
             const float4 t = prev[i4];
             acc_a = ffma2(make_float2(t.x, t.y), M2[2 * i4], acc_a);
             acc_b = ffma2(make_float2(t.z, t.w), M2[2 * i4 + 1], acc_b);
+            v[4 * i4 + 0] = t.x; v[4 * i4 + 1] = t.y; v[4 * i4 + 2] = t.z; v[4 * i4 + 3] = t.w;
         }
         const float2 s2 = fadd2(acc_a, acc_b);
         const float acc = s2.x + s2.y;
@@ -253,11 +264,13 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
         if (DIR == 1) bp2[u * 32] = acc * r_cur;
         wp[u * 32] = w;
         if (!PAD && j == 0) ep[u * MAXNS] = ksum;
-        // next step's power-of-two normaliser: exponent of the group's largest entry (one REDUX, off the chain)
-        const unsigned mx = __reduce_max_sync(gmask, lane_ok ? __float_as_uint(w) : 0u);
-        const unsigned eb = mx >> 23;
-        k_cur = (int)eb - 127;
-        r_cur = __uint_as_float((254u - eb) << 23);
+        if (NS == 1) {
+            set_scale(__reduce_max_sync(FULL_MASK, lane_ok ? __float_as_uint(w) : 0u));
+        } else {
+            // scale the new vector by what the previous one needed, times the growth r_cur already applied to it
+            const float vm = max_tree<KP>(v) * r_cur;
+            set_scale(__float_as_uint(vm));
+        }
         prev = reinterpret_cast<const float4 *>(wp + u * 32 - j);
         __syncwarp();
     };
@@ -279,10 +292,7 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
             if (DIR == 1) bp2[0] = lane_ok ? 1.f : 0.f;
             wp[0] = w;                                       // pad lane: ksum = 0
             if (!PAD && j == 0) ep[0] = 0;
-            const unsigned mx = __reduce_max_sync(gmask, lane_ok ? __float_as_uint(w) : 0u);
-            const unsigned eb = mx >> 23;
-            k_cur = (int)eb - 127;
-            r_cur = __uint_as_float((254u - eb) << 23);
+            if (NS == 1) set_scale(__reduce_max_sync(FULL_MASK, lane_ok ? __float_as_uint(w) : 0u));
             prev = reinterpret_cast<const float4 *>(wp - j);
             __syncwarp();
             u = 1;
@@ -402,9 +412,9 @@ __device__ __forceinline__ void fb_roles(const FbParams &p, uint8_t *smem) {
 template <int G, int KP>
 __global__ void __launch_bounds__(FB_THREADS) fb_sweep_kernel(FbParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
-    const bool pad = p.K < G;
-    if (blockIdx.y == 0) { if (pad) fb_roles<G, KP, 0, true>(p, smem); else fb_roles<G, KP, 0, false>(p, smem); }
-    else { if (pad) fb_roles<G, KP, 1, true>(p, smem); else fb_roles<G, KP, 1, false>(p, smem); }
+    constexpr bool PAD = KP < G;
+    if (blockIdx.y == 0) fb_roles<G, KP, 0, PAD>(p, smem);
+    else fb_roles<G, KP, 1, PAD>(p, smem);
 }
 
 // ----------------------------------------------------------------------------------------------------------
