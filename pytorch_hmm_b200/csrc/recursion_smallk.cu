@@ -194,7 +194,7 @@ struct FbParams {
 };
 
 constexpr int FB_NL = 2;                                   // loader warps
-constexpr int FB_ND = 1;                                   // drainer warps
+constexpr int FB_ND = 2;                                   // drainer warps
 constexpr int FB_THREADS = 32 * (1 + FB_NL + FB_ND);
 constexpr size_t FB_SMEM_BT = (size_t)NB * CH * BT_PITCH * sizeof(float);
 constexpr size_t FB_SMEM_WR = (size_t)NB * CH * 32 * sizeof(float);
@@ -313,7 +313,7 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
 // stores and turns the exponent / log-scale bookkeeping into the per-frame log scale la (alpha = a * exp(la)).
 template <int G, int KP, int DIR, bool PAD>
 __device__ __forceinline__ void fb_drainer(const FbParams &p, const float *wr, const float *br, const int *er,
-                                           const float *mraw) {
+                                           const float *mraw, int dw) {
     constexpr int NS = 32 / G;
     static_assert(CH == 64, "the log-scale scan assumes two frames per lane");
     const int lane = threadIdx.x & 31;
@@ -343,13 +343,16 @@ __device__ __forceinline__ void fb_drainer(const FbParams &p, const float *wr, c
             if (sq < B) {
                 const float *src = src_ring + (size_t)b * CH * 32 + s * G;
                 float *dst = ws + ((size_t)sq * T + f_lo) * K;
-                for (int fl0 = 0; fl0 < nf; fl0 += R) {
+                // rows are interleaved over the FB_ND drainer warps
+#pragma unroll 4
+                for (int fl0 = dw * R; fl0 < nf; fl0 += R * FB_ND) {
                     const int fl = fl0 + rr;
                     if (fl < nf && k < K) {
                         const int u = (DIR == 0) ? fl : nf - 1 - fl;
                         dst[(size_t)fl * K + k] = src[u * 32 + k];
                     }
                 }
+                if ((s % FB_ND) != dw) continue;                     // the log-scale of sequence s belongs to one drainer
                 // log scale: prefix of the per-frame m (inclusive for alpha, exclusive for beta) + ln2 * exponent
                 const int u0 = 2 * lane, u1 = 2 * lane + 1;
                 const double m0 = add_m ? (double)mraw[((size_t)(c % MR_BUFS) * CH + u0) * MAXNS + s] : 0.0;
@@ -406,7 +409,7 @@ __device__ __forceinline__ void fb_roles(const FbParams &p, uint8_t *smem) {
     const int warp = threadIdx.x >> 5;
     if (warp == 0) fb_consumer<G, KP, DIR, PAD>(p, bt, wr, br, er);
     else if (warp <= FB_NL) loader_loop<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, warp - 1, bt, mraw, FB_THREADS);
-    else fb_drainer<G, KP, DIR, PAD>(p, wr, br, er, mraw);
+    else fb_drainer<G, KP, DIR, PAD>(p, wr, br, er, mraw, warp - 1 - FB_NL);
 }
 
 template <int G, int KP>
@@ -489,7 +492,7 @@ struct VitParams {
 };
 
 constexpr int VIT_NL = 2;                                  // loader warps
-constexpr int VIT_ND = 3;                                  // drainer warps (delta store + backpointers)
+constexpr int VIT_ND = 5;                                  // drainer warps (delta store + backpointers)
 constexpr int VIT_THREADS = 32 * (1 + VIT_NL + VIT_ND);
 constexpr size_t VIT_SMEM_BT = (size_t)NB * CH * BT_PITCH * sizeof(float);
 constexpr size_t VIT_SMEM_DR = (size_t)NB * CH * 32 * sizeof(float);
@@ -609,21 +612,17 @@ __global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
                 const int n = c * CH + u;
                 const float dv = drb[u * 32 + lane];
                 if (lane_ok && p.delta) p.delta[((size_t)seq * T + n) * K + j] = dv;
-                int arg = 0;
-                if (n > 0) {
-                    const float4 *pv = reinterpret_cast<const float4 *>(
-                        (u > 0) ? (drb + (u - 1) * 32 + sub * G) : (carry + ((c - 1) & 1) * 32 + sub * G));
-                    float cv[KP], cw[KP];
-                    candidates(pv, cv);
+                // backpointer: lowest index attaining max_i(delta_{n-1}(i) + logP(i,j))  (torch.max tie rule, hmm.py:167),
+                // recomputed from the stored delta vector with the same fp32 adds as the consumer; psi_0 = 0.
+                const float4 *pv = reinterpret_cast<const float4 *>(
+                    (u > 0) ? (drb + (u - 1) * 32 + sub * G) : (carry + ((c - 1) & 1) * 32 + sub * G));
+                float cv[KP];
+                candidates(pv, cv);
+                const float best = max_tree<KP>(cv);
+                unsigned eqm = 1u << (KP - 1);                       // keeps the index in range if everything is NaN
 #pragma unroll
-                    for (int i = 0; i < KP; ++i) cw[i] = cv[i];
-                    const float best = max_tree<KP>(cw);
-                    // lowest index attaining the maximum (torch.max tie rule, hmm.py:167)
-                    unsigned eqm = 0u;
-#pragma unroll
-                    for (int i = 0; i < KP; ++i) eqm |= (cv[i] == best) ? (1u << i) : 0u;
-                    arg = eqm ? (__ffs(eqm) - 1) : 0;
-                }
+                for (int i = 0; i < KP - 1; ++i) eqm |= (cv[i] == best) ? (1u << i) : 0u;
+                const int arg = (n > 0) ? (__ffs(eqm) - 1) : 0;
                 if (lane_ok && p.psi_out) p.psi_out[((size_t)seq * T + n) * K + j] = (uint8_t)arg;
                 if (p.psi_in_smem) psi_s[((size_t)sub * T + n) * G + j] = (uint8_t)arg;
                 else if (seq_ok) p.psi_ws[((size_t)seq_c * T + n) * G + j] = (uint8_t)arg;
