@@ -29,4 +29,13 @@ inline int group_lanes(int K) { int g = 4; while (g < K) g <<= 1; return g; }
 // Number of broadcast slots (multiple of 4, >= K).
 inline int pad4(int K) { return (K + 3) & ~3; }
 
+// emission_tc.cu (tcgen05 path)
+bool tc_shape_ok(int K, int C, int D);
+size_t tc_floats(int K, int C, int D);
+int launch_pack_tc(const float *means, const float *log_vars, float scale, const float *logw, int K, int C, int D,
+                   float *tc, cudaStream_t s);
+// returns 0 launched, >0 not applicable (caller uses the fp32 kernel only), <0 error
+int launch_emission_tc(const float *x, const float *tc, const float *packed32, int64_t n_frames, int K, int C, int D,
+                       float *logb, cudaStream_t s);
+
 }  // namespace hmmb200

@@ -22,6 +22,7 @@ struct EmisParams {
     int K, C, D;
     int NP;            // ceil(K*C / 2): component pairs in the packed layout
     float *logb;
+    const float *skip_if_one;   // when non-null and *skip_if_one == 1 the tensor-core kernel has produced logb already
 };
 
 // packed layout: float4 prm[D][NP] = (s_{2p}, s_{2p+1}, nms_{2p}, nms_{2p+1}); then float cst[2*NP].
@@ -81,6 +82,7 @@ constexpr int EM_TILE = EM_THREADS * EM_FRAMES;    // frames per CTA tile
 template <int C, int NPAIR>
 __global__ void __launch_bounds__(EM_THREADS) gmm_emission_fp32_kernel(EmisParams p) {
     extern __shared__ __align__(16) float smem_f[];
+    if (p.skip_if_one != nullptr && *p.skip_if_one == 1.f) return;
     const int D = p.D, K = p.K, NP = p.NP;
     const int pitch = D + 1;
     float4 *prm = reinterpret_cast<float4 *>(smem_f);         // [D][NPAIR]
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(EM_THREADS) gmm_emission_fp32_kernel(EmisParam
 // Fallback for shapes the register-tiled kernel does not cover: one thread per (frame, state).
 __global__ void __launch_bounds__(128) gmm_emission_generic_kernel(EmisParams p) {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p.skip_if_one != nullptr && *p.skip_if_one == 1.f) return;
     if (idx >= p.n_frames * p.K) return;
     const int64_t n = idx / p.K;
     const int k = (int)(idx % p.K);
@@ -225,10 +228,14 @@ static int launch_emission_c(const EmisParams &p, cudaStream_t s) {
 
 using namespace hmmb200;
 
+static size_t fp32_section_floats(int K, int C, int D) {
+    const size_t NP = ((size_t)K * C + 1) / 2;
+    return ((size_t)D * NP * 4 + 2 * NP + 3) & ~(size_t)3;          // keeps the tensor-core section 16-byte aligned
+}
+
 HMMB200_EXPORT size_t hmmb200_gmm_packed_floats(int K, int C, int D) {
     if (K <= 0 || C <= 0 || D <= 0) return 0;
-    const size_t NP = ((size_t)K * C + 1) / 2;
-    return (size_t)D * NP * 4 + 2 * NP;
+    return fp32_section_floats(K, C, D) + tc_floats(K, C, D);
 }
 
 HMMB200_EXPORT int hmmb200_gmm_pack_f32(const float *means, const float *log_vars, float log_var_scale,
@@ -240,7 +247,11 @@ HMMB200_EXPORT int hmmb200_gmm_pack_f32(const float *means, const float *log_var
     const int KC = K * C, NP = (KC + 1) / 2;
     const int threads = 64, blocks = (2 * NP + threads - 1) / threads;
     gmm_pack_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(means, log_vars, log_var_scale, log_weights, KC, D, NP, packed);
-    return check_launch("gmm_pack_kernel");
+    if (int rc = check_launch("gmm_pack_kernel")) return rc;
+    if (tc_shape_ok(K, C, D))
+        return launch_pack_tc(means, log_vars, log_var_scale, log_weights, K, C, D, packed + fp32_section_floats(K, C, D),
+                              (cudaStream_t)stream);
+    return HMMB200_OK;
 }
 
 HMMB200_EXPORT int hmmb200_gmm_emission_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
@@ -252,7 +263,16 @@ HMMB200_EXPORT int hmmb200_gmm_emission_f32(const float *x, const float *packed,
     if (int rc = require_sm100()) return rc;
     EmisParams p;
     p.x = x; p.packed = packed; p.n_frames = n_frames; p.K = K; p.C = C; p.D = D; p.NP = (K * C + 1) / 2; p.logb = logb;
+    p.skip_if_one = nullptr;
     cudaStream_t s = (cudaStream_t)stream;
+    // tensor-core path first; it declines on the device (flag = 0) when the parameters leave the fp16 range, in which
+    // case the fp32 kernel below does the work.  Exactly one of the two kernels computes.
+    if (tc_shape_ok(K, C, D) && (((uintptr_t)x) & 15) == 0) {
+        const float *tc = packed + fp32_section_floats(K, C, D);
+        int trc = launch_emission_tc(x, tc, packed, n_frames, K, C, D, logb, s);
+        if (trc < 0) return trc;
+        if (trc == 0) p.skip_if_one = tc;
+    }
     int rc = 1;
     switch (C) {
         case 1: rc = launch_emission_c<1>(p, s); break;

@@ -1,0 +1,407 @@
+// emission_tc.cu -- GMM emission log-likelihoods on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a.
+//
+//   l_kc(x) = const_kc + sum_d z_d * W1_kcd + z_d^2 * W2_kcd,   z = x - center,  W1 = (mu - center)/var,  W2 = -1/(2 var)
+// is a dense [frames, 2D] x [2D, K*C] contraction.  fp32-grade accuracy on fp16 tensor-core inputs comes from a 3-term
+// split: z = z_hi + z_lo, W = W_hi + W_lo (each fp16, 11 significant bits), keeping hi*hi + hi*lo + lo*hi (the dropped
+// lo*lo term is 2^-22 relative).  fp16 products are exact in the fp32 accumulator.
+//
+// One persistent CTA per SM, tile = 128 frames (= the 128 TMEM lanes):
+//   warp 0        producer : cp.async.bulk (TMA bulk copy) of the tile's frame rows into a padded smem stage, mbarrier tx
+//   warp 1        MMA      : one thread issues 6 * D/16 tcgen05.mma (A from TMEM, B = W from smem, D accumulates in TMEM)
+//   warps 2-5     transform: thread = frame row; centre, square, split into fp16 hi/lo pairs, tcgen05.st into the A buffer
+//   warps 6-9     epilogue : tcgen05.ld the 128 x K*C accumulator rows, add const, mixture log-sum-exp, store log b
+// A and D are double-buffered in TMEM (2 x 2*DP + 2 x NP columns <= 512) so transform(i+1), MMA(i) and epilogue(i-1)
+// overlap; x stages are a 3-deep ring.  All hand-offs are mbarriers (tcgen05.commit for MMA completion).
+//
+// Range guard: fp16 needs |z| <= 240 (z^2 < 65504).  A frame outside that range is recomputed by its epilogue thread on
+// the CUDA cores from the fp32 packed parameters; parameter sets whose W exceed the fp16 range are flagged at pack time
+// and routed to the fp32 kernel (emission.cu).
+#include "common.cuh"
+
+#include <cuda_fp16.h>
+
+namespace hmmb200 {
+
+constexpr int TC_TILE = 128;
+constexpr int TC_STAGES = 3;
+constexpr int TC_THREADS = 320;
+constexpr float TC_ZMAX = 240.f;
+
+// ---- raw PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16 (fp16 inputs, fp32 accumulate), M = 128, K = 16 per instruction
+__device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1"): core matrix = 8 rows x 16 bytes,
+//   LBO = byte distance between the two 16-byte K chunks of one K = 16 slice, SBO = byte distance between 8-row groups.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3fffu) | ((uint64_t)((lbo >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+struct TcParams {
+    const float *x;
+    int64_t n_frames, n_tiles;
+    int D, K, C, KC;
+    int DP, NP;               // D and K*C padded to multiples of 16
+    const float *tc;          // tensor-core section of the packed buffer (see tc_section_* below)
+    const float *packed32;    // fp32 section (for out-of-range rows)
+    int NP2;                  // component pairs in the fp32 section
+    float *logb;
+};
+
+// tensor-core section layout (floats): [0] usable flag, [4 .. 4+DP) centre, [.. +NP) const, then 4 fp16 matrices
+// (W1_hi, W1_lo, W2_hi, W2_lo), each NP x DP halves in UMMA K-major no-swizzle order [n/8][k/8][n%8][k%8].
+__host__ __device__ inline size_t tc_off_center() { return 4; }
+__host__ __device__ inline size_t tc_off_const(int DP) { return 4 + (size_t)DP; }
+__host__ __device__ inline size_t tc_off_w(int DP, int NP) { return (4 + (size_t)DP + NP + 3) & ~(size_t)3; }
+__host__ __device__ inline size_t tc_section_floats(int DP, int NP) { return tc_off_w(DP, NP) + 2 * (size_t)NP * DP; }
+
+// reference-private logsumexp over a state's C components read from a staging row (mixture_gaussian.py:141-155)
+__device__ __forceinline__ float lse_row(const float *l, int C) {
+    if (C == 1) return l[0];
+    float m = l[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, l[c]);
+    if (isinf(m)) m = 0.f;
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(l[c] - m);
+    return logf(fmaxf(s, 1e-8f)) + m;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int D = p.D, DP = p.DP, NP = p.NP, K = p.K, C = p.C, KC = p.KC;
+    if (p.tc[0] == 0.f) return;                                   // parameters outside the fp16 range: fp32 kernel runs instead
+    const int XP = D + 4;                                         // padded row pitch (floats) of an x stage
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- carve shared memory ----
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem);          // x_full[S] x_empty[S] a_full[2] a_empty[2] d_full[2] d_empty[2]
+    uint64_t *x_full = bars, *x_empty = bars + TC_STAGES, *a_full = bars + 2 * TC_STAGES, *a_empty = a_full + 2;
+    uint64_t *d_full = a_empty + 2, *d_empty = d_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * TC_STAGES + 8);
+    size_t off = 128;
+    __half *wsm = reinterpret_cast<__half *>(smem + off);         off += (size_t)4 * NP * DP * sizeof(__half);
+    float *cst_s = reinterpret_cast<float *>(smem + off);         off += (size_t)NP * sizeof(float);
+    float *ctr_s = reinterpret_cast<float *>(smem + off);         off += (size_t)DP * sizeof(float);
+    uint8_t *bad_s = smem + off;                                  off += 4 * TC_TILE;   // 4-deep: see the epilogue
+    off = (off + 15) & ~(size_t)15;
+    float *est = reinterpret_cast<float *>(smem + off);           off += (size_t)TC_TILE * (NP + 1) * sizeof(float);
+    off = (off + 127) & ~(size_t)127;
+    float *xs = reinterpret_cast<float *>(smem + off);            // [S][128][XP]
+
+    // ---- one-time setup ----
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.tc + tc_off_w(DP, NP));
+        uint4 *dst = reinterpret_cast<uint4 *>(wsm);
+        const int n16 = 4 * NP * DP * 2 / 16;
+        for (int i = threadIdx.x; i < n16; i += TC_THREADS) dst[i] = __ldg(src + i);
+        for (int i = threadIdx.x; i < NP; i += TC_THREADS) cst_s[i] = __ldg(p.tc + tc_off_const(DP) + i);
+        for (int i = threadIdx.x; i < DP; i += TC_THREADS) ctr_s[i] = __ldg(p.tc + tc_off_center() + i);
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(a_full + a, 128); mbar_init(a_empty + a, 1); mbar_init(d_full + a, 1); mbar_init(d_empty + a, 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {                                              // TMEM: 512 columns, allocated (and later freed) by warp 2
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // W tile written with generic stores, read by the MMA (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t ACOLS = 2 * DP;                                // columns of one A buffer: 4 segments x DP/2
+    const uint32_t a_col0 = 0, d_col0 = 2 * ACOLS;                // [A0][A1][D0][D1]
+    const int n_my = (p.n_tiles > blockIdx.x) ? (int)((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (warp == 0) {
+        // ================= producer: bulk-async copy of frame rows into the padded stage =================
+        for (int it = 0; it < n_my; ++it) {
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            const int s = it % TC_STAGES;
+            const int rows = (int)min((int64_t)TC_TILE, p.n_frames - tile * TC_TILE);
+            mbar_wait(x_empty + s, ((it / TC_STAGES) & 1) ^ 1);
+            if (lane == 0) mbar_expect_tx(x_full + s, (uint32_t)rows * D * sizeof(float));
+            __syncwarp();
+            float *stage = xs + (size_t)s * TC_TILE * XP;
+            const float *src = p.x + tile * TC_TILE * D;
+            for (int r = lane; r < rows; r += 32)
+                bulk_copy_g2s(stage + (size_t)r * XP, src + (size_t)r * D, (uint32_t)D * sizeof(float), x_full + s);
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+            const uint32_t lbo = 128, sbo = (uint32_t)(DP / 8) * 128;
+            const uint32_t wbytes = (uint32_t)NP * DP * sizeof(__half);
+            const uint32_t w_addr = smem_u32(wsm);
+            const int KS = DP / 16;
+            for (int it = 0; it < n_my; ++it) {
+                const int a = it & 1;
+                mbar_wait(a_full + a, (it >> 1) & 1);
+                mbar_wait(d_empty + a, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t a_base = tmem_base + a_col0 + a * ACOLS;
+                const uint32_t d_addr = tmem_base + d_col0 + a * NP;
+                // A segments (columns): z_hi [0,DP/2)  z_lo [DP/2,DP)  q_hi [DP,3DP/2)  q_lo [3DP/2,2DP);  W: 0 W1_hi 1 W1_lo 2 W2_hi 3 W2_lo
+                const int seg_a[6] = {0, 0, 1, 2, 2, 3};
+                const int seg_w[6] = {0, 1, 0, 2, 3, 2};
+                uint32_t acc = 0;
+                for (int g = 0; g < 6; ++g) {
+                    for (int kk = 0; kk < KS; ++kk) {
+                        const uint32_t a_addr = a_base + seg_a[g] * (DP / 2) + kk * 8;
+                        const uint64_t bdesc = make_smem_desc(w_addr + seg_w[g] * wbytes + kk * 256, lbo, sbo);
+                        tc_mma_ts(d_addr, a_addr, bdesc, idesc, acc);
+                        acc = 1;
+                    }
+                }
+                tc_commit(a_empty + a);                           // A buffer free once these MMAs retire
+                tc_commit(d_full + a);                            // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp < 6) {
+        // ================= transform: thread = frame row -> fp16 hi/lo pairs of z and z^2 into TMEM =================
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        for (int it = 0; it < n_my; ++it) {
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            const int s = it % TC_STAGES, a = it & 1;
+            const int rows = (int)min((int64_t)TC_TILE, p.n_frames - tile * TC_TILE);
+            mbar_wait(x_full + s, (it / TC_STAGES) & 1);
+            mbar_wait(a_empty + a, ((it >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const float *xr = xs + ((size_t)s * TC_TILE + row) * XP;
+            const uint32_t a_base = tmem_base + lane_addr + a_col0 + a * ACOLS;
+            const bool live = row < rows;
+            float amax = 0.f;
+            for (int ch = 0; ch < DP / 16; ++ch) {                // 16 dims -> 8 packed columns per segment
+                float z[16];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    const int d0 = ch * 16 + v * 4;
+                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && d0 < D) t = *reinterpret_cast<const float4 *>(xr + d0);
+                    z[4 * v + 0] = t.x - ctr_s[d0 + 0]; z[4 * v + 1] = t.y - ctr_s[d0 + 1];
+                    z[4 * v + 2] = t.z - ctr_s[d0 + 2]; z[4 * v + 3] = t.w - ctr_s[d0 + 3];
+                    if (!(live && d0 < D)) { z[4 * v + 0] = 0.f; z[4 * v + 1] = 0.f; z[4 * v + 2] = 0.f; z[4 * v + 3] = 0.f; }
+                }
+                uint32_t zh[8], zl[8], qh[8], ql[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float z0 = z[2 * e], z1 = z[2 * e + 1];
+                    amax = fmaxf(amax, fmaxf(fabsf(z0), fabsf(z1)));
+                    const __half2 h = __floats2half2_rn(z0, z1);
+                    const float2 hf = __half22float2(h);
+                    const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
+                    const float q0 = z0 * z0, q1 = z1 * z1;
+                    const __half2 g = __floats2half2_rn(q0, q1);
+                    const float2 gf = __half22float2(g);
+                    const __half2 m = __floats2half2_rn(q0 - gf.x, q1 - gf.y);
+                    zh[e] = *reinterpret_cast<const uint32_t *>(&h); zl[e] = *reinterpret_cast<const uint32_t *>(&l);
+                    qh[e] = *reinterpret_cast<const uint32_t *>(&g); ql[e] = *reinterpret_cast<const uint32_t *>(&m);
+                }
+                const bool bad = !(amax <= TC_ZMAX);              // also catches NaN/inf
+                if (bad) {                                        // keep the tensor-core inputs finite; the row is redone in fp32
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { zh[e] = 0u; zl[e] = 0u; qh[e] = 0u; ql[e] = 0u; }
+                }
+                tc_st8(a_base + 0 * (DP / 2) + ch * 8, zh);
+                tc_st8(a_base + 1 * (DP / 2) + ch * 8, zl);
+                tc_st8(a_base + 2 * (DP / 2) + ch * 8, qh);
+                tc_st8(a_base + 3 * (DP / 2) + ch * 8, ql);
+            }
+            bad_s[(it & 3) * TC_TILE + row] = (uint8_t)((live && !(amax <= TC_ZMAX)) ? 1 : 0);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(a_full + a);
+            mbar_arrive(x_empty + s);
+        }
+    } else {
+        // ================= epilogue: accumulator rows -> + const -> mixture log-sum-exp -> log b =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        float *my = est + (size_t)row * (NP + 1);
+        for (int it = 0; it < n_my; ++it) {
+            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+            const int a = it & 1;
+            mbar_wait(d_full + a, (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t d_addr = tmem_base + lane_addr + d_col0 + a * NP;
+            for (int ch = 0; ch < NP / 16; ++ch) {
+                uint32_t v[16];
+                tc_ld16(d_addr + ch * 16, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) my[ch * 16 + i] = __uint_as_float(v[i]) + cst_s[ch * 16 + i];
+            }
+            // flag ring is 4 deep: transform(it+4) can only start after MMA(it+2), which waits for this d_empty arrive
+            const bool bad = bad_s[(it & 3) * TC_TILE + row] != 0;
+            tc_fence_before();
+            mbar_arrive(d_empty + a);
+            const int64_t frame = tile * TC_TILE + row;
+            if (frame < p.n_frames) {
+                if (bad) {
+                    // out-of-range frame: fp32 CUDA-core recomputation from the standardised parameters
+                    const float *xg = p.x + frame * D;
+                    const float *cst32 = p.packed32 + (size_t)D * p.NP2 * 4;
+                    for (int kc = 0; kc < KC; ++kc) {
+                        const int pr = kc >> 1, hi = kc & 1;
+                        float acc = 0.f;
+                        for (int d = 0; d < D; ++d) {
+                            const float u = fmaf(xg[d], __ldg(p.packed32 + ((size_t)d * p.NP2 + pr) * 4 + hi),
+                                                 __ldg(p.packed32 + ((size_t)d * p.NP2 + pr) * 4 + 2 + hi));
+                            acc = fmaf(u, u, acc);
+                        }
+                        my[kc] = fmaf(-0.5f, acc, cst32[kc]);
+                    }
+                }
+                float *o = p.logb + frame * K;
+                for (int k = 0; k < K; ++k) o[k] = lse_row(my + k * C, C);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- packing of the tensor-core section ----------------------------------------------------------------------
+__global__ void gmm_pack_tc_center_kernel(const float *means, int KC, int D, int DP, float *tc) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d == 0) tc[0] = 1.f;
+    if (d >= DP) return;
+    double s = 0.0;
+    if (d < D) for (int kc = 0; kc < KC; ++kc) s += (double)means[(size_t)kc * D + d];
+    tc[tc_off_center() + d] = (d < D) ? (float)(s / KC) : 0.f;
+}
+
+__global__ void gmm_pack_tc_kernel(const float *means, const float *log_vars, float scale, const float *logw,
+                                   int KC, int D, int DP, int NP, float *tc) {
+    const int kc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (kc >= NP) return;
+    __half *w = reinterpret_cast<__half *>(tc + tc_off_w(DP, NP));
+    const size_t wsz = (size_t)NP * DP;
+    double cst = 0.0;
+    bool unsafe = false;
+    for (int d = 0; d < DP; ++d) {
+        float w1 = 0.f, w2 = 0.f;
+        if (kc < KC && d < D) {
+            const double lv = (double)scale * (double)log_vars[(size_t)kc * D + d];
+            const double iv = exp(-lv);
+            const double dm = (double)means[(size_t)kc * D + d] - (double)tc[tc_off_center() + d];
+            w1 = (float)(dm * iv);
+            w2 = (float)(-0.5 * iv);
+            cst += -0.5 * (lv + 1.8378770664093454835606594728112) - 0.5 * dm * dm * iv;
+            if (!(fabsf(w1) < 60000.f) || !(fabsf(w2) < 60000.f)) unsafe = true;
+        }
+        const __half h1 = __float2half_rn(w1), h2 = __float2half_rn(w2);
+        const __half l1 = __float2half_rn(w1 - __half2float(h1)), l2 = __float2half_rn(w2 - __half2float(h2));
+        const size_t idx = (((size_t)(kc >> 3) * (DP / 8) + (d >> 3)) * 8 + (kc & 7)) * 8 + (d & 7);
+        w[0 * wsz + idx] = h1; w[1 * wsz + idx] = l1; w[2 * wsz + idx] = h2; w[3 * wsz + idx] = l2;
+    }
+    if (kc < KC) cst += logw ? (double)logw[kc] : 0.0;
+    tc[tc_off_const(DP) + kc] = (kc < KC) ? (float)cst : 0.f;
+    if (unsafe || !(fabs(cst) < 3.0e38)) tc[0] = 0.f;
+}
+
+bool tc_shape_ok(int K, int C, int D) {
+    const int KC = K * C;
+    return D % 4 == 0 && D >= 4 && D <= 80 && KC >= 1 && KC <= 96;
+}
+size_t tc_floats(int K, int C, int D) {
+    if (!tc_shape_ok(K, C, D)) return 0;
+    const int DP = (D + 15) & ~15, NP = (K * C + 15) & ~15;
+    return tc_section_floats(DP, NP);
+}
+
+int launch_pack_tc(const float *means, const float *log_vars, float scale, const float *logw, int K, int C, int D,
+                   float *tc, cudaStream_t s) {
+    const int KC = K * C, DP = (D + 15) & ~15, NP = (KC + 15) & ~15;
+    gmm_pack_tc_center_kernel<<<(DP + 63) / 64, 64, 0, s>>>(means, KC, D, DP, tc);
+    if (int rc = check_launch("gmm_pack_tc_center_kernel")) return rc;
+    gmm_pack_tc_kernel<<<(NP + 31) / 32, 32, 0, s>>>(means, log_vars, scale, logw, KC, D, DP, NP, tc);
+    return check_launch("gmm_pack_tc_kernel");
+}
+
+int launch_emission_tc(const float *x, const float *tc, const float *packed32, int64_t n_frames, int K, int C, int D,
+                       float *logb, cudaStream_t s) {
+    TcParams p;
+    p.x = x; p.n_frames = n_frames; p.n_tiles = (n_frames + TC_TILE - 1) / TC_TILE;
+    p.D = D; p.K = K; p.C = C; p.KC = K * C;
+    p.DP = (D + 15) & ~15; p.NP = (p.KC + 15) & ~15;
+    p.tc = tc; p.packed32 = packed32; p.NP2 = (p.KC + 1) / 2; p.logb = logb;
+    size_t smem = 128 + (size_t)4 * p.NP * p.DP * 2 + (size_t)(p.NP + p.DP) * 4 + 4 * TC_TILE;
+    smem = (smem + 15) & ~(size_t)15;
+    smem += (size_t)TC_TILE * (p.NP + 1) * 4;
+    smem = (smem + 127) & ~(size_t)127;
+    smem += (size_t)TC_STAGES * TC_TILE * (D + 4) * 4;
+    if (smem > 227 * 1024) return 1;
+    cudaError_t e = cudaFuncSetAttribute(gmm_emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "emission_tc smem opt-in: %s", cudaGetErrorString(e));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)min((int64_t)sms, p.n_tiles);
+    gmm_emission_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
+    return check_launch("gmm_emission_tc_kernel");
+}
+
+}  // namespace hmmb200

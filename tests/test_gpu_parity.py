@@ -238,20 +238,68 @@ def test_mixture_layer_vs_golden(hm, golden, tag):
     assert m(x)[1] is None
 
 
-@pytest.mark.parametrize("K,C,D,N", [(12, 4, 80, 1000), (10, 1, 80, 777), (3, 2, 5, 129), (6, 3, 33, 300),
-                                     (5, 5, 16, 200), (40, 2, 24, 150), (12, 4, 80, 1)])
-def test_gmm_emission_vs_float64(hm, K, C, D, N):
-    rng = np.random.default_rng(K * 100 + C * 10 + D)
-    means = (rng.standard_normal((K, C, D)) * 1.5).astype(np.float32)
-    log_vars = (0.4 * rng.standard_normal((K, C, D))).astype(np.float32)
+def _gmm_case(rng, K, C, D, N, mean_scale=1.5, lv_scale=0.4, offset=0.0):
+    means = (rng.standard_normal((K, C, D)) * mean_scale + offset).astype(np.float32)
+    log_vars = (lv_scale * rng.standard_normal((K, C, D))).astype(np.float32)
     logits = rng.standard_normal((K, C)).astype(np.float32)
-    logw = ref_port.safe_log(torch.softmax(torch.from_numpy(logits), -1)).numpy()
+    logw = ref_port.safe_log(torch.softmax(torch.from_numpy(logits), -1)).numpy() if C > 1 else None
     k = rng.integers(0, K, N); c = rng.integers(0, C, N)
     x = (means[k, c] + np.exp(0.5 * log_vars[k, c]) * rng.standard_normal((N, D))).astype(np.float32)
-    ref = c_oracle.gmm_emission_f64(x, means, log_vars, 1.0, logw if C > 1 else None)
-    packed = hm.ops.gmm_pack(_dev(means), _dev(log_vars), 1.0, _dev(logw) if C > 1 else None)
-    out = hm.ops.gmm_emission(_dev(x), packed, K, C, D)
-    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=2e-6, atol=2e-5)
+    return means, log_vars, logw, x
+
+
+# shapes with D % 4 == 0 and K*C <= 96 take the tcgen05 kernel, the others the fp32 CUDA-core kernels
+@pytest.mark.parametrize("K,C,D,N", [(12, 4, 80, 1000), (10, 1, 80, 777), (3, 2, 5, 129), (6, 3, 33, 300),
+                                     (5, 5, 16, 200), (40, 2, 24, 150), (12, 4, 80, 1), (12, 4, 80, 127),
+                                     (12, 4, 80, 128), (12, 4, 80, 129), (12, 4, 80, 40001), (24, 4, 64, 500),
+                                     (2, 2, 16, 333), (7, 3, 48, 260), (16, 1, 40, 300), (30, 4, 80, 64)])
+def test_gmm_emission_vs_float64(hm, K, C, D, N):
+    rng = np.random.default_rng(K * 100 + C * 10 + D)
+    means, log_vars, logw, x = _gmm_case(rng, K, C, D, N)
+    ref = c_oracle.gmm_emission_f64(x, means, log_vars, 1.0, logw)
+    packed = hm.ops.gmm_pack(_dev(means), _dev(log_vars), 1.0, None if logw is None else _dev(logw))
+    out = hm.ops.gmm_emission(_dev(x), packed, K, C, D).cpu().numpy()
+    err = np.abs(out - ref)
+    print(f"K={K} C={C} D={D} N={N}: max abs err {err.max():.3e}, max rel err {(err / np.abs(ref)).max():.3e}")
+    # log-likelihoods: 1e-5 relative (north star asks 1e-4); |l| is O(100), so this is ~1e-3 nats absolute
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_gmm_emission_offset_features_and_wide_dynamic_range(hm):
+    """Features far from zero (un-normalised log-mel style): the kernel centres x and mu, so the expanded quadratic
+    form does not cancel catastrophically."""
+    rng = np.random.default_rng(77)
+    means, log_vars, logw, x = _gmm_case(rng, 12, 4, 80, 3000, mean_scale=2.0, lv_scale=0.6, offset=25.0)
+    ref = c_oracle.gmm_emission_f64(x, means, log_vars, 1.0, logw)
+    packed = hm.ops.gmm_pack(_dev(means), _dev(log_vars), 1.0, _dev(logw))
+    out = hm.ops.gmm_emission(_dev(x), packed, 12, 4, 80).cpu().numpy()
+    print("offset features: max rel err", (np.abs(out - ref) / np.abs(ref)).max())
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_gmm_emission_out_of_fp16_range_rows_fall_back(hm):
+    """Frames with |x - centre| > 240 cannot use fp16 tensor-core inputs; those rows are recomputed in fp32
+    (reference test_mixture_gaussian.py:138-157 feeds 1e5-scaled inputs and expects finite outputs)."""
+    rng = np.random.default_rng(78)
+    means, log_vars, logw, x = _gmm_case(rng, 12, 4, 80, 1000)
+    x[::7] *= 1.0e3
+    x[5] = 1.0e5
+    ref = c_oracle.gmm_emission_f64(x, means, log_vars, 1.0, logw)
+    packed = hm.ops.gmm_pack(_dev(means), _dev(log_vars), 1.0, _dev(logw))
+    out = hm.ops.gmm_emission(_dev(x), packed, 12, 4, 80).cpu().numpy()
+    assert np.isfinite(out).all()
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-4)
+
+
+def test_gmm_emission_parameters_outside_fp16_range_use_fp32_kernel(hm):
+    rng = np.random.default_rng(79)
+    means, log_vars, logw, x = _gmm_case(rng, 12, 4, 80, 600)
+    log_vars[3, 1, :] = -14.0                      # 1/var = 1.2e6 > fp16 max: the pack kernel clears the tensor-core flag
+    x = (means[3, 1] + np.exp(0.5 * log_vars[3, 1]) * rng.standard_normal((600, 80))).astype(np.float32)
+    ref = c_oracle.gmm_emission_f64(x, means, log_vars, 1.0, logw)
+    packed = hm.ops.gmm_pack(_dev(means), _dev(log_vars), 1.0, _dev(logw))
+    out = hm.ops.gmm_emission(_dev(x), packed, 12, 4, 80).cpu().numpy()
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-3)
 
 
 # ---------------------------------------------------------------------------------------------------------

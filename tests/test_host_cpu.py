@@ -46,7 +46,9 @@ def test_no_cpu_fallback_fails_loudly():
 
 def test_size_queries_need_no_device():
     lib = _lib.load()
-    assert lib.hmmb200_gmm_packed_floats(12, 4, 80) == 80 * 24 * 4 + 48
+    # fp32 section (D * pairs * 4 + 2 * pairs) + tensor-core section (flag/centre/const + four fp16 W matrices)
+    assert lib.hmmb200_gmm_packed_floats(12, 4, 80) == (80 * 24 * 4 + 48) + (4 + 80 + 48 + 2 * 48 * 80)
+    assert lib.hmmb200_gmm_packed_floats(3, 5, 7) == ((7 * 8 * 4 + 16 + 3) // 4) * 4        # D % 4 != 0: fp32 section only
     assert lib.hmmb200_fb_workspace_bytes(256, 2000, 12) >= 256 * 2000 * (2 * 12 + 2) * 4
     assert lib.hmmb200_viterbi_workspace_bytes(256, 2000, 12) == 0          # backpointers fit in shared memory
     assert lib.hmmb200_viterbi_workspace_bytes(2, 9000, 16) == 2 * 9000 * 16
