@@ -6,10 +6,12 @@
 // lo*lo term is 2^-22 relative).  fp16 products are exact in the fp32 accumulator.
 //
 // One persistent CTA per SM, tile = 128 frames (= the 128 TMEM lanes):
-//   warp 0        producer : cp.async.bulk (TMA bulk copy) of the tile's frame rows into a padded smem stage, mbarrier tx
+//   warp 0        producer : TMA tensor copies (cp.async.bulk.tensor.2d, 128B swizzle) of the tile's frames, three
+//                            [128 rows x 32 floats] boxes per tile, completion by mbarrier transaction bytes
 //   warp 1        MMA      : one thread issues 6 * D/16 tcgen05.mma (A from TMEM, B = W from smem, D accumulates in TMEM)
-//   warps 2-5     transform: thread = frame row; centre, square, split into fp16 hi/lo pairs, tcgen05.st into the A buffer
-//   warps 6-9     epilogue : tcgen05.ld the 128 x K*C accumulator rows, add const, mixture log-sum-exp, store log b
+//   warps 2-9     transform: two groups of 4 warps; thread = frame row; centre, square, split into fp16 hi/lo pairs,
+//                            tcgen05.st into the A buffer (each group takes every other 16-dim chunk)
+//   warps 10-13   epilogue : tcgen05.ld the 128 x K*C accumulator rows, add const, mixture log-sum-exp, store log b
 // A and D are double-buffered in TMEM (2 x 2*DP + 2 x NP columns <= 512) so transform(i+1), MMA(i) and epilogue(i-1)
 // overlap; x stages are a 3-deep ring.  All hand-offs are mbarriers (tcgen05.commit for MMA completion).
 //
@@ -18,13 +20,15 @@
 // and routed to the fp32 kernel (emission.cu).
 #include "common.cuh"
 
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 namespace hmmb200 {
 
 constexpr int TC_TILE = 128;
 constexpr int TC_STAGES = 3;
-constexpr int TC_THREADS = 320;
+constexpr int TC_XF_GROUPS = 2;                                    // transform warp groups (4 warps each) per tile
+constexpr int TC_THREADS = 32 * (2 + 4 * TC_XF_GROUPS + 4);       // producer, MMA, transform groups, epilogue
 constexpr float TC_ZMAX = 240.f;
 
 // ---- raw PTX wrappers ------------------------------------------------------------------------------------------
@@ -50,9 +54,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "DONE_%=:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+// 2-D TMA tile load: box (32 floats x 128 rows) at element coordinates (c0 = column, c1 = row); rows past the end of
+// the tensor are zero-filled by the TMA unit.
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -80,6 +86,12 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
 
 // K-major, no-swizzle shared-memory matrix descriptor (sm_100 "version 1"): core matrix = 8 rows x 16 bytes,
 //   LBO = byte distance between the two 16-byte K chunks of one K = 16 slice, SBO = byte distance between 8-row groups.
@@ -117,11 +129,27 @@ __device__ __forceinline__ float lse_row(const float *l, int C) {
     return logf(fmaxf(s, 1e-8f)) + m;
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams p) {
-    extern __shared__ __align__(128) uint8_t smem[];
+constexpr int TC_BOXW = 32;                                       // floats per TMA box row (= the 128-byte swizzle span)
+constexpr int TC_BOX_FLOATS = TC_TILE * TC_BOXW;                  // 16 KB per box
+
+// same, over C register values with the hardware exp2/log2 approximations (relative error ~2^-21; the sum is O(1..C))
+template <int C>
+__device__ __forceinline__ float lse_fast(const float *l) {
+    float m = l[0];
+#pragma unroll
+    for (int c = 1; c < C; ++c) m = fmaxf(m, l[c]);
+    if (isinf(m)) m = 0.f;
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) s += __expf(l[c] - m);
+    return __logf(fmaxf(s, 1e-8f)) + m;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
     const int D = p.D, DP = p.DP, NP = p.NP, K = p.K, C = p.C, KC = p.KC;
     if (p.tc[0] == 0.f) return;                                   // parameters outside the fp16 range: fp32 kernel runs instead
-    const int XP = D + 4;                                         // padded row pitch (floats) of an x stage
+    const int NBOX = (D + TC_BOXW - 1) / TC_BOXW;                 // TMA boxes per tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     // ---- carve shared memory ----
@@ -133,11 +161,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams
     __half *wsm = reinterpret_cast<__half *>(smem + off);         off += (size_t)4 * NP * DP * sizeof(__half);
     float *cst_s = reinterpret_cast<float *>(smem + off);         off += (size_t)NP * sizeof(float);
     float *ctr_s = reinterpret_cast<float *>(smem + off);         off += (size_t)DP * sizeof(float);
-    uint8_t *bad_s = smem + off;                                  off += 4 * TC_TILE;   // 4-deep: see the epilogue
+    uint8_t *bad_s = smem + off;                                  off += 4 * TC_XF_GROUPS * TC_TILE;   // 4-deep ring x groups
     off = (off + 15) & ~(size_t)15;
     float *est = reinterpret_cast<float *>(smem + off);           off += (size_t)TC_TILE * (NP + 1) * sizeof(float);
-    off = (off + 127) & ~(size_t)127;
-    float *xs = reinterpret_cast<float *>(smem + off);            // [S][128][XP]
+    off += (1024u - ((smem_u32(smem) + (uint32_t)off) & 1023u)) & 1023u;   // 128B-swizzled TMA destinations: 1024-byte aligned ADDRESS
+    float *xs = reinterpret_cast<float *>(smem + off);            // [S][NBOX][128][32], chunk c of row r at (c ^ (r & 7))
 
     // ---- one-time setup ----
     {
@@ -149,8 +177,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams
         for (int i = threadIdx.x; i < DP; i += TC_THREADS) ctr_s[i] = __ldg(p.tc + tc_off_center() + i);
     }
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 128); }
-        for (int a = 0; a < 2; ++a) { mbar_init(a_full + a, 128); mbar_init(a_empty + a, 1); mbar_init(d_full + a, 1); mbar_init(d_empty + a, 128); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 128 * TC_XF_GROUPS); }
+        for (int a = 0; a < 2; ++a) { mbar_init(a_full + a, 128 * TC_XF_GROUPS); mbar_init(a_empty + a, 1); mbar_init(d_full + a, 1); mbar_init(d_empty + a, 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {                                              // TMEM: 512 columns, allocated (and later freed) by warp 2
@@ -167,18 +195,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams
     const int n_my = (p.n_tiles > blockIdx.x) ? (int)((p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
 
     if (warp == 0) {
-        // ================= producer: bulk-async copy of frame rows into the padded stage =================
-        for (int it = 0; it < n_my; ++it) {
-            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
-            const int s = it % TC_STAGES;
-            const int rows = (int)min((int64_t)TC_TILE, p.n_frames - tile * TC_TILE);
-            mbar_wait(x_empty + s, ((it / TC_STAGES) & 1) ^ 1);
-            if (lane == 0) mbar_expect_tx(x_full + s, (uint32_t)rows * D * sizeof(float));
-            __syncwarp();
-            float *stage = xs + (size_t)s * TC_TILE * XP;
-            const float *src = p.x + tile * TC_TILE * D;
-            for (int r = lane; r < rows; r += 32)
-                bulk_copy_g2s(stage + (size_t)r * XP, src + (size_t)r * D, (uint32_t)D * sizeof(float), x_full + s);
+        // ================= producer: one elected thread issues the TMA tile loads =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            for (int it = 0; it < n_my; ++it) {
+                const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
+                const int s = it % TC_STAGES;
+                mbar_wait(x_empty + s, ((it / TC_STAGES) & 1) ^ 1);
+                mbar_expect_tx(x_full + s, (uint32_t)NBOX * TC_BOX_FLOATS * sizeof(float));
+                float *stage = xs + (size_t)s * NBOX * TC_BOX_FLOATS;
+                for (int bx = 0; bx < NBOX; ++bx)
+                    tma_load_2d(stage + (size_t)bx * TC_BOX_FLOATS, &tmap, bx * TC_BOXW, (int)(tile * TC_TILE), x_full + s);
+            }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
@@ -211,59 +239,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams
                 tc_commit(d_full + a);                            // accumulator ready for the epilogue
             }
         }
-    } else if (warp < 6) {
+    } else if (warp < 2 + 4 * TC_XF_GROUPS) {
         // ================= transform: thread = frame row -> fp16 hi/lo pairs of z and z^2 into TMEM =================
+        // TC_XF_GROUPS warp groups share a tile: group g converts the 16-dim chunks ch = g, g + TC_XF_GROUPS, ...
         const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+        const int grp = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+        const int sw = row & 7;                                   // 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
         for (int it = 0; it < n_my; ++it) {
-            const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
             const int s = it % TC_STAGES, a = it & 1;
-            const int rows = (int)min((int64_t)TC_TILE, p.n_frames - tile * TC_TILE);
             mbar_wait(x_full + s, (it / TC_STAGES) & 1);
             mbar_wait(a_empty + a, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
-            const float *xr = xs + ((size_t)s * TC_TILE + row) * XP;
+            const float *srow = xs + (size_t)s * NBOX * TC_BOX_FLOATS + row * TC_BOXW;
             const uint32_t a_base = tmem_base + lane_addr + a_col0 + a * ACOLS;
-            const bool live = row < rows;
-            float amax = 0.f;
-            for (int ch = 0; ch < DP / 16; ++ch) {                // 16 dims -> 8 packed columns per segment
+            float qmax = 0.f;
+            for (int ch = grp; ch < DP / 16; ch += TC_XF_GROUPS) {   // 16 dims -> 8 packed columns per segment
+                // rows past the end of x and columns past D were zero-filled by the TMA unit (and the centre is 0 there)
                 float z[16];
 #pragma unroll
                 for (int v = 0; v < 4; ++v) {
-                    const int d0 = ch * 16 + v * 4;
-                    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live && d0 < D) t = *reinterpret_cast<const float4 *>(xr + d0);
-                    z[4 * v + 0] = t.x - ctr_s[d0 + 0]; z[4 * v + 1] = t.y - ctr_s[d0 + 1];
-                    z[4 * v + 2] = t.z - ctr_s[d0 + 2]; z[4 * v + 3] = t.w - ctr_s[d0 + 3];
-                    if (!(live && d0 < D)) { z[4 * v + 0] = 0.f; z[4 * v + 1] = 0.f; z[4 * v + 2] = 0.f; z[4 * v + 3] = 0.f; }
+                    const int cg = ch * 4 + v;                    // global 16-byte chunk index of the row
+                    const float4 t = *reinterpret_cast<const float4 *>(srow + (size_t)(cg >> 3) * TC_BOX_FLOATS + (((cg & 7) ^ sw) << 2));
+                    const float4 c4 = *reinterpret_cast<const float4 *>(ctr_s + cg * 4);
+                    z[4 * v + 0] = t.x - c4.x; z[4 * v + 1] = t.y - c4.y; z[4 * v + 2] = t.z - c4.z; z[4 * v + 3] = t.w - c4.w;
                 }
                 uint32_t zh[8], zl[8], qh[8], ql[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float z0 = z[2 * e], z1 = z[2 * e + 1];
-                    amax = fmaxf(amax, fmaxf(fabsf(z0), fabsf(z1)));
                     const __half2 h = __floats2half2_rn(z0, z1);
                     const float2 hf = __half22float2(h);
                     const __half2 l = __floats2half2_rn(z0 - hf.x, z1 - hf.y);
                     const float q0 = z0 * z0, q1 = z1 * z1;
+                    qmax = fmax3(qmax, q0, q1);
                     const __half2 g = __floats2half2_rn(q0, q1);
                     const float2 gf = __half22float2(g);
                     const __half2 m = __floats2half2_rn(q0 - gf.x, q1 - gf.y);
                     zh[e] = *reinterpret_cast<const uint32_t *>(&h); zl[e] = *reinterpret_cast<const uint32_t *>(&l);
                     qh[e] = *reinterpret_cast<const uint32_t *>(&g); ql[e] = *reinterpret_cast<const uint32_t *>(&m);
                 }
-                const bool bad = !(amax <= TC_ZMAX);              // also catches NaN/inf
-                if (bad) {                                        // keep the tensor-core inputs finite; the row is redone in fp32
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) { zh[e] = 0u; zl[e] = 0u; qh[e] = 0u; ql[e] = 0u; }
-                }
                 tc_st8(a_base + 0 * (DP / 2) + ch * 8, zh);
                 tc_st8(a_base + 1 * (DP / 2) + ch * 8, zl);
                 tc_st8(a_base + 2 * (DP / 2) + ch * 8, qh);
                 tc_st8(a_base + 3 * (DP / 2) + ch * 8, ql);
             }
-            bad_s[(it & 3) * TC_TILE + row] = (uint8_t)((live && !(amax <= TC_ZMAX)) ? 1 : 0);
+            // a frame with |z| > 240 (z^2 beyond fp16) or NaN is recomputed in fp32 by its epilogue thread
+            bad_s[((it & 3) * TC_XF_GROUPS + grp) * TC_TILE + row] = (uint8_t)(!(qmax <= TC_ZMAX * TC_ZMAX) ? 1 : 0);
             tc_wait_st();
             tc_fence_before();
             mbar_arrive(a_full + a);
@@ -275,6 +298,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams
         const int row = q * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
         float *my = est + (size_t)row * (NP + 1);
+        const bool fast = (16 % C) == 0;                          // every 16-column accumulator chunk holds whole states
+        const bool vec_out = (K % 4) == 0;
         for (int it = 0; it < n_my; ++it) {
             const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
             const int a = it & 1;
@@ -285,15 +310,40 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams
                 uint32_t v[16];
                 tc_ld16(d_addr + ch * 16, v);
                 tc_wait_ld();
+                float l[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) my[ch * 16 + i] = __uint_as_float(v[i]) + cst_s[ch * 16 + i];
+                for (int i = 0; i < 16; ++i) l[i] = __uint_as_float(v[i]) + cst_s[ch * 16 + i];
+                if (fast) {
+                    // the reference's private logsumexp (mixture_gaussian.py:141-155) per state, in registers
+                    if (C == 1) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) my[ch * 16 + i] = l[i];
+                    } else if (C == 2) {
+#pragma unroll
+                        for (int g = 0; g < 8; ++g) my[ch * 8 + g] = lse_fast<2>(&l[2 * g]);
+                    } else if (C == 4) {
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) my[ch * 4 + g] = lse_fast<4>(&l[4 * g]);
+                    } else if (C == 8) {
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) my[ch * 2 + g] = lse_fast<8>(&l[8 * g]);
+                    } else {
+                        my[ch] = lse_fast<16>(&l[0]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) my[ch * 16 + i] = l[i];
+                }
             }
             // flag ring is 4 deep: transform(it+4) can only start after MMA(it+2), which waits for this d_empty arrive
-            const bool bad = bad_s[(it & 3) * TC_TILE + row] != 0;
+            bool bad = false;
+#pragma unroll
+            for (int g = 0; g < TC_XF_GROUPS; ++g) bad |= bad_s[((it & 3) * TC_XF_GROUPS + g) * TC_TILE + row] != 0;
             tc_fence_before();
             mbar_arrive(d_empty + a);
             const int64_t frame = tile * TC_TILE + row;
             if (frame < p.n_frames) {
+                float *o = p.logb + frame * K;
                 if (bad) {
                     // out-of-range frame: fp32 CUDA-core recomputation from the standardised parameters
                     const float *xg = p.x + frame * D;
@@ -308,9 +358,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(TcParams
                         }
                         my[kc] = fmaf(-0.5f, acc, cst32[kc]);
                     }
+                    for (int k = 0; k < K; ++k) o[k] = lse_row(my + k * C, C);
+                } else if (!fast) {
+                    for (int k = 0; k < K; ++k) o[k] = lse_row(my + k * C, C);
+                } else if (vec_out) {
+                    for (int k = 0; k < K; k += 4)
+                        *reinterpret_cast<float4 *>(o + k) = make_float4(my[k], my[k + 1], my[k + 2], my[k + 3]);
+                } else {
+                    for (int k = 0; k < K; ++k) o[k] = my[k];
                 }
-                float *o = p.logb + frame * K;
-                for (int k = 0; k < K; ++k) o[k] = lse_row(my + k * C, C);
             }
         }
     }
@@ -381,6 +437,25 @@ int launch_pack_tc(const float *means, const float *log_vars, float scale, const
     return check_launch("gmm_pack_tc_kernel");
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda).
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
 int launch_emission_tc(const float *x, const float *tc, const float *packed32, int64_t n_frames, int K, int C, int D,
                        float *logb, cudaStream_t s) {
     TcParams p;
@@ -388,19 +463,33 @@ int launch_emission_tc(const float *x, const float *tc, const float *packed32, i
     p.D = D; p.K = K; p.C = C; p.KC = K * C;
     p.DP = (D + 15) & ~15; p.NP = (p.KC + 15) & ~15;
     p.tc = tc; p.packed32 = packed32; p.NP2 = (p.KC + 1) / 2; p.logb = logb;
-    size_t smem = 128 + (size_t)4 * p.NP * p.DP * 2 + (size_t)(p.NP + p.DP) * 4 + 4 * TC_TILE;
+    const int nbox = (D + TC_BOXW - 1) / TC_BOXW;
+    size_t smem = 128 + (size_t)4 * p.NP * p.DP * 2 + (size_t)(p.NP + p.DP) * 4 + 4 * TC_XF_GROUPS * TC_TILE;
     smem = (smem + 15) & ~(size_t)15;
     smem += (size_t)TC_TILE * (p.NP + 1) * 4;
-    smem = (smem + 127) & ~(size_t)127;
-    smem += (size_t)TC_STAGES * TC_TILE * (D + 4) * 4;
+    smem = (smem + 1023) & ~(size_t)1023;
+    smem += (size_t)TC_STAGES * nbox * TC_BOX_FLOATS * 4;
+    smem += 1024;                                                   // slack: the dynamic window itself is only 16-byte aligned
     if (smem > 227 * 1024) return 1;
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (encode == nullptr) return 1;
+    // x as a 2-D tensor [n_frames rows][D floats]; box = 32 floats x 128 rows, 128-byte swizzle, zero fill out of bounds
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)n_frames};
+    const cuuint64_t gstride[1] = {(cuuint64_t)D * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_BOXW, (cuuint32_t)TC_TILE};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return 1;
     cudaError_t e = cudaFuncSetAttribute(gmm_emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "emission_tc smem opt-in: %s", cudaGetErrorString(e));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)min((int64_t)sms, p.n_tiles);
-    gmm_emission_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
+    gmm_emission_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmap, p);
     return check_launch("gmm_emission_tc_kernel");
 }
 
