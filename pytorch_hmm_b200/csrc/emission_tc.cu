@@ -2,17 +2,19 @@
 //
 //   l_kc(x) = const_kc + sum_d z_d * W1_kcd + z_d^2 * W2_kcd,   z = x - center,  W1 = (mu - center)/var,  W2 = -1/(2 var)
 // is a dense [frames, 2D] x [2D, K*C] contraction.  fp32-grade accuracy on fp16 tensor-core inputs comes from a 3-term
-// split: z = z_hi + z_lo, W = W_hi + W_lo (each fp16, 11 significant bits), keeping hi*hi + hi*lo + lo*hi (the dropped
-// lo*lo term is 2^-22 relative).  fp16 products are exact in the fp32 accumulator.
+// split: z = z_hi + z_lo, W = W_hi + W_lo (each fp16, 11 significant bits); all four partial products are accumulated.
+// fp16 products are exact in the fp32 accumulator.
 //
 // One persistent CTA per SM, tile = 128 frames (= the 128 TMEM lanes):
 //   warp 0        producer : TMA tensor copies (cp.async.bulk.tensor.2d, 128B swizzle) of the tile's frames, three
 //                            [128 rows x 32 floats] boxes per tile, completion by mbarrier transaction bytes
-//   warp 1        MMA      : one thread issues 6 * D/16 tcgen05.mma (A from TMEM, B = W from smem, D accumulates in TMEM)
+//   warp 1        MMA      : one thread issues 4 * D/16 tcgen05.mma (A from TMEM, B = [W_hi; W_lo] from smem, N = 2*K*C,
+//                            D accumulates in TMEM)
 //   warps 2-9     transform: two groups of 4 warps; thread = frame row; centre, square, split into fp16 hi/lo pairs,
 //                            tcgen05.st into the A buffer (each group takes every other 16-dim chunk)
-//   warps 10-13   epilogue : tcgen05.ld the 128 x K*C accumulator rows, add const, mixture log-sum-exp, store log b
-// A and D are double-buffered in TMEM (2 x 2*DP + 2 x NP columns <= 512) so transform(i+1), MMA(i) and epilogue(i-1)
+//   warps 10-13   epilogue : tcgen05.ld the 128 x 2*K*C accumulator rows, add the hi/lo halves + const into a private smem
+//                            row, release the accumulator, mixture log-sum-exp, store log b
+// A and D are double-buffered in TMEM (2 x 2*DP + 2 x 2*NP columns <= 512) so transform(i+1), MMA(i) and epilogue(i-1)
 // overlap; x stages are a 3-deep ring.  All hand-offs are mbarriers (tcgen05.commit for MMA completion).
 //
 // Range guard: fp16 needs |z| <= 240 (z^2 < 65504).  A frame outside that range is recomputed by its epilogue thread on
@@ -21,6 +23,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_fp16.h>
 
 namespace hmmb200 {
@@ -28,7 +31,8 @@ namespace hmmb200 {
 constexpr int TC_TILE = 128;
 constexpr int TC_STAGES = 3;
 constexpr int TC_XF_GROUPS = 2;                                    // transform warp groups (4 warps each) per tile
-constexpr int TC_THREADS = 32 * (2 + 4 * TC_XF_GROUPS + 4);       // producer, MMA, transform groups, epilogue
+constexpr int TC_EP_GROUPS = 1;                                    // epilogue warp groups (4 warps each)
+constexpr int TC_THREADS = 32 * (2 + 4 * TC_XF_GROUPS + 4 * TC_EP_GROUPS);   // producer, MMA, transform groups, epilogue groups
 constexpr float TC_ZMAX = 240.f;
 
 // ---- raw PTX wrappers ------------------------------------------------------------------------------------------
@@ -48,11 +52,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"      // suspends up to %2 ns: waiting warps do not burn issue slots
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
 // 2-D TMA tile load: box (32 floats x 128 rows) at element coordinates (c0 = column, c1 = row); rows past the end of
 // the tensor are zero-filled by the TMA unit.
@@ -77,6 +81,11 @@ __device__ __forceinline__ void tc_mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint
 __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t (&v)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                  ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -109,6 +118,7 @@ struct TcParams {
     const float *packed32;    // fp32 section (for out-of-range rows)
     int NP2;                  // component pairs in the fp32 section
     float *logb;
+    int dbg;                  // timing experiments only (HMMB200_TC_DBG): 1 skip MMA, 2 skip transform math, 4 skip epilogue math
 };
 
 // tensor-core section layout (floats): [0] usable flag, [4 .. 4+DP) centre, [.. +NP) const, then 4 fp16 matrices
@@ -128,6 +138,10 @@ __device__ __forceinline__ float lse_row(const float *l, int C) {
     for (int c = 0; c < C; ++c) s += expf(l[c] - m);
     return logf(fmaxf(s, 1e-8f)) + m;
 }
+
+// timing trace (HMMB200_TC_DBG & 8): CTA 0 records clock64() at role hand-offs for its first 48 tiles
+__device__ long long g_tc_trace[6][48][2];
+#define TC_TRACE(role, ev) do { if ((p.dbg & 8) && blockIdx.x == 0 && it < 48 && lane == 0) g_tc_trace[role][it][ev] = clock64(); } while (0)
 
 constexpr int TC_BOXW = 32;                                       // floats per TMA box row (= the 128-byte swizzle span)
 constexpr int TC_BOX_FLOATS = TC_TILE * TC_BOXW;                  // 16 KB per box
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
     }
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(x_full + s, 1); mbar_init(x_empty + s, 128 * TC_XF_GROUPS); }
-        for (int a = 0; a < 2; ++a) { mbar_init(a_full + a, 128 * TC_XF_GROUPS); mbar_init(a_empty + a, 1); mbar_init(d_full + a, 1); mbar_init(d_empty + a, 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(a_full + a, 128 * TC_XF_GROUPS); mbar_init(a_empty + a, 1); mbar_init(d_full + a, 1); mbar_init(d_empty + a, 128 * TC_EP_GROUPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {                                              // TMEM: 512 columns, allocated (and later freed) by warp 2
@@ -202,41 +216,55 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
                 const int64_t tile = blockIdx.x + (int64_t)it * gridDim.x;
                 const int s = it % TC_STAGES;
                 mbar_wait(x_empty + s, ((it / TC_STAGES) & 1) ^ 1);
+                TC_TRACE(0, 0);
                 mbar_expect_tx(x_full + s, (uint32_t)NBOX * TC_BOX_FLOATS * sizeof(float));
                 float *stage = xs + (size_t)s * NBOX * TC_BOX_FLOATS;
                 for (int bx = 0; bx < NBOX; ++bx)
                     tma_load_2d(stage + (size_t)bx * TC_BOX_FLOATS, &tmap, bx * TC_BOXW, (int)(tile * TC_TILE), x_full + s);
+                TC_TRACE(0, 1);
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (one thread) =================
+        // The issue loop is a single thread's dependent instruction stream, so it is kept minimal: descriptor words
+        // are precomputed, a K = 16 step advances the B descriptor's address field by 256 B >> 4 and the A column by 8.
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(NP >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);   // f16 x f16 -> f32, K-major A and B
+            const uint32_t idesc = (1u << 4) | ((uint32_t)((2 * NP) >> 3) << 17) | ((uint32_t)(TC_TILE >> 4) << 24);   // f16 x f16 -> f32, M = 128, N = 2*NP, K-major A and B
             const uint32_t lbo = 128, sbo = (uint32_t)(DP / 8) * 128;
             const uint32_t wbytes = (uint32_t)NP * DP * sizeof(__half);
             const uint32_t w_addr = smem_u32(wsm);
-            const int KS = DP / 16;
+            const uint32_t desc_hi = (uint32_t)(make_smem_desc(0, lbo, sbo) >> 32);
+            uint32_t wlo[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) wlo[w] = (uint32_t)make_smem_desc(w_addr + w * wbytes, lbo, sbo);
+            const int KS = (p.dbg & 1) ? 0 : DP / 16;
+            const uint32_t half = DP / 2;
+            auto mma = [&](uint32_t d_addr, uint32_t a_addr, uint32_t b_lo, int kk, uint32_t acc) {
+                const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + kk * 16);
+                tc_mma_ts(d_addr, a_addr + kk * 8, bdesc, idesc, acc);
+            };
             for (int it = 0; it < n_my; ++it) {
                 const int a = it & 1;
                 mbar_wait(a_full + a, (it >> 1) & 1);
                 mbar_wait(d_empty + a, ((it >> 1) & 1) ^ 1);
                 tc_fence_after();
+                TC_TRACE(1, 0);
                 const uint32_t a_base = tmem_base + a_col0 + a * ACOLS;
-                const uint32_t d_addr = tmem_base + d_col0 + a * NP;
+                // One tcgen05.mma costs ~100 cycles here almost independently of N (N <= 96), so W_hi and W_lo are stacked
+                // along N: the two matrices are adjacent in shared memory with the same 8-row-group stride, i.e. they ARE
+                // one 2*NP-row K-major operand.  D[:, 0:NP] accumulates A*W_hi and D[:, NP:2NP] accumulates A*W_lo (the
+                // epilogue adds them); 4 * D/16 instructions per tile instead of 6 * D/16, and the lo*lo term comes free.
+                const uint32_t d_addr = tmem_base + d_col0 + (a * 2) * NP;
                 // A segments (columns): z_hi [0,DP/2)  z_lo [DP/2,DP)  q_hi [DP,3DP/2)  q_lo [3DP/2,2DP);  W: 0 W1_hi 1 W1_lo 2 W2_hi 3 W2_lo
-                const int seg_a[6] = {0, 0, 1, 2, 2, 3};
-                const int seg_w[6] = {0, 1, 0, 2, 3, 2};
-                uint32_t acc = 0;
-                for (int g = 0; g < 6; ++g) {
-                    for (int kk = 0; kk < KS; ++kk) {
-                        const uint32_t a_addr = a_base + seg_a[g] * (DP / 2) + kk * 8;
-                        const uint64_t bdesc = make_smem_desc(w_addr + seg_w[g] * wbytes + kk * 256, lbo, sbo);
-                        tc_mma_ts(d_addr, a_addr, bdesc, idesc, acc);
-                        acc = 1;
-                    }
+                for (int kk = 0; kk < KS; ++kk) {
+                    mma(d_addr, a_base + 0 * half, wlo[0], kk, kk > 0 ? 1u : 0u);   // z_hi * [W1_hi ; W1_lo]
+                    mma(d_addr, a_base + 2 * half, wlo[2], kk, 1u);                 // q_hi * [W2_hi ; W2_lo]
+                    mma(d_addr, a_base + 1 * half, wlo[0], kk, 1u);                 // z_lo * [W1_hi ; W1_lo]
+                    mma(d_addr, a_base + 3 * half, wlo[2], kk, 1u);                 // q_lo * [W2_hi ; W2_lo]
                 }
                 tc_commit(a_empty + a);                           // A buffer free once these MMAs retire
                 tc_commit(d_full + a);                            // accumulator ready for the epilogue
+                TC_TRACE(1, 1);
             }
         }
     } else if (warp < 2 + 4 * TC_XF_GROUPS) {
@@ -250,12 +278,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
         for (int it = 0; it < n_my; ++it) {
             const int s = it % TC_STAGES, a = it & 1;
             mbar_wait(x_full + s, (it / TC_STAGES) & 1);
+            if (q == 2) TC_TRACE(2 + grp, 0);
             mbar_wait(a_empty + a, ((it >> 1) & 1) ^ 1);
             tc_fence_after();
             const float *srow = xs + (size_t)s * NBOX * TC_BOX_FLOATS + row * TC_BOXW;
             const uint32_t a_base = tmem_base + lane_addr + a_col0 + a * ACOLS;
             float qmax = 0.f;
-            for (int ch = grp; ch < DP / 16; ch += TC_XF_GROUPS) {   // 16 dims -> 8 packed columns per segment
+            for (int ch = grp; ch < ((p.dbg & 2) ? 0 : DP / 16); ch += TC_XF_GROUPS) {   // 16 dims -> 8 packed columns per segment
                 // rows past the end of x and columns past D were zero-filled by the TMA unit (and the centre is 0 there)
                 float z[16];
 #pragma unroll
@@ -291,6 +320,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
             tc_fence_before();
             mbar_arrive(a_full + a);
             mbar_arrive(x_empty + s);
+            if (q == 2) TC_TRACE(2 + grp, 1);
         }
     } else {
         // ================= epilogue: accumulator rows -> + const -> mixture log-sum-exp -> log b =================
@@ -305,20 +335,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
             const int a = it & 1;
             mbar_wait(d_full + a, (it >> 1) & 1);
             tc_fence_after();
-            const uint32_t d_addr = tmem_base + lane_addr + d_col0 + a * NP;
+            if (q == 2) TC_TRACE(4, 0);
+            const uint32_t d_addr = tmem_base + lane_addr + d_col0 + (a * 2) * NP;      // A*W_hi part; the A*W_lo part follows at + NP
+            // phase 1: drain the accumulator row (hi + lo halves + const) into this thread's private smem row and release
+            // the TMEM buffer at once, so the next MMA never waits for the log-sum-exp arithmetic
             for (int ch = 0; ch < NP / 16; ++ch) {
-                uint32_t v[16];
-                tc_ld16(d_addr + ch * 16, v);
+                uint32_t v0[16], v1[16];
+                tc_ld16(d_addr + ch * 16, v0);
+                tc_ld16(d_addr + NP + ch * 16, v1);
+                // constants into registers BEFORE the stores: cst_s and the staging row are both shared memory, and the
+                // compiler must otherwise serialise every (load const, add, store) triple for fear of aliasing
+                float4 c0[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c0[i] = *reinterpret_cast<const float4 *>(cst_s + ch * 16 + 4 * i);
                 tc_wait_ld();
-                float l[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) l[i] = __uint_as_float(v[i]) + cst_s[ch * 16 + i];
-                if (fast) {
-                    // the reference's private logsumexp (mixture_gaussian.py:141-155) per state, in registers
-                    if (C == 1) {
+                for (int i = 0; i < 4; ++i) {
+                    my[ch * 16 + 4 * i + 0] = (__uint_as_float(v0[4 * i + 0]) + __uint_as_float(v1[4 * i + 0])) + c0[i].x;
+                    my[ch * 16 + 4 * i + 1] = (__uint_as_float(v0[4 * i + 1]) + __uint_as_float(v1[4 * i + 1])) + c0[i].y;
+                    my[ch * 16 + 4 * i + 2] = (__uint_as_float(v0[4 * i + 2]) + __uint_as_float(v1[4 * i + 2])) + c0[i].z;
+                    my[ch * 16 + 4 * i + 3] = (__uint_as_float(v0[4 * i + 3]) + __uint_as_float(v1[4 * i + 3])) + c0[i].w;
+                }
+            }
+            // flag ring is 4 deep: transform(it+4) can only start after MMA(it+2), which waits for this d_empty arrive
+            bool bad = false;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) my[ch * 16 + i] = l[i];
-                    } else if (C == 2) {
+            for (int g = 0; g < TC_XF_GROUPS; ++g) bad |= bad_s[((it & 3) * TC_XF_GROUPS + g) * TC_TILE + row] != 0;
+            tc_fence_before();
+            mbar_arrive(d_empty + a);
+            if (q == 2) TC_TRACE(4, 1);
+            // phase 2: the reference's private logsumexp (mixture_gaussian.py:141-155) per state, in place
+            if (fast && !bad && C > 1 && !(p.dbg & 4)) {
+                for (int ch = 0; ch < NP / 16; ++ch) {
+                    float l[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) l[i] = my[ch * 16 + i];
+                    if (C == 2) {
 #pragma unroll
                         for (int g = 0; g < 8; ++g) my[ch * 8 + g] = lse_fast<2>(&l[2 * g]);
                     } else if (C == 4) {
@@ -330,17 +382,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
                     } else {
                         my[ch] = lse_fast<16>(&l[0]);
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) my[ch * 16 + i] = l[i];
                 }
             }
-            // flag ring is 4 deep: transform(it+4) can only start after MMA(it+2), which waits for this d_empty arrive
-            bool bad = false;
-#pragma unroll
-            for (int g = 0; g < TC_XF_GROUPS; ++g) bad |= bad_s[((it & 3) * TC_XF_GROUPS + g) * TC_TILE + row] != 0;
-            tc_fence_before();
-            mbar_arrive(d_empty + a);
             const int64_t frame = tile * TC_TILE + row;
             if (frame < p.n_frames) {
                 float *o = p.logb + frame * K;
@@ -420,7 +463,9 @@ __global__ void gmm_pack_tc_kernel(const float *means, const float *log_vars, fl
 
 bool tc_shape_ok(int K, int C, int D) {
     const int KC = K * C;
-    return D % 4 == 0 && D >= 4 && D <= 80 && KC >= 1 && KC <= 96;
+    if (!(D % 4 == 0 && D >= 4 && D <= 80 && KC >= 1 && KC <= 96)) return false;
+    const int DP = (D + 15) & ~15, NP = (KC + 15) & ~15;
+    return 4 * (DP + NP) <= 512;                                    // TMEM: 2 A buffers (2*DP cols) + 2 x 2 accumulators (NP cols)
 }
 size_t tc_floats(int K, int C, int D) {
     if (!tc_shape_ok(K, C, D)) return 0;
@@ -463,6 +508,7 @@ int launch_emission_tc(const float *x, const float *tc, const float *packed32, i
     p.D = D; p.K = K; p.C = C; p.KC = K * C;
     p.DP = (D + 15) & ~15; p.NP = (p.KC + 15) & ~15;
     p.tc = tc; p.packed32 = packed32; p.NP2 = (p.KC + 1) / 2; p.logb = logb;
+    { const char *e = getenv("HMMB200_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
     const int nbox = (D + TC_BOXW - 1) / TC_BOXW;
     size_t smem = 128 + (size_t)4 * p.NP * p.DP * 2 + (size_t)(p.NP + p.DP) * 4 + 4 * TC_XF_GROUPS * TC_TILE;
     smem = (smem + 15) & ~(size_t)15;
@@ -494,3 +540,8 @@ int launch_emission_tc(const float *x, const float *tc, const float *packed32, i
 }
 
 }  // namespace hmmb200
+
+// debug aid (not part of the public ABI): copies the timing trace of the last traced launch to the host
+HMMB200_EXPORT int hmmb200_debug_tc_trace(long long *out) {
+    return cudaMemcpyFromSymbol(out, hmmb200::g_tc_trace, sizeof(long long) * 6 * 48 * 2) == cudaSuccess ? 0 : -1;
+}
