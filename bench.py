@@ -197,19 +197,42 @@ class Headline:
         self.fb_out["loglik"] = torch.empty(BATCH, device=dev)
         self.vit_out = {"states": torch.empty(BATCH, SEQ, dtype=torch.int64, device=dev),
                         "delta": torch.empty(n, device=dev), "score": torch.empty(BATCH, device=dev)}
-        self.launches_per_step = 4     # gmm_emission, fb_sweep, fb_combine, viterbi
+        self.fb_ws = hm.ops.fb_workspace(BATCH, SEQ, K_STATES, dev)
+        self.vit_ws = hm.ops.viterbi_workspace(BATCH, SEQ, K_STATES, dev)
+        self.launches_per_step = 4     # gmm_emission_tc, fb_sweep, fb_combine, viterbi
+        # forward-backward and Viterbi only share their input (log b): run them on two side streams so the two
+        # latency-bound recursions overlap
+        self.s_fb, self.s_vit = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        self.ev_emis, self.ev_fb, self.ev_vit = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
     def emission(self, x):
         self.hm.ops.gmm_emission(x, self.packed, K_STATES, N_MIX, FEAT, out=self.logb)
 
     def fb(self, want=("gamma", "fwd", "bwd")):
         out = self.fb_out if want else {"loglik": self.fb_out["loglik"]}
-        self.hm.ops.forward_backward(self.logb, self.hm.ops.EMIS_LOG_NORM_FLOOR, self.trans, self.init, want=want, out=out)
+        self.hm.ops.forward_backward(self.logb, self.hm.ops.EMIS_LOG_NORM_FLOOR, self.trans, self.init, want=want, out=out,
+                                     workspace=self.fb_ws)
 
     def vit(self):
-        self.hm.ops.viterbi(self.logb, self.hm.ops.EMIS_LOG, self.log_trans, self.prior, out=self.vit_out)
+        self.hm.ops.viterbi(self.logb, self.hm.ops.EMIS_LOG, self.log_trans, self.prior, out=self.vit_out,
+                            workspace=self.vit_ws)
 
     def step(self, x):
+        main = torch.cuda.current_stream(self.dev)
+        self.emission(x)
+        self.ev_emis.record(main)
+        with torch.cuda.stream(self.s_fb):
+            self.s_fb.wait_event(self.ev_emis)
+            self.fb()
+            self.ev_fb.record(self.s_fb)
+        with torch.cuda.stream(self.s_vit):
+            self.s_vit.wait_event(self.ev_emis)
+            self.vit()
+            self.ev_vit.record(self.s_vit)
+        main.wait_event(self.ev_fb)
+        main.wait_event(self.ev_vit)
+
+    def step_serial(self, x):
         self.emission(x); self.fb(); self.vit()
 
     def outputs(self):
@@ -274,7 +297,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     # ---- per-kernel durations (CUDA events on the launch stream, same loop) -> dominant kernel + roofline ----
     it = max(10, min(args.steps, 50))
     k_ms = {
-        "gmm_emission_fp32_kernel": event_ms(lambda: h.emission(x), it),
+        "gmm_emission_tc_kernel": event_ms(lambda: h.emission(x), it),
         "fb_sweep_kernel": event_ms(lambda: h.fb(want=()), it),
         "fb_sweep_kernel+fb_combine_kernel": event_ms(lambda: h.fb(), it),
         "viterbi_kernel": event_ms(lambda: h.vit(), it),
@@ -282,7 +305,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     k_ms["fb_combine_kernel"] = max(k_ms["fb_sweep_kernel+fb_combine_kernel"] - k_ms["fb_sweep_kernel"], 0.0)
     frames = BATCH * SEQ
     alg_bytes = {   # algorithmic bytes per launch (per-frame figure x frames per launch), DESIGN.md "Kernels"
-        "gmm_emission_fp32_kernel": (4 * FEAT + 4 * K_STATES) * frames,
+        "gmm_emission_tc_kernel": (4 * FEAT + 4 * K_STATES) * frames,
         "fb_sweep_kernel": (4 * K_STATES + 2 * (4 * K_STATES + 4)) * frames,
         "fb_combine_kernel": (2 * (4 * K_STATES + 4) + 3 * 4 * K_STATES) * frames,
         "viterbi_kernel": (4 * K_STATES + 4 * K_STATES + 8) * frames,

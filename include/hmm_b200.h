@@ -105,6 +105,43 @@ int    hmmb200_viterbi_f32(const float *emis, int emis_mode, float floor_eps,
                            float *delta, uint8_t *psi, int64_t *states, float *score,
                            void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Explicit-duration (semi-Markov) recursions.
+ *   hmmb200_hsmm_viterbi_f32 replaces  HSMMLayer._viterbi_decode_single      pytorch_hmm/hsmm.py:245-354
+ *                                      SemiMarkovHMM.viterbi_decode          pytorch_hmm/semi_markov.py:455-570
+ *   hmmb200_hsmm_forward_f32 replaces  SemiMarkovHMM._unsupervised_forward   pytorch_hmm/semi_markov.py:308-383
+ *
+ *   frame_logp [B,T,K] per-frame log-emission term; seg_const [K] (or NULL) is added ONCE per segment (SemiMarkovHMM counts the
+ *   Gaussian constant per segment, semi_markov.py:422-424; HSMMLayer per frame, hsmm.py:285 -> NULL); log_dur [K,Dm] with column
+ *   d-1 for duration d; log_trans [K,K] (self transitions are never taken); log_init [K] or NULL (HSMMLayer: no prior).
+ *   Viterbi: delta = ((delta_prev + log_trans) + seg) + log_dur maximised over (s' != s, d') in lexicographic order with a strict
+ *   '>' exactly like the reference; sum_order 0 sums seg(t,d,s) in ATen's strided-sum order (bit-identical scores), 1 sequentially.
+ *   outputs: states [B,T] int64, score [B];  forward: alpha [B,T,K,Dm] (NULL ok), end_scores [B,T,K] (NULL ok), total [B].
+ * --------------------------------------------------------------------------------------------------------- */
+size_t hmmb200_hsmm_viterbi_workspace_bytes(int B, int T, int K, int Dm);
+int    hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
+                                const float *log_trans, const float *log_init, int B, int T, int K, int Dm,
+                                int sum_order, int64_t *states, float *score,
+                                void *workspace, size_t workspace_bytes, void *stream);
+int    hmmb200_hsmm_forward_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
+                                const float *log_trans, const float *log_init, int B, int T, int K, int Dm,
+                                float *alpha, float *end_scores, float *total, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Streaming: per-chunk kernels with state carried between calls (one stream per batch row, K <= 32).
+ *   hmmb200_greedy_decode_f32 replaces  StreamingHMMProcessor._greedy_decode   pytorch_hmm/streaming.py:267-320
+ *     s_t = argmax_j(log_trans[s_{t-1}][j] + logb_t[j]); state_io[b] < 0 marks the first chunk (argmax_j(logb_0[j] - log K)),
+ *     and is updated to the chunk's last state.  states [B,T] int64, scores [B,T] (NULL ok) = the winning value.
+ *   hmmb200_forward_chunk_f32 is new (the reference's processor has no forward algorithm): the forward recursion over one
+ *     chunk; state_alpha [B,K] (filtered distribution), state_loglik [B] (double) and started [B] carry the stream state;
+ *     filtered [B,T,K] (NULL ok) receives p(state_t | o_1..t).  Chunked calls equal one unchunked pass.
+ * --------------------------------------------------------------------------------------------------------- */
+int    hmmb200_greedy_decode_f32(const float *logb, const float *log_trans, int B, int T, int K,
+                                 int32_t *state_io, int64_t *states, float *scores, void *stream);
+int    hmmb200_forward_chunk_f32(const float *emis, int emis_mode, float floor_eps, const float *trans_prob,
+                                 const float *init_prob, int B, int T, int K, float *state_alpha,
+                                 double *state_loglik, int32_t *started, float *filtered, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,249 @@
+// hsmm.cu -- explicit-duration (semi-Markov) recursions for sm_100a.
+//
+//   hsmm_viterbi_kernel   replaces HSMMLayer._viterbi_decode_single (pytorch_hmm/hsmm.py:245-354, a 5-deep Python loop that
+//                         runs at 2.4 frames/s) and SemiMarkovHMM.viterbi_decode (semi_markov.py:455-570).
+//   hsmm_forward_kernel   replaces SemiMarkovHMM._unsupervised_forward (semi_markov.py:308-383), in the two-vector form
+//                         begin[t][s] / end[t][s] (O(T K (K + Dmax)) instead of O(T K^2 Dmax^2)).
+//
+// Viterbi keeps the reference's exact floating-point semantics: delta[te][s][d] for a segment of state s, duration d, ending at
+// te = t + d - 1 is   ((delta[t-1][s'][d'] + logA[s'][s]) + seg(t,d,s)) + logdur[s][d]   maximised over (s' != s, d') in
+// lexicographic order with a strict '>' (first maximum wins), and seg(t,d,s) is summed in ATen's strided-sum order (four
+// interleaved partial sums).  One CTA per sequence; thread (s,d) scans its (K-1)*Dmax candidates in the reference's order, so
+// scores AND backpointers are bit-identical by construction.  The DP table is a (Dmax+1)-slot ring in shared memory; the
+// uint8 backpointers go to a workspace in HBM and are walked by one thread at the end.  The DP ring has Dmax+2 slots.
+#include "common.cuh"
+
+namespace hmmb200 {
+
+struct HsmmVitParams {
+    const float *f;        // [B,T,K] per-frame log-emission term
+    const float *segc;     // [K] per-segment constant or null (SemiMarkovHMM counts the Gaussian constant once per segment)
+    const float *logdur;   // [K,Dm]
+    const float *logA;     // [K,K]
+    const float *logpi;    // [K] or null (HSMMLayer has no prior on the first segment, hsmm.py:262-268)
+    int B, T, K, Dm;
+    int sum_order;         // 0: ATen strided row_sum (4 interleaved partials), 1: sequential
+    int64_t *states;       // [B,T]
+    float *score;          // [B]
+    uint8_t *psi_s, *psi_d;  // [B,T,K*Dm] workspace
+};
+
+// sum of d values col[0], col[stride], ... in the order torch.sum uses on a strided fp32 slice
+__device__ __forceinline__ float seg_sum(const float *col, int stride, int d, int order) {
+    if (order == 1) {
+        float a = 0.f;
+        for (int i = 0; i < d; ++i) a = __fadd_rn(a, col[(size_t)i * stride]);
+        return a;
+    }
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    const int q = d >> 2;
+    for (int i = 0; i < q; ++i) {
+        p0 = __fadd_rn(p0, col[(size_t)(4 * i + 0) * stride]);
+        p1 = __fadd_rn(p1, col[(size_t)(4 * i + 1) * stride]);
+        p2 = __fadd_rn(p2, col[(size_t)(4 * i + 2) * stride]);
+        p3 = __fadd_rn(p3, col[(size_t)(4 * i + 3) * stride]);
+    }
+    for (int i = 4 * q; i < d; ++i) p0 = __fadd_rn(p0, col[(size_t)i * stride]);
+    p0 = __fadd_rn(p0, p1);
+    p0 = __fadd_rn(p0, p2);
+    p0 = __fadd_rn(p0, p3);
+    return p0;
+}
+
+__global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
+    extern __shared__ __align__(16) float smem_h[];
+    const int K = p.K, Dm = p.Dm, T = p.T;
+    const int KD = K * Dm, R = Dm + 2;          // slots t-2 (being cleared), t-1 (read) and t .. t+Dm-1 (written) are distinct
+    float *ring = smem_h;                       // [R][K][Dm]   delta for segments ending at te, slot te % R
+    float *A_s = ring + (size_t)R * KD;         // [K][K]
+    float *dur_s = A_s + K * K;                 // [K][Dm]
+    const int b = blockIdx.x;
+    const float *f = p.f + (size_t)b * T * K;
+    uint8_t *ps = p.psi_s + (size_t)b * T * KD;
+    uint8_t *pd = p.psi_d + (size_t)b * T * KD;
+
+    for (int i = threadIdx.x; i < R * KD; i += blockDim.x) ring[i] = -INFINITY;
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) A_s[i] = p.logA[i];
+    for (int i = threadIdx.x; i < KD; i += blockDim.x) dur_s[i] = p.logdur[i];
+    __syncthreads();
+
+    for (int t = 0; t < T; ++t) {
+        const float *prev = ring + (size_t)((t + R - 1) % R) * KD;      // segments ending at t-1
+        for (int pr = threadIdx.x; pr < KD; pr += blockDim.x) {
+            const int s = pr / Dm, d = pr % Dm + 1;
+            const int te = t + d - 1;
+            if (te < T) {
+                const float osum = seg_sum(f + (size_t)t * K + s, K, d, p.sum_order);
+                const float oseg = p.segc ? __fadd_rn(p.segc[s], osum) : osum;
+                const float dsc = dur_s[s * Dm + d - 1];
+                float best;
+                int bs = 0, bd = 1;
+                if (t == 0) {
+                    best = p.logpi ? __fadd_rn(__fadd_rn(p.logpi[s], oseg), dsc) : __fadd_rn(oseg, dsc);
+                } else {
+                    best = -INFINITY;
+                    for (int sp = 0; sp < K; ++sp) {
+                        if (sp == s) continue;
+                        const float a = A_s[sp * K + s];
+                        const float *pv = prev + sp * Dm;
+                        for (int dp = 1; dp <= Dm; ++dp) {
+                            const float tot = __fadd_rn(__fadd_rn(__fadd_rn(pv[dp - 1], a), oseg), dsc);
+                            if (tot > best) { best = tot; bs = sp; bd = dp; }
+                        }
+                    }
+                }
+                ring[(size_t)(te % R) * KD + s * Dm + d - 1] = best;
+                ps[(size_t)te * KD + pr] = (uint8_t)bs;
+                pd[(size_t)te * KD + pr] = (uint8_t)bd;
+            }
+            // slot t-2 has been fully consumed by the previous step: clear it for reuse
+            if (t >= 2) ring[(size_t)((t + R - 2) % R) * KD + pr] = -INFINITY;
+        }
+        __syncthreads();
+    }
+
+    if (threadIdx.x == 0) {
+        const float *last = ring + (size_t)((T - 1) % R) * KD;
+        float best = -INFINITY;
+        int cs = 0, cd = 1;
+        for (int s = 0; s < K; ++s)
+            for (int d = 1; d <= Dm; ++d) {
+                const float v = last[s * Dm + d - 1];
+                if (v > best) { best = v; cs = s; cd = d; }
+            }
+        if (p.score) p.score[b] = best;
+        int64_t *st = p.states + (size_t)b * T;
+        int t = T - 1;
+        while (t >= 0) {
+            int st0 = t - cd + 1;
+            if (st0 < 0) st0 = 0;
+            for (int u = st0; u <= t; ++u) st[u] = cs;
+            if (st0 > 0) {
+                const int ns = ps[(size_t)t * KD + cs * Dm + cd - 1], nd = pd[(size_t)t * KD + cs * Dm + cd - 1];
+                t = st0 - 1; cs = ns; cd = nd;
+            } else break;
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------
+// forward (log-sum-exp semiring), one warp per sequence, lane = state
+//   alpha[te][s][d] = begin(te-d+1, s) + segc[s] + sum_{tau=te-d+1..te} f[tau][s] + logdur[s][d]
+//   begin(0, s) = logpi[s];  begin(t, s) = LSE_{s' != s}( end[t-1][s'] + logA[s'][s] ),  end[t][s] = LSE_d alpha[t][s][d]
+//   total = LSE_s end[T-1][s]                                                     (semi_markov.py:339-378)
+// ----------------------------------------------------------------------------------------------------------
+struct HsmmFwdParams {
+    const float *f, *segc, *logdur, *logA, *logpi;
+    int B, T, K, Dm;
+    float *alpha;          // [B,T,K,Dm] or null  ("forward_variables")
+    float *end_out;        // [B,T,K] or null
+    float *total;          // [B]
+};
+
+__device__ __forceinline__ float lse2f(float a, float b) {
+    const float m = fmaxf(a, b);
+    if (!(m > -INFINITY)) return -INFINITY;
+    return m + log1pf(expf(fminf(a, b) - m));
+}
+
+__global__ void __launch_bounds__(32) hsmm_forward_kernel(HsmmFwdParams p) {
+    extern __shared__ __align__(16) float smem_h[];
+    const int K = p.K, Dm = p.Dm, T = p.T;
+    float *begin_r = smem_h;                    // [Dm][K] ring: begin(t, s), slot t % Dm
+    float *f_r = begin_r + Dm * K;              // [Dm][K] ring of the last Dm frames of f
+    float *end_s = f_r + Dm * K;                // [K]
+    const int b = blockIdx.x, s = threadIdx.x;
+    const bool ok = s < K;
+    const float *f = p.f + (size_t)b * T * K;
+    const float segc = (ok && p.segc) ? p.segc[s] : 0.f;
+    for (int t = 0; t < T; ++t) {
+        if (ok) {
+            f_r[(t % Dm) * K + s] = f[(size_t)t * K + s];
+            float bg;
+            if (t == 0) bg = p.logpi ? p.logpi[s] : 0.f;
+            else {
+                bg = -INFINITY;
+                for (int sp = 0; sp < K; ++sp) if (sp != s) bg = lse2f(bg, end_s[sp] + p.logA[sp * K + s]);
+            }
+            begin_r[(t % Dm) * K + s] = bg;
+        }
+        __syncwarp();
+        if (ok) {
+            // segments of state s ending at t: duration d starts at t-d+1
+            float acc = 0.f, m = -INFINITY, sum = 0.f;
+            for (int d = 1; d <= Dm && d <= t + 1; ++d) {
+                const int st = t - d + 1;
+                acc += f_r[(st % Dm) * K + s];
+                const float a = begin_r[(st % Dm) * K + s] + (segc + acc) + p.logdur[s * Dm + d - 1];
+                if (p.alpha) p.alpha[(((size_t)b * T + t) * K + s) * Dm + d - 1] = a;
+                if (a > m) { sum = sum * expf(m - a) + 1.f; m = a; }
+                else if (a > -INFINITY) sum += expf(a - m);
+            }
+            if (p.alpha) for (int d = t + 2; d <= Dm; ++d) p.alpha[(((size_t)b * T + t) * K + s) * Dm + d - 1] = -INFINITY;
+            const float e = (m > -INFINITY) ? m + logf(sum) : -INFINITY;
+            if (p.end_out) p.end_out[((size_t)b * T + t) * K + s] = e;
+            end_s[s] = e;
+        }
+        __syncwarp();
+    }
+    if (s == 0) {
+        float tot = -INFINITY;
+        for (int k = 0; k < K; ++k) tot = lse2f(tot, end_s[k]);
+        p.total[b] = tot;
+    }
+}
+
+}  // namespace hmmb200
+
+using namespace hmmb200;
+
+HMMB200_EXPORT size_t hmmb200_hsmm_viterbi_workspace_bytes(int B, int T, int K, int Dm) {
+    if (B <= 0 || T <= 0 || K <= 0 || Dm <= 0) return 0;
+    return 2 * (size_t)B * T * K * Dm;
+}
+
+HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
+                                            const float *log_trans, const float *log_init, int B, int T, int K, int Dm,
+                                            int sum_order, int64_t *states, float *score,
+                                            void *workspace, size_t workspace_bytes, void *stream) {
+    if (B < 0 || T < 0 || K <= 0 || Dm <= 0) return set_error(HMMB200_EINVAL, "hsmm_viterbi: bad shape");
+    if (B == 0 || T == 0) return HMMB200_OK;
+    if (!frame_logp || !log_dur || !log_trans || !states) return set_error(HMMB200_EINVAL, "hsmm_viterbi: null argument");
+    if (K > 255 || Dm > 255) return set_error(HMMB200_EUNSUPPORTED, "hsmm_viterbi: K and max_duration must be <= 255");
+    const size_t need = hmmb200_hsmm_viterbi_workspace_bytes(B, T, K, Dm);
+    if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_viterbi: workspace %zu < %zu", workspace_bytes, need);
+    if (int rc = require_sm100()) return rc;
+    const size_t smem = ((size_t)(Dm + 2) * K * Dm + (size_t)K * K + (size_t)K * Dm) * sizeof(float);
+    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_viterbi: K=%d, max_duration=%d need %zu bytes of shared memory", K, Dm, smem);
+    cudaError_t e = cudaFuncSetAttribute(hsmm_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_viterbi smem opt-in: %s", cudaGetErrorString(e));
+    HsmmVitParams p;
+    p.f = frame_logp; p.segc = seg_const; p.logdur = log_dur; p.logA = log_trans; p.logpi = log_init;
+    p.B = B; p.T = T; p.K = K; p.Dm = Dm; p.sum_order = sum_order; p.states = states; p.score = score;
+    p.psi_s = (uint8_t *)workspace; p.psi_d = (uint8_t *)workspace + (size_t)B * T * K * Dm;
+    int threads = ((K * Dm + 31) / 32) * 32;
+    if (threads > 1024) threads = 1024;
+    hsmm_viterbi_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("hsmm_viterbi_kernel");
+}
+
+HMMB200_EXPORT int hmmb200_hsmm_forward_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
+                                            const float *log_trans, const float *log_init, int B, int T, int K, int Dm,
+                                            float *alpha, float *end_scores, float *total, void *stream) {
+    if (B < 0 || T < 0 || K <= 0 || Dm <= 0) return set_error(HMMB200_EINVAL, "hsmm_forward: bad shape");
+    if (B == 0 || T == 0) return HMMB200_OK;
+    if (!frame_logp || !log_dur || !log_trans || !total) return set_error(HMMB200_EINVAL, "hsmm_forward: null argument");
+    if (K > 32) return set_error(HMMB200_EUNSUPPORTED, "hsmm_forward: K <= 32 (got %d)", K);
+    if (int rc = require_sm100()) return rc;
+    const size_t smem = ((size_t)2 * Dm * K + K) * sizeof(float);
+    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_forward: max_duration too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(hsmm_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_forward smem opt-in: %s", cudaGetErrorString(e));
+    }
+    HsmmFwdParams p;
+    p.f = frame_logp; p.segc = seg_const; p.logdur = log_dur; p.logA = log_trans; p.logpi = log_init;
+    p.B = B; p.T = T; p.K = K; p.Dm = Dm; p.alpha = alpha; p.end_out = end_scores; p.total = total;
+    hsmm_forward_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("hsmm_forward_kernel");
+}

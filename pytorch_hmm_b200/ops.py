@@ -94,9 +94,20 @@ def gmm_emission(x: torch.Tensor, packed: torch.Tensor, K: int, Cn: int, D: int,
 # ------------------------------------------------------------------------------------------------------
 # recursions
 # ------------------------------------------------------------------------------------------------------
+def fb_workspace(B: int, T: int, K: int, dev) -> torch.Tensor:
+    """Scratch buffer for forward_backward (scaled alpha/beta + log-scales); reusable across calls on one stream."""
+    n = _lib.load().hmmb200_fb_workspace_bytes(B, T, K)
+    return torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+
+
+def viterbi_workspace(B: int, T: int, K: int, dev) -> torch.Tensor:
+    n = _lib.load().hmmb200_viterbi_workspace_bytes(B, T, K)
+    return torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+
+
 def forward_backward(emis: torch.Tensor, mode: int, trans_prob: torch.Tensor, init_prob: torch.Tensor,
                      eps: float = EPS, add_rowmax: bool = False, want=("gamma", "fwd", "bwd"),
-                     out: Optional[dict] = None) -> dict:
+                     out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None) -> dict:
     """emis [B,T,K] CUDA fp32.  Returns a dict with the requested tensors among
     gamma, fwd, bwd, log_alpha, log_beta (each [B,T,K]) and always 'loglik' [B]."""
     dev = require_cuda(emis.device)
@@ -111,7 +122,7 @@ def forward_backward(emis: torch.Tensor, mode: int, trans_prob: torch.Tensor, in
     if "loglik" not in res:
         res["loglik"] = torch.empty(B, dtype=torch.float32, device=dev)
     ws_bytes = lib.hmmb200_fb_workspace_bytes(B, T, K)
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _check(lib.hmmb200_forward_backward_f32(
             _p(emis), int(mode), float(eps), int(bool(add_rowmax)), _p(trans_prob), _p(init_prob), B, T, K,
@@ -123,7 +134,7 @@ def forward_backward(emis: torch.Tensor, mode: int, trans_prob: torch.Tensor, in
 
 def viterbi(emis: torch.Tensor, mode: int, log_trans: torch.Tensor, log_init: torch.Tensor, eps: float = EPS,
             want_delta: bool = True, want_psi: bool = False, want_score: bool = True,
-            out: Optional[dict] = None) -> dict:
+            out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None) -> dict:
     """emis [B,T,K] CUDA fp32 -> dict(states int64 [B,T], delta [B,T,K], psi uint8 [B,T,K], score [B])."""
     dev = require_cuda(emis.device)
     emis = _f32c(emis, dev)
@@ -140,10 +151,95 @@ def viterbi(emis: torch.Tensor, mode: int, log_trans: torch.Tensor, log_init: to
     if want_score and "score" not in res:
         res["score"] = torch.empty(B, dtype=torch.float32, device=dev)
     ws_bytes = lib.hmmb200_viterbi_workspace_bytes(B, T, K)
-    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         _check(lib.hmmb200_viterbi_f32(_p(emis), int(mode), float(eps), _p(log_trans), _p(log_init), B, T, K,
                                        _p(res.get("delta")), _p(res.get("psi")), _p(res["states"]),
                                        _p(res.get("score")), _p(ws), ws_bytes, _stream(dev)),
                "hmmb200_viterbi_f32")
     return res
+
+
+# ------------------------------------------------------------------------------------------------------
+# explicit-duration (semi-Markov) recursions
+# ------------------------------------------------------------------------------------------------------
+def hsmm_viterbi(frame_logp: torch.Tensor, log_dur: torch.Tensor, log_trans: torch.Tensor,
+                 seg_const: Optional[torch.Tensor] = None, log_init: Optional[torch.Tensor] = None,
+                 sum_order: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """frame_logp [B,T,K] -> (states int64 [B,T], score [B]); see include/hmm_b200.h for the recursion."""
+    dev = require_cuda(frame_logp.device)
+    f = _f32c(frame_logp, dev)
+    B, T, K = f.shape
+    log_dur, log_trans = _f32c(log_dur, dev), _f32c(log_trans, dev)
+    Dm = log_dur.shape[1]
+    sc = None if seg_const is None else _f32c(seg_const, dev)
+    li = None if log_init is None else _f32c(log_init, dev)
+    lib = _lib.load()
+    states = torch.empty(B, T, dtype=torch.int64, device=dev)
+    score = torch.empty(B, dtype=torch.float32, device=dev)
+    n = lib.hmmb200_hsmm_viterbi_workspace_bytes(B, T, K, Dm)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_hsmm_viterbi_f32(_p(f), _p(sc), _p(log_dur), _p(log_trans), _p(li), B, T, K, Dm, int(sum_order),
+                                            _p(states), _p(score), _p(ws), n, _stream(dev)), "hmmb200_hsmm_viterbi_f32")
+    return states, score
+
+
+def hsmm_forward(frame_logp: torch.Tensor, log_dur: torch.Tensor, log_trans: torch.Tensor,
+                 seg_const: Optional[torch.Tensor] = None, log_init: Optional[torch.Tensor] = None,
+                 want_alpha: bool = True) -> dict:
+    """frame_logp [B,T,K] -> dict(total [B], alpha [B,T,K,Dm] if want_alpha, end [B,T,K])."""
+    dev = require_cuda(frame_logp.device)
+    f = _f32c(frame_logp, dev)
+    B, T, K = f.shape
+    log_dur, log_trans = _f32c(log_dur, dev), _f32c(log_trans, dev)
+    Dm = log_dur.shape[1]
+    sc = None if seg_const is None else _f32c(seg_const, dev)
+    li = None if log_init is None else _f32c(log_init, dev)
+    lib = _lib.load()
+    res = {"total": torch.empty(B, dtype=torch.float32, device=dev),
+           "end": torch.empty(B, T, K, dtype=torch.float32, device=dev)}
+    if want_alpha:
+        res["alpha"] = torch.empty(B, T, K, Dm, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_hsmm_forward_f32(_p(f), _p(sc), _p(log_dur), _p(log_trans), _p(li), B, T, K, Dm,
+                                            _p(res.get("alpha")), _p(res["end"]), _p(res["total"]), _stream(dev)),
+               "hmmb200_hsmm_forward_f32")
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------
+# streaming (state carried between chunks)
+# ------------------------------------------------------------------------------------------------------
+def greedy_decode(logb: torch.Tensor, log_trans: torch.Tensor, state_io: torch.Tensor, want_scores: bool = True):
+    """logb [B,T,K]; state_io int32 [B] (-1 before the first chunk; updated in place) -> (states int64 [B,T], scores [B,T])."""
+    dev = require_cuda(logb.device)
+    logb, log_trans = _f32c(logb, dev), _f32c(log_trans, dev)
+    B, T, K = logb.shape
+    states = torch.empty(B, T, dtype=torch.int64, device=dev)
+    scores = torch.empty(B, T, dtype=torch.float32, device=dev) if want_scores else None
+    with torch.cuda.device(dev):
+        _check(_lib.load().hmmb200_greedy_decode_f32(_p(logb), _p(log_trans), B, T, K, _p(state_io), _p(states), _p(scores),
+                                                     _stream(dev)), "hmmb200_greedy_decode_f32")
+    return states, scores
+
+
+def forward_chunk(emis: torch.Tensor, mode: int, trans_prob: torch.Tensor, init_prob: torch.Tensor, state: dict,
+                  eps: float = EPS, want_filtered: bool = True) -> Optional[torch.Tensor]:
+    """One chunk of the forward recursion.  `state` = dict(alpha [B,K] f32, loglik [B] f64, started [B] i32), updated in place
+    (make one with new_forward_state).  Returns the filtered posteriors [B,T,K] (or None)."""
+    dev = require_cuda(emis.device)
+    emis = _f32c(emis, dev)
+    B, T, K = emis.shape
+    filt = torch.empty(B, T, K, dtype=torch.float32, device=dev) if want_filtered else None
+    with torch.cuda.device(dev):
+        _check(_lib.load().hmmb200_forward_chunk_f32(_p(emis), int(mode), float(eps), _p(_f32c(trans_prob, dev)),
+                                                     _p(_f32c(init_prob, dev)), B, T, K, _p(state["alpha"]), _p(state["loglik"]),
+                                                     _p(state["started"]), _p(filt), _stream(dev)), "hmmb200_forward_chunk_f32")
+    return filt
+
+
+def new_forward_state(B: int, K: int, dev) -> dict:
+    return {"alpha": torch.zeros(B, K, dtype=torch.float32, device=dev),
+            "loglik": torch.zeros(B, dtype=torch.float64, device=dev),
+            "started": torch.zeros(B, dtype=torch.int32, device=dev)}

@@ -1,0 +1,206 @@
+"""GPU parity tests (-m gpu) for the explicit-duration (HSMM) recursions and the streaming kernels, against the golden
+fixtures of the real reference and the C oracle.  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hm():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pytorch_hmm_b200 as m
+    return m
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _load_hsmm_layer(hm, g, tag, dist):
+    K, D = g[f"{tag}_observation_means"].shape
+    Dm = g[f"{tag}_dur_probs"].shape[1]
+    m = hm.HSMMLayer(K, D, duration_distribution=dist, max_duration=Dm).cuda()
+    sd = {k: torch.from_numpy(g[f"{tag}_{k}"]) for k in m.state_dict() if f"{tag}_{k}" in g.files}
+    m.load_state_dict(sd, strict=False)
+    return m
+
+
+@pytest.mark.parametrize("tag,dist", [("gamma", "gamma"), ("poisson", "poisson"), ("weibull", "weibull")])
+def test_hsmm_layer_vs_reference_golden(hm, golden, tag, dist):
+    g = golden("hsmm")
+    m = _load_hsmm_layer(hm, g, tag, dist)
+    # host-side tables equal the reference's (same torch formulas; GPU libm may differ in the last bits)
+    np.testing.assert_allclose(m.get_duration_probabilities().detach().cpu().numpy(), g[f"{tag}_dur_probs"], rtol=2e-5, atol=1e-30)
+    np.testing.assert_allclose(m.get_transition_matrix().detach().cpu().numpy(), g[f"{tag}_trans"], rtol=1e-6)
+    x = _dev(g[f"{tag}_x"])
+    logb = m.get_observation_log_probs(x)
+    np.testing.assert_allclose(logb.cpu().numpy(), g[f"{tag}_logb"], rtol=1e-5, atol=1e-4)
+    states, scores = m(x)
+    assert states.dtype == torch.int64 and states.shape == g[f"{tag}_states"].shape
+    np.testing.assert_allclose(scores.cpu().numpy(), g[f"{tag}_scores"], rtol=1e-5)
+    assert np.array_equal(states.cpu().numpy(), g[f"{tag}_states"])
+
+
+@pytest.mark.parametrize("tag", ["gamma", "poisson", "weibull"])
+def test_hsmm_viterbi_kernel_bit_exact_on_reference_inputs(hm, golden, tag):
+    """Identical fp32 tables and log-emissions in -> identical states AND scores out (hsmm.py:245-354 operation order)."""
+    g = golden("hsmm")
+    log_dur = torch.log(torch.from_numpy(g[f"{tag}_dur_probs"]) + 1e-8)
+    log_trans = torch.log(torch.from_numpy(g[f"{tag}_trans"]) + 1e-8)
+    states, scores = hm.ops.hsmm_viterbi(_dev(g[f"{tag}_logb"]), log_dur.cuda(), log_trans.cuda(), sum_order=0)
+    assert np.array_equal(states.cpu().numpy(), g[f"{tag}_states"])
+    assert np.array_equal(scores.cpu().numpy(), g[f"{tag}_scores"])
+
+
+@pytest.mark.parametrize("K,Dm,T,B", [(2, 3, 7, 2), (5, 8, 30, 3), (6, 10, 200, 4), (10, 20, 300, 2), (3, 1, 9, 1), (4, 25, 12, 2)])
+def test_hsmm_viterbi_vs_c_oracle(hm, K, Dm, T, B):
+    rng = np.random.default_rng(K * 31 + Dm)
+    logb = (rng.standard_normal((B, T, K)) * 4 - 20).astype(np.float32)
+    logdur = np.log(rng.random((K, Dm)) + 1e-3).astype(np.float32)
+    A = rng.random((K, K)).astype(np.float32) + 0.05
+    np.fill_diagonal(A, 0.0)
+    logA = np.log(A / A.sum(1, keepdims=True) + 1e-8).astype(np.float32)
+    st, sc = c_oracle.hsmm_viterbi_f32(logb, logdur, logA)
+    states, scores = hm.ops.hsmm_viterbi(_dev(logb), _dev(logdur), _dev(logA), sum_order=0)
+    assert np.array_equal(scores.cpu().numpy(), sc)
+    assert np.array_equal(states.cpu().numpy(), st)
+
+
+def _semimarkov(hm, g):
+    K, D = g["observation_means"].shape
+    Dm = g["forward_variables"].shape[2]
+    m = hm.SemiMarkovHMM(K, D, max_duration=Dm, duration_distribution="gamma").cuda()
+    sd = {"transition_logits": g["transition_logits"], "initial_logits": g["initial_logits"],
+          "observation_means": g["observation_means"], "observation_logvars": g["observation_logvars"],
+          "duration_model.alpha_params": g["duration_model.alpha_params"],
+          "duration_model.beta_params": g["duration_model.beta_params"]}
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    return m
+
+
+def test_semimarkov_forward_vs_reference_golden(hm, golden):
+    g = golden("semimarkov")
+    m = _semimarkov(hm, g)
+    np.testing.assert_allclose(m.duration_model.log_table().detach().cpu().numpy(), g["log_dur"], rtol=1e-5, atol=1e-6)
+    res = m(_dev(g["x"]))
+    # 1e-4 relative on the log-probability and on every finite forward variable (fp32 reference)
+    np.testing.assert_allclose(res["log_probability"].item(), float(g["log_probability"]), rtol=1e-4)
+    ref = g["forward_variables"]; ours = res["forward_variables"].cpu().numpy()
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(ours), fin)
+    np.testing.assert_allclose(ours[fin], ref[fin], rtol=1e-4)
+
+
+def test_semimarkov_viterbi_vs_reference_golden(hm, golden):
+    g = golden("semimarkov")
+    m = _semimarkov(hm, g)
+    st, du, lp = m.viterbi_decode(_dev(g["x"][0]))
+    assert np.array_equal(st.cpu().numpy(), g["vit_states"])
+    assert np.array_equal(du.cpu().numpy(), g["vit_durations"])
+    np.testing.assert_allclose(lp.item(), float(g["vit_logprob"]), rtol=1e-5)
+
+
+def test_hsmm_forward_vs_float64_oracle(hm):
+    rng = np.random.default_rng(12)
+    K, Dm, T = 5, 7, 60
+    f = (rng.standard_normal((1, T, K)) * 3 - 10).astype(np.float32)
+    segc = (rng.standard_normal(K) - 5).astype(np.float32)
+    logdur = np.log(rng.random((K, Dm)) + 1e-2).astype(np.float32)
+    A = rng.random((K, K)) + 0.05
+    np.fill_diagonal(A, 0.0)
+    logA = np.log(A / A.sum(1, keepdims=True) + 1e-8).astype(np.float32)
+    logpi = np.log(np.full(K, 1.0 / K)).astype(np.float32)
+    seg = np.full((T, K, Dm), -np.inf)
+    for t in range(T):
+        for s in range(K):
+            for d in range(1, min(Dm, t + 1) + 1):
+                seg[t, s, d - 1] = float(segc[s]) + f[0, t - d + 1:t + 1, s].astype(np.float64).sum()
+    alpha, beta, tot = c_oracle.hsmm_forward_f64(seg, logdur, logA, logpi)
+    r = hm.ops.hsmm_forward(_dev(f), _dev(logdur), _dev(logA), seg_const=_dev(segc), log_init=_dev(logpi))
+    np.testing.assert_allclose(r["total"].item(), tot, rtol=1e-5)
+    fin = np.isfinite(alpha)
+    np.testing.assert_allclose(r["alpha"][0].cpu().numpy()[fin], alpha[fin], rtol=1e-4, atol=1e-3)
+
+
+def test_streaming_greedy_vs_reference_golden(hm, golden):
+    g = golden("streaming")
+    p = hm.StreamingHMMProcessor(6, 8, chunk_size=16, overlap_size=4, lookahead_frames=2, max_delay_frames=64,
+                                 use_beam_search=False).cuda()
+    sd = {k.replace("__", "."): torch.from_numpy(g[k]) for k in g.files if k.startswith(("transition_logits", "emission_net"))}
+    p.load_state_dict(sd)
+    p.eval()
+    feats = torch.from_numpy(g["feats"]).cuda()
+    r1 = p.process_chunk(feats[:24])
+    r2 = p.process_chunk(feats[24:48])
+    assert r1.status == "decoded" and r2.status == "decoded"
+    assert r1.metadata["frames_processed"] == int(g["chunk1_frames"]) and r2.metadata["frames_processed"] == int(g["chunk2_frames"])
+    assert np.array_equal(r1.decoded_states.cpu().numpy(), g["chunk1_states"])
+    assert np.array_equal(r2.decoded_states.cpu().numpy(), g["chunk2_states"])
+    np.testing.assert_allclose(r1.confidence, float(g["chunk1_conf"]), rtol=1e-4)
+    np.testing.assert_allclose(r2.confidence, float(g["chunk2_conf"]), rtol=1e-4)
+    assert p.process_chunk(feats[:2]).status in ("decoded", "waiting_for_lookahead", "buffering")
+    p.reset_streaming_state()
+    assert p.process_chunk(feats[:4]).status == "buffering"
+
+
+def test_greedy_kernel_vs_c_oracle(hm):
+    rng = np.random.default_rng(3)
+    K, T = 9, 150
+    logb = np.log(rng.dirichlet(np.ones(K), size=T)).astype(np.float32)
+    logA = np.log(rng.dirichlet(np.ones(K), size=K) + 1e-8).astype(np.float32)
+    s1, sc1 = c_oracle.greedy_decode_f32(logb[:70], logA, -1)
+    s2, sc2 = c_oracle.greedy_decode_f32(logb[70:], logA, int(s1[-1]))
+    state = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+    a, sa = hm.ops.greedy_decode(_dev(logb[None, :70]), _dev(logA), state)
+    b, sb = hm.ops.greedy_decode(_dev(logb[None, 70:]), _dev(logA), state)
+    assert np.array_equal(a[0].cpu().numpy(), s1) and np.array_equal(b[0].cpu().numpy(), s2)
+    np.testing.assert_allclose(sa[0].cpu().numpy(), sc1, rtol=1e-6)
+    assert int(state.item()) == int(s2[-1])
+
+
+def test_forward_chunk_equals_unchunked_and_float64(hm):
+    """New functionality (no reference): the carried-state forward over chunks must equal one pass, and the float64 oracle."""
+    rng = np.random.default_rng(5)
+    B, T, K = 3, 400, 12
+    l = (rng.standard_normal((B, T, K)) * 3 - 40).astype(np.float32)
+    P = rng.dirichlet(np.ones(K), size=K).astype(np.float32)
+    p0 = rng.dirichlet(np.ones(K)).astype(np.float32)
+    la, lb, gam, ll = c_oracle.forward_backward_f64(l.astype(np.float64), np.log(P.astype(np.float64)), np.log(p0.astype(np.float64)))
+    full = hm.ops.new_forward_state(B, K, "cuda")
+    f_full = hm.ops.forward_chunk(_dev(l), hm.ops.EMIS_LOG, _dev(P), _dev(p0), full)
+    st = hm.ops.new_forward_state(B, K, "cuda")
+    parts = [hm.ops.forward_chunk(_dev(l[:, a:b]), hm.ops.EMIS_LOG, _dev(P), _dev(p0), st) for a, b in ((0, 37), (37, 160), (160, 161), (161, 400))]
+    f_chunks = torch.cat(parts, dim=1)
+    assert torch.equal(f_chunks, f_full)                                   # bit-identical: same arithmetic, state carried
+    assert torch.equal(st["loglik"], full["loglik"])
+    np.testing.assert_allclose(full["loglik"].cpu().numpy(), ll, rtol=1e-5)
+    filt64 = np.exp(la - np.logaddexp.reduce(la, axis=-1, keepdims=True))
+    np.testing.assert_allclose(f_full.cpu().numpy(), filt64, rtol=1e-4, atol=1e-7)
+
+
+def test_streaming_forward_chunk_api(hm):
+    p = hm.StreamingHMMProcessor(6, 8, use_beam_search=False).cuda().eval()
+    x = torch.randn(50, 8).cuda()
+    a = p.forward_chunk(x[:20]); b = p.forward_chunk(x[20:])
+    p.reset_streaming_state()
+    c = p.forward_chunk(x)
+    assert torch.allclose(torch.cat([a["filtered"], b["filtered"]]), c["filtered"])
+    assert torch.allclose(b["log_likelihood"], c["log_likelihood"])
+    np.testing.assert_allclose(c["filtered"].sum(-1).cpu().numpy(), 1.0, atol=1e-5)
+
+
+def test_factories(hm):
+    m = hm.create_speech_hmm(12, 80, "mixture_gaussian", num_mixtures=4).cuda()     # the README call that raises in the reference
+    st, sc = m(torch.randn(2, 30, 80).cuda(), return_log_probs=True)
+    assert st.shape == (2, 30) and sc.shape == (2,)
+    h = hm.create_speech_hmm(5, 16, "hsmm", max_duration=6).cuda()
+    st, sc = h(torch.randn(2, 25, 16).cuda())
+    assert st.shape == (2, 25) and torch.isfinite(sc).all()
+    assert isinstance(hm.ModelFactory.create_realtime_model(4, 8), hm.StreamingHMMProcessor)
+    with pytest.raises(ValueError):
+        hm.create_speech_hmm(3, 4, "nope")
