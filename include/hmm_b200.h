@@ -142,6 +142,24 @@ int    hmmb200_forward_chunk_f32(const float *emis, int emis_mode, float floor_e
                                  const float *init_prob, int B, int T, int K, float *state_alpha,
                                  double *state_loglik, int32_t *started, float *filtered, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Baum-Welch E-step statistics for a GMM-HMM (new functionality; formulas docs/01_hmm_theory.md:196-227 + the
+ * standard Gaussian-mixture extension).  Multi-GPU: each rank accumulates its shard of utterances, the host all-reduces
+ * the stats vector (NCCL) once per EM iteration.
+ *   hmmb200_gmm_components_f32: comp [n_frames, K*C] = log w_kc + log N(x | mu_kc, var_kc)  (per-component, no log-sum-exp)
+ *   hmmb200_bw_accumulate_f32 : ADDS into stats (double, hmmb200_bw_stats_doubles(K,C,D) values, zeroed by the caller):
+ *       gamma1[K] | xi[K,K] | occ[K,C] | sx[K,C,D] | sxx[K,C,D]
+ *     inputs: x [B,T,D]; comp; logb [B,T,K] (= LSE_c comp); gamma [B,T,K]; emis/emis_mode/floor_eps/trans_prob exactly as passed
+ *     to hmmb200_forward_backward_f32, and that call's workspace (it still holds the scaled forward/backward vectors).
+ * --------------------------------------------------------------------------------------------------------- */
+int    hmmb200_gmm_components_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
+                                  float *comp, void *stream);
+size_t hmmb200_bw_stats_doubles(int K, int C, int D);
+int    hmmb200_bw_accumulate_f32(const float *x, const float *comp, const float *logb, const float *gamma,
+                                 const float *emis, int emis_mode, float floor_eps, const float *trans_prob,
+                                 const void *fb_workspace, int B, int T, int K, int C, int D,
+                                 double *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,221 @@
+// bw.cu -- Baum-Welch E-step sufficient statistics for a GMM-HMM (sm_100a).
+//
+// The reference has no Baum-Welch code; the formulas are docs/01_hmm_theory.md:196-227 (gamma :204, xi :209, pi :216, a_ij :221)
+// and the standard Gaussian-mixture extension.  Statistics are accumulated in double:
+//   gamma1[K]   += gamma_0[k]                      xi[K,K]     += sum_t xi_t(i,j)
+//   occ[K,C]    += sum_t gamma_t[k] r_t[k,c]       sx[K,C,D]   += sum_t gamma_t[k] r_t[k,c] x_t
+//   sxx[K,C,D]  += sum_t gamma_t[k] r_t[k,c] x_t^2           (r = component responsibility within the state)
+// Kernels:
+//   gmm_components_kernel   per-component log-likelihoods log w_kc + log N(x | mu_kc, var_kc)  [n, K*C]
+//   bw_xi_kernel            xi and gamma_0 from the scaled forward/backward vectors left in the fb workspace
+//   bw_gmm_stats_kernel     occ / sx / sxx: register-tiled (component x dim) outer-product accumulation, fp32 partials per
+//                           CTA, one double atomicAdd per statistic per CTA
+// Multi-GPU: each rank accumulates its shard; the host all-reduces the ~8 k doubles once per EM iteration (NCCL).
+#include "common.cuh"
+
+namespace hmmb200 {
+
+__global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, const float *packed, int64_t n, int KC, int D,
+                                                             int NP2, float *comp) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * KC) return;
+    const int64_t fr = idx / KC;
+    const int kc = (int)(idx % KC), pr = kc >> 1, hi = kc & 1;
+    const float *xn = x + fr * D;
+    float acc = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float u = fmaf(xn[d], __ldg(packed + ((size_t)d * NP2 + pr) * 4 + hi), __ldg(packed + ((size_t)d * NP2 + pr) * 4 + 2 + hi));
+        acc = fmaf(u, u, acc);
+    }
+    comp[idx] = fmaf(-0.5f, acc, __ldg(packed + (size_t)D * NP2 * 4 + kc));
+}
+
+// one warp per (sequence, block of frames); lane j owns column j of xi
+__global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode, float eps, const float *trans,
+                                                    const float *ws_a, const float *ws_b, int B, int T, int K, int frames_per_warp,
+                                                    double *xi, double *gamma1) {
+    extern __shared__ double xi_s[];                       // [K*K] per CTA
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) xi_s[i] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int blocks_per_seq = (T - 1 + frames_per_warp - 1) / frames_per_warp;
+    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
+    const bool ok = lane < K;
+    float col[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) col[i] = (ok && i < K) ? trans[i * K + lane] : 0.f;
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    if (wid < (int64_t)B * max(blocks_per_seq, 1) && T > 1) {
+        const int b = (int)(wid / blocks_per_seq), blk = (int)(wid % blocks_per_seq);
+        const int t0 = blk * frames_per_warp, t1 = min(T - 1, t0 + frames_per_warp);
+        for (int t = t0; t < t1; ++t) {
+            // u_j = b~_{t+1}(j) * beta_{t+1}(j)
+            float e = ok ? emis[((size_t)b * T + t + 1) * K + lane] : 0.f, bt;
+            if (mode == HMMB200_EMIS_PROB_FLOOR) bt = ok ? e + eps : 0.f;
+            else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) bt = ok ? expf(e) + eps : 0.f;
+            else {
+                float mx = ok ? e : -INFINITY;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+                if (!(mx > -INFINITY)) mx = 0.f;
+                bt = ok ? expf(e - mx) + ((mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f) : 0.f;
+            }
+            const float u = ok ? bt * ws_b[((size_t)b * T + t + 1) * K + lane] : 0.f;
+            const float a = ok ? ws_a[((size_t)b * T + t) * K + lane] : 0.f;
+            float v[32], cs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { v[i] = __shfl_sync(FULL_MASK, a, i) * col[i] * u; cs += v[i]; }
+            float Z = cs;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
+            const float inv = (Z > 0.f) ? 1.f / Z : 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = fmaf(v[i], inv, acc[i]);
+        }
+        if (blk == 0 && gamma1 != nullptr) {               // gamma_0 = a_0 .* b_0 / sum
+            const float g = ok ? ws_a[(size_t)b * T * K + lane] * ws_b[(size_t)b * T * K + lane] : 0.f;
+            float Z = g;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
+            if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)(g / Z));
+        }
+    } else if (T == 1 && wid < B && gamma1 != nullptr) {
+        const int b = (int)wid;
+        const float g = ok ? ws_a[(size_t)b * K + lane] * ws_b[(size_t)b * K + lane] : 0.f;
+        float Z = g;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
+        if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)(g / Z));
+    }
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) if (i < K) atomicAdd(&xi_s[i * K + lane], (double)acc[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) if (xi_s[i] != 0.0) atomicAdd(xi + i, xi_s[i]);
+}
+
+// occ / sx / sxx.  CTA = 256 threads, tile of BW_F frames staged in shared memory; thread (gc, gd) owns a TC x TD block of
+// (component, dim) accumulators for x and x^2.
+constexpr int BW_F = 32;
+constexpr int BW_TC = 6, BW_TD = 5;
+__global__ void __launch_bounds__(1024) bw_gmm_stats_kernel(const float *x, const float *comp, const float *logb, const float *gamma,
+                                                            int64_t n, int K, int C, int D, double *occ, double *sx, double *sxx) {
+    extern __shared__ float sm_bw[];
+    const int KC = K * C;
+    float *w_s = sm_bw;                    // [BW_F][KC]
+    float *x_s = w_s + BW_F * KC;          // [BW_F][D]
+    const int ndg = (D + BW_TD - 1) / BW_TD, ncg = (KC + BW_TC - 1) / BW_TC;
+    const int tid = threadIdx.x;
+    const bool has_cell = tid < ncg * ndg;                 // the launch sizes the CTA to cover every cell
+    const int gc = tid / ndg, gd = tid % ndg;
+    float ax[BW_TC][BW_TD], axx[BW_TC][BW_TD], aocc[BW_TC];
+#pragma unroll
+    for (int i = 0; i < BW_TC; ++i) {
+        aocc[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < BW_TD; ++j) { ax[i][j] = 0.f; axx[i][j] = 0.f; }
+    }
+    const int64_t n_tiles = (n + BW_F - 1) / BW_F;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * BW_F;
+        const int nf = (int)min((int64_t)BW_F, n - base);
+        __syncthreads();
+        for (int i = tid; i < nf * KC; i += blockDim.x) {
+            const int f = i / KC, kc = i % KC, k = kc / C;
+            const int64_t fr = base + f;
+            w_s[i] = gamma[fr * K + k] * expf(comp[fr * KC + kc] - logb[fr * K + k]);     // gamma_t(k) * responsibility(c | k)
+        }
+        for (int i = tid; i < nf * D; i += blockDim.x) x_s[i] = x[base * D + i];
+        __syncthreads();
+        if (has_cell) {
+            for (int f = 0; f < nf; ++f) {
+                float wv[BW_TC], xv[BW_TD];
+#pragma unroll
+                for (int i = 0; i < BW_TC; ++i) { const int kc = gc * BW_TC + i; wv[i] = kc < KC ? w_s[f * KC + kc] : 0.f; }
+#pragma unroll
+                for (int j = 0; j < BW_TD; ++j) { const int d = gd * BW_TD + j; xv[j] = d < D ? x_s[f * D + d] : 0.f; }
+#pragma unroll
+                for (int i = 0; i < BW_TC; ++i) {
+                    aocc[i] += wv[i];
+#pragma unroll
+                    for (int j = 0; j < BW_TD; ++j) { const float wx = wv[i] * xv[j]; ax[i][j] += wx; axx[i][j] = fmaf(wx, xv[j], axx[i][j]); }
+                }
+            }
+        }
+    }
+    if (has_cell) {
+#pragma unroll
+        for (int i = 0; i < BW_TC; ++i) {
+            const int kc = gc * BW_TC + i;
+            if (kc < KC) {
+                if (gd == 0) atomicAdd(occ + kc, (double)aocc[i]);
+#pragma unroll
+                for (int j = 0; j < BW_TD; ++j) {
+                    const int d = gd * BW_TD + j;
+                    if (d < D) { atomicAdd(sx + (size_t)kc * D + d, (double)ax[i][j]); atomicAdd(sxx + (size_t)kc * D + d, (double)axx[i][j]); }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace hmmb200
+
+using namespace hmmb200;
+
+HMMB200_EXPORT int hmmb200_gmm_components_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
+                                              float *comp, void *stream) {
+    if (n_frames < 0 || K <= 0 || C <= 0 || D <= 0) return set_error(HMMB200_EINVAL, "gmm_components: bad shape");
+    if (n_frames == 0) return HMMB200_OK;
+    if (!x || !packed || !comp) return set_error(HMMB200_EINVAL, "gmm_components: null argument");
+    if (int rc = require_sm100()) return rc;
+    const int KC = K * C;
+    const int64_t total = n_frames * KC;
+    gmm_components_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp);
+    return check_launch("gmm_components_kernel");
+}
+
+// stats layout (doubles): gamma1[K] | xi[K*K] | occ[K*C] | sx[K*C*D] | sxx[K*C*D]   (accumulated; zero it before the first call)
+HMMB200_EXPORT size_t hmmb200_bw_stats_doubles(int K, int C, int D) {
+    if (K <= 0 || C <= 0 || D <= 0) return 0;
+    return (size_t)K + (size_t)K * K + (size_t)K * C + 2 * (size_t)K * C * D;
+}
+
+HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, const float *logb, const float *gamma,
+                                             const float *emis, int emis_mode, float floor_eps, const float *trans_prob,
+                                             const void *fb_workspace, int B, int T, int K, int C, int D,
+                                             double *stats, void *stream) {
+    if (B < 0 || T < 0 || K <= 0 || C <= 0 || D <= 0) return set_error(HMMB200_EINVAL, "bw_accumulate: bad shape");
+    if (B == 0 || T == 0) return HMMB200_OK;
+    if (K > 32) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K <= 32 (got %d)", K);
+    if (!x || !comp || !logb || !gamma || !emis || !trans_prob || !fb_workspace || !stats)
+        return set_error(HMMB200_EINVAL, "bw_accumulate: null argument");
+    if (int rc = require_sm100()) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    double *gamma1 = stats, *xi = stats + K, *occ = xi + (size_t)K * K, *sx = occ + (size_t)K * C, *sxx = sx + (size_t)K * C * D;
+    const size_t n = (size_t)B * T;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const float *ws_a = (const float *)fb_workspace;
+    const float *ws_b = (const float *)((const uint8_t *)fb_workspace + al(n * K * sizeof(float)));
+    const int fpw = 64, warps = 4;
+    const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
+    const int64_t n_warps = (int64_t)B * blocks_per_seq;
+    bw_xi_kernel<<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), s>>>(
+        emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, B, T, K, fpw, xi, gamma1);
+    if (int rc = check_launch("bw_xi_kernel")) return rc;
+    const size_t smem = (size_t)BW_F * (K * C + D) * sizeof(float);
+    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K*C + D too large");
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bw_gmm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n_tiles = ((int64_t)n + BW_F - 1) / BW_F;
+    const int cells = ((K * C + BW_TC - 1) / BW_TC) * ((D + BW_TD - 1) / BW_TD);
+    if (cells > 1024) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K*C*D = %d*%d*%d too large for one CTA of accumulators", K, C, D);
+    const int threads = ((cells + 31) / 32) * 32;
+    bw_gmm_stats_kernel<<<(unsigned)min((int64_t)sms * 4, n_tiles), threads, smem, s>>>(x, comp, logb, gamma, (int64_t)n, K, C, D, occ, sx, sxx);
+    return check_launch("bw_gmm_stats_kernel");
+}
