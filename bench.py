@@ -34,6 +34,9 @@ if ROOT not in sys.path:
 K_STATES, N_MIX, FEAT, BATCH, SEQ = 12, 4, 80, 256, 2000
 BYTES_PER_FRAME = 4 * FEAT + 4 * K_STATES * 4 + 8          # x in; posterior, forward, backward, log_delta + int64 state out
 METRIC = "frames/sec forward-backward+Viterbi (K=12,T=2000,B=256)"
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
+NCU_TRAFFIC_SRC = "profiles/r01_ncu_full_summary.md"
+NCU_TRAFFIC = {"gmm_emission_tc_kernel": 175.0e6, "fb_sweep_kernel": 29.6e6, "fb_combine_kernel": 99.2e6, "viterbi_kernel": 24.7e6}
 
 
 def measured_peaks():
@@ -176,67 +179,46 @@ def run_reference_arm(args, rank):
 # GPU arm
 # ------------------------------------------------------------------------------------------------------------
 class Headline:
-    """Device-side state of the headline step, through the public classes / ops of pytorch_hmm_b200."""
+    """Device-side state of the headline step, through the public engine / ops of pytorch_hmm_b200."""
 
-    def __init__(self, model, dev):
+    def __init__(self, model, dev, shard=None, n_streams=1, host_io=False):
         import pytorch_hmm_b200 as hm
+        from pytorch_hmm_b200.engine import HMMInferenceEngine
         self.hm, self.dev = hm, dev
         self.layer = hm.MixtureGaussianHMMLayer(K_STATES, FEAT, num_components=N_MIX).to(dev)
         self.layer.load_state_dict({k: v.to(dev) for k, v in model.items()})
         self.layer.eval()
-        P = self.layer.get_transition_matrix().detach()
-        self.hmm = hm.HMMPyTorch(P, None, device=str(dev))
-        self.trans, self.init = self.hmm._effective_probs(dev)
-        self.log_trans = self.layer._safe_log(P).contiguous()
-        import math
-        self.prior = torch.full((K_STATES,), -math.log(K_STATES), dtype=torch.float32, device=dev)
-        self.packed = self.layer._packed()
-        n = (BATCH, SEQ, K_STATES)
-        self.logb = torch.empty(n, device=dev)
-        self.fb_out = {k: torch.empty(n, device=dev) for k in ("gamma", "fwd", "bwd")}
-        self.fb_out["loglik"] = torch.empty(BATCH, device=dev)
-        self.vit_out = {"states": torch.empty(BATCH, SEQ, dtype=torch.int64, device=dev),
-                        "delta": torch.empty(n, device=dev), "score": torch.empty(BATCH, device=dev)}
-        self.fb_ws = hm.ops.fb_workspace(BATCH, SEQ, K_STATES, dev)
-        self.vit_ws = hm.ops.viterbi_workspace(BATCH, SEQ, K_STATES, dev)
-        self.launches_per_step = 4     # gmm_emission_tc, fb_sweep, fb_combine, viterbi
-        # forward-backward and Viterbi only share their input (log b): run them on two side streams so the two
-        # latency-bound recursions overlap
-        self.s_fb, self.s_vit = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        self.ev_emis, self.ev_fb, self.ev_vit = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
+        self.eng = HMMInferenceEngine(self.layer, BATCH, SEQ, shard=shard or BATCH, n_streams=n_streams, device=dev,
+                                      host_io=host_io)
+        e = self.eng
+        self.logb = e.slots[0].logb
+        self.launches_per_step = e.kernels_per_shard * e.n_shards
 
+    # single kernels on the current stream (per-kernel timing only)
     def emission(self, x):
-        self.hm.ops.gmm_emission(x, self.packed, K_STATES, N_MIX, FEAT, out=self.logb)
+        e = self.eng
+        self.hm.ops.gmm_emission(x, e.packed, K_STATES, N_MIX, FEAT, out=self.logb)
 
     def fb(self, want=("gamma", "fwd", "bwd")):
-        out = self.fb_out if want else {"loglik": self.fb_out["loglik"]}
-        self.hm.ops.forward_backward(self.logb, self.hm.ops.EMIS_LOG_NORM_FLOOR, self.trans, self.init, want=want, out=out,
-                                     workspace=self.fb_ws)
+        e, o = self.eng, self.eng.out
+        out = {"loglik": o["loglik"]}
+        if want:
+            out.update({"gamma": o["posterior"], "fwd": o["forward"], "bwd": o["backward"]})
+        self.hm.ops.forward_backward(self.logb, self.hm.ops.EMIS_LOG_NORM_FLOOR, e.trans, e.init, want=want, out=out,
+                                     workspace=e.slots[0].fb_ws)
 
     def vit(self):
-        self.hm.ops.viterbi(self.logb, self.hm.ops.EMIS_LOG, self.log_trans, self.prior, out=self.vit_out,
-                            workspace=self.vit_ws)
+        e, o = self.eng, self.eng.out
+        self.hm.ops.viterbi(self.logb, self.hm.ops.EMIS_LOG, e.log_trans, e.prior,
+                            out={"states": o["states"], "delta": o["log_delta"], "score": o["score"]},
+                            workspace=e.slots[0].vit_ws)
 
     def step(self, x):
-        main = torch.cuda.current_stream(self.dev)
-        self.emission(x)
-        self.ev_emis.record(main)
-        with torch.cuda.stream(self.s_fb):
-            self.s_fb.wait_event(self.ev_emis)
-            self.fb()
-            self.ev_fb.record(self.s_fb)
-        with torch.cuda.stream(self.s_vit):
-            self.s_vit.wait_event(self.ev_emis)
-            self.vit()
-            self.ev_vit.record(self.s_vit)
-        main.wait_event(self.ev_fb)
-        main.wait_event(self.ev_vit)
-
-    def step_serial(self, x):
-        self.emission(x); self.fb(); self.vit()
+        self.eng.run_device(x)
 
     def outputs(self):
-        return [self.fb_out["gamma"], self.fb_out["fwd"], self.fb_out["bwd"], self.vit_out["delta"], self.vit_out["states"]]
+        o = self.eng.out
+        return [o[k] for k in ("posterior", "forward", "backward", "log_delta", "states")]
 
 
 def event_ms(fn, iters):
@@ -261,6 +243,17 @@ def run_gpu_arm(args, rank, world, local_rank):
     x = x_host.to(dev, non_blocking=True)
     h = Headline(model, dev)
     torch.cuda.synchronize()
+    # one pass = one CUDA-graph launch (emission, then forward-backward || Viterbi on two streams); falls back to
+    # eager stream launches if capture is refused
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = h.eng.capture_device(x)
+        except Exception as exc:                                  # noqa: BLE001
+            print(f"bench.py: CUDA-graph capture failed ({exc}); timing eager launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    step = (lambda: graph.replay()) if graph is not None else (lambda: h.step(x))
 
     def barrier():
         if world > 1:
@@ -271,13 +264,13 @@ def run_gpu_arm(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     for _ in range(max(args.warmup, 3)):
-        h.step(x)
+        step()
     # ---- timed region: K steps, inputs resident in HBM; x (164 MB) + logb + outputs exceed the 126 MB L2 ----
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(args.steps):
-        h.step(x)
+        step()
     e.record()
     barrier()
     ms_total = s.elapsed_time(e)
@@ -290,7 +283,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     t_end = time.perf_counter() + 1.5
     while time.perf_counter() < t_end:
         for _ in range(20):
-            h.step(x)
+            step()
         torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -314,35 +307,45 @@ def run_gpu_arm(args, rank, world, local_rank):
     peak, peak_src = measured_peaks()
     achieved = alg_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()},
+                "traffic": NCU_TRAFFIC.get(dom), "traffic_source": NCU_TRAFFIC_SRC, "peak_source": peak_src,
+                "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()},
+                "note": "the recursion kernels are bound by the latency of T dependent steps, not by HBM (DESIGN.md 4.2); "
+                        "per-kernel fractions: " + ", ".join(
+                            f"{k} {alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak:.3f}" for k in alg_bytes),
                 "path": {"bytes_per_frame": BYTES_PER_FRAME, "achieved": value / world * BYTES_PER_FRAME / 1e9,
                          "frac": value / world * BYTES_PER_FRAME / 1e9 / peak}}
 
-    # ---- end to end: host buffers in, host buffers out, copies inside the timed region ----
-    outs_host = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in h.outputs()]
+    # ---- end to end: pinned host buffers in, pinned host buffers out, copies inside the timed region.  The public
+    #      engine shards the batch over 4 streams so that H2D, kernels and D2H of different shards overlap. ----
+    he = Headline(model, dev, shard=args.e2e_shard, n_streams=args.e2e_streams, host_io=True)
+    names = ("posterior", "forward", "backward", "log_delta", "states")
+    outs_host = [{k: torch.empty(he.eng.out[k].shape, dtype=he.eng.out[k].dtype).pin_memory() for k in names} for _ in range(2)]
     h2d = x_host.numel() * 4
-    d2h = sum(o.numel() * o.element_size() for o in outs_host)
+    d2h = sum(o.numel() * o.element_size() for o in outs_host[0].values())
 
-    def e2e_step():
-        x.copy_(x_host, non_blocking=True)
-        h.step(x)
-        for dst, src in zip(outs_host, h.outputs()):
-            dst.copy_(src, non_blocking=True)
-        torch.cuda.synchronize()
+    def e2e_step(i):
+        he.eng.run_host(x_host, outs_host[i & 1], join=False)     # consecutive passes pipeline; results alternate host sets
 
-    for _ in range(3):
-        e2e_step()
+    for i in range(3):
+        e2e_step(i)
+    he.eng.join(); torch.cuda.synchronize()
     n_e2e = max(3, min(args.steps, 20))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(n_e2e):
-        e2e_step()
+    for i in range(n_e2e):
+        e2e_step(i)
+    he.eng.join()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / n_e2e
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
     e2e = {"value": world * BATCH * SEQ / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
+           "api": f"HMMInferenceEngine.run_host (shard={he.eng.shard}, streams={he.eng.n_streams})"}
+    # spot check: the pipelined host path returns what the single-pass device path computed
+    torch.cuda.synchronize()
+    same = all(torch.equal(outs_host[(n_e2e - 1) & 1][k], h.eng.out[k].cpu()) for k in names)
+    e2e["matches_device_pass"] = bool(same)
 
     if rank == 0:
         line = {
@@ -355,7 +358,8 @@ def run_gpu_arm(args, rank, world, local_rank):
                        "l2": "no flush: per-step inputs+outputs (164 MB x, 25 MB log b, 102 MB outputs) exceed the 126 MB L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": h.launches_per_step * args.steps, "roofline": roofline,
         }
-        if world == 1 or True:
+        line["config"]["launch"] = "cuda-graph replay per step" if not args.no_graph else "eager stream launches"
+        if world == 1:
             torch.set_num_threads(os.cpu_count() or 1)
             bs = 32
             xs = x_host[:bs].clone()
@@ -375,6 +379,9 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
+    ap.add_argument("--e2e-shard", type=int, default=32, help="utterances per in-flight shard on the host path")
+    ap.add_argument("--e2e-streams", type=int, default=4)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
