@@ -235,11 +235,37 @@ def segsum_probe():
     np.savez_compressed(os.path.join(OUT, "segsum.npz"), x=_np(x), sums=sums)
 
 
+def largek(ref):
+    """A2/A3 at K > 32 (BASELINE config 5 family): K = 64 skip-left-to-right and K = 512 ergodic on
+    softmax(randn) observations (examples/benchmark.py:160-162)."""
+    from pytorch_hmm.utils import create_transition_matrix
+    out = {}
+    g = torch.Generator().manual_seed(5001)
+    for tag, K, kind, B, T in (("k64", 64, "left_to_right_skip", 3, 40), ("k512", 512, "ergodic", 2, 24)):
+        P = create_transition_matrix(K, kind)
+        obs = torch.softmax(torch.randn(B, T, K, generator=g), dim=-1)
+        hmm = ref.HMMPyTorch(P, None)
+        post, fwd, bwd = hmm.forward_backward(obs)
+        states, delta = hmm.viterbi_decode(obs)
+        out.update({f"{tag}_P": _np(P), f"{tag}_obs": _np(obs), f"{tag}_log_P": _np(hmm.log_P), f"{tag}_log_p0": _np(hmm.log_p0),
+                    f"{tag}_posterior": _np(post), f"{tag}_forward": _np(fwd), f"{tag}_backward": _np(bwd),
+                    f"{tag}_states": _np(states), f"{tag}_log_delta": _np(delta),
+                    f"{tag}_likelihood": _np(hmm.compute_likelihood(obs))})
+    np.savez_compressed(os.path.join(OUT, "largek.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = _import_reference()
     torch.set_num_threads(1)
-    core(ref); gaussian(ref); mixture(ref); hsmm(ref); semimarkov(ref); streaming(ref); segsum_probe()
+    sections = {"core": core, "gaussian": gaussian, "mixture": mixture, "hsmm": hsmm, "semimarkov": semimarkov,
+                "streaming": streaming, "largek": largek}
+    only = [a for a in sys.argv[1:] if a in sections or a == "segsum"]        # e.g. `make_golden.py largek`
+    for name, fn in sections.items():
+        if not only or name in only:
+            fn(ref)
+    if not only or "segsum" in only:
+        segsum_probe()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -38,4 +38,14 @@ int launch_pack_tc(const float *means, const float *log_vars, float scale, const
 int launch_emission_tc(const float *x, const float *tc, const float *packed32, int64_t n_frames, int K, int C, int D,
                        float *logb, cudaStream_t s);
 
+// recursion_largek.cu (32 < K <= 512: cluster kernels)
+bool largek_shape_ok(int K);
+size_t largek_fb_workspace_bytes(int B, int T, int K);
+size_t largek_viterbi_workspace_bytes(int B, int T, int K);
+int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, int add_rowmax, const float *trans_prob,
+                            const float *init_prob, int B, int T, int K, float *gamma, float *fwd_prob, float *bwd_prob,
+                            float *log_alpha, float *log_beta, float *loglik, void *workspace, cudaStream_t s);
+int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
+                   int B, int T, int K, float *delta, int64_t *states, float *score, void *workspace, cudaStream_t s);
+
 }  // namespace hmmb200

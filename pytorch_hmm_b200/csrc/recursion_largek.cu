@@ -1,0 +1,636 @@
+// recursion_largek.cu -- HMM recursions for 32 < K <= 512 states on sm_100a: one thread-block CLUSTER per group of
+// sequences, the transition matrix resident in registers, the state vector exchanged through distributed shared memory.
+//
+//   lk_sweep_kernel<FWD/BWD>  scaled-probability forward / backward sweeps      (pytorch_hmm/hmm.py:95-117)
+//   lk_sweep_kernel<VIT>      max-plus recursion, bit-identical delta           (hmm.py:159-168)
+//   lk_traceback_kernel       arg-max + backpointers recomputed on the path     (hmm.py:167, :174-178)
+//   lk_combine_kernel         posterior / exp(log alpha) / exp(log beta)        (hmm.py:120-128)
+//   lk_rowmax_kernel          per-frame max_k of the log-emissions (scaling of the LOG emission modes)
+//
+// Why a cluster: one step is a [n_seq, K] x [K, K] product followed by a dependency on ALL K results, T times.  A K = 512
+// fp32 matrix is 1 MB: it fits in no single SM, and re-reading it from L2 every step (1 MB x 4000 steps x 64 sequences)
+// would make the sweep L2-bound.  So the CS CTAs of a cluster each own NC = 64 output states: their [K, 64] slab of P lives
+// in REGISTERS (64 per thread: warp w holds source states 32w..32w+31, lane l the two output states 2l, 2l+1), read
+// from HBM exactly once.  Per step a warp multiplies its 32-state slice of the previous vector (broadcast LDS.128 from
+// shared memory) into the slab with packed FFMA2, the 16 slices are summed through shared memory, the 256 "final"
+// threads apply emission and scaling, and the new 64-state slice is pushed to every CTA of the cluster with
+// st.async (DSMEM store + mbarrier complete_tx): the receiver's mbarrier flips exactly when all CS slices have landed,
+// so there is no cluster-wide barrier on the critical path, only the data's own arrival.  The vector is double-buffered;
+// a sender can never run more than one step ahead of a receiver because it needs the receiver's slice to do so.
+//
+// Scaling (forward/backward): every step is multiplied by 2^-k, k = exponent of the previous vector's largest entry
+// (each CTA ships its local maxima with its slice), exact power-of-two scaling with integer bookkeeping -- the same
+// scheme as the small-K kernels (recursion_smallk.cu), so alpha_t = w_t * 2^ksum_t * exp(sum m).
+// Viterbi: the max over source states is exact and order-independent, then ONE fp32 add of log b -- the reference's two
+// roundings (hmm.py:164-168) -- so delta is bit-identical; backpointers are not stored for all K states (K x T x B bytes
+// nobody reads): the traceback kernel recomputes argmax_i(delta_{t-1}(i) + logP(i, s_t)) with the same fp32 add and the
+// lowest-index tie rule only for the states on the path.
+#include "common.cuh"
+
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
+namespace cg = cooperative_groups;
+
+namespace hmmb200 {
+
+constexpr int LK_NSQ = 4;                       // sequences per group
+constexpr int LK_NG = 2;                        // independent sequence groups per cluster (software-pipelined)
+constexpr int LK_NC = 64;                       // output states per CTA
+constexpr int LK_KS = 32;                       // source states per warp (k-slice)
+constexpr int LK_NW = 16;                       // warps per CTA = k-slices
+constexpr int LK_THREADS = LK_NW * 32;          // 512
+constexpr int LK_KMAX = LK_NW * LK_KS;          // 512
+constexpr int LK_BLK = LK_NC + 4;               // floats per (CTA, sequence) block: 64 states + 2 local maxima + pad (272 B)
+constexpr int LK_CSMAX = LK_KMAX / LK_NC;       // 8 CTAs per cluster at most (portable cluster size)
+constexpr int LK_FINAL = LK_NSQ * LK_NC;        // 256 final threads: (sequence, output state)
+constexpr int LK_PF = 8;                        // emission prefetch distance in steps
+
+enum { LK_FWD = 0, LK_BWD = 1, LK_VIT = 2 };
+
+struct LkParams {
+    const float *emis;     // [B,T,K]
+    int mode;
+    float eps;
+    int add_rowmax;
+    const float *trans;    // [K,K]  fb: effective probabilities; viterbi: log transitions
+    const float *init;     // [K]    fb: probabilities; viterbi: log
+    const float *rowmax;   // [B,T] per-frame max of the log-emissions (LOG emission modes) or null
+    int B, T, K, CS;
+    float *ws_a, *ws_b;    // [B,T,K] scaled alpha / beta (fb)
+    float *ws_la, *ws_lb;  // [B,T]
+    float *loglik;         // [B] or null
+    float *delta;          // [B,T,K] (viterbi)
+    int *err;              // device flag: set to 1 if an exchange wait times out (never in a correct run)
+    int trace;
+};
+
+__device__ __forceinline__ uint32_t lk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float2 lk_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 lk_fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float lk_fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t lk_mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// bulk copy shared::cta -> (remote) shared::cluster, completion as transaction bytes on the receiver's mbarrier
+__device__ __forceinline__ void lk_bulk_push(uint32_t rdst, uint32_t src, uint32_t bytes, uint32_t rbar) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rdst), "r"(src), "r"(bytes), "r"(rbar) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(lk_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void lk_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(lk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// returns false if the phase did not complete within ~4 s (a protocol bug; never in a correct run)
+__device__ __forceinline__ bool lk_mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = lk_smem_u32(bar);
+    uint32_t done = 0;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                     "selp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity), "r"(1000u) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void lk_cp_async4(float *dst_smem, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lk_smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void lk_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void lk_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct LkSmem {
+    float vec[LK_NG][2][LK_CSMAX][LK_NSQ][LK_BLK];   // the exchanged state vector: one block per source CTA, double-buffered
+    float part[2][LK_NW][LK_NSQ][LK_NC];             // per-k-slice partial sums (alternating buffers)
+    float stage[LK_NG][2][LK_NSQ][LK_BLK];           // this CTA's new block before it is pushed (double-buffered)
+    float eraw[LK_NG][LK_PF][LK_FINAL];              // prefetched emissions, one slot per final thread
+    float mraw[LK_NG][LK_PF][LK_FINAL];              // prefetched per-frame max
+    double msum[LK_NG][LK_NSQ];                      // running sum of per-frame log scales (one owner thread each)
+    float la_last[LK_NG][LK_NSQ];                    // log scale of the last forward frame (for loglik)
+    uint64_t bar[LK_NG][2];
+};
+
+// timing trace (debug aid, tools/lk_trace.py): clock64 at the phase boundaries of steps 64..71 of CTA 0, thread 0, group 0
+__device__ long long lk_trace_buf[8 * 8];
+#define LK_TRACE(slot)                                                                          \
+    do {                                                                                        \
+        if (p.trace && g == 0 && blockIdx.x == 0 && tid == 0 && t >= 64 && t < 72) lk_trace_buf[(t - 64) * 8 + (slot)] = clock64(); \
+    } while (0)
+
+// One cluster = CS CTAs x LK_NG groups of LK_NSQ sequences.  The groups are independent recursions that share the CTA's
+// register-resident slab of P: while group g's new block is in flight through DSMEM, the CTA computes group g+1, so the
+// exchange latency is hidden behind arithmetic instead of being waited for.
+template <int MODE>
+__global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
+    extern __shared__ __align__(16) uint8_t lk_smem_raw[];
+    LkSmem &sm = *reinterpret_cast<LkSmem *>(lk_smem_raw);
+    constexpr bool VIT = (MODE == LK_VIT);
+    constexpr int DIR = (MODE == LK_BWD) ? 1 : 0;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K = p.K, T = p.T, B = p.B, CS = p.CS;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int cluster_id = blockIdx.x / CS;
+    const int seq0 = cluster_id * (LK_NSQ * LK_NG);
+    const int col0 = rank * LK_NC;
+    const int nkw = (K + LK_KS - 1) / LK_KS;                 // active k-slices
+    const float PADV = VIT ? -INFINITY : 0.f;
+    const int n_groups = min(LK_NG, (B - seq0 + LK_NSQ - 1) / LK_NSQ);   // groups of this cluster that hold sequences
+
+    // ---- the CTA's slab of the transition matrix, in registers: warp = source slice, lane = two output states -------
+    // forward / viterbi: out(j) = sum_i v(i) M(i,j)  -> M[i][j];   backward: out(i) = sum_j M(i,j) v(j) -> M[out][src]
+    float2 P0[LK_KS / 2], P1[LK_KS / 2];
+    {
+        const int o0 = col0 + 2 * lane, o1 = o0 + 1;
+#pragma unroll
+        for (int i = 0; i < LK_KS / 2; ++i) {
+            const int s0 = warp * LK_KS + 2 * i, s1 = s0 + 1;
+            auto ld = [&](int src, int out) -> float {
+                if (src >= K || out >= K) return PADV;
+                return (DIR == 0) ? __ldg(p.trans + (size_t)src * K + out) : __ldg(p.trans + (size_t)out * K + src);
+            };
+            P0[i] = make_float2(ld(s0, o0), ld(s1, o0));
+            P1[i] = make_float2(ld(s0, o1), ld(s1, o1));
+        }
+    }
+
+    // ---- final-thread identity: warps 8g..8g+7 finish group g; thread = (sequence fs of the group, output state fc) ----
+    static_assert(LK_NG * LK_FINAL == LK_THREADS, "one final thread per (group, sequence, output state)");
+    const int fg = tid / LK_FINAL, ft = tid % LK_FINAL, fwarp = ft >> 5;
+    const int fs = ft / LK_NC, fc = ft % LK_NC;
+    const int gcol = col0 + fc;
+    const bool need_m = (p.rowmax != nullptr);
+    const bool add_m = !VIT && ((p.mode == HMMB200_EMIS_LOG) || (p.mode == HMMB200_EMIS_LOG_NORM_FLOOR && p.add_rowmax));
+    auto frame_of = [&](int t) { return (DIR == 0) ? t : T - 1 - t; };
+    auto prefetch = [&](int t) {
+        if (fg < n_groups && t < T) {
+            const int f = frame_of(t);
+            const int sq = seq0 + fg * LK_NSQ + fs;
+            const bool okk = sq < B && gcol < K;
+            lk_cp_async4(&sm.eraw[fg][t % LK_PF][ft], p.emis + ((size_t)(okk ? sq : 0) * T + f) * K + (okk ? gcol : 0));
+            if (need_m) lk_cp_async4(&sm.mraw[fg][t % LK_PF][ft], p.rowmax + (size_t)(sq < B ? sq : 0) * T + f);
+        }
+        lk_cp_commit();
+    };
+
+    for (int i = tid; i < LK_NG * 2 * LK_CSMAX * LK_NSQ * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
+    for (int i = tid; i < LK_NG * 2 * LK_NSQ * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
+    if (tid < LK_NG * LK_NSQ) (&sm.msum[0][0])[tid] = 0.0;
+    if (tid == 0) {
+#pragma unroll
+        for (int g = 0; g < LK_NG; ++g) { lk_mbar_init(&sm.bar[g][0], 1); lk_mbar_init(&sm.bar[g][1], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int t = 0; t < LK_PF - 1; ++t) prefetch(t);
+    cluster.sync();                                          // every CTA's mbarriers exist before anyone pushes
+
+    // bytes every receiver gets per step and group: one [NSQ][BLK] block from each of the CS CTAs
+    constexpr uint32_t BLOCK_BYTES = LK_NSQ * LK_BLK * sizeof(float);
+    const uint32_t tx_bytes = (uint32_t)CS * BLOCK_BYTES;
+
+    int ksum_own = 0;                                        // running power-of-two exponent of the thread's own group
+    bool ok = true;
+    int pb = 0;                                              // partial-sum buffer, alternates every (step, group)
+
+    for (int t = 0; t < T; ++t) {
+        const int cur = t & 1, prv = cur ^ 1;
+        prefetch(t + LK_PF - 1);
+        lk_cp_wait<LK_PF - 1>();                             // this step's emissions have landed (own slots only)
+#pragma unroll
+        for (int g = 0; g < LK_NG; ++g) {
+            if (g >= n_groups) continue;
+            LK_TRACE(0);
+            if (tid == 0) lk_mbar_expect_tx(&sm.bar[g][cur], tx_bytes);
+            if (t > 0) {
+                if (ok) ok = lk_mbar_wait(&sm.bar[g][prv], ((t - 1) >> 1) & 1);   // after a time-out: drain without waiting
+                LK_TRACE(1);
+                if (warp < nkw) {
+                    const float *v = &sm.vec[g][prv][warp >> 1][0][(warp & 1) * LK_KS];   // states 32w.. live in CTA w/2's block
+                    if (!VIT) {
+                        float2 a0[LK_NSQ], a1[LK_NSQ];
+#pragma unroll
+                        for (int s = 0; s < LK_NSQ; ++s) a0[s] = a1[s] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int kk = 0; kk < LK_KS; kk += 4) {
+#pragma unroll
+                            for (int s = 0; s < LK_NSQ; ++s) {
+                                const float4 x = *reinterpret_cast<const float4 *>(v + s * LK_BLK + kk);
+                                a0[s] = lk_ffma2(make_float2(x.x, x.y), P0[kk / 2], a0[s]);
+                                a1[s] = lk_ffma2(make_float2(x.x, x.y), P1[kk / 2], a1[s]);
+                                a0[s] = lk_ffma2(make_float2(x.z, x.w), P0[kk / 2 + 1], a0[s]);
+                                a1[s] = lk_ffma2(make_float2(x.z, x.w), P1[kk / 2 + 1], a1[s]);
+                            }
+                        }
+#pragma unroll
+                        for (int s = 0; s < LK_NSQ; ++s)
+                            *reinterpret_cast<float2 *>(&sm.part[pb][warp][s][2 * lane]) =
+                                make_float2(a0[s].x + a0[s].y, a1[s].x + a1[s].y);
+                    } else {
+                        float m0[LK_NSQ], m1[LK_NSQ];
+#pragma unroll
+                        for (int s = 0; s < LK_NSQ; ++s) m0[s] = m1[s] = -INFINITY;
+#pragma unroll
+                        for (int kk = 0; kk < LK_KS; kk += 4) {
+#pragma unroll
+                            for (int s = 0; s < LK_NSQ; ++s) {
+                                const float4 x = *reinterpret_cast<const float4 *>(v + s * LK_BLK + kk);
+                                const float2 c0 = lk_fadd2(make_float2(x.x, x.y), P0[kk / 2]);
+                                const float2 c1 = lk_fadd2(make_float2(x.x, x.y), P1[kk / 2]);
+                                const float2 c2 = lk_fadd2(make_float2(x.z, x.w), P0[kk / 2 + 1]);
+                                const float2 c3 = lk_fadd2(make_float2(x.z, x.w), P1[kk / 2 + 1]);
+                                m0[s] = lk_fmax3(m0[s], c0.x, c0.y);
+                                m1[s] = lk_fmax3(m1[s], c1.x, c1.y);
+                                m0[s] = lk_fmax3(m0[s], c2.x, c2.y);
+                                m1[s] = lk_fmax3(m1[s], c3.x, c3.y);
+                            }
+                        }
+#pragma unroll
+                        for (int s = 0; s < LK_NSQ; ++s)
+                            *reinterpret_cast<float2 *>(&sm.part[pb][warp][s][2 * lane]) = make_float2(m0[s], m1[s]);
+                    }
+                }
+            }
+            LK_TRACE(2);
+            __syncthreads();
+            LK_TRACE(4);
+
+            if (fg == g) {
+                const int f = frame_of(t);
+                const int fseq = seq0 + g * LK_NSQ + fs;
+                const bool f_ok = fseq < B && gcol < K;
+                const float raw = sm.eraw[g][t % LK_PF][ft];
+                const float mf = need_m ? sm.mraw[g][t % LK_PF][ft] : 0.f;
+                float wv, pre = 0.f;                         // wv: the value pushed to the cluster
+                if (!VIT) {
+                    float bq;                                // emission in probability form
+                    if (p.mode == HMMB200_EMIS_PROB_FLOOR) bq = raw + p.eps;
+                    else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) bq = expf(raw) + p.eps;
+                    else bq = expf(raw - mf) + ((p.mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? p.eps : 0.f);
+                    if (!f_ok) bq = 0.f;
+                    float acc, r = 1.f;
+                    if (t == 0) {
+                        acc = (DIR == 0) ? (f_ok ? __ldg(p.init + gcol) : 0.f) : (f_ok ? 1.f : 0.f);
+                    } else {
+                        float a4[4] = {0.f, 0.f, 0.f, 0.f};  // fixed summation order: deterministic
+#pragma unroll
+                        for (int w = 0; w < LK_NW; ++w)
+                            if (w < nkw) a4[w & 3] += sm.part[pb][w][fs][fc];
+                        acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+                        // power-of-two normaliser from the largest entry of the previous vector (all CTAs' local maxima)
+                        float m = 0.f;
+#pragma unroll
+                        for (int q = 0; q < LK_CSMAX; ++q) {
+                            const float2 y = *reinterpret_cast<const float2 *>(&sm.vec[g][prv][q][fs][LK_NC]);
+                            m = fmaxf(m, fmaxf(y.x, y.y));
+                        }
+                        const unsigned eb = __float_as_uint(m) >> 23;
+                        ksum_own += (int)eb - 127;
+                        r = __uint_as_float((254u - eb) << 23);
+                    }
+                    pre = acc * r;                           // beta_t (scaled) for the backward sweep
+                    wv = acc * (bq * r);
+                } else {
+                    float lb;                                // log emission, the reference's formula per input kind
+                    if (p.mode == HMMB200_EMIS_LOG) lb = raw;
+                    else if (p.mode == HMMB200_EMIS_PROB_FLOOR) lb = logf(raw + p.eps);
+                    else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) lb = logf(expf(raw) + p.eps);
+                    else lb = logf(expf(raw - mf) + p.eps);
+                    float acc;
+                    if (t == 0) {
+                        acc = f_ok ? __ldg(p.init + gcol) : -INFINITY;
+                    } else {
+                        float a4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                        for (int w = 0; w < LK_NW; ++w)
+                            if (w < nkw) a4[w & 3] = fmaxf(a4[w & 3], sm.part[pb][w][fs][fc]);
+                        acc = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
+                    }
+                    wv = f_ok ? __fadd_rn(acc, lb) : -INFINITY;   // delta_t = max_i(..) + log b_t  (hmm.py:168)
+                }
+                // ---- push the block: stage in shared memory, then ONE bulk DSMEM copy per CTA of the cluster --------
+                sm.stage[g][cur][fs][fc] = wv;
+                if (!VIT) {
+                    const float lmax = __uint_as_float(__reduce_max_sync(FULL_MASK, __float_as_uint(wv)));   // wv >= 0
+                    if (lane == 0) sm.stage[g][cur][fs][LK_NC + (fwarp & 1)] = lmax;
+                }
+                LK_TRACE(5);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async-proxy reads
+                asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(LK_FINAL) : "memory");   // this group's 256 final threads only
+                LK_TRACE(6);
+                // (the bulk copy is a per-warp uniform-datapath instruction: one destination per final warp)
+                if (lane == 0 && fwarp < CS)
+                    lk_bulk_push(lk_mapa(lk_smem_u32(&sm.vec[g][cur][rank][0][0]), fwarp), lk_smem_u32(&sm.stage[g][cur][0][0]),
+                                 BLOCK_BYTES, lk_mapa(lk_smem_u32(&sm.bar[g][cur]), fwarp));
+                LK_TRACE(7);
+                // ---- results to HBM and log-scale bookkeeping: after the push, off the step's critical path ----------
+                if (f_ok) {
+                    const size_t o = ((size_t)fseq * T + f) * K + gcol;
+                    if (VIT) p.delta[o] = wv;
+                    else if (DIR == 0) p.ws_a[o] = wv;
+                    else p.ws_b[o] = pre;
+                }
+                if (!VIT && rank == 0 && fc == 0 && fseq < B) {
+                    double ms = sm.msum[g][fs];
+                    if (DIR == 0) {
+                        if (add_m) ms += (double)mf;
+                        const float la = (float)(ms + 0.69314718055994530942 * (double)ksum_own);
+                        p.ws_la[(size_t)fseq * T + f] = la;
+                        if (t == T - 1) sm.la_last[g][fs] = la;
+                    } else {
+                        p.ws_lb[(size_t)fseq * T + f] = (float)(ms + 0.69314718055994530942 * (double)ksum_own);
+                        if (add_m) ms += (double)mf;
+                    }
+                    if (add_m) sm.msum[g][fs] = ms;
+                }
+            }
+            pb ^= 1;
+        }
+    }
+
+    // ---- epilogue: everybody waits for the last vectors (no CTA may exit while blocks are still in flight to it) ------
+#pragma unroll
+    for (int g = 0; g < LK_NG; ++g)
+        if (g < n_groups && ok) ok = lk_mbar_wait(&sm.bar[g][(T - 1) & 1], ((T - 1) >> 1) & 1);
+    __syncthreads();
+    if (MODE == LK_FWD && p.loglik != nullptr && rank == 0 && warp < LK_NG * LK_NSQ) {
+        const int g = warp / LK_NSQ, s = warp % LK_NSQ, sq = seq0 + warp;
+        if (sq < B) {
+            float tot = 0.f;
+            for (int k = lane; k < K; k += 32) tot += sm.vec[g][(T - 1) & 1][k / LK_NC][s][k % LK_NC];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL_MASK, tot, o);
+            if (lane == 0) p.loglik[sq] = sm.la_last[g][s] + logf(tot);
+        }
+    }
+    if (!ok && p.err != nullptr) atomicExch(p.err, 1);
+    cluster.sync();
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// per-frame max over K of the log-emissions (one warp per frame)
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) lk_rowmax_kernel(const float *emis, int64_t n_frames, int K, float *rowmax) {
+    const int64_t fr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (fr >= n_frames) return;
+    const float *row = emis + fr * K;
+    float m = -INFINITY;
+    for (int k = lane; k < K; k += 32) m = fmaxf(m, __ldg(row + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+    if (!(m > -INFINITY)) m = 0.f;                           // all states impossible: keep the frame finite
+    if (lane == 0) rowmax[fr] = m;
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// combine (one warp per frame): gamma = a.*b / sum, fwd = a*exp(la), bwd = b*exp(lb)            (hmm.py:120-128)
+// ----------------------------------------------------------------------------------------------------------------------
+struct LkCombineParams {
+    const float *ws_a, *ws_b, *ws_la, *ws_lb;
+    int64_t n_frames;
+    int K;
+    float *gamma, *fwd, *bwd, *log_alpha, *log_beta;
+};
+
+__global__ void __launch_bounds__(256) lk_combine_kernel(LkCombineParams p) {
+    const int64_t fr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (fr >= p.n_frames) return;
+    const int K = p.K;
+    const float *a = p.ws_a + fr * K, *b = p.ws_b + fr * K;
+    float Z = 0.f;
+    for (int k = lane; k < K; k += 32) Z += a[k] * b[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
+    const float inv = 1.f / Z;
+    const float la = p.ws_la[fr], lb = p.ws_lb[fr];
+    const float ea = expf(la), eb = expf(lb);
+    for (int k = lane; k < K; k += 32) {
+        const float x = a[k], y = b[k];
+        if (p.gamma) p.gamma[fr * K + k] = x * y * inv;
+        if (p.fwd) p.fwd[fr * K + k] = x * ea;
+        if (p.bwd) p.bwd[fr * K + k] = y * eb;
+        if (p.log_alpha) p.log_alpha[fr * K + k] = logf(x) + la;
+        if (p.log_beta) p.log_beta[fr * K + k] = logf(y) + lb;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// traceback (one warp per sequence): s_{T-1} = first argmax delta_{T-1}; s_{t-1} = first argmax_i(delta_{t-1}(i) +
+// logP(i, s_t)) -- the backpointer psi_t[s_t] of hmm.py:167 recomputed with the same fp32 add, lowest index on ties.
+// logPT is the transposed log-transition matrix so that the needed column is a contiguous row.
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void lk_transpose_kernel(const float *src, int K, float *dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < K * K) dst[(size_t)(i % K) * K + i / K] = src[i];
+}
+
+__device__ __forceinline__ void lk_warp_argmax(float &v, int &i) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(FULL_MASK, v, o);
+        const int oi = __shfl_xor_sync(FULL_MASK, i, o);
+        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+    }
+}
+
+__global__ void __launch_bounds__(128) lk_traceback_kernel(const float *delta, const float *logPT, int B, int T, int K,
+                                                           int64_t *states, float *score) {
+    const int sq = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (sq >= B) return;
+    const float *d = delta + (size_t)sq * T * K;
+    constexpr int MAXR = LK_KMAX / 32;
+    float bv = -INFINITY;
+    int bi = K;
+    for (int k = lane; k < K; k += 32) {
+        const float v = d[(size_t)(T - 1) * K + k];
+        if (v > bv) { bv = v; bi = k; }
+    }
+    if (bi == K) bi = lane < K ? lane : 0;                   // all -inf / NaN row: still a valid index
+    lk_warp_argmax(bv, bi);
+    int s = bi;
+    if (lane == 0) {
+        states[(size_t)sq * T + (T - 1)] = s;
+        if (score) score[sq] = bv;
+    }
+    float nxt[MAXR];
+#pragma unroll
+    for (int m = 0; m < MAXR; ++m) nxt[m] = (T >= 2 && lane + 32 * m < K) ? d[(size_t)(T - 2) * K + lane + 32 * m] : -INFINITY;
+    for (int t = T - 1; t >= 1; --t) {
+        float cur[MAXR];
+#pragma unroll
+        for (int m = 0; m < MAXR; ++m) cur[m] = nxt[m];
+        if (t >= 2) {                                        // the next delta row does not depend on s: fetch it now
+#pragma unroll
+            for (int m = 0; m < MAXR; ++m) nxt[m] = (lane + 32 * m < K) ? d[(size_t)(t - 2) * K + lane + 32 * m] : -INFINITY;
+        }
+        const float *col = logPT + (size_t)s * K;
+        float v = -INFINITY;
+        int vi = K;
+#pragma unroll
+        for (int m = 0; m < MAXR; ++m) {
+            const int i = lane + 32 * m;
+            if (i < K) {
+                const float c = __fadd_rn(cur[m], __ldg(col + i));
+                if (c > v) { v = c; vi = i; }
+            }
+        }
+        if (vi == K) vi = lane < K ? lane : 0;
+        lk_warp_argmax(v, vi);
+        s = vi;
+        if (lane == 0) states[(size_t)sq * T + (t - 1)] = s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------------------------------
+static size_t lk_align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+bool largek_shape_ok(int K) { return K > 32 && K <= LK_KMAX; }
+
+// fb workspace: ws_a, ws_b [B,T,K]; la, lb, rowmax [B,T]; err flag
+size_t largek_fb_workspace_bytes(int B, int T, int K) {
+    const size_t n = (size_t)B * T;
+    return 2 * lk_align256(n * K * sizeof(float)) + 3 * lk_align256(n * sizeof(float)) + 256;
+}
+// viterbi workspace: delta [B,T,K] (used when the caller does not want delta), logPT [K,K], rowmax [B,T], err flag
+size_t largek_viterbi_workspace_bytes(int B, int T, int K) {
+    const size_t n = (size_t)B * T;
+    return lk_align256(n * K * sizeof(float)) + lk_align256((size_t)K * K * sizeof(float)) + lk_align256(n * sizeof(float)) + 256;
+}
+
+static int lk_cluster_size(int K) {
+    const int need = (K + LK_NC - 1) / LK_NC;
+    int cs = 1;
+    while (cs < need) cs <<= 1;
+    return cs;                                               // 1, 2, 4 or 8
+}
+
+template <int MODE>
+static int lk_launch(const LkParams &p, cudaStream_t s) {
+    auto kern = lk_sweep_kernel<MODE>;
+    const size_t smem = sizeof(LkSmem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K smem opt-in: %s", cudaGetErrorString(e));
+    const int n_clusters = (p.B + LK_NSQ * LK_NG - 1) / (LK_NSQ * LK_NG);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_clusters * p.CS), 1, 1);
+    cfg.blockDim = dim3(LK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, p);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K sweep launch: %s", cudaGetErrorString(e));
+    return check_launch("lk_sweep_kernel");
+}
+
+int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, int add_rowmax, const float *trans_prob,
+                            const float *init_prob, int B, int T, int K, float *gamma, float *fwd_prob, float *bwd_prob,
+                            float *log_alpha, float *log_beta, float *loglik, void *workspace, cudaStream_t s) {
+    const size_t n = (size_t)B * T;
+    uint8_t *w = (uint8_t *)workspace;
+    LkParams p = {};
+    p.emis = emis; p.mode = emis_mode; p.eps = floor_eps; p.add_rowmax = add_rowmax;
+    p.trans = trans_prob; p.init = init_prob; p.B = B; p.T = T; p.K = K; p.CS = lk_cluster_size(K);
+    p.ws_a = (float *)w;  w += lk_align256(n * K * sizeof(float));
+    p.ws_b = (float *)w;  w += lk_align256(n * K * sizeof(float));
+    p.ws_la = (float *)w; w += lk_align256(n * sizeof(float));
+    p.ws_lb = (float *)w; w += lk_align256(n * sizeof(float));
+    float *rowmax = (float *)w; w += lk_align256(n * sizeof(float));
+    p.err = (int *)w;
+    cudaMemsetAsync(p.err, 0, sizeof(int), s);
+    p.trace = getenv("HMMB200_LK_TRACE") != nullptr;
+    p.loglik = loglik;
+    if (emis_mode == HMMB200_EMIS_LOG || emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR) {
+        lk_rowmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(emis, (int64_t)n, K, rowmax);
+        if (int rc = check_launch("lk_rowmax_kernel")) return rc;
+        p.rowmax = rowmax;
+    }
+    if (int rc = lk_launch<LK_FWD>(p, s)) return rc;
+    if (gamma || fwd_prob || bwd_prob || log_alpha || log_beta) {
+        LkParams q = p;
+        q.loglik = nullptr;
+        if (int rc = lk_launch<LK_BWD>(q, s)) return rc;
+        LkCombineParams c;
+        c.ws_a = p.ws_a; c.ws_b = p.ws_b; c.ws_la = p.ws_la; c.ws_lb = p.ws_lb; c.n_frames = (int64_t)n; c.K = K;
+        c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
+        lk_combine_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(c);
+        if (int rc = check_launch("lk_combine_kernel")) return rc;
+    }
+    return HMMB200_OK;
+}
+
+int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
+                   int B, int T, int K, float *delta, int64_t *states, float *score, void *workspace, cudaStream_t s) {
+    const size_t n = (size_t)B * T;
+    uint8_t *w = (uint8_t *)workspace;
+    float *ws_delta = (float *)w; w += lk_align256(n * K * sizeof(float));
+    float *logPT = (float *)w;    w += lk_align256((size_t)K * K * sizeof(float));
+    float *rowmax = (float *)w;   w += lk_align256(n * sizeof(float));
+    LkParams p = {};
+    p.emis = emis; p.mode = emis_mode; p.eps = floor_eps; p.trans = log_trans; p.init = log_init;
+    p.B = B; p.T = T; p.K = K; p.CS = lk_cluster_size(K);
+    p.delta = delta ? delta : ws_delta;
+    p.err = (int *)w;
+    cudaMemsetAsync(p.err, 0, sizeof(int), s);
+    if (emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR) {
+        lk_rowmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(emis, (int64_t)n, K, rowmax);
+        if (int rc = check_launch("lk_rowmax_kernel")) return rc;
+        p.rowmax = rowmax;
+    }
+    lk_transpose_kernel<<<(K * K + 255) / 256, 256, 0, s>>>(log_trans, K, logPT);
+    if (int rc = check_launch("lk_transpose_kernel")) return rc;
+    if (int rc = lk_launch<LK_VIT>(p, s)) return rc;
+    lk_traceback_kernel<<<(B + 3) / 4, 128, 0, s>>>(p.delta, logPT, B, T, K, states, score);
+    return check_launch("lk_traceback_kernel");
+}
+
+}  // namespace hmmb200
+
+HMMB200_EXPORT int hmmb200_debug_lk_max_clusters(int cs) {
+    using namespace hmmb200;
+    auto kern = lk_sweep_kernel<LK_FWD>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
+    cfg.blockDim = dim3(LK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(LkSmem);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = -1;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+    return e == cudaSuccess ? n : -(int)e;
+}
+
+HMMB200_EXPORT int hmmb200_debug_lk_trace(long long *host64) {
+    return (int)cudaMemcpyFromSymbol(host64, hmmb200::lk_trace_buf, sizeof(long long) * 64);
+}

@@ -766,6 +766,7 @@ using namespace hmmb200;
 
 HMMB200_EXPORT size_t hmmb200_fb_workspace_bytes(int B, int T, int K) {
     if (B <= 0 || T <= 0 || K <= 0) return 0;
+    if (K > 32) return largek_shape_ok(K) ? largek_fb_workspace_bytes(B, T, K) : 0;
     size_t n = (size_t)B * T;
     return 2 * align256(n * K * sizeof(float)) + 2 * align256(n * sizeof(float));
 }
@@ -777,7 +778,8 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
                                                 void *workspace, size_t workspace_bytes, void *stream) {
     if (B < 0 || T < 0 || K <= 0) return set_error(HMMB200_EINVAL, "forward_backward: bad shape B=%d T=%d K=%d", B, T, K);
     if (B == 0 || T == 0) return HMMB200_OK;
-    if (K > 32) return set_error(HMMB200_EUNSUPPORTED, "forward_backward: small-K path covers K <= 32 (got %d)", K);
+    if (K > 32 && !largek_shape_ok(K))
+        return set_error(HMMB200_EUNSUPPORTED, "forward_backward: K <= 512 states supported (got %d)", K);
     if (!emis || !trans_prob || !init_prob) return set_error(HMMB200_EINVAL, "forward_backward: null input");
     if (emis_mode < 0 || emis_mode > 3) return set_error(HMMB200_EINVAL, "forward_backward: bad emis_mode %d", emis_mode);
     if (!workspace || workspace_bytes < hmmb200_fb_workspace_bytes(B, T, K))
@@ -785,6 +787,9 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
                          hmmb200_fb_workspace_bytes(B, T, K));
     if (int rc = require_sm100()) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    if (K > 32)
+        return largek_forward_backward(emis, emis_mode, floor_eps, add_rowmax, trans_prob, init_prob, B, T, K, gamma, fwd_prob,
+                                       bwd_prob, log_alpha, log_beta, loglik, workspace, s);
     size_t n = (size_t)B * T;
     uint8_t *w = (uint8_t *)workspace;
     FbParams p;
@@ -814,7 +819,8 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
 }
 
 HMMB200_EXPORT size_t hmmb200_viterbi_workspace_bytes(int B, int T, int K) {
-    if (B <= 0 || T <= 0 || K <= 0 || K > 32) return 0;
+    if (B <= 0 || T <= 0 || K <= 0) return 0;
+    if (K > 32) return largek_shape_ok(K) ? largek_viterbi_workspace_bytes(B, T, K) : 0;
     int G = group_lanes(K), L, nC; bool in_smem; size_t smem;
     vit_plan(T, G, L, nC, in_smem, smem);
     return in_smem ? 0 : (size_t)B * T * G;
@@ -826,13 +832,18 @@ HMMB200_EXPORT int hmmb200_viterbi_f32(const float *emis, int emis_mode, float f
                                        void *workspace, size_t workspace_bytes, void *stream) {
     if (B < 0 || T < 0 || K <= 0) return set_error(HMMB200_EINVAL, "viterbi: bad shape B=%d T=%d K=%d", B, T, K);
     if (B == 0 || T == 0) return HMMB200_OK;
-    if (K > 32) return set_error(HMMB200_EUNSUPPORTED, "viterbi: small-K path covers K <= 32 (got %d)", K);
+    if (K > 32 && !largek_shape_ok(K)) return set_error(HMMB200_EUNSUPPORTED, "viterbi: K <= 512 states supported (got %d)", K);
+    if (K > 32 && psi) return set_error(HMMB200_EUNSUPPORTED, "viterbi: the backpointer table is only materialised for K <= 32 "
+                                        "(for larger K the traceback recomputes them on the path)");
     if (!emis || !log_trans || !log_init || !states) return set_error(HMMB200_EINVAL, "viterbi: null argument");
     if (emis_mode < 0 || emis_mode > 3) return set_error(HMMB200_EINVAL, "viterbi: bad emis_mode %d", emis_mode);
     size_t need = hmmb200_viterbi_workspace_bytes(B, T, K);
     if (need && (!workspace || workspace_bytes < need))
         return set_error(HMMB200_EWORKSPACE, "viterbi: workspace %zu < %zu bytes", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
+    if (K > 32)
+        return largek_viterbi(emis, emis_mode, floor_eps, log_trans, log_init, B, T, K, delta, states, score, workspace,
+                              (cudaStream_t)stream);
     VitParams p;
     p.emis = emis; p.mode = emis_mode; p.eps = floor_eps; p.log_trans = log_trans; p.log_init = log_init;
     p.B = B; p.T = T; p.K = K; p.delta = delta; p.psi_out = psi; p.states = states; p.score = score;

@@ -215,3 +215,23 @@ def test_bw_stats_consistency():
     np.testing.assert_allclose(st["occ"].sum(), B * T, rtol=1e-10)
     resp = gam[..., None] * np.exp(comp - lb[..., None])
     np.testing.assert_allclose(st["sx"], np.einsum("btkc,btd->kcd", resp, x.astype(np.float64)), rtol=1e-9, atol=1e-12)
+
+
+def test_oracle_pinned_at_large_k(golden):
+    """K = 64 and K = 512 (BASELINE config 5 family): the torch port and the C Viterbi reproduce the reference bit for
+    bit; the float64 forward-backward agrees with the reference's fp32 posteriors."""
+    g = golden("largek")
+    for tag in ("k64", "k512"):
+        obs = _t(g[f"{tag}_obs"])
+        log_P, log_p0 = ref_port.prepare_hmm(_t(g[f"{tag}_P"]), None)
+        assert np.array_equal(log_P.numpy(), g[f"{tag}_log_P"])
+        post, fwd, bwd = ref_port.forward_backward(obs, log_P, log_p0)
+        assert np.array_equal(post.numpy(), g[f"{tag}_posterior"]), tag
+        states, delta = ref_port.viterbi_decode(obs, log_P, log_p0)
+        assert np.array_equal(states.numpy(), g[f"{tag}_states"]), tag
+        log_obs = torch.log(obs + 1e-8).numpy()
+        st, dl, _, _ = c_oracle.viterbi_f32(log_obs, g[f"{tag}_log_P"], g[f"{tag}_log_p0"])
+        assert np.array_equal(st, g[f"{tag}_states"]) and np.array_equal(dl, g[f"{tag}_log_delta"]), tag
+        _, _, gam, _ = c_oracle.forward_backward_f64(log_obs.astype(np.float64), g[f"{tag}_log_P"].astype(np.float64),
+                                                      g[f"{tag}_log_p0"].astype(np.float64))
+        np.testing.assert_allclose(gam, g[f"{tag}_posterior"], rtol=1e-4, atol=1e-7)
