@@ -126,6 +126,15 @@ int    hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float *seg_const,
 int    hmmb200_hsmm_forward_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
                                 const float *log_trans, const float *log_init, int B, int T, int K, int Dm,
                                 float *alpha, float *end_scores, float *total, void *stream);
+/* Duration-augmented forward-BACKWARD (new: the reference has no HSMM backward pass; BASELINE config 4).  Same model arguments.
+ *   gamma [B,T,K] = P(state_t = s | o) summed over all segmentations, total [B] = log p(o);
+ *   beta_begin / beta_end [B,T,K] (NULL ok): log p(o_{t..} | a segment of s begins at t) / log p(o_{t+1..} | a segment of s ends at t).
+ *   workspace: hmmb200_hsmm_fb_workspace_bytes(B, T, K) bytes. */
+size_t hmmb200_hsmm_fb_workspace_bytes(int B, int T, int K);
+int    hmmb200_hsmm_forward_backward_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
+                                         const float *log_trans, const float *log_init, int B, int T, int K, int Dm,
+                                         float *gamma, float *total, float *beta_begin, float *beta_end,
+                                         void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Streaming: per-chunk kernels with state carried between calls (one stream per batch row, K <= 32).

@@ -36,6 +36,9 @@ SIGNATURES = {
                                            c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "hmmb200_hsmm_forward_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int,
                                            c_ptr, c_ptr, c_ptr, c_ptr]),
+    "hmmb200_hsmm_fb_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hmmb200_hsmm_forward_backward_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "hmmb200_greedy_decode_f32": (C.c_int, [c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "hmmb200_forward_chunk_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),

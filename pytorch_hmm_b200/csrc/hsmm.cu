@@ -193,6 +193,170 @@ __global__ void __launch_bounds__(32) hsmm_forward_kernel(HsmmFwdParams p) {
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------
+// forward-backward + posteriors (new functionality: the reference has no HSMM backward pass; BASELINE config 4).
+// One warp per sequence, lane = state, SCALED PROBABILITY space in double precision:
+//   log-space fp32 cannot carry this recursion -- log p(o) is O(-100 T), one fp32 ulp there is ~1e-2, and the
+//   posteriors are exponentials of differences of such numbers.  Instead every quantity is a double with the per-frame
+//   emission maxima m_t divided out (b~_t(s) = exp(f_t(s) - m_t)) and one shared power-of-two exponent that is pushed
+//   out of the (Dmax x K) ring whenever the values drift; no transcendental on the recursion.
+//     Bg(t,s)  = pi(s) (t = 0) | sum_{s' != s} E(t-1,s') A(s',s)            a segment of s begins at t
+//     E(t,s)   = sum_d Bg(t-d+1,s) dur(s,d) c(s) prod_{tau=t-d+1..t} b~_tau(s)   a segment of s ends at t
+//     bend(T-1,s) = 1;  bend(t,s) = sum_{s' != s} A(s,s') bbeg(t+1,s')
+//     bbeg(t,s)   = sum_d dur(s,d) c(s) prod_{tau=t..t+d-1} b~_tau(s) bend(t+d-1,s)
+//     P(begin at t) = Bg bbeg / p(o),  P(end at t) = E bend / p(o),  gamma_t(s) = sum_{tau<=t} P(begin) - sum_{tau<t} P(end)
+// ----------------------------------------------------------------------------------------------------------
+struct HsmmFbParams {
+    const float *f, *segc, *logdur, *logA, *logpi;
+    int B, T, K, Dm;
+    float *gamma, *total;                     // [B,T,K], [B]
+    float *bbegin_out, *bend_out;             // [B,T,K] log values or null
+    double *ws_E, *ws_Bg;                     // [B,T,K] scaled forward values
+    double *ws_M;                             // [B,T]   cumulative emission maxima
+    int *ws_k;                                // [B,T]   forward exponent at frame t
+    float *ws_pend;                           // [B,T,K] end posteriors
+};
+
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+
+__global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
+    extern __shared__ __align__(16) double smem_d[];
+    const int K = p.K, Dm = p.Dm, T = p.T;
+    double *ring = smem_d;                      // [Dm][K]  Bg (forward) / bend (backward), slot t % Dm
+    double *bt_r = ring + Dm * K;               // [Dm][K]  b~ of the last Dm frames
+    double *durc = bt_r + Dm * K;               // [Dm][K]  dur(s,d) * c(s)
+    double *A_s = durc + Dm * K;                // [K][K]   A(s',s) as probabilities
+    double *vec = A_s + K * K;                  // [K]      E(t-1,.) / bbeg(t+1,.)
+    const int b = blockIdx.x, s = threadIdx.x;
+    const bool ok = s < K;
+    const float *f = p.f + (size_t)b * T * K;
+    const size_t base = (size_t)b * T;
+    for (int i = s; i < K * K; i += 32) A_s[i] = exp((double)p.logA[i]);
+    if (ok) {
+        const double c = p.segc ? exp((double)p.segc[s]) : 1.0;
+        for (int d = 0; d < Dm; ++d) durc[d * K + s] = exp((double)p.logdur[s * Dm + d]) * c;
+        for (int d = 0; d < Dm; ++d) ring[d * K + s] = 0.0;
+    }
+    __syncwarp();
+    // a shared power-of-two exponent keeps the ring near 1: rescale when the newest values drift by more than 2^24
+    auto rescale = [&](double &v, int &kexp) {
+        const double mx = warp_max_d(ok ? v : 0.0);
+        if (mx > 0.0) {
+            const int ex = ilogb(mx);
+            if (ex > 24 || ex < -24) {
+                const double sc = scalbn(1.0, -ex);
+                v *= sc;
+                if (ok) for (int d = 0; d < Dm; ++d) ring[d * K + s] *= sc;
+                kexp += ex;
+            }
+        }
+    };
+
+    // ---------------- forward ----------------
+    int kf = 0;
+    double Mc = 0.0;
+    for (int t = 0; t < T; ++t) {
+        const float ft = ok ? f[(size_t)t * K + s] : -INFINITY;
+        float m = ft;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+        if (!(m > -INFINITY)) m = 0.f;
+        Mc += (double)m;
+        double e = 0.0;
+        if (ok) {
+            bt_r[(t % Dm) * K + s] = (double)expf(ft - m);
+            double bg;
+            if (t == 0) bg = p.logpi ? exp((double)p.logpi[s]) : 1.0;
+            else {
+                bg = 0.0;
+                for (int sp = 0; sp < K; ++sp) if (sp != s) bg = fma(vec[sp], A_s[sp * K + s], bg);
+            }
+            ring[(t % Dm) * K + s] = bg;
+            double prod = 1.0;
+            for (int d = 1; d <= Dm && d <= t + 1; ++d) {
+                const int st = (t - d + 1) % Dm;
+                prod *= bt_r[st * K + s];
+                e = fma(ring[st * K + s] * prod, durc[(d - 1) * K + s], e);
+            }
+        }
+        __syncwarp();                                       // every lane has read E(t-1,.)
+        rescale(e, kf);
+        if (ok) {
+            vec[s] = e;
+            p.ws_E[(base + t) * K + s] = e;
+            p.ws_Bg[(base + t) * K + s] = ring[(t % Dm) * K + s];
+        }
+        if (s == 0) { p.ws_k[base + t] = kf; p.ws_M[base + t] = Mc; }
+        __syncwarp();
+    }
+    double sumE = ok ? vec[s] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sumE += __shfl_xor_sync(FULL_MASK, sumE, o);
+    const int kfT = kf;
+    const double Mtot = Mc;
+    if (s == 0) p.total[b] = (float)(log(sumE) + 0.69314718055994530942 * (double)kfT + Mtot);
+    const double inv = 1.0 / sumE;
+
+    // ---------------- backward + begin/end posteriors ----------------
+    if (ok) for (int d = 0; d < Dm; ++d) ring[d * K + s] = 0.0;
+    __syncwarp();
+    int kb = 0;
+    for (int t = T - 1; t >= 0; --t) {
+        const float ft = ok ? f[(size_t)t * K + s] : -INFINITY;
+        float m = ft;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
+        if (!(m > -INFINITY)) m = 0.f;
+        double bb = 0.0;
+        if (ok) {
+            bt_r[(t % Dm) * K + s] = (double)expf(ft - m);
+            double be = 1.0;
+            if (t < T - 1) {
+                be = 0.0;
+                for (int sn = 0; sn < K; ++sn) if (sn != s) be = fma(A_s[s * K + sn], vec[sn], be);
+            } else {
+                be = scalbn(1.0, -kb);
+            }
+            ring[(t % Dm) * K + s] = be;
+            double prod = 1.0;
+            for (int d = 1; d <= Dm && t + d <= T; ++d) {
+                const int en = (t + d - 1) % Dm;
+                prod *= bt_r[en * K + s];
+                bb = fma(ring[en * K + s] * prod, durc[(d - 1) * K + s], bb);
+            }
+        }
+        __syncwarp();                                       // every lane has read bbeg(t+1,.)
+        rescale(bb, kb);
+        if (ok) {
+            vec[s] = bb;
+            const size_t o = (base + t) * K + s;
+            const double be = ring[(t % Dm) * K + s];       // after the rescale
+            const int ke = p.ws_k[base + t] + kb - kfT;
+            p.gamma[o] = (float)scalbn(p.ws_Bg[o] * bb * inv, ke);      // P(begins at t); turned into gamma below
+            p.ws_pend[o] = (float)scalbn(p.ws_E[o] * be * inv, ke);     // P(ends at t)
+            if (p.bend_out) p.bend_out[o] = (float)(log(be) + 0.69314718055994530942 * (double)kb + (Mtot - p.ws_M[base + t]));
+            if (p.bbegin_out)
+                p.bbegin_out[o] = (float)(log(bb) + 0.69314718055994530942 * (double)kb + (Mtot - (t > 0 ? p.ws_M[base + t - 1] : 0.0)));
+        }
+        __syncwarp();
+    }
+    // ---------------- state-occupancy posterior (same thread wrote both arrays: program order suffices) ----------------
+    if (ok) {
+        double cum = 0.0;
+        for (int t = 0; t < T; ++t) {
+            const size_t o = (base + t) * K + s;
+            cum += (double)p.gamma[o];
+            const float g = (float)cum;
+            cum -= (double)p.ws_pend[o];
+            p.gamma[o] = fminf(fmaxf(g, 0.f), 1.f);
+        }
+    }
+}
+
 }  // namespace hmmb200
 
 using namespace hmmb200;
@@ -246,4 +410,41 @@ HMMB200_EXPORT int hmmb200_hsmm_forward_f32(const float *frame_logp, const float
     p.B = B; p.T = T; p.K = K; p.Dm = Dm; p.alpha = alpha; p.end_out = end_scores; p.total = total;
     hsmm_forward_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(p);
     return check_launch("hsmm_forward_kernel");
+}
+
+HMMB200_EXPORT size_t hmmb200_hsmm_fb_workspace_bytes(int B, int T, int K) {
+    if (B <= 0 || T <= 0 || K <= 0) return 0;
+    const size_t n = (size_t)B * T;
+    return n * K * (2 * sizeof(double) + sizeof(float)) + n * (sizeof(double) + sizeof(int)) + 64;
+}
+
+HMMB200_EXPORT int hmmb200_hsmm_forward_backward_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
+                                                     const float *log_trans, const float *log_init, int B, int T, int K, int Dm,
+                                                     float *gamma, float *total, float *beta_begin, float *beta_end,
+                                                     void *workspace, size_t workspace_bytes, void *stream) {
+    if (B < 0 || T < 0 || K <= 0 || Dm <= 0) return set_error(HMMB200_EINVAL, "hsmm_forward_backward: bad shape");
+    if (B == 0 || T == 0) return HMMB200_OK;
+    if (!frame_logp || !log_dur || !log_trans || !gamma || !total) return set_error(HMMB200_EINVAL, "hsmm_forward_backward: null argument");
+    if (K > 32) return set_error(HMMB200_EUNSUPPORTED, "hsmm_forward_backward: K <= 32 (got %d)", K);
+    const size_t need = hmmb200_hsmm_fb_workspace_bytes(B, T, K);
+    if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_forward_backward: workspace %zu < %zu", workspace_bytes, need);
+    if (int rc = require_sm100()) return rc;
+    const size_t smem = ((size_t)3 * Dm * K + (size_t)K * K + K) * sizeof(double);
+    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_forward_backward: max_duration too large");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(hsmm_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_forward_backward smem opt-in: %s", cudaGetErrorString(e));
+    }
+    const size_t n = (size_t)B * T;
+    uint8_t *w = (uint8_t *)workspace;
+    HsmmFbParams p;
+    p.f = frame_logp; p.segc = seg_const; p.logdur = log_dur; p.logA = log_trans; p.logpi = log_init;
+    p.B = B; p.T = T; p.K = K; p.Dm = Dm; p.gamma = gamma; p.total = total; p.bbegin_out = beta_begin; p.bend_out = beta_end;
+    p.ws_E = (double *)w;  w += n * K * sizeof(double);
+    p.ws_Bg = (double *)w; w += n * K * sizeof(double);
+    p.ws_M = (double *)w;  w += n * sizeof(double);
+    p.ws_pend = (float *)w; w += n * K * sizeof(float);
+    p.ws_k = (int *)w;
+    hsmm_fb_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(p);
+    return check_launch("hsmm_fb_kernel");
 }

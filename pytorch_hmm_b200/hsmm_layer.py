@@ -113,6 +113,20 @@ class HSMMLayer(nn.Module):
     def forward(self, observations: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         return self.viterbi_decode_hsmm(observations)
 
+    def forward_backward(self, observations: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Duration-augmented forward-backward (BASELINE config 4; new -- the reference's HSMMLayer is Viterbi only,
+        hsmm.py:426-437).  Same model as viterbi_decode_hsmm (per-frame Gaussian log-density, log(pmf + 1e-8) durations,
+        log(A + 1e-8) transitions without self loops, no prior on the first segment), sums instead of maxima.
+        (B,T,D) -> (posterior (B,T,S) = P(state_t = s | x), log_likelihood (B,))."""
+        dev = self._cuda()
+        logb = self.get_observation_log_probs(observations.to(dev))
+        log_dur, log_trans = self._tables(dev)
+        r = ops.hsmm_forward_backward(logb, log_dur, log_trans)
+        g, ll = r["gamma"], r["total"]
+        if observations.device != g.device:
+            g, ll = g.to(observations.device), ll.to(observations.device)
+        return g, ll
+
     def get_expected_durations(self) -> torch.Tensor:
         if self.duration_distribution == "gamma":
             return F.softplus(self.duration_shape) / F.softplus(self.duration_rate)

@@ -208,6 +208,32 @@ def hsmm_forward(frame_logp: torch.Tensor, log_dur: torch.Tensor, log_trans: tor
     return res
 
 
+def hsmm_forward_backward(frame_logp: torch.Tensor, log_dur: torch.Tensor, log_trans: torch.Tensor,
+                          seg_const: Optional[torch.Tensor] = None, log_init: Optional[torch.Tensor] = None,
+                          want_beta: bool = False) -> dict:
+    """frame_logp [B,T,K] -> dict(gamma [B,T,K] state-occupancy posterior, total [B], beta_begin/beta_end [B,T,K] if want_beta)."""
+    dev = require_cuda(frame_logp.device)
+    f = _f32c(frame_logp, dev)
+    B, T, K = f.shape
+    log_dur, log_trans = _f32c(log_dur, dev), _f32c(log_trans, dev)
+    Dm = log_dur.shape[1]
+    sc = None if seg_const is None else _f32c(seg_const, dev)
+    li = None if log_init is None else _f32c(log_init, dev)
+    lib = _lib.load()
+    res = {"gamma": torch.empty(B, T, K, dtype=torch.float32, device=dev), "total": torch.empty(B, dtype=torch.float32, device=dev)}
+    if want_beta:
+        res["beta_begin"] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+        res["beta_end"] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    n = lib.hmmb200_hsmm_fb_workspace_bytes(B, T, K)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_hsmm_forward_backward_f32(_p(f), _p(sc), _p(log_dur), _p(log_trans), _p(li), B, T, K, Dm,
+                                                     _p(res["gamma"]), _p(res["total"]), _p(res.get("beta_begin")),
+                                                     _p(res.get("beta_end")), _p(ws), n, _stream(dev)),
+               "hmmb200_hsmm_forward_backward_f32")
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------
 # streaming (state carried between chunks)
 # ------------------------------------------------------------------------------------------------------

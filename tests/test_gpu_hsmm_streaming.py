@@ -127,6 +127,56 @@ def test_hsmm_forward_vs_float64_oracle(hm):
     np.testing.assert_allclose(r["alpha"][0].cpu().numpy()[fin], alpha[fin], rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("K,Dm,T,B", [(2, 3, 6, 2), (3, 4, 7, 1), (5, 7, 60, 3), (10, 20, 300, 2), (12, 5, 150, 4), (32, 6, 40, 2),
+                                      (4, 30, 25, 1)])
+def test_hsmm_forward_backward_vs_float64_oracle(hm, K, Dm, T, B):
+    """Duration-augmented forward-backward (BASELINE config 4 family).  No reference implementation exists (SURVEY finding 5):
+    the oracle is the float64 restatement, itself pinned by brute-force enumeration in tests/test_host_cpu.py.
+    Tolerance: posteriors 1e-4 relative (atol 1e-6: they are differences of running sums), log-likelihood 1e-5 relative."""
+    from oracle import hsmm_post
+    rng = np.random.default_rng(300 + K + Dm + T)
+    f = (rng.standard_normal((B, T, K)) * 3 - 10).astype(np.float32)
+    segc = (rng.standard_normal(K) - 5).astype(np.float32)
+    logdur = np.log(rng.random((K, Dm)) + 1e-2).astype(np.float32)
+    A = rng.random((K, K)) + 0.05
+    np.fill_diagonal(A, 0.0)
+    logA = np.log(A / A.sum(1, keepdims=True) + 1e-8).astype(np.float32)
+    logpi = np.log(rng.dirichlet(np.ones(K))).astype(np.float32)
+    r = hm.ops.hsmm_forward_backward(_dev(f), _dev(logdur), _dev(logA), seg_const=_dev(segc), log_init=_dev(logpi), want_beta=True)
+    gam = r["gamma"].cpu().numpy()
+    for b in range(B):
+        g64, tot = hsmm_post.posteriors_f64(f[b].astype(np.float64), segc.astype(np.float64), logdur.astype(np.float64),
+                                            logA.astype(np.float64), logpi.astype(np.float64))
+        np.testing.assert_allclose(r["total"][b].item(), tot, rtol=1e-5)
+        np.testing.assert_allclose(gam[b], g64, rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(gam.sum(-1), 1.0, atol=1e-4)                    # every frame is covered by exactly one segment
+    assert r["beta_end"][:, -1].abs().max().item() == 0.0
+
+
+def test_hsmm_forward_backward_config4_shape_properties(hm):
+    """BASELINE config 4 shape (K=10, Dmax=20, T=2000) at B=4: posteriors in [0,1] and summing to 1 on every frame, sequence 0
+    against the float64 oracle at full length (1e-4 relative, atol 2e-6), and the fp32 log-space forward kernel's total
+    (its own rounding is ~1e-7 |log p|, hence 1e-5 relative here)."""
+    rng = np.random.default_rng(4001)
+    K, Dm, T, B = 10, 20, 2000, 4
+    f = (rng.standard_normal((B, T, K)) * 2 - 100).astype(np.float32)
+    logdur = np.log(rng.random((K, Dm)) + 1e-3).astype(np.float32)
+    A = rng.random((K, K)) + 0.05
+    np.fill_diagonal(A, 0.0)
+    logA = np.log(A / A.sum(1, keepdims=True) + 1e-8).astype(np.float32)
+    r = hm.ops.hsmm_forward_backward(_dev(f), _dev(logdur), _dev(logA))
+    g = r["gamma"].cpu().numpy()
+    assert np.isfinite(g).all() and g.min() >= 0.0 and g.max() <= 1.0
+    np.testing.assert_allclose(g.sum(-1), 1.0, atol=1e-4)
+    from oracle import hsmm_post
+    g64, tot = hsmm_post.posteriors_f64(f[0].astype(np.float64), np.zeros(K), logdur.astype(np.float64), logA.astype(np.float64),
+                                        np.zeros(K))
+    np.testing.assert_allclose(r["total"][0].item(), tot, rtol=1e-6)
+    np.testing.assert_allclose(g[0], g64, rtol=1e-4, atol=2e-6)
+    fw = hm.ops.hsmm_forward(_dev(f), _dev(logdur), _dev(logA), want_alpha=False)
+    np.testing.assert_allclose(r["total"].cpu().numpy(), fw["total"].cpu().numpy(), rtol=1e-5)
+
+
 def test_streaming_greedy_vs_reference_golden(hm, golden):
     g = golden("streaming")
     p = hm.StreamingHMMProcessor(6, 8, chunk_size=16, overlap_size=4, lookahead_frames=2, max_delay_frames=64,

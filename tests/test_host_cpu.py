@@ -99,3 +99,24 @@ def test_layer_parameter_names_and_state_dict_compat(golden):
         hm.MixtureGaussianHMMLayer(4, 3, covariance_type="bogus")
     with pytest.raises(ValueError):
         hm.GaussianHMMLayer(4, 3, covariance_type="bogus")
+
+
+def test_hsmm_posterior_oracle_vs_brute_force():
+    """HSMM backward / posteriors have no reference implementation: pin the float64 oracle by enumerating every
+    segmentation at tiny sizes."""
+    import numpy as np
+    from oracle import hsmm_post
+    rng = np.random.default_rng(41)
+    for K, Dm, T in ((2, 3, 6), (3, 2, 5), (3, 4, 7)):
+        f = rng.standard_normal((T, K)) * 2 - 3
+        segc = rng.standard_normal(K) - 1
+        logdur = np.log(rng.random((K, Dm)) + 0.05)
+        A = rng.random((K, K)) + 0.05
+        np.fill_diagonal(A, 0.0)
+        logA = np.log(A / A.sum(1, keepdims=True) + 1e-8)
+        logpi = np.log(rng.dirichlet(np.ones(K)))
+        g1, t1 = hsmm_post.posteriors_f64(f, segc, logdur, logA, logpi)
+        g2, t2 = hsmm_post.brute_force(f, segc, logdur, logA, logpi)
+        np.testing.assert_allclose(t1, t2, rtol=1e-12)
+        np.testing.assert_allclose(g1, g2, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(g1.sum(-1), 1.0, rtol=1e-9)
