@@ -25,7 +25,7 @@ struct HsmmVitParams {
     int sum_order;         // 0: ATen strided row_sum (4 interleaved partials), 1: sequential
     int64_t *states;       // [B,T]
     float *score;          // [B]
-    uint8_t *psi_s, *psi_d;  // [B,T,K*Dm] workspace
+    uint8_t *psi_s, *psi_d;  // [B,T,K*Dm] workspace: predecessor (state, duration) of the segment (s,d) STARTING at frame t
 };
 
 // sum of d values col[0], col[stride], ... in the order torch.sum uses on a strided fp32 slice
@@ -50,6 +50,36 @@ __device__ __forceinline__ float seg_sum(const float *col, int stride, int d, in
     return p0;
 }
 
+// Candidate evaluation without the reference's (K-1)*Dmax scan per cell, still bit-identical:
+//   tot(s',d') = fl(fl(fl(prev[s'][d'] + a) + oseg) + dsc) is a composition of fp32 roundings, each monotone non-decreasing
+//   in prev[s'][d'].  Hence max_{d'} tot(s',d') = tot evaluated at Mx[s'] = max_{d'} prev[s'][d'] (computed once per step and
+//   shared by all cells), the best value is max_{s'} of those K-1 numbers, and the reference's winner -- the FIRST (s',d') in
+//   lexicographic order with tot == best (strict '>') -- is the first s' attaining best and, within it, the first d' whose own
+//   tot rounds to best (checked up to the first arg-max of prev[s'][.], which certainly does).  Work per cell drops from
+//   3(K-1)Dmax adds to about 3(K-1) + 3 Dmax/2.
+__device__ __forceinline__ float seg_sum_win(const float *win, int K, int Dm, int head, int s, int d, int order) {
+    // win: ring of the frames t .. t+Dm-1 (row `head` = frame t); same summation orders as seg_sum
+    auto at = [&](int i) { int r = head + i; if (r >= Dm) r -= Dm; return win[r * K + s]; };
+    if (order == 1) {
+        float a = 0.f;
+        for (int i = 0; i < d; ++i) a = __fadd_rn(a, at(i));
+        return a;
+    }
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    const int q = d >> 2;
+    for (int i = 0; i < q; ++i) {
+        p0 = __fadd_rn(p0, at(4 * i + 0));
+        p1 = __fadd_rn(p1, at(4 * i + 1));
+        p2 = __fadd_rn(p2, at(4 * i + 2));
+        p3 = __fadd_rn(p3, at(4 * i + 3));
+    }
+    for (int i = 4 * q; i < d; ++i) p0 = __fadd_rn(p0, at(i));
+    p0 = __fadd_rn(p0, p1);
+    p0 = __fadd_rn(p0, p2);
+    p0 = __fadd_rn(p0, p3);
+    return p0;
+}
+
 __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
     extern __shared__ __align__(16) float smem_h[];
     const int K = p.K, Dm = p.Dm, T = p.T;
@@ -57,23 +87,52 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
     float *ring = smem_h;                       // [R][K][Dm]   delta for segments ending at te, slot te % R
     float *A_s = ring + (size_t)R * KD;         // [K][K]
     float *dur_s = A_s + K * K;                 // [K][Dm]
+    float *win = dur_s + KD;                    // [Dm][K]      frames t .. t+Dm-1 of f (ring, row `head` = frame t)
+    float *mx_s = win + KD;                     // [K]          max_d' prev[s'][d']
+    int *arg_s = reinterpret_cast<int *>(mx_s + K);   // [K]    first d' (0-based) attaining it
     const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const float *f = p.f + (size_t)b * T * K;
     uint8_t *ps = p.psi_s + (size_t)b * T * KD;
     uint8_t *pd = p.psi_d + (size_t)b * T * KD;
 
-    for (int i = threadIdx.x; i < R * KD; i += blockDim.x) ring[i] = -INFINITY;
-    for (int i = threadIdx.x; i < K * K; i += blockDim.x) A_s[i] = p.logA[i];
-    for (int i = threadIdx.x; i < KD; i += blockDim.x) dur_s[i] = p.logdur[i];
+    for (int i = tid; i < R * KD; i += blockDim.x) ring[i] = -INFINITY;
+    for (int i = tid; i < K * K; i += blockDim.x) A_s[i] = p.logA[i];
+    for (int i = tid; i < KD; i += blockDim.x) dur_s[i] = p.logdur[i];
+    for (int i = tid; i < KD; i += blockDim.x) {                        // frames 0 .. Dm-1
+        const int fr = i / K, s = i % K;
+        win[i] = (fr < T) ? f[(size_t)fr * K + s] : 0.f;
+    }
     __syncthreads();
 
+    int head = 0, slot_prev = R - 1, slot_t = 0;                         // ring rows without integer division on the loop
     for (int t = 0; t < T; ++t) {
-        const float *prev = ring + (size_t)((t + R - 1) % R) * KD;      // segments ending at t-1
-        for (int pr = threadIdx.x; pr < KD; pr += blockDim.x) {
+        const float *prev = ring + (size_t)slot_prev * KD;              // segments ending at t-1
+        // ---- phase A: Mx[s'] and its first arg-max, one warp per s' ----
+        if (t > 0) {
+            for (int sp = warp; sp < K; sp += nwarps) {
+                float m = -INFINITY;
+                int mi = Dm;
+                for (int dp = lane; dp < Dm; dp += 32) {
+                    const float v = prev[sp * Dm + dp];
+                    if (v > m) { m = v; mi = dp; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float om = __shfl_xor_sync(FULL_MASK, m, o);
+                    const int oi = __shfl_xor_sync(FULL_MASK, mi, o);
+                    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+                }
+                if (lane == 0) { mx_s[sp] = m; arg_s[sp] = (mi < Dm) ? mi : 0; }
+            }
+        }
+        __syncthreads();
+        // ---- phase B: one thread per cell (s, d) ----
+        for (int pr = tid; pr < KD; pr += blockDim.x) {
             const int s = pr / Dm, d = pr % Dm + 1;
             const int te = t + d - 1;
             if (te < T) {
-                const float osum = seg_sum(f + (size_t)t * K + s, K, d, p.sum_order);
+                const float osum = seg_sum_win(win, K, Dm, head, s, d, p.sum_order);
                 const float oseg = p.segc ? __fadd_rn(p.segc[s], osum) : osum;
                 const float dsc = dur_s[s * Dm + d - 1];
                 float best;
@@ -82,25 +141,43 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                     best = p.logpi ? __fadd_rn(__fadd_rn(p.logpi[s], oseg), dsc) : __fadd_rn(oseg, dsc);
                 } else {
                     best = -INFINITY;
+                    int bsp = -1;
                     for (int sp = 0; sp < K; ++sp) {
                         if (sp == s) continue;
-                        const float a = A_s[sp * K + s];
-                        const float *pv = prev + sp * Dm;
-                        for (int dp = 1; dp <= Dm; ++dp) {
-                            const float tot = __fadd_rn(__fadd_rn(__fadd_rn(pv[dp - 1], a), oseg), dsc);
-                            if (tot > best) { best = tot; bs = sp; bd = dp; }
-                        }
+                        const float tot = __fadd_rn(__fadd_rn(__fadd_rn(mx_s[sp], A_s[sp * K + s]), oseg), dsc);
+                        if (tot > best) { best = tot; bsp = sp; }
+                    }
+                    if (bsp >= 0) {
+                        const float a = A_s[bsp * K + s];
+                        const float *pv = prev + bsp * Dm;
+                        const int last = arg_s[bsp];
+                        int dp = 0;
+                        for (; dp < last; ++dp)
+                            if (__fadd_rn(__fadd_rn(__fadd_rn(pv[dp], a), oseg), dsc) == best) break;
+                        bs = bsp; bd = dp + 1;
                     }
                 }
-                ring[(size_t)(te % R) * KD + s * Dm + d - 1] = best;
-                ps[(size_t)te * KD + pr] = (uint8_t)bs;
-                pd[(size_t)te * KD + pr] = (uint8_t)bd;
+                int slot = slot_t + d - 1;
+                if (slot >= R) slot -= R;
+                ring[(size_t)slot * KD + s * Dm + d - 1] = best;
+                ps[(size_t)t * KD + pr] = (uint8_t)bs;              // indexed by the segment's START frame: a step's
+                pd[(size_t)t * KD + pr] = (uint8_t)bd;              // backpointers are KD contiguous bytes (coalesced)
             }
             // slot t-2 has been fully consumed by the previous step: clear it for reuse
-            if (t >= 2) ring[(size_t)((t + R - 2) % R) * KD + pr] = -INFINITY;
+            if (t >= 2) {
+                int sc = slot_t - 2;
+                if (sc < 0) sc += R;
+                ring[(size_t)sc * KD + pr] = -INFINITY;
+            }
         }
         __syncthreads();
+        // slide the frame window: row `head` (frame t) becomes frame t + Dm
+        for (int s = tid; s < K; s += blockDim.x) win[head * K + s] = (t + Dm < T) ? f[(size_t)(t + Dm) * K + s] : 0.f;
+        if (++head == Dm) head = 0;
+        slot_prev = slot_t;
+        if (++slot_t == R) slot_t = 0;
     }
+    __syncthreads();
 
     if (threadIdx.x == 0) {
         const float *last = ring + (size_t)((T - 1) % R) * KD;
@@ -119,7 +196,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
             if (st0 < 0) st0 = 0;
             for (int u = st0; u <= t; ++u) st[u] = cs;
             if (st0 > 0) {
-                const int ns = ps[(size_t)t * KD + cs * Dm + cd - 1], nd = pd[(size_t)t * KD + cs * Dm + cd - 1];
+                const int ns = ps[(size_t)st0 * KD + cs * Dm + cd - 1], nd = pd[(size_t)st0 * KD + cs * Dm + cd - 1];
                 t = st0 - 1; cs = ns; cd = nd;
             } else break;
         }
@@ -259,6 +336,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     // ---------------- forward ----------------
     int kf = 0;
     double Mc = 0.0;
+    int cur = 0;                                            // t % Dm, kept without integer division
     for (int t = 0; t < T; ++t) {
         const float ft = ok ? f[(size_t)t * K + s] : -INFINITY;
         float m = ft;
@@ -268,19 +346,20 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
         Mc += (double)m;
         double e = 0.0;
         if (ok) {
-            bt_r[(t % Dm) * K + s] = (double)expf(ft - m);
+            bt_r[cur * K + s] = (double)expf(ft - m);
             double bg;
             if (t == 0) bg = p.logpi ? exp((double)p.logpi[s]) : 1.0;
             else {
                 bg = 0.0;
                 for (int sp = 0; sp < K; ++sp) if (sp != s) bg = fma(vec[sp], A_s[sp * K + s], bg);
             }
-            ring[(t % Dm) * K + s] = bg;
+            ring[cur * K + s] = bg;
             double prod = 1.0;
+            int st = cur;                                   // (t - d + 1) % Dm
             for (int d = 1; d <= Dm && d <= t + 1; ++d) {
-                const int st = (t - d + 1) % Dm;
                 prod *= bt_r[st * K + s];
                 e = fma(ring[st * K + s] * prod, durc[(d - 1) * K + s], e);
+                st = (st == 0) ? Dm - 1 : st - 1;
             }
         }
         __syncwarp();                                       // every lane has read E(t-1,.)
@@ -288,10 +367,11 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
         if (ok) {
             vec[s] = e;
             p.ws_E[(base + t) * K + s] = e;
-            p.ws_Bg[(base + t) * K + s] = ring[(t % Dm) * K + s];
+            p.ws_Bg[(base + t) * K + s] = ring[cur * K + s];
         }
         if (s == 0) { p.ws_k[base + t] = kf; p.ws_M[base + t] = Mc; }
         __syncwarp();
+        if (++cur == Dm) cur = 0;
     }
     double sumE = ok ? vec[s] : 0.0;
 #pragma unroll
@@ -305,6 +385,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     if (ok) for (int d = 0; d < Dm; ++d) ring[d * K + s] = 0.0;
     __syncwarp();
     int kb = 0;
+    cur = (T - 1) % Dm;
     for (int t = T - 1; t >= 0; --t) {
         const float ft = ok ? f[(size_t)t * K + s] : -INFINITY;
         float m = ft;
@@ -313,7 +394,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
         if (!(m > -INFINITY)) m = 0.f;
         double bb = 0.0;
         if (ok) {
-            bt_r[(t % Dm) * K + s] = (double)expf(ft - m);
+            bt_r[cur * K + s] = (double)expf(ft - m);
             double be = 1.0;
             if (t < T - 1) {
                 be = 0.0;
@@ -321,12 +402,13 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
             } else {
                 be = scalbn(1.0, -kb);
             }
-            ring[(t % Dm) * K + s] = be;
+            ring[cur * K + s] = be;
             double prod = 1.0;
+            int en = cur;                                   // (t + d - 1) % Dm
             for (int d = 1; d <= Dm && t + d <= T; ++d) {
-                const int en = (t + d - 1) % Dm;
                 prod *= bt_r[en * K + s];
                 bb = fma(ring[en * K + s] * prod, durc[(d - 1) * K + s], bb);
+                if (++en == Dm) en = 0;
             }
         }
         __syncwarp();                                       // every lane has read bbeg(t+1,.)
@@ -334,7 +416,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
         if (ok) {
             vec[s] = bb;
             const size_t o = (base + t) * K + s;
-            const double be = ring[(t % Dm) * K + s];       // after the rescale
+            const double be = ring[cur * K + s];            // after the rescale
             const int ke = p.ws_k[base + t] + kb - kfT;
             p.gamma[o] = (float)scalbn(p.ws_Bg[o] * bb * inv, ke);      // P(begins at t); turned into gamma below
             p.ws_pend[o] = (float)scalbn(p.ws_E[o] * be * inv, ke);     // P(ends at t)
@@ -343,6 +425,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
                 p.bbegin_out[o] = (float)(log(bb) + 0.69314718055994530942 * (double)kb + (Mtot - (t > 0 ? p.ws_M[base + t - 1] : 0.0)));
         }
         __syncwarp();
+        cur = (cur == 0) ? Dm - 1 : cur - 1;
     }
     // ---------------- state-occupancy posterior (same thread wrote both arrays: program order suffices) ----------------
     if (ok) {
@@ -377,7 +460,7 @@ HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float
     const size_t need = hmmb200_hsmm_viterbi_workspace_bytes(B, T, K, Dm);
     if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_viterbi: workspace %zu < %zu", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
-    const size_t smem = ((size_t)(Dm + 2) * K * Dm + (size_t)K * K + (size_t)K * Dm) * sizeof(float);
+    const size_t smem = ((size_t)(Dm + 2) * K * Dm + (size_t)K * K + (size_t)2 * K * Dm + 2 * (size_t)K) * sizeof(float);
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_viterbi: K=%d, max_duration=%d need %zu bytes of shared memory", K, Dm, smem);
     cudaError_t e = cudaFuncSetAttribute(hsmm_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_viterbi smem opt-in: %s", cudaGetErrorString(e));

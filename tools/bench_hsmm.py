@@ -26,5 +26,9 @@ res = {"config": "HSMM K=10 Dmax=20 D=80 B=128 T=2000",
        "emission_ms": ms(lambda: m.get_observation_log_probs(x)),
        "forward_backward_ms": ms(lambda: m.forward_backward(x)),
        "viterbi_ms": ms(lambda: m(x))}
+logb = m.get_observation_log_probs(x)
+log_dur, log_trans = m._tables(x.device)
+res["kernel_only"] = {"hsmm_viterbi_ms": ms(lambda: hm.ops.hsmm_viterbi(logb, log_dur, log_trans, sum_order=0)),
+                      "hsmm_forward_backward_ms": ms(lambda: hm.ops.hsmm_forward_backward(logb, log_dur, log_trans))}
 res["frames_per_s_fb_plus_viterbi"] = B * T / ((res["forward_backward_ms"] + res["viterbi_ms"]) * 1e-3)
 print(json.dumps(res))
