@@ -67,7 +67,7 @@ int    hmmb200_gmm_emission_f32(const float *x, const float *packed, int64_t n_f
                                 float *logb, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Forward-backward (small K: K <= 32).
+ * Forward-backward (K <= 32: warp-per-sequence sweeps; 32 < K <= 512: cluster kernels, BASELINE config 5).
  *   replaces  HMMPyTorch.forward_backward / compute_likelihood    pytorch_hmm/hmm.py:66-130, :186-211
  *
  *   emis [B,T,K] read according to emis_mode / floor_eps (see HMMB200_EMIS_*).
@@ -87,8 +87,21 @@ int    hmmb200_forward_backward_f32(const float *emis, int emis_mode, float floo
                                     float *log_alpha, float *log_beta, float *loglik,
                                     void *workspace, size_t workspace_bytes, void *stream);
 
+/* Time-parallel variant for LONG sequences at SMALL batch (K <= 32): same arguments, same results (1e-4), different schedule.
+ * The step alpha_t = alpha_{t-1} P diag(b_t) is associative: time is cut into segments, the K x K segment products are computed
+ * in parallel (K x the sequential arithmetic), chained by one warp per sequence, and every segment is then filled from its true
+ * boundary vectors.  Pays off when B is far below the ~300 sequences the sequential sweeps need to fill a B200.
+ *   workspace: hmmb200_fb_scan_workspace_bytes(B, T, K) bytes. */
+size_t hmmb200_fb_scan_workspace_bytes(int B, int T, int K);
+int    hmmb200_forward_backward_scan_f32(const float *emis, int emis_mode, float floor_eps, int add_rowmax,
+                                         const float *trans_prob, const float *init_prob, int B, int T, int K,
+                                         float *gamma, float *fwd_prob, float *bwd_prob,
+                                         float *log_alpha, float *log_beta, float *loglik,
+                                         void *workspace, size_t workspace_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
- * Viterbi (small K: K <= 32), packed uint8 backpointers, on-device traceback.
+ * Viterbi.  K <= 32: packed uint8 backpointers in shared memory, chunk-parallel on-device traceback.
+ *           32 < K <= 512: cluster kernel, backpointers recomputed on the path by the traceback (psi must be NULL).
  *   replaces  HMMPyTorch.viterbi_decode                           pytorch_hmm/hmm.py:132-184
  *             MixtureGaussianHMMLayer._viterbi_decode             pytorch_hmm/mixture_gaussian.py:290-338
  *

@@ -28,6 +28,9 @@ SIGNATURES = {
     "hmmb200_fb_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hmmb200_forward_backward_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, C.c_int, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
                                                c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "hmmb200_fb_scan_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hmmb200_forward_backward_scan_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, C.c_int, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
+                                                    c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
     "hmmb200_viterbi_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hmmb200_viterbi_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

@@ -105,14 +105,23 @@ def viterbi_workspace(B: int, T: int, K: int, dev) -> torch.Tensor:
     return torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
 
 
+def use_time_parallel_scan(B: int, T: int, K: int) -> bool:
+    """Schedule choice for forward-backward: the sequential sweeps take ~65 ns per frame of the LONGEST sequence whatever
+    the batch; the scan does K x the arithmetic but in parallel over time.  Measured crossover (tools/bench_scan.py)."""
+    return K <= 32 and T >= 8192 and B <= 64          # 2.3x at (B=1, T=16k), 17.7x at (B=1, T=1M), 1.5x at (B=64, T=16k)
+
+
 def forward_backward(emis: torch.Tensor, mode: int, trans_prob: torch.Tensor, init_prob: torch.Tensor,
                      eps: float = EPS, add_rowmax: bool = False, want=("gamma", "fwd", "bwd"),
-                     out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None) -> dict:
+                     out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None, method: str = "auto") -> dict:
     """emis [B,T,K] CUDA fp32.  Returns a dict with the requested tensors among
-    gamma, fwd, bwd, log_alpha, log_beta (each [B,T,K]) and always 'loglik' [B]."""
+    gamma, fwd, bwd, log_alpha, log_beta (each [B,T,K]) and always 'loglik' [B].
+    method: "sweep" (sequential in time), "scan" (time-parallel, K <= 32) or "auto"."""
     dev = require_cuda(emis.device)
     emis = _f32c(emis, dev)
     B, T, K = emis.shape
+    if method == "scan" or (method == "auto" and use_time_parallel_scan(B, T, K)):
+        return _forward_backward_scan(emis, mode, trans_prob, init_prob, eps, add_rowmax, want, out, dev)
     trans_prob, init_prob = _f32c(trans_prob, dev), _f32c(init_prob, dev)
     lib = _lib.load()
     res = {} if out is None else out
@@ -129,6 +138,27 @@ def forward_backward(emis: torch.Tensor, mode: int, trans_prob: torch.Tensor, in
             _p(res.get("gamma")), _p(res.get("fwd")), _p(res.get("bwd")), _p(res.get("log_alpha")),
             _p(res.get("log_beta")), _p(res["loglik"]), _p(ws), ws_bytes, _stream(dev)),
             "hmmb200_forward_backward_f32")
+    return res
+
+
+def _forward_backward_scan(emis, mode, trans_prob, init_prob, eps, add_rowmax, want, out, dev) -> dict:
+    B, T, K = emis.shape
+    trans_prob, init_prob = _f32c(trans_prob, dev), _f32c(init_prob, dev)
+    lib = _lib.load()
+    res = {} if out is None else out
+    for name in ("gamma", "fwd", "bwd", "log_alpha", "log_beta"):
+        if name in want and name not in res:
+            res[name] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    if "loglik" not in res:
+        res["loglik"] = torch.empty(B, dtype=torch.float32, device=dev)
+    n = lib.hmmb200_fb_scan_workspace_bytes(B, T, K)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_forward_backward_scan_f32(
+            _p(emis), int(mode), float(eps), int(bool(add_rowmax)), _p(trans_prob), _p(init_prob), B, T, K,
+            _p(res.get("gamma")), _p(res.get("fwd")), _p(res.get("bwd")), _p(res.get("log_alpha")),
+            _p(res.get("log_beta")), _p(res["loglik"]), _p(ws), n, _stream(dev)),
+            "hmmb200_forward_backward_scan_f32")
     return res
 
 
