@@ -182,6 +182,14 @@ int    hmmb200_bw_accumulate_f32(const float *x, const float *comp, const float 
                                  const void *fb_workspace, int B, int T, int K, int C, int D,
                                  double *stats, void *stream);
 
+/* Transition / initial-state statistics alone, optionally weighted per sequence (seq_weights [B] or NULL = 1):
+ *   xi[K,K] += sum_b w_b sum_t xi_t(i,j);  gamma1[K] += sum_b w_b gamma_0(k)   (gamma1 may be NULL).
+ * Arguments as for hmmb200_bw_accumulate_f32.  With w_b = d loss / d loglik_b these are d loss / d log P and d loss / d log p0:
+ * the backward pass of the training callers (HMMLayer.compute_loss, pytorch_hmm/hmm_layer.py:144-173). */
+int    hmmb200_xi_sum_f32(const float *emis, int emis_mode, float floor_eps, const float *trans_prob,
+                          const void *fb_workspace, const float *seq_weights, int B, int T, int K,
+                          double *xi, double *gamma1, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -106,7 +106,16 @@ class HMMPyTorch(HMM):
         dev = self._cuda()
         trans, init = self._effective_probs(dev)
         r = ops.forward_backward(obs.detach().to(dev), ops.EMIS_PROB_FLOOR, trans, init, eps=EPS, want=("fwd",))
-        ll = torch.logsumexp(torch.log(r["fwd"][:, -1] + EPS), dim=-1)
+        last = r["fwd"][:, -1]
+        ll = torch.logsumexp(torch.log(last + EPS), dim=-1)
+        from . import autograd as ag
+        if ag.needs_grad(observations, self.log_P, self.log_p0) and self.K <= 32:
+            # Training callers (HMMLayer.compute_loss, hmm_layer.py:144-173).  The VALUE is the reference's saturating
+            # formula; the gradient is that of the true log-likelihood damped by the saturation factor
+            # sum_k alpha_k / sum_k (alpha_k + 1e-8) (equal to the reference's own gradient when no state is floored).
+            true_ll = ag.hmm_log_likelihood(obs, self.log_P, self.log_p0, ops.EMIS_PROB_FLOOR, EPS).to(dev)
+            sat = (last.sum(-1) / (last + EPS).sum(-1)).detach()
+            ll = ll.detach() + sat * (true_ll - true_ll.detach())
         ll = self._back(ll)
         return ll.squeeze(0) if squeeze else ll
 
@@ -123,9 +132,9 @@ class HMMPyTorch(HMM):
         """Ancestral sampling of a state path with one-hot 'observations' (reference hmm.py:213-245).  Host-side
         convenience, not on the hot path."""
         states = torch.zeros(batch_size, seq_length, dtype=torch.long, device=self.device)
-        states[:, 0] = torch.multinomial(self.p0.expand(batch_size, -1), 1).squeeze(1)
+        states[:, 0] = torch.multinomial(self.p0.detach().expand(batch_size, -1), 1).squeeze(1)
         for t in range(1, seq_length):
-            states[:, t] = torch.multinomial(self.P[states[:, t - 1]], 1).squeeze(1)
+            states[:, t] = torch.multinomial(self.P.detach()[states[:, t - 1]], 1).squeeze(1)
         observations = torch.nn.functional.one_hot(states, self.K).to(torch.float32)
         return states, observations
 

@@ -32,8 +32,8 @@ __global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, con
 
 // one warp per (sequence, block of frames); lane j owns column j of xi
 __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode, float eps, const float *trans,
-                                                    const float *ws_a, const float *ws_b, int B, int T, int K, int frames_per_warp,
-                                                    double *xi, double *gamma1) {
+                                                    const float *ws_a, const float *ws_b, const float *wseq, int B, int T, int K,
+                                                    int frames_per_warp, double *xi, double *gamma1) {
     extern __shared__ double xi_s[];                       // [K*K] per CTA
     for (int i = threadIdx.x; i < K * K; i += blockDim.x) xi_s[i] = 0.0;
     __syncthreads();
@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
     if (wid < (int64_t)B * max(blocks_per_seq, 1) && T > 1) {
         const int b = (int)(wid / blocks_per_seq), blk = (int)(wid % blocks_per_seq);
         const int t0 = blk * frames_per_warp, t1 = min(T - 1, t0 + frames_per_warp);
+        const float wb = wseq ? wseq[b] : 1.f;                 // per-sequence weight (autograd: d loss / d loglik_b)
         for (int t = t0; t < t1; ++t) {
             // u_j = b~_{t+1}(j) * beta_{t+1}(j)
             float e = ok ? emis[((size_t)b * T + t + 1) * K + lane] : 0.f, bt;
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
             float Z = cs;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
-            const float inv = (Z > 0.f) ? 1.f / Z : 0.f;
+            const float inv = (Z > 0.f) ? wb / Z : 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = fmaf(v[i], inv, acc[i]);
         }
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
             float Z = g;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
-            if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)(g / Z));
+            if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)(wb * g / Z));
         }
     } else if (T == 1 && wid < B && gamma1 != nullptr) {
         const int b = (int)wid;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
         float Z = g;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
-        if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)(g / Z));
+        if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)((wseq ? wseq[b] : 1.f) * g / Z));
     }
     if (ok) {
 #pragma unroll
@@ -204,7 +205,7 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
     const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
     const int64_t n_warps = (int64_t)B * blocks_per_seq;
     bw_xi_kernel<<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), s>>>(
-        emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, B, T, K, fpw, xi, gamma1);
+        emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, nullptr, B, T, K, fpw, xi, gamma1);
     if (int rc = check_launch("bw_xi_kernel")) return rc;
     const size_t smem = (size_t)BW_F * (K * C + D) * sizeof(float);
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K*C + D too large");
@@ -218,4 +219,26 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
     const int threads = ((cells + 31) / 32) * 32;
     bw_gmm_stats_kernel<<<(unsigned)min((int64_t)sms * 4, n_tiles), threads, smem, s>>>(x, comp, logb, gamma, (int64_t)n, K, C, D, occ, sx, sxx);
     return check_launch("bw_gmm_stats_kernel");
+}
+
+// Weighted transition / initial-state statistics alone: xi[i][j] += sum_b w_b sum_t xi_t(i,j), gamma1[k] += sum_b w_b gamma_0(k).
+// With w_b = d loss / d loglik_b these are the gradients of the loss w.r.t. log P and log p0.
+HMMB200_EXPORT int hmmb200_xi_sum_f32(const float *emis, int emis_mode, float floor_eps, const float *trans_prob,
+                                      const void *fb_workspace, const float *seq_weights, int B, int T, int K,
+                                      double *xi, double *gamma1, void *stream) {
+    if (B < 0 || T < 0 || K <= 0) return set_error(HMMB200_EINVAL, "xi_sum: bad shape");
+    if (B == 0 || T == 0) return HMMB200_OK;
+    if (K > 32) return set_error(HMMB200_EUNSUPPORTED, "xi_sum: K <= 32 (got %d)", K);
+    if (!emis || !trans_prob || !fb_workspace || !xi) return set_error(HMMB200_EINVAL, "xi_sum: null argument");
+    if (int rc = require_sm100()) return rc;
+    const size_t n = (size_t)B * T;
+    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const float *ws_a = (const float *)fb_workspace;
+    const float *ws_b = (const float *)((const uint8_t *)fb_workspace + al(n * K * sizeof(float)));
+    const int fpw = 64, warps = 4;
+    const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
+    const int64_t n_warps = (int64_t)B * blocks_per_seq;
+    bw_xi_kernel<<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), (cudaStream_t)stream>>>(
+        emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, seq_weights, B, T, K, fpw, xi, gamma1);
+    return check_launch("bw_xi_kernel");
 }

@@ -105,9 +105,28 @@ class MixtureGaussianHMMLayer(nn.Module):
                                 self.feature_dim)
         log_trans = self._safe_log(self.get_transition_matrix())                     # mixture_gaussian.py:357
         states, scores = self._viterbi_decode(logb, log_trans)
+        if return_log_probs and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            scores = self._path_score(observations.to(dev), states, log_trans)
         if observations.device != states.device:
             states, scores = states.to(observations.device), scores.to(observations.device)
         return (states, scores) if return_log_probs else (states, None)
+
+    def _path_score(self, x: torch.Tensor, states: torch.Tensor, log_trans: torch.Tensor) -> torch.Tensor:
+        """The Viterbi score as a differentiable function of the parameters along the decoded path (the sub-gradient the
+        reference's autograd produces through torch.max, exercised by tests/test_mixture_gaussian.py:159-176):
+        score = -log K + sum_t log b_t(s_t) + sum_t log A(s_{t-1}, s_t).  Plain torch ops on the path states only
+        ([B,T,C,D] temporaries) -- this is the training caller, not the inference hot path."""
+        S, Cn, D = self.num_states, self.num_components, self.feature_dim
+        logw = self._safe_log(F.softmax(self.mixture_weights_logits, dim=-1))        # [S,C]
+        mu, lv = self.means[states], self._diag_log_vars()[states]                    # [B,T,C,D]
+        diff = x.unsqueeze(2) - mu
+        comp = -0.5 * ((diff * diff / torch.exp(lv)).sum(-1) + lv.sum(-1) + D * math.log(2 * math.pi)) + logw[states]
+        m = comp.max(-1, keepdim=True)[0]
+        logb = (m + torch.log(torch.clamp(torch.exp(comp - m).sum(-1, keepdim=True), min=self.eps))).squeeze(-1)   # [B,T]
+        score = logb.sum(1) - math.log(S)
+        if states.shape[1] > 1:
+            score = score + log_trans[states[:, :-1], states[:, 1:]].sum(1)
+        return score
 
     def get_model_info(self) -> dict:
         total = sum(p.numel() for p in self.parameters())

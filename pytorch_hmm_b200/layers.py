@@ -52,8 +52,10 @@ class HMMLayer(nn.Module):
         return F.softmax(self.log_initial_logits, dim=0)
 
     def _get_hmm(self) -> HMMPyTorch:
-        P = self._get_transition_matrix().detach()
-        p0 = self._get_initial_probabilities().detach()
+        # (not detached: compute_loss differentiates the likelihood w.r.t. the transition / initial logits through
+        # log_P / log_p0, like the reference, hmm_layer.py:73-89; the kernels always receive detached copies)
+        P = self._get_transition_matrix()
+        p0 = self._get_initial_probabilities()
         if self._hmm is None:
             self._hmm = HMMPyTorch(P, p0, device=str(P.device))
         else:

@@ -1,0 +1,130 @@
+"""GPU tests (-m gpu) of the training callers' gradients: the hand-written backward passes against
+torch autograd through a float64 restatement of the reference's per-time-step recursion (hmm.py:92-101, :203-206;
+mixture_gaussian.py:141-214, :312-336).  Tolerance 1e-3 relative (fp32 kernels vs float64 autograd)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hm():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import pytorch_hmm_b200 as m
+    return m
+
+
+def _ref_loglik(log_b, log_P, log_p0):
+    """log p(o) by the reference's forward recursion (hmm.py:92-101), float64 torch with autograd."""
+    la = log_p0 + log_b[:, 0]
+    for t in range(1, log_b.shape[1]):
+        la = torch.logsumexp(la.unsqueeze(2) + log_P.unsqueeze(0), dim=1) + log_b[:, t]
+    return la
+
+
+@pytest.mark.parametrize("K,T,B", [(3, 12, 2), (5, 40, 3), (12, 130, 4), (17, 33, 2), (32, 20, 1)])
+def test_loglik_gradients_vs_float64_autograd(hm, K, T, B):
+    from pytorch_hmm_b200.autograd import hmm_log_likelihood
+    g = torch.Generator().manual_seed(K * 100 + T)
+    log_b = (torch.randn(B, T, K, generator=g) * 2 - 5)
+    log_P = torch.log_softmax(torch.randn(K, K, generator=g), -1)
+    log_p0 = torch.log_softmax(torch.randn(K, generator=g), -1)
+    w = torch.rand(B, generator=g) + 0.5
+    # float64 autograd
+    a, b, c = (t.double().clone().requires_grad_(True) for t in (log_b, log_P, log_p0))
+    ll64 = torch.logsumexp(_ref_loglik(a, b, c), -1)
+    (ll64 * w.double()).sum().backward()
+    # kernels
+    x, y, z = (t.cuda().clone().requires_grad_(True) for t in (log_b, log_P, log_p0))
+    ll = hmm_log_likelihood(x, y, z, hm.ops.EMIS_LOG)
+    (ll * w.cuda()).sum().backward()
+    np.testing.assert_allclose(ll.detach().cpu().numpy(), ll64.detach().numpy(), rtol=1e-5)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), a.grad.numpy(), rtol=1e-3, atol=1e-6)
+    np.testing.assert_allclose(y.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=1e-5)
+    np.testing.assert_allclose(z.grad.cpu().numpy(), c.grad.numpy(), rtol=1e-3, atol=1e-6)
+
+
+def test_probability_emissions_gradient(hm):
+    from pytorch_hmm_b200.autograd import hmm_log_likelihood
+    g = torch.Generator().manual_seed(5)
+    K, T, B = 6, 25, 3
+    p = torch.rand(B, T, K, generator=g) * 0.9 + 0.05
+    log_P = torch.log_softmax(torch.randn(K, K, generator=g), -1)
+    log_p0 = torch.log_softmax(torch.randn(K, generator=g), -1)
+    a = p.double().clone().requires_grad_(True)
+    torch.logsumexp(_ref_loglik(torch.log(a + 1e-8), log_P.double(), log_p0.double()), -1).sum().backward()
+    x = p.cuda().clone().requires_grad_(True)
+    hmm_log_likelihood(x, log_P.cuda(), log_p0.cuda(), hm.ops.EMIS_PROB_FLOOR).sum().backward()
+    np.testing.assert_allclose(x.grad.cpu().numpy(), a.grad.numpy(), rtol=1e-3, atol=1e-6)
+
+
+def test_hmm_layer_training_step_matches_reference_formula(hm):
+    """reference tests/test_hmm.py:189-208: one optimiser step changes the transitions; the gradient equals autograd through
+    the reference's own loss -logsumexp_k log(exp(log alpha_{T-1,k}) + 1e-8) (hmm.py:203-206) for a short sequence."""
+    torch.manual_seed(11)
+    K, T, B = 5, 10, 2
+    layer = hm.HMMLayer(K).cuda()
+    obs = torch.rand(B, T, K).cuda()
+    layer.train()
+    loss = layer.compute_loss(obs)
+    loss.backward()
+    gt, gi = layer.log_transition_logits.grad.clone(), layer.log_initial_logits.grad.clone()
+    assert torch.isfinite(gt).all() and torch.isfinite(gi).all() and gt.abs().sum() > 0
+    # float64 restatement of the reference's loss
+    lt = layer.log_transition_logits.detach().double().cpu().requires_grad_(True)
+    li = layer.log_initial_logits.detach().double().cpu().requires_grad_(True)
+    P = torch.softmax(lt, 1); P = P / P.sum(1, keepdim=True)
+    p0 = torch.softmax(li, 0); p0 = p0 / p0.sum()
+    la = _ref_loglik(torch.log(torch.sigmoid(obs.double().cpu()) + 1e-8), torch.log(P + 1e-8), torch.log(p0 + 1e-8))
+    ref = -torch.logsumexp(torch.log(torch.exp(la) + 1e-8), -1).mean()
+    ref.backward()
+    np.testing.assert_allclose(loss.item(), ref.item(), rtol=1e-4)
+    np.testing.assert_allclose(gt.cpu().numpy(), lt.grad.numpy(), rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(gi.cpu().numpy(), li.grad.numpy(), rtol=2e-3, atol=1e-6)
+    before = layer.get_transition_matrix().detach().clone()
+    opt = torch.optim.Adam(layer.parameters(), lr=0.01)
+    opt.step()
+    assert not torch.allclose(before, layer.get_transition_matrix().detach())
+
+
+def test_mixture_layer_gradient_flow_matches_reference_autograd(hm):
+    """reference tests/test_mixture_gaussian.py:159-176: loss = -scores.mean() back-propagates to every parameter.  The
+    sub-gradient along the decoded path equals autograd through a torch.max Viterbi (mixture_gaussian.py:312-336)."""
+    torch.manual_seed(3)
+    K, C, D, B, T = 6, 3, 16, 2, 30
+    m = hm.MixtureGaussianHMMLayer(K, D, num_components=C).cuda()
+    with torch.no_grad():
+        m.means.mul_(4.0)
+    x = (m.means.detach()[torch.randint(0, K, (B, T)), torch.randint(0, C, (B, T))] + torch.randn(B, T, D).cuda())
+    m.train()
+    states, scores = m(x, return_log_probs=True)
+    (-scores.mean()).backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+    # the kernel's own score is the same number
+    m.eval()
+    with torch.no_grad():
+        st2, sc2 = m(x, return_log_probs=True)
+    assert torch.equal(states, st2)
+    np.testing.assert_allclose(scores.detach().cpu().numpy(), sc2.cpu().numpy(), rtol=1e-5)
+    # float64 torch.max Viterbi with autograd
+    P = {n: p.detach().double().cpu().requires_grad_(True) for n, p in m.named_parameters()}
+    xd = x.double().cpu()
+    logw = torch.log(torch.clamp(torch.softmax(P["mixture_weights_logits"], -1), min=1e-8))
+    diff = xd[:, :, None, None, :] - P["means"][None, None]
+    comp = -0.5 * ((diff ** 2 / torch.exp(P["log_vars"])).sum(-1) + P["log_vars"].sum(-1) + D * math.log(2 * math.pi)) + logw
+    mx = comp.max(-1, keepdim=True)[0]
+    logb = (mx + torch.log(torch.clamp(torch.exp(comp - mx).sum(-1, keepdim=True), min=1e-8))).squeeze(-1)
+    ltr = torch.log(torch.clamp(torch.softmax(P["transition_logits"], -1), min=1e-8))
+    delta = logb[:, 0] - math.log(K)
+    for t in range(1, T):
+        delta = (delta.unsqueeze(2) + ltr.unsqueeze(0)).max(1)[0] + logb[:, t]
+    ref = delta.max(-1)[0]
+    (-ref.mean()).backward()
+    np.testing.assert_allclose(scores.detach().cpu().numpy(), ref.detach().numpy(), rtol=1e-5)
+    for n, p in m.named_parameters():
+        np.testing.assert_allclose(p.grad.cpu().numpy(), P[n].grad.numpy(), rtol=1e-3, atol=1e-6, err_msg=n)
