@@ -294,6 +294,16 @@ struct HsmmFbParams {
     float *ws_pend;                           // [B,T,K] end posteriors
 };
 
+constexpr int HSF_PF = 8;
+__device__ __forceinline__ void hs_cp4(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void hs_cp8(void *dst, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void hs_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void hs_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(HSF_PF - 1) : "memory"); }
+
 __device__ __forceinline__ double warp_max_d(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
@@ -308,6 +318,11 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     double *durc = bt_r + Dm * K;               // [Dm][K]  dur(s,d) * c(s)
     double *A_s = durc + Dm * K;                // [K][K]   A(s',s) as probabilities
     double *vec = A_s + K * K;                  // [K]      E(t-1,.) / bbeg(t+1,.)
+    // prefetch rings (cp.async, HSF_PF steps ahead): the per-step global reads must not sit on the serial chain
+    double *pf_E = vec + K;                     // [PF][32]
+    double *pf_Bg = pf_E + HSF_PF * 32;         // [PF][32]
+    float *pf_f = reinterpret_cast<float *>(pf_Bg + HSF_PF * 32);   // [PF][32]
+    int *pf_k = reinterpret_cast<int *>(pf_f + HSF_PF * 32);        // [PF]
     const int b = blockIdx.x, s = threadIdx.x;
     const bool ok = s < K;
     const float *f = p.f + (size_t)b * T * K;
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     }
     __syncwarp();
     // a shared power-of-two exponent keeps the ring near 1: rescale when the newest values drift by more than 2^24
-    auto rescale = [&](double &v, int &kexp) {
+    auto rescale = [&](double &v, int &kexp) -> double {
         const double mx = warp_max_d(ok ? v : 0.0);
         if (mx > 0.0) {
             const int ex = ilogb(mx);
@@ -329,45 +344,69 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
                 v *= sc;
                 if (ok) for (int d = 0; d < Dm; ++d) ring[d * K + s] *= sc;
                 kexp += ex;
+                return sc;
             }
         }
+        return 1.0;
     };
 
     // ---------------- forward ----------------
     int kf = 0;
     double Mc = 0.0;
     int cur = 0;                                            // t % Dm, kept without integer division
+    auto pf_fwd = [&](int t) {
+        if (ok && t < T) hs_cp4(pf_f + (t % HSF_PF) * 32 + s, f + (size_t)t * K + s);
+        hs_commit();
+    };
+    for (int t = 0; t < HSF_PF - 1; ++t) pf_fwd(t);
     for (int t = 0; t < T; ++t) {
-        const float ft = ok ? f[(size_t)t * K + s] : -INFINITY;
+        pf_fwd(t + HSF_PF - 1);
+        hs_wait();
+        const float ft = ok ? pf_f[(t % HSF_PF) * 32 + s] : -INFINITY;
         float m = ft;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
         if (!(m > -INFINITY)) m = 0.f;
         Mc += (double)m;
-        double e = 0.0;
+        double e = 0.0, bg = 0.0;
         if (ok) {
-            bt_r[cur * K + s] = (double)expf(ft - m);
-            double bg;
+            const double bq = (double)expf(ft - m);
             if (t == 0) bg = p.logpi ? exp((double)p.logpi[s]) : 1.0;
             else {
-                bg = 0.0;
-                for (int sp = 0; sp < K; ++sp) if (sp != s) bg = fma(vec[sp], A_s[sp * K + s], bg);
+                double g0 = 0.0, g1 = 0.0;
+                for (int sp = 0; sp + 1 < K; sp += 2) {
+                    if (sp != s) g0 = fma(vec[sp], A_s[sp * K + s], g0);
+                    if (sp + 1 != s) g1 = fma(vec[sp + 1], A_s[(sp + 1) * K + s], g1);
+                }
+                if ((K & 1) && K - 1 != s) g0 = fma(vec[K - 1], A_s[(K - 1) * K + s], g0);
+                bg = g0 + g1;
             }
+            // the ring holds RUNNING segment products R[st] = Bg(st,s) prod_{tau=st..t} b~_tau(s): one independent multiply
+            // per open segment and step instead of a dependent prefix-product chain over the durations
             ring[cur * K + s] = bg;
-            double prod = 1.0;
+            double e0 = 0.0, e1 = 0.0;
             int st = cur;                                   // (t - d + 1) % Dm
-            for (int d = 1; d <= Dm && d <= t + 1; ++d) {
-                prod *= bt_r[st * K + s];
-                e = fma(ring[st * K + s] * prod, durc[(d - 1) * K + s], e);
-                st = (st == 0) ? Dm - 1 : st - 1;
+            const int nd = min(Dm, t + 1);
+            for (int d = 1; d <= nd; d += 2) {
+                const int st1 = (st == 0) ? Dm - 1 : st - 1;
+                const double r0 = ring[st * K + s] * bq;
+                ring[st * K + s] = r0;
+                e0 = fma(r0, durc[(d - 1) * K + s], e0);
+                if (d + 1 <= nd) {
+                    const double r1 = ring[st1 * K + s] * bq;
+                    ring[st1 * K + s] = r1;
+                    e1 = fma(r1, durc[d * K + s], e1);
+                }
+                st = (st1 == 0) ? Dm - 1 : st1 - 1;
             }
+            e = e0 + e1;
         }
         __syncwarp();                                       // every lane has read E(t-1,.)
-        rescale(e, kf);
+        bg *= rescale(e, kf);
         if (ok) {
             vec[s] = e;
             p.ws_E[(base + t) * K + s] = e;
-            p.ws_Bg[(base + t) * K + s] = ring[cur * K + s];
+            p.ws_Bg[(base + t) * K + s] = bg;
         }
         if (s == 0) { p.ws_k[base + t] = kf; p.ws_M[base + t] = Mc; }
         __syncwarp();
@@ -386,40 +425,71 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     __syncwarp();
     int kb = 0;
     cur = (T - 1) % Dm;
+    auto pf_bwd = [&](int t) {                              // frame t, slot t % PF
+        if (t >= 0) {
+            const int sl = t % HSF_PF;
+            if (ok) {
+                hs_cp4(pf_f + sl * 32 + s, f + (size_t)t * K + s);
+                hs_cp8(pf_E + sl * 32 + s, p.ws_E + (base + t) * K + s);
+                hs_cp8(pf_Bg + sl * 32 + s, p.ws_Bg + (base + t) * K + s);
+            }
+            if (s == 0) hs_cp4(pf_k + sl, p.ws_k + base + t);
+        }
+        hs_commit();
+    };
+    __syncwarp();
+    for (int i = 0; i < HSF_PF - 1; ++i) pf_bwd(T - 1 - i);
     for (int t = T - 1; t >= 0; --t) {
-        const float ft = ok ? f[(size_t)t * K + s] : -INFINITY;
+        pf_bwd(t - (HSF_PF - 1));
+        hs_wait();
+        __syncwarp();                                       // lane 0's ws_k copy is read by every lane
+        const float ft = ok ? pf_f[(t % HSF_PF) * 32 + s] : -INFINITY;
         float m = ft;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
         if (!(m > -INFINITY)) m = 0.f;
-        double bb = 0.0;
+        double bb = 0.0, be = 0.0;
         if (ok) {
-            bt_r[cur * K + s] = (double)expf(ft - m);
-            double be = 1.0;
+            const double bq = (double)expf(ft - m);
             if (t < T - 1) {
-                be = 0.0;
-                for (int sn = 0; sn < K; ++sn) if (sn != s) be = fma(A_s[s * K + sn], vec[sn], be);
+                double g0 = 0.0, g1 = 0.0;
+                for (int sn = 0; sn + 1 < K; sn += 2) {
+                    if (sn != s) g0 = fma(A_s[s * K + sn], vec[sn], g0);
+                    if (sn + 1 != s) g1 = fma(A_s[s * K + sn + 1], vec[sn + 1], g1);
+                }
+                if ((K & 1) && K - 1 != s) g0 = fma(A_s[s * K + K - 1], vec[K - 1], g0);
+                be = g0 + g1;
             } else {
                 be = scalbn(1.0, -kb);
             }
+            // ring: Q[en] = bend(en,s) prod_{tau=t..en} b~_tau(s), updated by one multiply per open segment
             ring[cur * K + s] = be;
-            double prod = 1.0;
+            double b0 = 0.0, b1 = 0.0;
             int en = cur;                                   // (t + d - 1) % Dm
-            for (int d = 1; d <= Dm && t + d <= T; ++d) {
-                prod *= bt_r[en * K + s];
-                bb = fma(ring[en * K + s] * prod, durc[(d - 1) * K + s], bb);
-                if (++en == Dm) en = 0;
+            const int nd = min(Dm, T - t);
+            for (int d = 1; d <= nd; d += 2) {
+                const int en1 = (en + 1 == Dm) ? 0 : en + 1;
+                const double q0 = ring[en * K + s] * bq;
+                ring[en * K + s] = q0;
+                b0 = fma(q0, durc[(d - 1) * K + s], b0);
+                if (d + 1 <= nd) {
+                    const double q1 = ring[en1 * K + s] * bq;
+                    ring[en1 * K + s] = q1;
+                    b1 = fma(q1, durc[d * K + s], b1);
+                }
+                en = (en1 + 1 == Dm) ? 0 : en1 + 1;
             }
+            bb = b0 + b1;
         }
         __syncwarp();                                       // every lane has read bbeg(t+1,.)
-        rescale(bb, kb);
+        be *= rescale(bb, kb);
         if (ok) {
             vec[s] = bb;
             const size_t o = (base + t) * K + s;
-            const double be = ring[cur * K + s];            // after the rescale
-            const int ke = p.ws_k[base + t] + kb - kfT;
-            p.gamma[o] = (float)scalbn(p.ws_Bg[o] * bb * inv, ke);      // P(begins at t); turned into gamma below
-            p.ws_pend[o] = (float)scalbn(p.ws_E[o] * be * inv, ke);     // P(ends at t)
+            const int sl = t % HSF_PF;
+            const int ke = pf_k[sl] + kb - kfT;
+            p.gamma[o] = (float)scalbn(pf_Bg[sl * 32 + s] * bb * inv, ke);      // P(begins at t); turned into gamma below
+            p.ws_pend[o] = (float)scalbn(pf_E[sl * 32 + s] * be * inv, ke);     // P(ends at t)
             if (p.bend_out) p.bend_out[o] = (float)(log(be) + 0.69314718055994530942 * (double)kb + (Mtot - p.ws_M[base + t]));
             if (p.bbegin_out)
                 p.bbegin_out[o] = (float)(log(bb) + 0.69314718055994530942 * (double)kb + (Mtot - (t > 0 ? p.ws_M[base + t - 1] : 0.0)));
@@ -428,14 +498,27 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
         cur = (cur == 0) ? Dm - 1 : cur - 1;
     }
     // ---------------- state-occupancy posterior (same thread wrote both arrays: program order suffices) ----------------
+    // (loads are batched 8 frames at a time: a load-use-store loop over T would expose the global latency 2T times)
     if (ok) {
         double cum = 0.0;
-        for (int t = 0; t < T; ++t) {
-            const size_t o = (base + t) * K + s;
-            cum += (double)p.gamma[o];
-            const float g = (float)cum;
-            cum -= (double)p.ws_pend[o];
-            p.gamma[o] = fminf(fmaxf(g, 0.f), 1.f);
+        for (int t0 = 0; t0 < T; t0 += 8) {
+            float gb[8], pe[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int t = min(t0 + i, T - 1);
+                const size_t o = (base + t) * K + s;
+                gb[i] = p.gamma[o];
+                pe[i] = p.ws_pend[o];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (t0 + i < T) {
+                    cum += (double)gb[i];
+                    const float g = (float)cum;
+                    cum -= (double)pe[i];
+                    p.gamma[(base + t0 + i) * K + s] = fminf(fmaxf(g, 0.f), 1.f);
+                }
+            }
         }
     }
 }
@@ -512,7 +595,7 @@ HMMB200_EXPORT int hmmb200_hsmm_forward_backward_f32(const float *frame_logp, co
     const size_t need = hmmb200_hsmm_fb_workspace_bytes(B, T, K);
     if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_forward_backward: workspace %zu < %zu", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
-    const size_t smem = ((size_t)3 * Dm * K + (size_t)K * K + K) * sizeof(double);
+    const size_t smem = ((size_t)3 * Dm * K + (size_t)K * K + K) * sizeof(double) + (size_t)HSF_PF * 32 * (8 + 8 + 4) + HSF_PF * 4 + 64;
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_forward_backward: max_duration too large");
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(hsmm_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

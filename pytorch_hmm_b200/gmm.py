@@ -106,7 +106,9 @@ class MixtureGaussianHMMLayer(nn.Module):
         log_trans = self._safe_log(self.get_transition_matrix())                     # mixture_gaussian.py:357
         states, scores = self._viterbi_decode(logb, log_trans)
         if return_log_probs and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            scores = self._path_score(observations.to(dev), states, log_trans)
+            # value: the kernel's score, bit for bit; gradient: along the decoded path
+            ps = self._path_score(observations.to(dev), states, log_trans)
+            scores = scores.detach() + (ps - ps.detach())
         if observations.device != states.device:
             states, scores = states.to(observations.device), scores.to(observations.device)
         return (states, scores) if return_log_probs else (states, None)
