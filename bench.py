@@ -230,11 +230,41 @@ def event_ms(fn, iters):
     return s.elapsed_time(e) / iters
 
 
+_ORIG_AFFINITY = None
+
+
+def pin_to_gpu_numa_node(local_rank):
+    """Host side of the end-to-end path: run this rank (and allocate its pinned buffers) on the NUMA node its GPU hangs
+    off, so that PCIe copies do not cross the socket interconnect.  Best effort; returns a note for the JSON line."""
+    global _ORIG_AFFINITY
+    try:
+        _ORIG_AFFINITY = os.sched_getaffinity(0)
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa: rank pinned to node {node} ({len(cpus)} cpus)"
+        return f"numa: node {node} has no allowed cpus"
+    except Exception as exc:                                      # noqa: BLE001
+        return f"numa: not pinned ({type(exc).__name__})"
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; pytorch_hmm_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    numa_note = pin_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
@@ -341,7 +371,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         t = torch.tensor([e2e_ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_ms = float(t.item())
     e2e = {"value": world * BATCH * SEQ / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
-           "api": f"HMMInferenceEngine.run_host (shard={he.eng.shard}, streams={he.eng.n_streams})"}
+           "api": f"HMMInferenceEngine.run_host (shard={he.eng.shard}, streams={he.eng.n_streams})", "host": numa_note}
     # spot check: the pipelined host path returns what the single-pass device path computed
     torch.cuda.synchronize()
     same = all(torch.equal(outs_host[(n_e2e - 1) & 1][k], h.eng.out[k].cpu()) for k in names)
@@ -360,6 +390,8 @@ def run_gpu_arm(args, rank, world, local_rank):
         }
         line["config"]["launch"] = "cuda-graph replay per step" if not args.no_graph else "eager stream launches"
         if world == 1:
+            if _ORIG_AFFINITY:
+                os.sched_setaffinity(0, _ORIG_AFFINITY)          # the CPU baseline gets every host core again
             torch.set_num_threads(os.cpu_count() or 1)
             bs = 32
             xs = x_host[:bs].clone()
