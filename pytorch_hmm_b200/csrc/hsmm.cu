@@ -84,12 +84,18 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
     extern __shared__ __align__(16) float smem_h[];
     const int K = p.K, Dm = p.Dm, T = p.T;
     const int KD = K * Dm, R = Dm + 2;          // slots t-2 (being cleared), t-1 (read) and t .. t+Dm-1 (written) are distinct
+    const int NQ = Dm / 4 + 1;                  // prefix-table rows per state (order 0: 4 partial sums per row)
+    const int TABW = (p.sum_order == 0) ? NQ * 4 : Dm + 1;
     float *ring = smem_h;                       // [R][K][Dm]   delta for segments ending at te, slot te % R
     float *A_s = ring + (size_t)R * KD;         // [K][K]
     float *dur_s = A_s + K * K;                 // [K][Dm]
     float *win = dur_s + KD;                    // [Dm][K]      frames t .. t+Dm-1 of f (ring, row `head` = frame t)
     float *mx_s = win + KD;                     // [K]          max_d' prev[s'][d']
-    int *arg_s = reinterpret_cast<int *>(mx_s + K);   // [K]    first d' (0-based) attaining it
+    int *arg_s = reinterpret_cast<int *>(mx_s + K);        // [K]   first d' (0-based) attaining it
+    float *U_s = reinterpret_cast<float *>(arg_s + K);     // [K][K] fl(Mx[s'] + logA[s'][s])
+    float *V_s = U_s + K * K;                   // [K]          max_{s' != s} U[s'][s]
+    int *varg_s = reinterpret_cast<int *>(V_s + K);        // [K]   first s' attaining it
+    float *tab = reinterpret_cast<float *>(varg_s + K);    // [K][TABW] prefix sums of the frame window in the reference's order
     const int b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const float *f = p.f + (size_t)b * T * K;
@@ -108,7 +114,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
     int head = 0, slot_prev = R - 1, slot_t = 0;                         // ring rows without integer division on the loop
     for (int t = 0; t < T; ++t) {
         const float *prev = ring + (size_t)slot_prev * KD;              // segments ending at t-1
-        // ---- phase A: Mx[s'] and its first arg-max, one warp per s' ----
+        // ---- phase A: Mx[s'] and its first arg-max (one warp per s'); prefix table of the frame window (one thread per s) ----
         if (t > 0) {
             for (int sp = warp; sp < K; sp += nwarps) {
                 float m = -INFINITY;
@@ -126,13 +132,67 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                 if (lane == 0) { mx_s[sp] = m; arg_s[sp] = (mi < Dm) ? mi : 0; }
             }
         }
+        // The segment sum seg(t,d,s) in ATen's order is four interleaved running sums plus a tail: the running sums depend on
+        // d only through q = d/4, so they are tabulated once per (t, s) and shared by the Dmax cells of the state.
+        for (int s = blockDim.x - 1 - tid; s < K; s += blockDim.x) {   // the LAST threads: they have no Mx work in warp 0
+            int r = head;
+            float *tb = tab + s * TABW;
+            if (p.sum_order == 0) {
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+                tb[0] = 0.f; tb[1] = 0.f; tb[2] = 0.f; tb[3] = 0.f;
+                for (int q = 1; q < NQ; ++q) {
+                    float x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { x[j] = win[r * K + s]; if (++r == Dm) r = 0; }
+                    p0 = __fadd_rn(p0, x[0]); p1 = __fadd_rn(p1, x[1]); p2 = __fadd_rn(p2, x[2]); p3 = __fadd_rn(p3, x[3]);
+                    tb[q * 4 + 0] = p0; tb[q * 4 + 1] = p1; tb[q * 4 + 2] = p2; tb[q * 4 + 3] = p3;
+                }
+            } else {
+                float a = 0.f;
+                tb[0] = 0.f;
+                for (int d = 1; d <= Dm; ++d) { a = __fadd_rn(a, win[r * K + s]); if (++r == Dm) r = 0; tb[d] = a; }
+            }
+        }
+        __syncthreads();
+        // ---- phase A2: U[s'][s] = fl(Mx[s'] + logA[s'][s]), then V[s] = max_{s' != s} U[s'][s] with its first arg-max ----
+        if (t > 0) {
+            for (int i = tid; i < K * K; i += blockDim.x) U_s[i] = __fadd_rn(mx_s[i / K], A_s[i]);
+        }
+        __syncthreads();
+        if (t > 0) {
+            for (int s = tid; s < K; s += blockDim.x) {
+                float v = -INFINITY;
+                int vi = -1;
+                for (int sp = 0; sp < K; ++sp) {
+                    if (sp == s) continue;
+                    const float u = U_s[sp * K + s];
+                    if (u > v) { v = u; vi = sp; }
+                }
+                V_s[s] = v; varg_s[s] = vi;
+            }
+        }
         __syncthreads();
         // ---- phase B: one thread per cell (s, d) ----
         for (int pr = tid; pr < KD; pr += blockDim.x) {
             const int s = pr / Dm, d = pr % Dm + 1;
             const int te = t + d - 1;
             if (te < T) {
-                const float osum = seg_sum_win(win, K, Dm, head, s, d, p.sum_order);
+                float osum;
+                {
+                    const float *tb = tab + s * TABW;
+                    if (p.sum_order == 0) {
+                        const int q = d >> 2;
+                        float p0 = tb[q * 4];
+                        int r = head + 4 * q;
+                        if (r >= Dm) r -= Dm;
+                        for (int i = 4 * q; i < d; ++i) { p0 = __fadd_rn(p0, win[r * K + s]); if (++r == Dm) r = 0; }
+                        p0 = __fadd_rn(p0, tb[q * 4 + 1]);
+                        p0 = __fadd_rn(p0, tb[q * 4 + 2]);
+                        osum = __fadd_rn(p0, tb[q * 4 + 3]);
+                    } else {
+                        osum = tb[d];
+                    }
+                }
                 const float oseg = p.segc ? __fadd_rn(p.segc[s], osum) : osum;
                 const float dsc = dur_s[s * Dm + d - 1];
                 float best;
@@ -140,14 +200,16 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                 if (t == 0) {
                     best = p.logpi ? __fadd_rn(__fadd_rn(p.logpi[s], oseg), dsc) : __fadd_rn(oseg, dsc);
                 } else {
-                    best = -INFINITY;
-                    int bsp = -1;
-                    for (int sp = 0; sp < K; ++sp) {
-                        if (sp == s) continue;
-                        const float tot = __fadd_rn(__fadd_rn(__fadd_rn(mx_s[sp], A_s[sp * K + s]), oseg), dsc);
-                        if (tot > best) { best = tot; bsp = sp; }
-                    }
-                    if (bsp >= 0) {
+                    // fp32 rounding is monotone: the maximum over all (s', d') is the cell's map applied to V[s]
+                    best = __fadd_rn(__fadd_rn(V_s[s], oseg), dsc);
+                    if (best > -INFINITY) {
+                        // the reference's winner is the FIRST (s', d') in lexicographic order whose own total equals best
+                        const int sp_last = varg_s[s];
+                        int bsp = sp_last;
+                        for (int sp = 0; sp < sp_last; ++sp) {
+                            if (sp == s) continue;
+                            if (__fadd_rn(__fadd_rn(U_s[sp * K + s], oseg), dsc) == best) { bsp = sp; break; }
+                        }
                         const float a = A_s[bsp * K + s];
                         const float *pv = prev + bsp * Dm;
                         const int last = arg_s[bsp];
@@ -543,7 +605,7 @@ HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float
     const size_t need = hmmb200_hsmm_viterbi_workspace_bytes(B, T, K, Dm);
     if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_viterbi: workspace %zu < %zu", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
-    const size_t smem = ((size_t)(Dm + 2) * K * Dm + (size_t)K * K + (size_t)2 * K * Dm + 2 * (size_t)K) * sizeof(float);
+    const size_t smem = ((size_t)(Dm + 2) * K * Dm + 2 * (size_t)K * K + (size_t)2 * K * Dm + 4 * (size_t)K + (size_t)K * (Dm + 8)) * sizeof(float);
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_viterbi: K=%d, max_duration=%d need %zu bytes of shared memory", K, Dm, smem);
     cudaError_t e = cudaFuncSetAttribute(hsmm_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_viterbi smem opt-in: %s", cudaGetErrorString(e));
