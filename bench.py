@@ -197,7 +197,7 @@ class Headline:
     # single kernels on the current stream (per-kernel timing only)
     def emission(self, x):
         e = self.eng
-        self.hm.ops.gmm_emission(x, e.packed, K_STATES, N_MIX, FEAT, out=self.logb)
+        self.hm.ops.gmm_emission(x, e.packed, K_STATES, N_MIX, FEAT, out=self.logb, tc_known=e.tc_known)
 
     def fb(self, want=("gamma", "fwd", "bwd")):
         e, o = self.eng, self.eng.out

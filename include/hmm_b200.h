@@ -65,6 +65,12 @@ int    hmmb200_gmm_pack_f32(const float *means, const float *log_vars, float log
                             const float *log_weights, int K, int C, int D, float *packed, void *stream);
 int    hmmb200_gmm_emission_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
                                 float *logb, void *stream);
+/* Setup-time query (the ONE entry point that synchronises `stream`): 1 if `packed` runs on the tcgen05 kernel, 0 if it needs the
+ * fp32 kernel (shape outside the TMEM budget, or weights outside the fp16 range).  When it returns 1, hmmb200_gmm_emission_tc_f32
+ * may be used per batch: same result as hmmb200_gmm_emission_f32, one kernel launch instead of two. */
+int    hmmb200_gmm_pack_on_tensor_cores(const float *packed, int K, int C, int D, void *stream);
+int    hmmb200_gmm_emission_tc_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
+                                   float *logb, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Forward-backward (K <= 32: warp-per-sequence sweeps; 32 < K <= 512: cluster kernels, BASELINE config 5).

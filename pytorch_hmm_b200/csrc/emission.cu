@@ -254,8 +254,35 @@ HMMB200_EXPORT int hmmb200_gmm_pack_f32(const float *means, const float *log_var
     return HMMB200_OK;
 }
 
+// 1 if the packed parameters take the tensor-core kernel (shape supported AND every weight inside the fp16 range), 0 if not.
+// SYNCHRONISES the stream (it reads the flag the pack kernel wrote): call it once after packing, never per batch.
+HMMB200_EXPORT int hmmb200_gmm_pack_on_tensor_cores(const float *packed, int K, int C, int D, void *stream) {
+    if (!packed || K <= 0 || C <= 0 || D <= 0) return set_error(HMMB200_EINVAL, "gmm_pack_on_tensor_cores: bad argument");
+    if (!tc_shape_ok(K, C, D)) return 0;
+    float flag = 0.f;
+    cudaError_t e = cudaMemcpyAsync(&flag, packed + fp32_section_floats(K, C, D), sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "gmm_pack_on_tensor_cores: %s", cudaGetErrorString(e));
+    return flag != 0.f ? 1 : 0;
+}
+
+static int gmm_emission_impl(const float *x, const float *packed, int64_t n_frames, int K, int C, int D, float *logb, void *stream,
+                             int tc_known);
+
 HMMB200_EXPORT int hmmb200_gmm_emission_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
                                             float *logb, void *stream) {
+    return gmm_emission_impl(x, packed, n_frames, K, C, D, logb, stream, 0);
+}
+
+// Same, for a caller that has checked hmmb200_gmm_pack_on_tensor_cores() == 1 for `packed`: only the tcgen05 kernel is
+// launched (the plain entry point also enqueues the fp32 kernel, which then exits at once on a device-side flag).
+HMMB200_EXPORT int hmmb200_gmm_emission_tc_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
+                                               float *logb, void *stream) {
+    return gmm_emission_impl(x, packed, n_frames, K, C, D, logb, stream, 1);
+}
+
+static int gmm_emission_impl(const float *x, const float *packed, int64_t n_frames, int K, int C, int D, float *logb, void *stream,
+                             int tc_known) {
     if (n_frames < 0 || K <= 0 || C <= 0 || D <= 0) return set_error(HMMB200_EINVAL, "gmm_emission: bad shape");
     if (n_frames == 0) return HMMB200_OK;
     if (!x || !packed || !logb) return set_error(HMMB200_EINVAL, "gmm_emission: null argument");
@@ -271,7 +298,10 @@ HMMB200_EXPORT int hmmb200_gmm_emission_f32(const float *x, const float *packed,
         const float *tc = packed + fp32_section_floats(K, C, D);
         int trc = launch_emission_tc(x, tc, packed, n_frames, K, C, D, logb, s);
         if (trc < 0) return trc;
-        if (trc == 0) p.skip_if_one = tc;
+        if (trc == 0) {
+            if (tc_known) return HMMB200_OK;
+            p.skip_if_one = tc;
+        }
     }
     int rc = 1;
     switch (C) {

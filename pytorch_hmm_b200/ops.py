@@ -74,9 +74,19 @@ def gmm_pack(means: torch.Tensor, log_vars: torch.Tensor, log_var_scale: float,
     return packed
 
 
+def gmm_pack_on_tensor_cores(packed: torch.Tensor, K: int, Cn: int, D: int) -> bool:
+    """Setup-time query (synchronises the stream once): do these packed parameters run on the tcgen05 emission kernel?"""
+    dev = packed.device
+    with torch.cuda.device(dev):
+        rc = _lib.load().hmmb200_gmm_pack_on_tensor_cores(_p(packed), K, Cn, D, _stream(dev))
+    if rc < 0:
+        _check(rc, "hmmb200_gmm_pack_on_tensor_cores")
+    return rc == 1
+
+
 def gmm_emission(x: torch.Tensor, packed: torch.Tensor, K: int, Cn: int, D: int,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x [..., D] (CUDA) -> log b [..., K]."""
+                 out: Optional[torch.Tensor] = None, tc_known: bool = False) -> torch.Tensor:
+    """x [..., D] (CUDA) -> log b [..., K].  tc_known: the caller has seen gmm_pack_on_tensor_cores(packed) == True."""
     dev = packed.device
     x = _f32c(x, dev)
     if x.shape[-1] != D:
@@ -85,9 +95,9 @@ def gmm_emission(x: torch.Tensor, packed: torch.Tensor, K: int, Cn: int, D: int,
     if out is None:
         out = torch.empty(x.shape[:-1] + (K,), dtype=torch.float32, device=dev)
     lib = _lib.load()
+    fn = lib.hmmb200_gmm_emission_tc_f32 if tc_known else lib.hmmb200_gmm_emission_f32
     with torch.cuda.device(dev):
-        _check(lib.hmmb200_gmm_emission_f32(_p(x), _p(packed), n, K, Cn, D, _p(out), _stream(dev)),
-               "hmmb200_gmm_emission_f32")
+        _check(fn(_p(x), _p(packed), n, K, Cn, D, _p(out), _stream(dev)), "hmmb200_gmm_emission_f32")
     return out
 
 
