@@ -430,44 +430,70 @@ struct CombineParams {
     float *gamma, *fwd, *bwd, *log_alpha, *log_beta;
 };
 
-template <int VEC>
+// Each thread finishes COMBINE_FPT frames (idx, idx + stride, ...) and issues all of their loads before the first use: the
+// kernel is a pure stream (2 x K floats in, 3 x K floats out per frame) and needs bytes in flight, not arithmetic.
+constexpr int COMBINE_FPT = 2;
+
+template <int VEC, int KV>
 __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.n_frames) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int K = p.K;
-    const float *a = p.ws_a + idx * K, *b = p.ws_b + idx * K;
-    const float la = p.ws_la[idx], lb = p.ws_lb[idx];
-    const float ea = expf(la), eb = expf(lb);
-    float Z = 0.f;
     if (VEC == 4) {
-        for (int k = 0; k < K; k += 4) {
-            float4 x = *reinterpret_cast<const float4 *>(a + k), y = *reinterpret_cast<const float4 *>(b + k);
-            Z += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        // KV = K / 4 vector pieces per frame (compile-time: registers)
+        float4 xa[COMBINE_FPT][KV], xb[COMBINE_FPT][KV];
+        float la[COMBINE_FPT], lb[COMBINE_FPT];
+#pragma unroll
+        for (int f = 0; f < COMBINE_FPT; ++f) {
+            const int64_t idx = idx0 + f * stride;
+            const bool ok = idx < p.n_frames;
+            const int64_t i = ok ? idx : 0;
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                xa[f][q] = __ldcs(reinterpret_cast<const float4 *>(p.ws_a + i * K) + q);
+                xb[f][q] = __ldcs(reinterpret_cast<const float4 *>(p.ws_b + i * K) + q);
+            }
+            la[f] = __ldcs(p.ws_la + i); lb[f] = __ldcs(p.ws_lb + i);
+        }
+#pragma unroll
+        for (int f = 0; f < COMBINE_FPT; ++f) {
+            const int64_t idx = idx0 + f * stride;
+            if (idx >= p.n_frames) continue;
+            float Z = 0.f;
+#pragma unroll
+            for (int q = 0; q < KV; ++q)
+                Z += xa[f][q].x * xb[f][q].x + xa[f][q].y * xb[f][q].y + xa[f][q].z * xb[f][q].z + xa[f][q].w * xb[f][q].w;
+            const float inv = 1.f / Z, ea = expf(la[f]), eb = expf(lb[f]);
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                const float4 x = xa[f][q], y = xb[f][q];
+                if (p.gamma) __stcs(reinterpret_cast<float4 *>(p.gamma + idx * K) + q, make_float4(x.x * y.x * inv, x.y * y.y * inv, x.z * y.z * inv, x.w * y.w * inv));
+                if (p.fwd) __stcs(reinterpret_cast<float4 *>(p.fwd + idx * K) + q, make_float4(x.x * ea, x.y * ea, x.z * ea, x.w * ea));
+                if (p.bwd) __stcs(reinterpret_cast<float4 *>(p.bwd + idx * K) + q, make_float4(y.x * eb, y.y * eb, y.z * eb, y.w * eb));
+                if (p.log_alpha) __stcs(reinterpret_cast<float4 *>(p.log_alpha + idx * K) + q,
+                                        make_float4(logf(x.x) + la[f], logf(x.y) + la[f], logf(x.z) + la[f], logf(x.w) + la[f]));
+                if (p.log_beta) __stcs(reinterpret_cast<float4 *>(p.log_beta + idx * K) + q,
+                                       make_float4(logf(y.x) + lb[f], logf(y.y) + lb[f], logf(y.z) + lb[f], logf(y.w) + lb[f]));
+            }
         }
     } else {
-        for (int k = 0; k < K; ++k) Z += a[k] * b[k];
-    }
-    const float inv = 1.f / Z;
-    if (VEC == 4) {
-        for (int k = 0; k < K; k += 4) {
-            float4 x = *reinterpret_cast<const float4 *>(a + k), y = *reinterpret_cast<const float4 *>(b + k);
-            if (p.gamma) *reinterpret_cast<float4 *>(p.gamma + idx * K + k) =
-                make_float4(x.x * y.x * inv, x.y * y.y * inv, x.z * y.z * inv, x.w * y.w * inv);
-            if (p.fwd) *reinterpret_cast<float4 *>(p.fwd + idx * K + k) = make_float4(x.x * ea, x.y * ea, x.z * ea, x.w * ea);
-            if (p.bwd) *reinterpret_cast<float4 *>(p.bwd + idx * K + k) = make_float4(y.x * eb, y.y * eb, y.z * eb, y.w * eb);
-            if (p.log_alpha) *reinterpret_cast<float4 *>(p.log_alpha + idx * K + k) =
-                make_float4(logf(x.x) + la, logf(x.y) + la, logf(x.z) + la, logf(x.w) + la);
-            if (p.log_beta) *reinterpret_cast<float4 *>(p.log_beta + idx * K + k) =
-                make_float4(logf(y.x) + lb, logf(y.y) + lb, logf(y.z) + lb, logf(y.w) + lb);
-        }
-    } else {
-        for (int k = 0; k < K; ++k) {
-            float x = a[k], y = b[k];
-            if (p.gamma) p.gamma[idx * K + k] = x * y * inv;
-            if (p.fwd) p.fwd[idx * K + k] = x * ea;
-            if (p.bwd) p.bwd[idx * K + k] = y * eb;
-            if (p.log_alpha) p.log_alpha[idx * K + k] = logf(x) + la;
-            if (p.log_beta) p.log_beta[idx * K + k] = logf(y) + lb;
+        for (int f = 0; f < COMBINE_FPT; ++f) {
+            const int64_t idx = idx0 + f * stride;
+            if (idx >= p.n_frames) continue;
+            const float *a = p.ws_a + idx * K, *b = p.ws_b + idx * K;
+            const float la = p.ws_la[idx], lb = p.ws_lb[idx];
+            const float ea = expf(la), eb = expf(lb);
+            float Z = 0.f;
+            for (int k = 0; k < K; ++k) Z += a[k] * b[k];
+            const float inv = 1.f / Z;
+            for (int k = 0; k < K; ++k) {
+                float x = a[k], y = b[k];
+                if (p.gamma) p.gamma[idx * K + k] = x * y * inv;
+                if (p.fwd) p.fwd[idx * K + k] = x * ea;
+                if (p.bwd) p.bwd[idx * K + k] = y * eb;
+                if (p.log_alpha) p.log_alpha[idx * K + k] = logf(x) + la;
+                if (p.log_beta) p.log_beta[idx * K + k] = logf(y) + lb;
+            }
         }
     }
 }
@@ -807,12 +833,20 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
         c.n_frames = (int64_t)n; c.K = K;
         c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
         const int threads = 256;
-        const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+        const unsigned blocks = (unsigned)((n + (size_t)threads * COMBINE_FPT - 1) / ((size_t)threads * COMBINE_FPT));
         auto al16 = [](const void *q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
-        if (K % 4 == 0 && al16(gamma) && al16(fwd_prob) && al16(bwd_prob) && al16(log_alpha) && al16(log_beta))
-            fb_combine_kernel<4><<<blocks, threads, 0, s>>>(c);
-        else
-            fb_combine_kernel<1><<<blocks, threads, 0, s>>>(c);
+        const bool vec = K % 4 == 0 && al16(gamma) && al16(fwd_prob) && al16(bwd_prob) && al16(log_alpha) && al16(log_beta);
+        switch (vec ? K / 4 : 0) {
+            case 1: fb_combine_kernel<4, 1><<<blocks, threads, 0, s>>>(c); break;
+            case 2: fb_combine_kernel<4, 2><<<blocks, threads, 0, s>>>(c); break;
+            case 3: fb_combine_kernel<4, 3><<<blocks, threads, 0, s>>>(c); break;
+            case 4: fb_combine_kernel<4, 4><<<blocks, threads, 0, s>>>(c); break;
+            case 5: fb_combine_kernel<4, 5><<<blocks, threads, 0, s>>>(c); break;
+            case 6: fb_combine_kernel<4, 6><<<blocks, threads, 0, s>>>(c); break;
+            case 7: fb_combine_kernel<4, 7><<<blocks, threads, 0, s>>>(c); break;
+            case 8: fb_combine_kernel<4, 8><<<blocks, threads, 0, s>>>(c); break;
+            default: fb_combine_kernel<1, 1><<<blocks, threads, 0, s>>>(c); break;
+        }
         if (int rc = check_launch("fb_combine_kernel")) return rc;
     }
     return HMMB200_OK;
