@@ -107,21 +107,23 @@ int    hmmb200_forward_backward_scan_f32(const float *emis, int emis_mode, float
 
 /* ---------------------------------------------------------------------------------------------------------
  * Viterbi.  K <= 32: packed uint8 backpointers in shared memory, chunk-parallel on-device traceback.
- *           32 < K <= 512: cluster kernel, backpointers recomputed on the path by the traceback (psi must be NULL).
+ *           32 < K <= 512: cluster kernel; the traceback recomputes backpointers on the path, the full table is written only
+ *           when psi is given.
  *   replaces  HMMPyTorch.viterbi_decode                           pytorch_hmm/hmm.py:132-184
  *             MixtureGaussianHMMLayer._viterbi_decode             pytorch_hmm/mixture_gaussian.py:290-338
  *
  *   delta_0 = log_init + log b_0;  (m, psi_t[j]) = max_i(delta_{t-1}[i] + log_trans[i][j]) with the LOWEST i on
  *   ties;  delta_t = m + log b_t (two fp32 roundings in that order);  s_{T-1} = first argmax; s_t = psi_{t+1}[s_{t+1}].
  *   With emis_mode == HMMB200_EMIS_LOG the result is bit-identical to the reference given the same fp32 inputs.
- *   outputs (NULL allowed except states): delta [B,T,K]; psi [B,T,K] uint8 (psi_0 = 0); states [B,T] int64;
+ *   outputs (NULL allowed except states): delta [B,T,K]; psi [B,T,K] packed backpointers, uint8 for K <= 256 and uint16 above
+ *     (psi_0 = 0); states [B,T] int64;
  *     score [B] = max_k delta_{T-1}.
  *   workspace: hmmb200_viterbi_workspace_bytes(B, T, K) bytes (0 when the backpointers fit in shared memory).
  * --------------------------------------------------------------------------------------------------------- */
 size_t hmmb200_viterbi_workspace_bytes(int B, int T, int K);
 int    hmmb200_viterbi_f32(const float *emis, int emis_mode, float floor_eps,
                            const float *log_trans, const float *log_init, int B, int T, int K,
-                           float *delta, uint8_t *psi, int64_t *states, float *score,
+                           float *delta, void *psi, int64_t *states, float *score,
                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -46,6 +46,6 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
                             const float *init_prob, int B, int T, int K, float *gamma, float *fwd_prob, float *bwd_prob,
                             float *log_alpha, float *log_beta, float *loglik, void *workspace, cudaStream_t s);
 int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
-                   int B, int T, int K, float *delta, int64_t *states, float *score, void *workspace, cudaStream_t s);
+                   int B, int T, int K, float *delta, void *psi, int64_t *states, float *score, void *workspace, cudaStream_t s);
 
 }  // namespace hmmb200

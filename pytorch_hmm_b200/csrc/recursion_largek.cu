@@ -502,6 +502,38 @@ __global__ void __launch_bounds__(128) lk_traceback_kernel(const float *delta, c
     }
 }
 
+// Full backpointer table on request (the traceback does not need it): psi_t[j] = first argmax_i(delta_{t-1}(i) + logP(i,j)),
+// psi_0 = 0 (hmm.py:156, :167).  One warp per (sequence, frame, group of 32 target states): lane = target state j, the
+// delta_{t-1} row is broadcast through shuffles, logPT rows are read coalesced.  uint8 for K <= 256, uint16 above.
+template <typename PsiT>
+__global__ void __launch_bounds__(256) lk_psi_kernel(const float *delta, const float *log_trans, int B, int T, int K, PsiT *psi) {
+    const int64_t wid = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int jg = (K + 31) / 32;
+    if (wid >= (int64_t)B * T * jg) return;
+    const int g = (int)(wid % jg);
+    const int64_t fr = wid / jg;                             // b * T + t
+    const int t = (int)(fr % T);
+    const int j = g * 32 + lane;
+    int best_i = 0;
+    if (t > 0) {
+        const float *dprev = delta + (fr - 1) * K;
+        float best = -INFINITY;
+        for (int i0 = 0; i0 < K; i0 += 32) {
+            const float dv = (i0 + lane < K) ? dprev[i0 + lane] : -INFINITY;
+            const int n = min(32, K - i0);
+            for (int ii = 0; ii < n; ++ii) {
+                const float di = __shfl_sync(FULL_MASK, dv, ii);
+                if (j < K) {
+                    const float c = __fadd_rn(di, __ldg(log_trans + (size_t)(i0 + ii) * K + j));
+                    if (c > best) { best = c; best_i = i0 + ii; }
+                }
+            }
+        }
+    }
+    if (j < K) psi[fr * K + j] = (PsiT)best_i;
+}
+
 // ----------------------------------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------------------------------
@@ -588,7 +620,7 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
 }
 
 int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
-                   int B, int T, int K, float *delta, int64_t *states, float *score, void *workspace, cudaStream_t s) {
+                   int B, int T, int K, float *delta, void *psi, int64_t *states, float *score, void *workspace, cudaStream_t s) {
     const size_t n = (size_t)B * T;
     uint8_t *w = (uint8_t *)workspace;
     float *ws_delta = (float *)w; w += lk_align256(n * K * sizeof(float));
@@ -609,7 +641,15 @@ int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const floa
     if (int rc = check_launch("lk_transpose_kernel")) return rc;
     if (int rc = lk_launch<LK_VIT>(p, s)) return rc;
     lk_traceback_kernel<<<(B + 3) / 4, 128, 0, s>>>(p.delta, logPT, B, T, K, states, score);
-    return check_launch("lk_traceback_kernel");
+    if (int rc = check_launch("lk_traceback_kernel")) return rc;
+    if (psi != nullptr) {
+        const int64_t n_warps = (int64_t)n * ((K + 31) / 32);
+        const unsigned blocks = (unsigned)((n_warps + 7) / 8);
+        if (K <= 256) lk_psi_kernel<uint8_t><<<blocks, 256, 0, s>>>(p.delta, log_trans, B, T, K, (uint8_t *)psi);
+        else lk_psi_kernel<uint16_t><<<blocks, 256, 0, s>>>(p.delta, log_trans, B, T, K, (uint16_t *)psi);
+        return check_launch("lk_psi_kernel");
+    }
+    return HMMB200_OK;
 }
 
 }  // namespace hmmb200

@@ -862,13 +862,12 @@ HMMB200_EXPORT size_t hmmb200_viterbi_workspace_bytes(int B, int T, int K) {
 
 HMMB200_EXPORT int hmmb200_viterbi_f32(const float *emis, int emis_mode, float floor_eps,
                                        const float *log_trans, const float *log_init, int B, int T, int K,
-                                       float *delta, uint8_t *psi, int64_t *states, float *score,
+                                       float *delta, void *psi_out, int64_t *states, float *score,
                                        void *workspace, size_t workspace_bytes, void *stream) {
+    uint8_t *psi = (uint8_t *)psi_out;
     if (B < 0 || T < 0 || K <= 0) return set_error(HMMB200_EINVAL, "viterbi: bad shape B=%d T=%d K=%d", B, T, K);
     if (B == 0 || T == 0) return HMMB200_OK;
     if (K > 32 && !largek_shape_ok(K)) return set_error(HMMB200_EUNSUPPORTED, "viterbi: K <= 512 states supported (got %d)", K);
-    if (K > 32 && psi) return set_error(HMMB200_EUNSUPPORTED, "viterbi: the backpointer table is only materialised for K <= 32 "
-                                        "(for larger K the traceback recomputes them on the path)");
     if (!emis || !log_trans || !log_init || !states) return set_error(HMMB200_EINVAL, "viterbi: null argument");
     if (emis_mode < 0 || emis_mode > 3) return set_error(HMMB200_EINVAL, "viterbi: bad emis_mode %d", emis_mode);
     size_t need = hmmb200_viterbi_workspace_bytes(B, T, K);
@@ -876,7 +875,7 @@ HMMB200_EXPORT int hmmb200_viterbi_f32(const float *emis, int emis_mode, float f
         return set_error(HMMB200_EWORKSPACE, "viterbi: workspace %zu < %zu bytes", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
     if (K > 32)
-        return largek_viterbi(emis, emis_mode, floor_eps, log_trans, log_init, B, T, K, delta, states, score, workspace,
+        return largek_viterbi(emis, emis_mode, floor_eps, log_trans, log_init, B, T, K, delta, psi, states, score, workspace,
                               (cudaStream_t)stream);
     VitParams p;
     p.emis = emis; p.mode = emis_mode; p.eps = floor_eps; p.log_trans = log_trans; p.log_init = log_init;

@@ -187,7 +187,7 @@ def viterbi(emis: torch.Tensor, mode: int, log_trans: torch.Tensor, log_init: to
     if want_delta and "delta" not in res:
         res["delta"] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
     if want_psi and "psi" not in res:
-        res["psi"] = torch.empty(B, T, K, dtype=torch.uint8, device=dev)
+        res["psi"] = torch.empty(B, T, K, dtype=torch.uint8 if K <= 256 else torch.int16, device=dev)   # packed: 1 or 2 bytes
     if want_score and "score" not in res:
         res["score"] = torch.empty(B, dtype=torch.float32, device=dev)
     ws_bytes = lib.hmmb200_viterbi_workspace_bytes(B, T, K)

@@ -44,12 +44,15 @@ def test_largek_viterbi_bit_exact(hm, K, T, B):
     logP[0, 1] = logP[0, 2]
     logP[:, 5] = logP[:, 4]                                               # whole columns tie: lowest predecessor wins
     logp0 = np.log(np.full(K, 1.0 / K)).astype(np.float32)
-    st, delta, _, score = c_oracle.viterbi_f32(logb, logP, logp0)
+    st, delta, psi, score = c_oracle.viterbi_f32(logb, logP, logp0)
     ws = hm.ops.viterbi_workspace(B, T, K, "cuda")
-    r = hm.ops.viterbi(_dev(logb), hm.ops.EMIS_LOG, _dev(logP), _dev(logp0), want_delta=True, workspace=ws)
+    r = hm.ops.viterbi(_dev(logb), hm.ops.EMIS_LOG, _dev(logP), _dev(logp0), want_delta=True, want_psi=True, workspace=ws)
     torch.cuda.synchronize()
     assert _exchange_ok(ws)
     assert np.array_equal(r["delta"].cpu().numpy(), delta)
+    # packed backpointers: uint8 up to K = 256, uint16 above (int16 storage; K <= 512 so no sign issue)
+    assert r["psi"].dtype == (torch.uint8 if K <= 256 else torch.int16)
+    assert np.array_equal(r["psi"].cpu().numpy().astype(np.int32), psi)
     assert np.array_equal(r["states"].cpu().numpy(), st)
     assert np.array_equal(r["score"].cpu().numpy(), score)
     # without the delta output the trellis lives in the workspace; same path
