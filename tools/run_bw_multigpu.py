@@ -30,10 +30,25 @@ def main():
     model = bench.make_model(3001)
     lo, hi = bw.shard_range(a.utts, rank, world)
     batches = []
+    P = torch.softmax(model["transition_logits"], -1).to(dev)
+    cdf = torch.cumsum(P, -1)
     for s in range(lo, hi, a.batch):
         e = min(hi, s + a.batch)
-        xs = torch.stack([bench.make_frames(model, 1, a.seq, 3_000_000 + u)[0] for u in range(s, e)])
-        batches.append(xs.to(dev))
+        # every random number of utterance u comes from torch.Generator().manual_seed(3_000_000 + u): the data are a function
+        # of the utterance id only, whatever the sharding; the Markov chain itself is stepped for the whole
+        # batch at once by inverse-CDF sampling
+        us, cs, zs = [], [], []
+        for u in range(s, e):
+            g = torch.Generator().manual_seed(3_000_000 + u)
+            us.append(torch.rand(a.seq, generator=g)); cs.append(torch.randint(0, bench.N_MIX, (a.seq,), generator=g))
+            zs.append(torch.randn(a.seq, bench.FEAT, generator=g))
+        ur, comp, z = torch.stack(us).to(dev), torch.stack(cs).to(dev), torch.stack(zs).to(dev)
+        st = torch.empty(e - s, a.seq, dtype=torch.long, device=dev)
+        st[:, 0] = (ur[:, 0] * bench.K_STATES).long().clamp_(max=bench.K_STATES - 1)
+        for t in range(1, a.seq):
+            st[:, t] = (ur[:, t, None] > cdf[st[:, t - 1]]).sum(-1).clamp_(max=bench.K_STATES - 1)
+        means, lv = model["means"].to(dev), model["log_vars"].to(dev)
+        batches.append((means[st, comp] + torch.exp(0.5 * lv[st, comp]) * z).contiguous())
     K, C, D = bench.K_STATES, bench.N_MIX, bench.FEAT
     g = torch.Generator().manual_seed(3001)
     start = bw.GMMHMMParams(torch.softmax(model["transition_logits"], -1), torch.full((K,), 1.0 / K),
