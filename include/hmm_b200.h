@@ -184,6 +184,9 @@ int    hmmb200_forward_chunk_f32(const float *emis, int emis_mode, float floor_e
  * --------------------------------------------------------------------------------------------------------- */
 int    hmmb200_gmm_components_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
                                   float *comp, void *stream);
+/* logb [n_frames, K] and comp [n_frames, K*C] in ONE pass over x (the tcgen05 emission kernel writes both from its epilogue). */
+int    hmmb200_gmm_emission_components_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
+                                           float *logb, float *comp, void *stream);
 size_t hmmb200_bw_stats_doubles(int K, int C, int D);
 int    hmmb200_bw_accumulate_f32(const float *x, const float *comp, const float *logb, const float *gamma,
                                  const float *emis, int emis_mode, float floor_eps, const float *trans_prob,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "hmmb200_forward_chunk_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
                                             c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "hmmb200_gmm_components_f32": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
+    "hmmb200_gmm_emission_components_f32": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
     "hmmb200_bw_stats_doubles": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hmmb200_xi_sum_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
     "hmmb200_bw_accumulate_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_float, c_ptr, c_ptr,

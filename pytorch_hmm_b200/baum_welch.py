@@ -117,12 +117,12 @@ class BaumWelch:
         K, C = self.K, self.C
         lib = _lib.load()
         packed = self._pack()
-        logb = ops.gmm_emission(x, packed, K, C, D)
+        logb = torch.empty(B, T, K, dtype=torch.float32, device=self.dev)
         comp = torch.empty(B, T, K * C, dtype=torch.float32, device=self.dev)
         ws = ops.fb_workspace(B, T, K, self.dev)
-        with torch.cuda.device(self.dev):
-            ops._check(lib.hmmb200_gmm_components_f32(ops._p(x), ops._p(packed), B * T, K, C, D, ops._p(comp), ops._stream(self.dev)),
-                       "hmmb200_gmm_components_f32")
+        with torch.cuda.device(self.dev):          # log b and the per-component values in one pass over x
+            ops._check(lib.hmmb200_gmm_emission_components_f32(ops._p(x), ops._p(packed), B * T, K, C, D, ops._p(logb), ops._p(comp),
+                                                               ops._stream(self.dev)), "hmmb200_gmm_emission_components_f32")
         r = ops.forward_backward(logb, ops.EMIS_LOG, self.p.trans, self.p.init, want=("gamma",), workspace=ws)
         trans = self.p.trans.float().contiguous()
         with torch.cuda.device(self.dev):

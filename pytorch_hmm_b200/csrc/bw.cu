@@ -16,7 +16,8 @@
 namespace hmmb200 {
 
 __global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, const float *packed, int64_t n, int KC, int D,
-                                                             int NP2, float *comp) {
+                                                             int NP2, float *comp, const float *skip_if_one) {
+    if (skip_if_one != nullptr && *skip_if_one == 1.f) return;         // the tcgen05 emission kernel wrote comp already
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n * KC) return;
     const int64_t fr = idx / KC;
@@ -98,20 +99,29 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
     for (int i = threadIdx.x; i < K * K; i += blockDim.x) if (xi_s[i] != 0.0) atomicAdd(xi + i, xi_s[i]);
 }
 
-// occ / sx / sxx.  CTA = 256 threads, tile of BW_F frames staged in shared memory; thread (gc, gd) owns a TC x TD block of
-// (component, dim) accumulators for x and x^2.
-constexpr int BW_F = 32;
-constexpr int BW_TC = 6, BW_TD = 5;
-__global__ void __launch_bounds__(1024) bw_gmm_stats_kernel(const float *x, const float *comp, const float *logb, const float *gamma,
-                                                            int64_t n, int K, int C, int D, double *occ, double *sx, double *sxx) {
-    extern __shared__ float sm_bw[];
+// occ / sx / sxx are one [K*C, N] x [N, D] product (twice: with x and with x^2) over the N frames of the batch.  Per CTA a tile
+// of BW_F frames is staged in shared memory: w = gamma_t(k) * responsibility(c | k) as [f][KCp], x and x^2 as [f][Dp].  A thread
+// owns a 4 (components) x 8 (dims) block of both accumulators and one of FG frame sub-sequences of the tile: per frame it reads
+// five 16-byte vectors for 64 FMAs.  Partials stay in fp32 registers over the CTA's tiles and are committed once with double
+// atomics (every statistic gets (CTAs x FG) adds per call).
+constexpr int BW_F = 64;
+constexpr int BW_TC = 4, BW_TD = 8;
+__global__ void __launch_bounds__(512) bw_gmm_stats_kernel(const float *x, const float *comp, const float *logb, const float *gamma,
+                                                            int64_t n, int K, int C, int D, int FG, double *occ, double *sx, double *sxx) {
+    extern __shared__ __align__(16) float sm_bw[];
     const int KC = K * C;
-    float *w_s = sm_bw;                    // [BW_F][KC]
-    float *x_s = w_s + BW_F * KC;          // [BW_F][D]
-    const int ndg = (D + BW_TD - 1) / BW_TD, ncg = (KC + BW_TC - 1) / BW_TC;
+    const int KCp = (KC + BW_TC - 1) / BW_TC * BW_TC, Dp = (D + BW_TD - 1) / BW_TD * BW_TD;
+    float *w_s = sm_bw;                    // [BW_F][KCp]
+    float *x_s = w_s + BW_F * KCp;         // [BW_F][Dp]
+    float *x2_s = x_s + BW_F * Dp;         // [BW_F][Dp]
+    // blockIdx.y selects a slice of the component groups when (K*C/4) x (D/8) cells exceed one CTA
+    const int ndg = Dp / BW_TD, ncg_all = KCp / BW_TC;
+    const int ncg = (ncg_all + gridDim.y - 1) / gridDim.y;
+    const int cells = ncg * ndg;
     const int tid = threadIdx.x;
-    const bool has_cell = tid < ncg * ndg;                 // the launch sizes the CTA to cover every cell
-    const int gc = tid / ndg, gd = tid % ndg;
+    const int fg = tid / cells, cell = tid % cells;        // the launch sizes the CTA to cells * FG threads
+    const int gc = blockIdx.y * ncg + cell / ndg, gd = cell % ndg;
+    const bool live = gc < ncg_all;
     float ax[BW_TC][BW_TD], axx[BW_TC][BW_TD], aocc[BW_TC];
 #pragma unroll
     for (int i = 0; i < BW_TC; ++i) {
@@ -124,40 +134,48 @@ __global__ void __launch_bounds__(1024) bw_gmm_stats_kernel(const float *x, cons
         const int64_t base = tile * BW_F;
         const int nf = (int)min((int64_t)BW_F, n - base);
         __syncthreads();
-        for (int i = tid; i < nf * KC; i += blockDim.x) {
-            const int f = i / KC, kc = i % KC, k = kc / C;
-            const int64_t fr = base + f;
-            w_s[i] = gamma[fr * K + k] * expf(comp[fr * KC + kc] - logb[fr * K + k]);     // gamma_t(k) * responsibility(c | k)
+        for (int i = tid; i < BW_F * KCp; i += blockDim.x) {
+            const int f = i / KCp, kc = i % KCp;
+            float w = 0.f;
+            if (f < nf && kc < KC) {
+                const int k = kc / C;
+                const int64_t fr = base + f;
+                w = gamma[fr * K + k] * expf(comp[fr * KC + kc] - logb[fr * K + k]);      // gamma_t(k) * responsibility(c | k)
+            }
+            w_s[i] = w;
         }
-        for (int i = tid; i < nf * D; i += blockDim.x) x_s[i] = x[base * D + i];
+        for (int i = tid; i < BW_F * Dp; i += blockDim.x) {
+            const int f = i / Dp, d = i % Dp;
+            const float v = (f < nf && d < D) ? x[(base + f) * D + d] : 0.f;
+            x_s[i] = v; x2_s[i] = v * v;
+        }
         __syncthreads();
-        if (has_cell) {
-            for (int f = 0; f < nf; ++f) {
-                float wv[BW_TC], xv[BW_TD];
+        for (int f = fg; live && f < nf; f += FG) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(w_s + f * KCp + gc * BW_TC);
+            const float4 xa = *reinterpret_cast<const float4 *>(x_s + f * Dp + gd * BW_TD);
+            const float4 xb = *reinterpret_cast<const float4 *>(x_s + f * Dp + gd * BW_TD + 4);
+            const float4 qa = *reinterpret_cast<const float4 *>(x2_s + f * Dp + gd * BW_TD);
+            const float4 qb = *reinterpret_cast<const float4 *>(x2_s + f * Dp + gd * BW_TD + 4);
+            const float wv[BW_TC] = {w4.x, w4.y, w4.z, w4.w};
+            const float xv[BW_TD] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            const float qv[BW_TD] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-                for (int i = 0; i < BW_TC; ++i) { const int kc = gc * BW_TC + i; wv[i] = kc < KC ? w_s[f * KC + kc] : 0.f; }
+            for (int i = 0; i < BW_TC; ++i) {
+                aocc[i] += wv[i];
 #pragma unroll
-                for (int j = 0; j < BW_TD; ++j) { const int d = gd * BW_TD + j; xv[j] = d < D ? x_s[f * D + d] : 0.f; }
-#pragma unroll
-                for (int i = 0; i < BW_TC; ++i) {
-                    aocc[i] += wv[i];
-#pragma unroll
-                    for (int j = 0; j < BW_TD; ++j) { const float wx = wv[i] * xv[j]; ax[i][j] += wx; axx[i][j] = fmaf(wx, xv[j], axx[i][j]); }
-                }
+                for (int j = 0; j < BW_TD; ++j) { ax[i][j] = fmaf(wv[i], xv[j], ax[i][j]); axx[i][j] = fmaf(wv[i], qv[j], axx[i][j]); }
             }
         }
     }
-    if (has_cell) {
 #pragma unroll
-        for (int i = 0; i < BW_TC; ++i) {
-            const int kc = gc * BW_TC + i;
-            if (kc < KC) {
-                if (gd == 0) atomicAdd(occ + kc, (double)aocc[i]);
+    for (int i = 0; i < BW_TC; ++i) {
+        const int kc = gc * BW_TC + i;
+        if (live && kc < KC) {
+            if (gd == 0) atomicAdd(occ + kc, (double)aocc[i]);
 #pragma unroll
-                for (int j = 0; j < BW_TD; ++j) {
-                    const int d = gd * BW_TD + j;
-                    if (d < D) { atomicAdd(sx + (size_t)kc * D + d, (double)ax[i][j]); atomicAdd(sxx + (size_t)kc * D + d, (double)axx[i][j]); }
-                }
+            for (int j = 0; j < BW_TD; ++j) {
+                const int d = gd * BW_TD + j;
+                if (d < D) { atomicAdd(sx + (size_t)kc * D + d, (double)ax[i][j]); atomicAdd(sxx + (size_t)kc * D + d, (double)axx[i][j]); }
             }
         }
     }
@@ -175,7 +193,21 @@ HMMB200_EXPORT int hmmb200_gmm_components_f32(const float *x, const float *packe
     if (int rc = require_sm100()) return rc;
     const int KC = K * C;
     const int64_t total = n_frames * KC;
-    gmm_components_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp);
+    gmm_components_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp, nullptr);
+    return check_launch("gmm_components_kernel");
+}
+
+// log b AND the per-component values in one pass over x: the tcgen05 emission kernel holds the components in its epilogue just
+// before the mixture log-sum-exp and writes both; when the pack is outside its range the two fp32 kernels run instead.
+HMMB200_EXPORT int hmmb200_gmm_emission_components_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
+                                                       float *logb, float *comp, void *stream) {
+    if (!comp) return set_error(HMMB200_EINVAL, "gmm_emission_components: null argument");
+    const float *flag = nullptr;
+    if (int rc = gmm_emission_dispatch(x, packed, n_frames, K, C, D, logb, comp, (cudaStream_t)stream, 0, &flag)) return rc;
+    if (n_frames == 0) return HMMB200_OK;
+    const int KC = K * C;
+    const int64_t total = n_frames * KC;
+    gmm_components_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp, flag);
     return check_launch("gmm_components_kernel");
 }
 
@@ -207,17 +239,25 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
     bw_xi_kernel<<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), s>>>(
         emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, nullptr, B, T, K, fpw, xi, gamma1);
     if (int rc = check_launch("bw_xi_kernel")) return rc;
-    const size_t smem = (size_t)BW_F * (K * C + D) * sizeof(float);
+    const int KCp = (K * C + BW_TC - 1) / BW_TC * BW_TC, Dp = (D + BW_TD - 1) / BW_TD * BW_TD;
+    const size_t smem = (size_t)BW_F * (KCp + 2 * Dp) * sizeof(float);
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K*C + D too large");
     if (smem > 48 * 1024) cudaFuncSetAttribute(bw_gmm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int64_t n_tiles = ((int64_t)n + BW_F - 1) / BW_F;
-    const int cells = ((K * C + BW_TC - 1) / BW_TC) * ((D + BW_TD - 1) / BW_TD);
-    if (cells > 1024) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K*C*D = %d*%d*%d too large for one CTA of accumulators", K, C, D);
-    const int threads = ((cells + 31) / 32) * 32;
-    bw_gmm_stats_kernel<<<(unsigned)min((int64_t)sms * 4, n_tiles), threads, smem, s>>>(x, comp, logb, gamma, (int64_t)n, K, C, D, occ, sx, sxx);
+    const int ndg = Dp / BW_TD, ncg_all = KCp / BW_TC;
+    if (ndg > 512) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: D = %d too large", D);
+    int gy = 1;                                                     // slices of the component groups (<= 512 cells per CTA)
+    while (((ncg_all + gy - 1) / gy) * ndg > 512) ++gy;
+    const int cells = ((ncg_all + gy - 1) / gy) * ndg;
+    int FG = 512 / cells;                                           // frame sub-sequences per tile: up to 512 threads per CTA
+    FG = FG < 1 ? 1 : (FG > 8 ? 8 : FG);
+    const int threads = cells * FG;
+    const int per_sm = (smem <= 100 * 1024) ? 2 : 1;
+    dim3 grid((unsigned)min((int64_t)sms * per_sm, n_tiles), (unsigned)gy);
+    bw_gmm_stats_kernel<<<grid, threads, smem, s>>>(x, comp, logb, gamma, (int64_t)n, K, C, D, FG, occ, sx, sxx);
     return check_launch("bw_gmm_stats_kernel");
 }
 

@@ -36,7 +36,11 @@ int launch_pack_tc(const float *means, const float *log_vars, float scale, const
                    float *tc, cudaStream_t s);
 // returns 0 launched, >0 not applicable (caller uses the fp32 kernel only), <0 error
 int launch_emission_tc(const float *x, const float *tc, const float *packed32, int64_t n_frames, int K, int C, int D,
-                       float *logb, cudaStream_t s);
+                       float *logb, cudaStream_t s, float *comp = nullptr);
+// emission.cu: log b (and, with comp != null, the per-component values from the tcgen05 kernel).  *tc_flag_out receives the device
+// flag that is 1 when the tensor-core kernel did the work (null when it was not launched).
+int gmm_emission_dispatch(const float *x, const float *packed, int64_t n_frames, int K, int C, int D, float *logb, float *comp,
+                          cudaStream_t s, int tc_known, const float **tc_flag_out);
 
 // recursion_largek.cu (32 < K <= 512: cluster kernels)
 bool largek_shape_ok(int K);

@@ -267,7 +267,9 @@ HMMB200_EXPORT int hmmb200_gmm_pack_on_tensor_cores(const float *packed, int K, 
 }
 
 static int gmm_emission_impl(const float *x, const float *packed, int64_t n_frames, int K, int C, int D, float *logb, void *stream,
-                             int tc_known);
+                             int tc_known) {
+    return gmm_emission_dispatch(x, packed, n_frames, K, C, D, logb, nullptr, (cudaStream_t)stream, tc_known, nullptr);
+}
 
 HMMB200_EXPORT int hmmb200_gmm_emission_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
                                             float *logb, void *stream) {
@@ -281,8 +283,10 @@ HMMB200_EXPORT int hmmb200_gmm_emission_tc_f32(const float *x, const float *pack
     return gmm_emission_impl(x, packed, n_frames, K, C, D, logb, stream, 1);
 }
 
-static int gmm_emission_impl(const float *x, const float *packed, int64_t n_frames, int K, int C, int D, float *logb, void *stream,
-                             int tc_known) {
+namespace hmmb200 {
+int gmm_emission_dispatch(const float *x, const float *packed, int64_t n_frames, int K, int C, int D, float *logb, float *comp,
+                          cudaStream_t s, int tc_known, const float **tc_flag_out) {
+    if (tc_flag_out) *tc_flag_out = nullptr;
     if (n_frames < 0 || K <= 0 || C <= 0 || D <= 0) return set_error(HMMB200_EINVAL, "gmm_emission: bad shape");
     if (n_frames == 0) return HMMB200_OK;
     if (!x || !packed || !logb) return set_error(HMMB200_EINVAL, "gmm_emission: null argument");
@@ -291,14 +295,14 @@ static int gmm_emission_impl(const float *x, const float *packed, int64_t n_fram
     EmisParams p;
     p.x = x; p.packed = packed; p.n_frames = n_frames; p.K = K; p.C = C; p.D = D; p.NP = (K * C + 1) / 2; p.logb = logb;
     p.skip_if_one = nullptr;
-    cudaStream_t s = (cudaStream_t)stream;
     // tensor-core path first; it declines on the device (flag = 0) when the parameters leave the fp16 range, in which
     // case the fp32 kernel below does the work.  Exactly one of the two kernels computes.
     if (tc_shape_ok(K, C, D) && (((uintptr_t)x) & 15) == 0) {
         const float *tc = packed + fp32_section_floats(K, C, D);
-        int trc = launch_emission_tc(x, tc, packed, n_frames, K, C, D, logb, s);
+        int trc = launch_emission_tc(x, tc, packed, n_frames, K, C, D, logb, s, comp);
         if (trc < 0) return trc;
         if (trc == 0) {
+            if (tc_flag_out) *tc_flag_out = tc;
             if (tc_known) return HMMB200_OK;
             p.skip_if_one = tc;
         }
@@ -317,3 +321,4 @@ static int gmm_emission_impl(const float *x, const float *packed, int64_t n_fram
     gmm_emission_generic_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(p);
     return check_launch("gmm_emission_generic_kernel");
 }
+}  // namespace hmmb200

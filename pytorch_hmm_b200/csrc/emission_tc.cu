@@ -118,6 +118,7 @@ struct TcParams {
     const float *packed32;    // fp32 section (for out-of-range rows)
     int NP2;                  // component pairs in the fp32 section
     float *logb;
+    float *comp;              // optional [n_frames, K*C] per-component log-likelihoods (Baum-Welch E-step) or null
     int dbg;                  // timing experiments only (HMMB200_TC_DBG): 1 skip MMA, 2 skip transform math, 4 skip epilogue math
 };
 
@@ -159,6 +160,9 @@ __device__ __forceinline__ float lse_fast(const float *l) {
     return __logf(fmaxf(s, 1e-8f)) + m;
 }
 
+// WITH_COMP: also write the per-component values log w_kc + log N(x | mu_kc, var_kc) the epilogue holds before the mixture
+// log-sum-exp (they are what the Baum-Welch E-step needs for the component responsibilities).
+template <bool WITH_COMP>
 __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int D = p.D, DP = p.DP, NP = p.NP, K = p.K, C = p.C, KC = p.KC;
@@ -364,6 +368,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
             tc_fence_before();
             mbar_arrive(d_empty + a);
             if (q == 2) TC_TRACE(4, 1);
+            if (WITH_COMP) {
+                const int64_t fr = tile * TC_TILE + row;
+                if (fr < p.n_frames && !bad) {
+                    float *co = p.comp + fr * KC;
+                    if ((KC & 3) == 0) {
+                        for (int kc = 0; kc < KC; kc += 4)
+                            *reinterpret_cast<float4 *>(co + kc) = make_float4(my[kc], my[kc + 1], my[kc + 2], my[kc + 3]);
+                    } else {
+                        for (int kc = 0; kc < KC; ++kc) co[kc] = my[kc];
+                    }
+                }
+            }
             // phase 2: the reference's private logsumexp (mixture_gaussian.py:141-155) per state, in place
             if (fast && !bad && C > 1 && !(p.dbg & 4)) {
                 for (int ch = 0; ch < NP / 16; ++ch) {
@@ -400,6 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __
                             acc = fmaf(u, u, acc);
                         }
                         my[kc] = fmaf(-0.5f, acc, cst32[kc]);
+                        if (WITH_COMP) p.comp[frame * KC + kc] = my[kc];
                     }
                     for (int k = 0; k < K; ++k) o[k] = lse_row(my + k * C, C);
                 } else if (!fast) {
@@ -502,12 +519,12 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 int launch_emission_tc(const float *x, const float *tc, const float *packed32, int64_t n_frames, int K, int C, int D,
-                       float *logb, cudaStream_t s) {
+                       float *logb, cudaStream_t s, float *comp) {
     TcParams p;
     p.x = x; p.n_frames = n_frames; p.n_tiles = (n_frames + TC_TILE - 1) / TC_TILE;
     p.D = D; p.K = K; p.C = C; p.KC = K * C;
     p.DP = (D + 15) & ~15; p.NP = (p.KC + 15) & ~15;
-    p.tc = tc; p.packed32 = packed32; p.NP2 = (p.KC + 1) / 2; p.logb = logb;
+    p.tc = tc; p.packed32 = packed32; p.NP2 = (p.KC + 1) / 2; p.logb = logb; p.comp = comp;
     { const char *e = getenv("HMMB200_TC_DBG"); p.dbg = e ? atoi(e) : 0; }
     const int nbox = (D + TC_BOXW - 1) / TC_BOXW;
     size_t smem = 128 + (size_t)4 * p.NP * p.DP * 2 + (size_t)(p.NP + p.DP) * 4 + 4 * TC_XF_GROUPS * TC_TILE;
@@ -529,13 +546,15 @@ int launch_emission_tc(const float *x, const float *tc, const float *packed32, i
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return 1;
-    cudaError_t e = cudaFuncSetAttribute(gmm_emission_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gmm_emission_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gmm_emission_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "emission_tc smem opt-in: %s", cudaGetErrorString(e));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = (int)min((int64_t)sms, p.n_tiles);
-    gmm_emission_tc_kernel<<<grid, TC_THREADS, smem, s>>>(tmap, p);
+    if (comp != nullptr) gmm_emission_tc_kernel<true><<<grid, TC_THREADS, smem, s>>>(tmap, p);
+    else gmm_emission_tc_kernel<false><<<grid, TC_THREADS, smem, s>>>(tmap, p);
     return check_launch("gmm_emission_tc_kernel");
 }
 
