@@ -18,8 +18,7 @@ namespace hmmb200 {
 __global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, const float *packed, int64_t n, int KC, int D,
                                                              int NP2, float *comp, const float *skip_if_one) {
     if (skip_if_one != nullptr && *skip_if_one == 1.f) return;         // the tcgen05 emission kernel wrote comp already
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * KC) return;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n * KC; idx += (int64_t)gridDim.x * blockDim.x) {
     const int64_t fr = idx / KC;
     const int kc = (int)(idx % KC), pr = kc >> 1, hi = kc & 1;
     const float *xn = x + fr * D;
@@ -29,6 +28,7 @@ __global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, con
         acc = fmaf(u, u, acc);
     }
     comp[idx] = fmaf(-0.5f, acc, __ldg(packed + (size_t)D * NP2 * 4 + kc));
+    }
 }
 
 // one warp per (sequence, block of frames); lane j owns column j of xi
@@ -167,6 +167,31 @@ __global__ void __launch_bounds__(512) bw_gmm_stats_kernel(const float *x, const
             }
         }
     }
+    // fold the FG frame sub-sequences inside the CTA (through the staging buffer) so that only `cells` threads touch the global
+    // double accumulators: every statistic then receives one atomic per CTA instead of FG
+    constexpr int NACC = 2 * BW_TC * BW_TD + BW_TC;
+    for (int r = 1; r < FG; ++r) {
+        __syncthreads();
+        float *slot = sm_bw + (size_t)cell * NACC;
+        if (fg == r) {
+#pragma unroll
+            for (int i = 0; i < BW_TC; ++i) {
+                slot[2 * BW_TC * BW_TD + i] = aocc[i];
+#pragma unroll
+                for (int j = 0; j < BW_TD; ++j) { slot[i * BW_TD + j] = ax[i][j]; slot[BW_TC * BW_TD + i * BW_TD + j] = axx[i][j]; }
+            }
+        }
+        __syncthreads();
+        if (fg == 0) {
+#pragma unroll
+            for (int i = 0; i < BW_TC; ++i) {
+                aocc[i] += slot[2 * BW_TC * BW_TD + i];
+#pragma unroll
+                for (int j = 0; j < BW_TD; ++j) { ax[i][j] += slot[i * BW_TD + j]; axx[i][j] += slot[BW_TC * BW_TD + i * BW_TD + j]; }
+            }
+        }
+    }
+    if (fg != 0) return;
 #pragma unroll
     for (int i = 0; i < BW_TC; ++i) {
         const int kc = gc * BW_TC + i;
@@ -193,7 +218,7 @@ HMMB200_EXPORT int hmmb200_gmm_components_f32(const float *x, const float *packe
     if (int rc = require_sm100()) return rc;
     const int KC = K * C;
     const int64_t total = n_frames * KC;
-    gmm_components_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp, nullptr);
+    gmm_components_kernel<<<(unsigned)min((total + 127) / 128, (int64_t)148 * 16), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp, nullptr);
     return check_launch("gmm_components_kernel");
 }
 
@@ -207,7 +232,7 @@ HMMB200_EXPORT int hmmb200_gmm_emission_components_f32(const float *x, const flo
     if (n_frames == 0) return HMMB200_OK;
     const int KC = K * C;
     const int64_t total = n_frames * KC;
-    gmm_components_kernel<<<(unsigned)((total + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp, flag);
+    gmm_components_kernel<<<(unsigned)min((total + 127) / 128, (int64_t)148 * 16), 128, 0, (cudaStream_t)stream>>>(x, packed, n_frames, KC, D, (KC + 1) / 2, comp, flag);
     return check_launch("gmm_components_kernel");
 }
 
@@ -240,7 +265,8 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
         emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, nullptr, B, T, K, fpw, xi, gamma1);
     if (int rc = check_launch("bw_xi_kernel")) return rc;
     const int KCp = (K * C + BW_TC - 1) / BW_TC * BW_TC, Dp = (D + BW_TD - 1) / BW_TD * BW_TD;
-    const size_t smem = (size_t)BW_F * (KCp + 2 * Dp) * sizeof(float);
+    size_t smem = (size_t)BW_F * (KCp + 2 * Dp) * sizeof(float);
+    smem = smem > 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float) ? smem : 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float);   // also the fold buffer
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K*C + D too large");
     if (smem > 48 * 1024) cudaFuncSetAttribute(bw_gmm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dev = 0, sms = 148;
@@ -255,8 +281,7 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
     int FG = 512 / cells;                                           // frame sub-sequences per tile: up to 512 threads per CTA
     FG = FG < 1 ? 1 : (FG > 8 ? 8 : FG);
     const int threads = cells * FG;
-    const int per_sm = (smem <= 100 * 1024) ? 2 : 1;
-    dim3 grid((unsigned)min((int64_t)sms * per_sm, n_tiles), (unsigned)gy);
+    dim3 grid((unsigned)min((int64_t)sms, n_tiles), (unsigned)gy);      // one CTA per SM (128 registers x ~480 threads)
     bw_gmm_stats_kernel<<<grid, threads, smem, s>>>(x, comp, logb, gamma, (int64_t)n, K, C, D, FG, occ, sx, sxx);
     return check_launch("bw_gmm_stats_kernel");
 }
