@@ -31,7 +31,8 @@ __global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, con
     }
 }
 
-// one warp per (sequence, block of frames); lane j owns column j of xi
+// one warp per (sequence, block of frames); lane j owns column j of xi.  KP = K padded to a multiple of 4 bounds the unrolled loops.
+template <int KP>
 __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode, float eps, const float *trans,
                                                     const float *ws_a, const float *ws_b, const float *wseq, int B, int T, int K,
                                                     int frames_per_warp, double *xi, double *gamma1) {
@@ -42,12 +43,12 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
     const int blocks_per_seq = (T - 1 + frames_per_warp - 1) / frames_per_warp;
     const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
     const bool ok = lane < K;
-    float col[32];
+    float col[KP];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) col[i] = (ok && i < K) ? trans[i * K + lane] : 0.f;
-    float acc[32];
+    for (int i = 0; i < KP; ++i) col[i] = (ok && i < K) ? trans[i * K + lane] : 0.f;
+    float acc[KP];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+    for (int i = 0; i < KP; ++i) acc[i] = 0.f;
     if (wid < (int64_t)B * max(blocks_per_seq, 1) && T > 1) {
         const int b = (int)(wid / blocks_per_seq), blk = (int)(wid % blocks_per_seq);
         const int t0 = blk * frames_per_warp, t1 = min(T - 1, t0 + frames_per_warp);
@@ -66,15 +67,15 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
             }
             const float u = ok ? bt * ws_b[((size_t)b * T + t + 1) * K + lane] : 0.f;
             const float a = ok ? ws_a[((size_t)b * T + t) * K + lane] : 0.f;
-            float v[32], cs = 0.f;
+            float v[KP], cs = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) { v[i] = __shfl_sync(FULL_MASK, a, i) * col[i] * u; cs += v[i]; }
+            for (int i = 0; i < KP; ++i) { v[i] = __shfl_sync(FULL_MASK, a, i) * col[i] * u; cs += v[i]; }
             float Z = cs;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
             const float inv = (Z > 0.f) ? wb / Z : 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) acc[i] = fmaf(v[i], inv, acc[i]);
+            for (int i = 0; i < KP; ++i) acc[i] = fmaf(v[i], inv, acc[i]);
         }
         if (blk == 0 && gamma1 != nullptr) {               // gamma_0 = a_0 .* b_0 / sum
             const float g = ok ? ws_a[(size_t)b * T * K + lane] * ws_b[(size_t)b * T * K + lane] : 0.f;
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode,
     }
     if (ok) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) if (i < K) atomicAdd(&xi_s[i * K + lane], (double)acc[i]);
+        for (int i = 0; i < KP; ++i) if (i < K) atomicAdd(&xi_s[i * K + lane], (double)acc[i]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < K * K; i += blockDim.x) if (xi_s[i] != 0.0) atomicAdd(xi + i, xi_s[i]);
@@ -206,6 +207,26 @@ __global__ void __launch_bounds__(512) bw_gmm_stats_kernel(const float *x, const
     }
 }
 
+template <int KP>
+static int launch_xi_kp(const float *emis, int mode, float eps, const float *trans, const float *ws_a, const float *ws_b,
+                        const float *wseq, int B, int T, int K, double *xi, double *gamma1, cudaStream_t s) {
+    const int fpw = 64, warps = 4;
+    const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
+    const int64_t n_warps = (int64_t)B * blocks_per_seq;
+    bw_xi_kernel<KP><<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), s>>>(
+        emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, fpw, xi, gamma1);
+    return check_launch("bw_xi_kernel");
+}
+
+static int launch_xi(const float *emis, int mode, float eps, const float *trans, const float *ws_a, const float *ws_b,
+                     const float *wseq, int B, int T, int K, double *xi, double *gamma1, cudaStream_t s) {
+    const int kp = pad4(K);
+#define XI_CASE(N) if (kp <= N) return launch_xi_kp<N>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, xi, gamma1, s)
+    XI_CASE(4); XI_CASE(8); XI_CASE(12); XI_CASE(16); XI_CASE(20); XI_CASE(24); XI_CASE(28);
+#undef XI_CASE
+    return launch_xi_kp<32>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, xi, gamma1, s);
+}
+
 }  // namespace hmmb200
 
 using namespace hmmb200;
@@ -258,12 +279,7 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const float *ws_a = (const float *)fb_workspace;
     const float *ws_b = (const float *)((const uint8_t *)fb_workspace + al(n * K * sizeof(float)));
-    const int fpw = 64, warps = 4;
-    const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
-    const int64_t n_warps = (int64_t)B * blocks_per_seq;
-    bw_xi_kernel<<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), s>>>(
-        emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, nullptr, B, T, K, fpw, xi, gamma1);
-    if (int rc = check_launch("bw_xi_kernel")) return rc;
+    if (int rc = launch_xi(emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, nullptr, B, T, K, xi, gamma1, s)) return rc;
     const int KCp = (K * C + BW_TC - 1) / BW_TC * BW_TC, Dp = (D + BW_TD - 1) / BW_TD * BW_TD;
     size_t smem = (size_t)BW_F * (KCp + 2 * Dp) * sizeof(float);
     smem = smem > 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float) ? smem : 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float);   // also the fold buffer
@@ -300,10 +316,5 @@ HMMB200_EXPORT int hmmb200_xi_sum_f32(const float *emis, int emis_mode, float fl
     auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const float *ws_a = (const float *)fb_workspace;
     const float *ws_b = (const float *)((const uint8_t *)fb_workspace + al(n * K * sizeof(float)));
-    const int fpw = 64, warps = 4;
-    const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
-    const int64_t n_warps = (int64_t)B * blocks_per_seq;
-    bw_xi_kernel<<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), (cudaStream_t)stream>>>(
-        emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, seq_weights, B, T, K, fpw, xi, gamma1);
-    return check_launch("bw_xi_kernel");
+    return launch_xi(emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, seq_weights, B, T, K, xi, gamma1, (cudaStream_t)stream);
 }

@@ -385,17 +385,29 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     double *pf_Bg = pf_E + HSF_PF * 32;         // [PF][32]
     float *pf_f = reinterpret_cast<float *>(pf_Bg + HSF_PF * 32);   // [PF][32]
     int *pf_k = reinterpret_cast<int *>(pf_f + HSF_PF * 32);        // [PF]
-    const int b = blockIdx.x, s = threadIdx.x;
+    // LPS lanes per state (K = 10 -> 3, K = 12 or 16 -> 2, K <= 8 -> 4, K > 16 -> 1): lane (s, r) takes the durations
+    // d = 1 + r, 1 + r + LPS, ... of state s, so the Dmax-long inner loops shrink by LPS and the partial sums meet in shuffles
+    const int LPS = (K <= 8) ? 4 : ((K <= 10) ? 3 : ((K <= 16) ? 2 : 1));
+    const int b = blockIdx.x, lane_id = threadIdx.x;
+    const int s = lane_id / LPS, r = lane_id % LPS;
     const bool ok = s < K;
+    const bool lead = ok && r == 0;                          // one lane per state does the stores
     const float *f = p.f + (size_t)b * T * K;
     const size_t base = (size_t)b * T;
-    for (int i = s; i < K * K; i += 32) A_s[i] = exp((double)p.logA[i]);
-    if (ok) {
+    for (int i = lane_id; i < K * K; i += 32) A_s[i] = exp((double)p.logA[i]);
+    if (lead) {
         const double c = p.segc ? exp((double)p.segc[s]) : 1.0;
         for (int d = 0; d < Dm; ++d) durc[d * K + s] = exp((double)p.logdur[s * Dm + d]) * c;
         for (int d = 0; d < Dm; ++d) ring[d * K + s] = 0.0;
     }
     __syncwarp();
+    // sum of the LPS lanes of a state, identical in all of them (fixed order)
+    auto group_sum = [&](double v) {
+        const int g0 = ok ? s * LPS : lane_id;
+        double t = __shfl_sync(FULL_MASK, v, g0);
+        for (int i = 1; i < LPS; ++i) t += __shfl_sync(FULL_MASK, v, ok ? g0 + i : lane_id);
+        return ok ? t : 0.0;
+    };
     // a shared power-of-two exponent keeps the ring near 1: rescale when the newest values drift by more than 2^24
     auto rescale = [&](double &v, int &kexp) -> double {
         const double mx = warp_max_d(ok ? v : 0.0);
@@ -404,7 +416,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
             if (ex > 24 || ex < -24) {
                 const double sc = scalbn(1.0, -ex);
                 v *= sc;
-                if (ok) for (int d = 0; d < Dm; ++d) ring[d * K + s] *= sc;
+                if (ok) for (int d = r; d < Dm; d += LPS) ring[d * K + s] *= sc;
                 kexp += ex;
                 return sc;
             }
@@ -417,13 +429,14 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     double Mc = 0.0;
     int cur = 0;                                            // t % Dm, kept without integer division
     auto pf_fwd = [&](int t) {
-        if (ok && t < T) hs_cp4(pf_f + (t % HSF_PF) * 32 + s, f + (size_t)t * K + s);
+        if (lead && t < T) hs_cp4(pf_f + (t % HSF_PF) * 32 + s, f + (size_t)t * K + s);
         hs_commit();
     };
     for (int t = 0; t < HSF_PF - 1; ++t) pf_fwd(t);
     for (int t = 0; t < T; ++t) {
         pf_fwd(t + HSF_PF - 1);
         hs_wait();
+        __syncwarp();                                       // the lead lane's copy is read by the state's other lanes
         const float ft = ok ? pf_f[(t % HSF_PF) * 32 + s] : -INFINITY;
         float m = ft;
 #pragma unroll
@@ -445,57 +458,54 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
             }
             // the ring holds RUNNING segment products R[st] = Bg(st,s) prod_{tau=st..t} b~_tau(s): one independent multiply
             // per open segment and step instead of a dependent prefix-product chain over the durations
-            ring[cur * K + s] = bg;
-            double e0 = 0.0, e1 = 0.0;
-            int st = cur;                                   // (t - d + 1) % Dm
+            if (r == 0) ring[cur * K + s] = bg;             // duration 1 belongs to lane r = 0, which reads it back below
+            double e0 = 0.0;
+            int st = cur - r;                               // slot of duration d = 1 + r: (t - d + 1) % Dm
+            if (st < 0) st += Dm;
             const int nd = min(Dm, t + 1);
-            for (int d = 1; d <= nd; d += 2) {
-                const int st1 = (st == 0) ? Dm - 1 : st - 1;
+            for (int d = 1 + r; d <= nd; d += LPS) {
                 const double r0 = ring[st * K + s] * bq;
                 ring[st * K + s] = r0;
                 e0 = fma(r0, durc[(d - 1) * K + s], e0);
-                if (d + 1 <= nd) {
-                    const double r1 = ring[st1 * K + s] * bq;
-                    ring[st1 * K + s] = r1;
-                    e1 = fma(r1, durc[d * K + s], e1);
-                }
-                st = (st1 == 0) ? Dm - 1 : st1 - 1;
+                st -= LPS;
+                if (st < 0) st += Dm;
             }
-            e = e0 + e1;
+            e = e0;
         }
+        e = group_sum(e);
         __syncwarp();                                       // every lane has read E(t-1,.)
         bg *= rescale(e, kf);
-        if (ok) {
+        if (lead) {
             vec[s] = e;
             p.ws_E[(base + t) * K + s] = e;
             p.ws_Bg[(base + t) * K + s] = bg;
         }
-        if (s == 0) { p.ws_k[base + t] = kf; p.ws_M[base + t] = Mc; }
+        if (lane_id == 0) { p.ws_k[base + t] = kf; p.ws_M[base + t] = Mc; }
         __syncwarp();
         if (++cur == Dm) cur = 0;
     }
-    double sumE = ok ? vec[s] : 0.0;
+    double sumE = lead ? vec[s] : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sumE += __shfl_xor_sync(FULL_MASK, sumE, o);
     const int kfT = kf;
     const double Mtot = Mc;
-    if (s == 0) p.total[b] = (float)(log(sumE) + 0.69314718055994530942 * (double)kfT + Mtot);
+    if (lane_id == 0) p.total[b] = (float)(log(sumE) + 0.69314718055994530942 * (double)kfT + Mtot);
     const double inv = 1.0 / sumE;
 
     // ---------------- backward + begin/end posteriors ----------------
-    if (ok) for (int d = 0; d < Dm; ++d) ring[d * K + s] = 0.0;
+    if (lead) for (int d = 0; d < Dm; ++d) ring[d * K + s] = 0.0;
     __syncwarp();
     int kb = 0;
     cur = (T - 1) % Dm;
     auto pf_bwd = [&](int t) {                              // frame t, slot t % PF
         if (t >= 0) {
             const int sl = t % HSF_PF;
-            if (ok) {
+            if (lead) {
                 hs_cp4(pf_f + sl * 32 + s, f + (size_t)t * K + s);
                 hs_cp8(pf_E + sl * 32 + s, p.ws_E + (base + t) * K + s);
                 hs_cp8(pf_Bg + sl * 32 + s, p.ws_Bg + (base + t) * K + s);
             }
-            if (s == 0) hs_cp4(pf_k + sl, p.ws_k + base + t);
+            if (lane_id == 0) hs_cp4(pf_k + sl, p.ws_k + base + t);
         }
         hs_commit();
     };
@@ -525,27 +535,24 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
                 be = scalbn(1.0, -kb);
             }
             // ring: Q[en] = bend(en,s) prod_{tau=t..en} b~_tau(s), updated by one multiply per open segment
-            ring[cur * K + s] = be;
-            double b0 = 0.0, b1 = 0.0;
-            int en = cur;                                   // (t + d - 1) % Dm
+            if (r == 0) ring[cur * K + s] = be;
+            double b0 = 0.0;
+            int en = cur + r;                               // slot of duration d = 1 + r: (t + d - 1) % Dm
+            if (en >= Dm) en -= Dm;
             const int nd = min(Dm, T - t);
-            for (int d = 1; d <= nd; d += 2) {
-                const int en1 = (en + 1 == Dm) ? 0 : en + 1;
+            for (int d = 1 + r; d <= nd; d += LPS) {
                 const double q0 = ring[en * K + s] * bq;
                 ring[en * K + s] = q0;
                 b0 = fma(q0, durc[(d - 1) * K + s], b0);
-                if (d + 1 <= nd) {
-                    const double q1 = ring[en1 * K + s] * bq;
-                    ring[en1 * K + s] = q1;
-                    b1 = fma(q1, durc[d * K + s], b1);
-                }
-                en = (en1 + 1 == Dm) ? 0 : en1 + 1;
+                en += LPS;
+                if (en >= Dm) en -= Dm;
             }
-            bb = b0 + b1;
+            bb = b0;
         }
+        bb = group_sum(bb);
         __syncwarp();                                       // every lane has read bbeg(t+1,.)
         be *= rescale(bb, kb);
-        if (ok) {
+        if (lead) {
             vec[s] = bb;
             const size_t o = (base + t) * K + s;
             const int sl = t % HSF_PF;
@@ -561,7 +568,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     }
     // ---------------- state-occupancy posterior (same thread wrote both arrays: program order suffices) ----------------
     // (loads are batched 8 frames at a time: a load-use-store loop over T would expose the global latency 2T times)
-    if (ok) {
+    if (lead) {
         double cum = 0.0;
         for (int t0 = 0; t0 < T; t0 += 8) {
             float gb[8], pe[8];
