@@ -34,7 +34,7 @@ def _exchange_ok(ws):
 
 @pytest.mark.parametrize("K,T,B", [(33, 7, 1), (40, 50, 3), (64, 64, 4), (65, 30, 5), (100, 45, 2), (128, 33, 9),
                                    (129, 20, 4), (200, 25, 3), (256, 40, 2), (257, 12, 1), (384, 18, 6), (500, 16, 2),
-                                   (512, 30, 5), (512, 1, 2), (48, 2, 1)])
+                                   (512, 30, 5), (512, 1, 2), (48, 2, 1), (512, 10, 130), (64, 20, 150)])
 def test_largek_viterbi_bit_exact(hm, K, T, B):
     rng = np.random.default_rng(7000 + K + T)
     logb = (rng.standard_normal((B, T, K)) * 3.0).astype(np.float32)
@@ -61,7 +61,7 @@ def test_largek_viterbi_bit_exact(hm, K, T, B):
 
 
 @pytest.mark.parametrize("K,T,B", [(33, 9, 2), (50, 60, 3), (64, 100, 4), (96, 40, 5), (130, 50, 2), (256, 64, 3),
-                                   (300, 30, 1), (512, 80, 6), (512, 1, 1)])
+                                   (300, 30, 1), (512, 80, 6), (512, 1, 1), (512, 8, 130)])
 @pytest.mark.parametrize("mode", ["prob", "log", "norm_floor"])
 def test_largek_forward_backward_vs_float64(hm, K, T, B, mode):
     rng = np.random.default_rng(8000 + K + T)
