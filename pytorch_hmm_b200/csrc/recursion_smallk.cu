@@ -459,15 +459,19 @@ __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
         for (int f = 0; f < COMBINE_FPT; ++f) {
             const int64_t idx = idx0 + f * stride;
             if (idx >= p.n_frames) continue;
+            // explicit fused / rounded operations in a fixed order: the result of a frame must not depend on which unrolled
+            // copy (f) it lands in, i.e. on how the batch was sharded
             float Z = 0.f;
 #pragma unroll
-            for (int q = 0; q < KV; ++q)
-                Z += xa[f][q].x * xb[f][q].x + xa[f][q].y * xb[f][q].y + xa[f][q].z * xb[f][q].z + xa[f][q].w * xb[f][q].w;
-            const float inv = 1.f / Z, ea = expf(la[f]), eb = expf(lb[f]);
+            for (int q = 0; q < KV; ++q)               // KV independent 4-term chains, then one rounded add each
+                Z = __fadd_rn(Z, fmaf(xa[f][q].x, xb[f][q].x, fmaf(xa[f][q].y, xb[f][q].y,
+                                 fmaf(xa[f][q].z, xb[f][q].z, __fmul_rn(xa[f][q].w, xb[f][q].w)))));
+            const float inv = __fdiv_rn(1.f, Z), ea = expf(la[f]), eb = expf(lb[f]);
+            auto g = [&](float u, float v) { return __fmul_rn(__fmul_rn(u, v), inv); };
 #pragma unroll
             for (int q = 0; q < KV; ++q) {
                 const float4 x = xa[f][q], y = xb[f][q];
-                if (p.gamma) __stcs(reinterpret_cast<float4 *>(p.gamma + idx * K) + q, make_float4(x.x * y.x * inv, x.y * y.y * inv, x.z * y.z * inv, x.w * y.w * inv));
+                if (p.gamma) __stcs(reinterpret_cast<float4 *>(p.gamma + idx * K) + q, make_float4(g(x.x, y.x), g(x.y, y.y), g(x.z, y.z), g(x.w, y.w)));
                 if (p.fwd) __stcs(reinterpret_cast<float4 *>(p.fwd + idx * K) + q, make_float4(x.x * ea, x.y * ea, x.z * ea, x.w * ea));
                 if (p.bwd) __stcs(reinterpret_cast<float4 *>(p.bwd + idx * K) + q, make_float4(y.x * eb, y.y * eb, y.z * eb, y.w * eb));
                 if (p.log_alpha) __stcs(reinterpret_cast<float4 *>(p.log_alpha + idx * K) + q,
@@ -484,11 +488,11 @@ __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
             const float la = p.ws_la[idx], lb = p.ws_lb[idx];
             const float ea = expf(la), eb = expf(lb);
             float Z = 0.f;
-            for (int k = 0; k < K; ++k) Z += a[k] * b[k];
-            const float inv = 1.f / Z;
+            for (int k = 0; k < K; ++k) Z = fmaf(a[k], b[k], Z);
+            const float inv = __fdiv_rn(1.f, Z);
             for (int k = 0; k < K; ++k) {
                 float x = a[k], y = b[k];
-                if (p.gamma) p.gamma[idx * K + k] = x * y * inv;
+                if (p.gamma) p.gamma[idx * K + k] = __fmul_rn(__fmul_rn(x, y), inv);
                 if (p.fwd) p.fwd[idx * K + k] = x * ea;
                 if (p.bwd) p.bwd[idx * K + k] = y * eb;
                 if (p.log_alpha) p.log_alpha[idx * K + k] = logf(x) + la;

@@ -189,3 +189,36 @@ def test_streaming_processor_api(hm):
     p.reset_streaming_state()
     assert p.process_chunk(torch.randn(4, 8).cuda()).status == "buffering"
     assert isinstance(p.get_performance_stats(), dict)
+
+
+# ---- the throughput front end returns exactly what the plain calls return -------------------------------------------------
+def test_engine_sharded_and_host_paths_match_single_pass_bit_for_bit(hm):
+    """HMMInferenceEngine cuts the batch into shards on several streams (and, with host_io, pipelines the PCIe copies):
+    utterances are independent, so every output must equal the un-sharded pass bit for bit -- including the posterior,
+    whose arithmetic must not depend on where a frame lands in a launch."""
+    from pytorch_hmm_b200.engine import HMMInferenceEngine
+    torch.manual_seed(9)
+    K, C, D, B, T = 12, 4, 80, 10, 333
+    layer = hm.MixtureGaussianHMMLayer(K, D, num_components=C).cuda().eval()
+    x = torch.randn(B, T, D).cuda() + layer.means.detach()[torch.randint(0, K, (B, T)), torch.randint(0, C, (B, T))]
+    whole = HMMInferenceEngine(layer, B, T, shard=B, n_streams=1)
+    ref = {k: v.clone() for k, v in whole.run_device(x).items()}
+    torch.cuda.synchronize()
+    sharded = HMMInferenceEngine(layer, B, T, shard=3, n_streams=3, host_io=True)
+    out = sharded.run_device(x)
+    torch.cuda.synchronize()
+    for k in ("posterior", "forward", "backward", "log_delta", "states", "score", "loglik"):
+        assert torch.equal(out[k], ref[k]), k
+    xh = x.cpu().pin_memory()
+    host = {k: torch.empty(ref[k].shape, dtype=ref[k].dtype).pin_memory() for k in ("posterior", "log_delta", "states")}
+    sharded.run_host(xh, host)
+    torch.cuda.synchronize()
+    for k, v in host.items():
+        assert torch.equal(v, ref[k].cpu()), k
+    g = whole.capture_device(x)
+    whole.out["posterior"].zero_()
+    g.replay(); torch.cuda.synchronize()
+    assert torch.equal(whole.out["posterior"], ref["posterior"])
+    # and the plain drop-in calls agree with the engine
+    st, sc = layer(x, return_log_probs=True)
+    assert torch.equal(st, ref["states"]) and torch.equal(sc.detach(), ref["score"])
