@@ -57,7 +57,8 @@ SIGNATURES = {
 
 
 def lib_path() -> str:
-    return _build.lib_path()
+    # HMMB200_LIB_PATH: load another build of the same ABI (A/B timing of kernel variants); default = the in-tree build
+    return os.environ.get("HMMB200_LIB_PATH") or _build.lib_path()
 
 
 def load(build_if_missing: bool = True):

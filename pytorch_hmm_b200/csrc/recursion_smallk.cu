@@ -461,13 +461,15 @@ __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
             if (idx >= p.n_frames) continue;
             // explicit fused / rounded operations in a fixed order: the result of a frame must not depend on which unrolled
             // copy (f) it lands in, i.e. on how the batch was sharded
-            float Z = 0.f;
+            float2 z2 = make_float2(0.f, 0.f);            // explicit packed FMAs: same instruction sequence in every copy
 #pragma unroll
-            for (int q = 0; q < KV; ++q)               // KV independent 4-term chains, then one rounded add each
-                Z = __fadd_rn(Z, fmaf(xa[f][q].x, xb[f][q].x, fmaf(xa[f][q].y, xb[f][q].y,
-                                 fmaf(xa[f][q].z, xb[f][q].z, __fmul_rn(xa[f][q].w, xb[f][q].w)))));
-            const float inv = __fdiv_rn(1.f, Z), ea = expf(la[f]), eb = expf(lb[f]);
-            auto g = [&](float u, float v) { return __fmul_rn(__fmul_rn(u, v), inv); };
+            for (int q = 0; q < KV; ++q) {
+                z2 = ffma2(make_float2(xa[f][q].x, xa[f][q].y), make_float2(xb[f][q].x, xb[f][q].y), z2);
+                z2 = ffma2(make_float2(xa[f][q].z, xa[f][q].w), make_float2(xb[f][q].z, xb[f][q].w), z2);
+            }
+            const float Z = __fadd_rn(z2.x, z2.y);
+            const float inv = 1.f / Z, ea = expf(la[f]), eb = expf(lb[f]);
+            auto g = [&](float u, float v) { return u * v * inv; };   // products only: nothing to contract, packs as f32x2
 #pragma unroll
             for (int q = 0; q < KV; ++q) {
                 const float4 x = xa[f][q], y = xb[f][q];
