@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(512) bw_gmm_stats_kernel(const float *x, const
     const int tid = threadIdx.x;
     const int fg = tid / cells, cell = tid % cells;        // the launch sizes the CTA to cells * FG threads
     const int gc = blockIdx.y * ncg + cell / ndg, gd = cell % ndg;
-    const bool live = gc < ncg_all;
+    const bool live = gc < ncg_all && fg < FG;               // the CTA is rounded up to whole warps: surplus threads only help staging
     float ax[BW_TC][BW_TD], axx[BW_TC][BW_TD], aocc[BW_TC];
 #pragma unroll
     for (int i = 0; i < BW_TC; ++i) {
@@ -135,22 +135,26 @@ __global__ void __launch_bounds__(512) bw_gmm_stats_kernel(const float *x, const
         const int64_t base = tile * BW_F;
         const int nf = (int)min((int64_t)BW_F, n - base);
         __syncthreads();
-        for (int i = tid; i < BW_F * KCp; i += blockDim.x) {
-            const int f = i / KCp, kc = i % KCp;
-            float w = 0.f;
-            if (f < nf && kc < KC) {
-                const int k = kc / C;
-                const int64_t fr = base + f;
-                w = gamma[fr * K + k] * expf(comp[fr * KC + kc] - logb[fr * K + k]);      // gamma_t(k) * responsibility(c | k)
+        // staging: one warp per frame row (no integer division by runtime sizes on the fill path)
+        for (int f = tid >> 5; f < BW_F; f += (int)(blockDim.x >> 5)) {
+            const int lane = tid & 31;
+            const bool fok = f < nf;
+            const int64_t fr = base + (fok ? f : 0);
+            for (int kc = lane; kc < KCp; kc += 32) {
+                float w = 0.f;
+                if (fok && kc < KC) {
+                    const int k = kc / C;
+                    w = gamma[fr * K + k] * expf(comp[fr * KC + kc] - logb[fr * K + k]);   // gamma_t(k) * responsibility(c | k)
+                }
+                w_s[f * KCp + kc] = w;
             }
-            w_s[i] = w;
-        }
-        for (int i = tid; i < BW_F * Dp; i += blockDim.x) {
-            const int f = i / Dp, d = i % Dp;
-            const float v = (f < nf && d < D) ? x[(base + f) * D + d] : 0.f;
-            x_s[i] = v; x2_s[i] = v * v;
+            for (int d = lane; d < Dp; d += 32) {
+                const float v = (fok && d < D) ? x[fr * D + d] : 0.f;
+                x_s[f * Dp + d] = v; x2_s[f * Dp + d] = v * v;
+            }
         }
         __syncthreads();
+#pragma unroll 2
         for (int f = fg; live && f < nf; f += FG) {
             const float4 w4 = *reinterpret_cast<const float4 *>(w_s + f * KCp + gc * BW_TC);
             const float4 xa = *reinterpret_cast<const float4 *>(x_s + f * Dp + gd * BW_TD);
@@ -296,7 +300,7 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
     const int cells = ((ncg_all + gy - 1) / gy) * ndg;
     int FG = 512 / cells;                                           // frame sub-sequences per tile: up to 512 threads per CTA
     FG = FG < 1 ? 1 : (FG > 8 ? 8 : FG);
-    const int threads = cells * FG;
+    const int threads = (cells * FG + 31) & ~31;                   // whole warps (the staging loops are warp-per-row)
     dim3 grid((unsigned)min((int64_t)sms, n_tiles), (unsigned)gy);      // one CTA per SM (128 registers x ~480 threads)
     bw_gmm_stats_kernel<<<grid, threads, smem, s>>>(x, comp, logb, gamma, (int64_t)n, K, C, D, FG, occ, sx, sxx);
     return check_launch("bw_gmm_stats_kernel");
