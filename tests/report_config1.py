@@ -2,7 +2,7 @@
 GPU times (CUDA events, inputs resident) and, with --cpu, the op-for-op CPU port of the reference on the same inputs."""
 import argparse, json, os, sys, time
 import torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import pytorch_hmm_b200 as hm
 
 K, D, B, T = 10, 80, 32, 1000

@@ -3,7 +3,7 @@ recursion like the reference's vs float64, engine vs that reference-like recursi
 bit-exactness counts.  Uses oracle/ (checker) on the GPU box; prints JSON."""
 import json, math, os, sys
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import pytorch_hmm_b200 as hm
 from oracle import c_oracle, ref_port
 import bench
