@@ -37,10 +37,17 @@ namespace hmmb200 {
 constexpr int LK_NSQ = 4;                       // sequences per group
 constexpr int LK_NG = 2;                        // independent sequence groups per cluster (software-pipelined)
 constexpr int LK_NC = 64;                       // output states per CTA
-constexpr int LK_KS = 32;                       // source states per warp (k-slice)
-constexpr int LK_NW = 16;                       // warps per CTA = k-slices
+constexpr int LK_KS = 64;                       // source states per compute warp (k-slice) = one CTA's block of the vector
+constexpr int LK_NWC = 8;                       // compute warps per CTA (warps 0-7); warps 8-15 are the final warps
+constexpr int LK_KH = LK_KS / 2;                // source states per half-warp
+constexpr int LK_NSL = 2 * LK_NWC;              // k-slices of partial sums: one per compute half-warp
+constexpr int LK_NW = 2 * LK_NWC;               // warps per CTA
 constexpr int LK_THREADS = LK_NW * 32;          // 512
-constexpr int LK_KMAX = LK_NW * LK_KS;          // 512
+constexpr int LK_KMAX = LK_NWC * LK_KS;         // 512
+constexpr int LK_REGS_COMPUTE = 184;            // setmaxnreg: 256 x 184 + 256 x 72 = 64 K registers
+constexpr int LK_REGS_FINAL = 72;
+constexpr int LK_BAR_PART = 1;                  // named barriers 1 + g: partial sums of group g are in shared memory
+constexpr int LK_BAR_FINAL = 1 + LK_NG;         // the 256 final threads, between staging and the push
 constexpr int LK_BLK = LK_NC + 4;               // floats per (CTA, sequence) block: 64 states + 2 local maxima + pad (272 B)
 constexpr int LK_CSMAX = LK_KMAX / LK_NC;       // 8 CTAs per cluster at most (portable cluster size)
 constexpr int LK_FINAL = LK_NSQ * LK_NC;        // 256 final threads: (sequence, output state)
@@ -120,12 +127,10 @@ __device__ __forceinline__ void lk_cp_wait() { asm volatile("cp.async.wait_group
 
 struct LkSmem {
     float vec[LK_NG][2][LK_CSMAX][LK_NSQ][LK_BLK];   // the exchanged state vector: one block per source CTA, double-buffered
-    float part[2][LK_NW][LK_NSQ][LK_NC];             // per-k-slice partial sums (alternating buffers)
+    float part[LK_NG][LK_NSL][LK_NSQ][LK_NC];        // per-k-slice partial sums, one buffer per group
     float stage[LK_NG][2][LK_NSQ][LK_BLK];           // this CTA's new block before it is pushed (double-buffered)
     float eraw[LK_NG][LK_PF][LK_FINAL];              // prefetched emissions, one slot per final thread
     float mraw[LK_NG][LK_PF][LK_FINAL];              // prefetched per-frame max
-    double msum[LK_NG][LK_NSQ];                      // running sum of per-frame log scales (one owner thread each)
-    float la_last[LK_NG][LK_NSQ];                    // log scale of the last forward frame (for loglik)
     uint64_t bar[LK_NG][2];
 };
 
@@ -133,12 +138,22 @@ struct LkSmem {
 __device__ long long lk_trace_buf[8 * 8];
 #define LK_TRACE(slot)                                                                          \
     do {                                                                                        \
-        if (p.trace && g == 0 && blockIdx.x == 0 && tid == 0 && t >= 64 && t < 72) lk_trace_buf[(t - 64) * 8 + (slot)] = clock64(); \
+        if (p.trace && g == 0 && blockIdx.x == 0 && (tid & (LK_FINAL - 1)) == 0 && t >= 64 && t < 72) lk_trace_buf[(t - 64) * 8 + (slot)] = clock64(); \
     } while (0)
 
 // One cluster = CS CTAs x LK_NG groups of LK_NSQ sequences.  The groups are independent recursions that share the CTA's
-// register-resident slab of P: while group g's new block is in flight through DSMEM, the CTA computes group g+1, so the
-// exchange latency is hidden behind arithmetic instead of being waited for.
+// register-resident slab of P.  Warp roles (register budgets moved between them with setmaxnreg):
+//   warps 0-7  COMPUTE: warp w keeps P[64w..64w+63][the CTA's 64 output states] (128 registers per thread: 4 output
+//              states x 32 source states per lane) and, per
+//              (step, group), multiplies CTA w's block of the previous vector into it -- nothing else;
+//   warps 8-15 FINAL: one thread per (sequence, output state) adds the 16 k-slice partials, applies emission and scaling,
+//              stages the CTA's new block and pushes it to the cluster.
+// While the final warps finish group g, the compute warps are already on group g+1, and group g's exchange flies during
+// both: the FMA-bound phase and the latency-bound phase overlap instead of alternating.  (The first version used all 16
+// warps for the product and half of them for each group's finals: 1 800-cycle finals serialised with 1 150-cycle products.)
+__device__ __forceinline__ void lk_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void lk_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
 template <int MODE>
 __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     extern __shared__ __align__(16) uint8_t lk_smem_raw[];
@@ -152,176 +167,204 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     const int cluster_id = blockIdx.x / CS;
     const int seq0 = cluster_id * (LK_NSQ * LK_NG);
     const int col0 = rank * LK_NC;
-    const int nkw = (K + LK_KS - 1) / LK_KS;                 // active k-slices
     const float PADV = VIT ? -INFINITY : 0.f;
     const int n_groups = min(LK_NG, (B - seq0 + LK_NSQ - 1) / LK_NSQ);   // groups of this cluster that hold sequences
 
-    // ---- the CTA's slab of the transition matrix, in registers: warp = source slice, lane = two output states -------
-    // forward / viterbi: out(j) = sum_i v(i) M(i,j)  -> M[i][j];   backward: out(i) = sum_j M(i,j) v(j) -> M[out][src]
-    float2 P0[LK_KS / 2], P1[LK_KS / 2];
-    {
-        const int o0 = col0 + 2 * lane, o1 = o0 + 1;
-#pragma unroll
-        for (int i = 0; i < LK_KS / 2; ++i) {
-            const int s0 = warp * LK_KS + 2 * i, s1 = s0 + 1;
-            auto ld = [&](int src, int out) -> float {
-                if (src >= K || out >= K) return PADV;
-                return (DIR == 0) ? __ldg(p.trans + (size_t)src * K + out) : __ldg(p.trans + (size_t)out * K + src);
-            };
-            P0[i] = make_float2(ld(s0, o0), ld(s1, o0));
-            P1[i] = make_float2(ld(s0, o1), ld(s1, o1));
-        }
-    }
-
-    // ---- final-thread identity: warps 8g..8g+7 finish group g; thread = (sequence fs of the group, output state fc) ----
-    static_assert(LK_NG * LK_FINAL == LK_THREADS, "one final thread per (group, sequence, output state)");
-    const int fg = tid / LK_FINAL, ft = tid % LK_FINAL, fwarp = ft >> 5;
-    const int fs = ft / LK_NC, fc = ft % LK_NC;
-    const int gcol = col0 + fc;
-    const bool need_m = (p.rowmax != nullptr);
-    const bool add_m = !VIT && ((p.mode == HMMB200_EMIS_LOG) || (p.mode == HMMB200_EMIS_LOG_NORM_FLOOR && p.add_rowmax));
-    auto frame_of = [&](int t) { return (DIR == 0) ? t : T - 1 - t; };
-    auto prefetch = [&](int t) {
-        if (fg < n_groups && t < T) {
-            const int f = frame_of(t);
-            const int sq = seq0 + fg * LK_NSQ + fs;
-            const bool okk = sq < B && gcol < K;
-            lk_cp_async4(&sm.eraw[fg][t % LK_PF][ft], p.emis + ((size_t)(okk ? sq : 0) * T + f) * K + (okk ? gcol : 0));
-            if (need_m) lk_cp_async4(&sm.mraw[fg][t % LK_PF][ft], p.rowmax + (size_t)(sq < B ? sq : 0) * T + f);
-        }
-        lk_cp_commit();
-    };
-
     for (int i = tid; i < LK_NG * 2 * LK_CSMAX * LK_NSQ * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
     for (int i = tid; i < LK_NG * 2 * LK_NSQ * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
-    if (tid < LK_NG * LK_NSQ) (&sm.msum[0][0])[tid] = 0.0;
+    for (int i = tid; i < LK_NG * LK_NSL * LK_NSQ * LK_NC; i += LK_THREADS) (&sm.part[0][0][0][0])[i] = PADV;   // idle k-slices: neutral element
     if (tid == 0) {
 #pragma unroll
         for (int g = 0; g < LK_NG; ++g) { lk_mbar_init(&sm.bar[g][0], 1); lk_mbar_init(&sm.bar[g][1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int t = 0; t < LK_PF - 1; ++t) prefetch(t);
     cluster.sync();                                          // every CTA's mbarriers exist before anyone pushes
 
     // bytes every receiver gets per step and group: one [NSQ][BLK] block from each of the CS CTAs
     constexpr uint32_t BLOCK_BYTES = LK_NSQ * LK_BLK * sizeof(float);
     const uint32_t tx_bytes = (uint32_t)CS * BLOCK_BYTES;
-
-    int ksum_own = 0;                                        // running power-of-two exponent of the thread's own group
     bool ok = true;
-    int pb = 0;                                              // partial-sum buffer, alternates every (step, group)
 
-    for (int t = 0; t < T; ++t) {
-        const int cur = t & 1, prv = cur ^ 1;
-        prefetch(t + LK_PF - 1);
-        lk_cp_wait<LK_PF - 1>();                             // this step's emissions have landed (own slots only)
+    if (warp < LK_NWC) {
+        // ================================ COMPUTE warps ================================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(LK_REGS_COMPUTE));
+        // forward / viterbi: out(j) = sum_i v(i) M(i,j)  -> M[i][j];   backward: out(i) = sum_j M(i,j) v(j) -> M[out][src]
+        // Lane (hw, c): FOUR output states 4c..4c+3 x the 32 source states of half hw of the warp's 64 (128 registers).
+        // One LDS.128 of the vector then feeds 8 packed FMAs -- with two output states per lane the product was bound
+        // by the shared-memory return path (a broadcast LDS.128 still delivers 512 B per warp), not by the FMA pipe.
+        const int hw = lane >> 4, c4 = (lane & 15) * 4;
+        float2 Pj[4][LK_KH / 2];
 #pragma unroll
-        for (int g = 0; g < LK_NG; ++g) {
-            if (g >= n_groups) continue;
-            LK_TRACE(0);
-            if (tid == 0) lk_mbar_expect_tx(&sm.bar[g][cur], tx_bytes);
-            if (t > 0) {
+        for (int j = 0; j < 4; ++j) {
+            const int out = col0 + c4 + j;
+#pragma unroll
+            for (int i = 0; i < LK_KH / 2; ++i) {
+                const int s0 = warp * LK_KS + hw * LK_KH + 2 * i, s1 = s0 + 1;
+                auto ld = [&](int src) -> float {
+                    if (src >= K || out >= K) return PADV;
+                    return (DIR == 0) ? __ldg(p.trans + (size_t)src * K + out) : __ldg(p.trans + (size_t)out * K + src);
+                };
+                Pj[j][i] = make_float2(ld(s0), ld(s1));
+            }
+        }
+        const bool active = warp < CS;                       // source states 64w.. exist
+        for (int t = 0; t < T; ++t) {
+            const int cur = t & 1, prv = cur ^ 1;
+#pragma unroll
+            for (int g = 0; g < LK_NG; ++g) {
+                if (g >= n_groups) continue;
+                LK_TRACE(0);
+                if (tid == 0) lk_mbar_expect_tx(&sm.bar[g][cur], tx_bytes);
+                if (t == 0) continue;                        // step 0 has no product
+                // (idle warps wait too: nobody may arrive on the named barrier twice within one of its phases)
                 if (ok) ok = lk_mbar_wait(&sm.bar[g][prv], ((t - 1) >> 1) & 1);   // after a time-out: drain without waiting
                 LK_TRACE(1);
-                if (warp < nkw) {
-                    const float *v = &sm.vec[g][prv][warp >> 1][0][(warp & 1) * LK_KS];   // states 32w.. live in CTA w/2's block
+                if (active) {
+                    const float *v = &sm.vec[g][prv][warp][0][hw * LK_KH];             // states 64w.. = CTA w's block
+                    float *po = &sm.part[g][2 * warp + hw][0][c4];
                     if (!VIT) {
-                        float2 a0[LK_NSQ], a1[LK_NSQ];
+                        float2 acc[LK_NSQ][4];
 #pragma unroll
-                        for (int s = 0; s < LK_NSQ; ++s) a0[s] = a1[s] = make_float2(0.f, 0.f);
+                        for (int s = 0; s < LK_NSQ; ++s)
 #pragma unroll
-                        for (int kk = 0; kk < LK_KS; kk += 4) {
+                            for (int j = 0; j < 4; ++j) acc[s][j] = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int kk = 0; kk < LK_KH; kk += 4) {
 #pragma unroll
                             for (int s = 0; s < LK_NSQ; ++s) {
                                 const float4 x = *reinterpret_cast<const float4 *>(v + s * LK_BLK + kk);
-                                a0[s] = lk_ffma2(make_float2(x.x, x.y), P0[kk / 2], a0[s]);
-                                a1[s] = lk_ffma2(make_float2(x.x, x.y), P1[kk / 2], a1[s]);
-                                a0[s] = lk_ffma2(make_float2(x.z, x.w), P0[kk / 2 + 1], a0[s]);
-                                a1[s] = lk_ffma2(make_float2(x.z, x.w), P1[kk / 2 + 1], a1[s]);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[s][j] = lk_ffma2(make_float2(x.x, x.y), Pj[j][kk / 2], acc[s][j]);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) acc[s][j] = lk_ffma2(make_float2(x.z, x.w), Pj[j][kk / 2 + 1], acc[s][j]);
                             }
                         }
 #pragma unroll
                         for (int s = 0; s < LK_NSQ; ++s)
-                            *reinterpret_cast<float2 *>(&sm.part[pb][warp][s][2 * lane]) =
-                                make_float2(a0[s].x + a0[s].y, a1[s].x + a1[s].y);
+                            *reinterpret_cast<float4 *>(po + s * LK_NC) = make_float4(acc[s][0].x + acc[s][0].y, acc[s][1].x + acc[s][1].y,
+                                                                                      acc[s][2].x + acc[s][2].y, acc[s][3].x + acc[s][3].y);
                     } else {
-                        float m0[LK_NSQ], m1[LK_NSQ];
+                        float m[LK_NSQ][4];
 #pragma unroll
-                        for (int s = 0; s < LK_NSQ; ++s) m0[s] = m1[s] = -INFINITY;
+                        for (int s = 0; s < LK_NSQ; ++s)
 #pragma unroll
-                        for (int kk = 0; kk < LK_KS; kk += 4) {
+                            for (int j = 0; j < 4; ++j) m[s][j] = -INFINITY;
+#pragma unroll
+                        for (int kk = 0; kk < LK_KH; kk += 4) {
 #pragma unroll
                             for (int s = 0; s < LK_NSQ; ++s) {
                                 const float4 x = *reinterpret_cast<const float4 *>(v + s * LK_BLK + kk);
-                                const float2 c0 = lk_fadd2(make_float2(x.x, x.y), P0[kk / 2]);
-                                const float2 c1 = lk_fadd2(make_float2(x.x, x.y), P1[kk / 2]);
-                                const float2 c2 = lk_fadd2(make_float2(x.z, x.w), P0[kk / 2 + 1]);
-                                const float2 c3 = lk_fadd2(make_float2(x.z, x.w), P1[kk / 2 + 1]);
-                                m0[s] = lk_fmax3(m0[s], c0.x, c0.y);
-                                m1[s] = lk_fmax3(m1[s], c1.x, c1.y);
-                                m0[s] = lk_fmax3(m0[s], c2.x, c2.y);
-                                m1[s] = lk_fmax3(m1[s], c3.x, c3.y);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 c0 = lk_fadd2(make_float2(x.x, x.y), Pj[j][kk / 2]);
+                                    const float2 c1 = lk_fadd2(make_float2(x.z, x.w), Pj[j][kk / 2 + 1]);
+                                    m[s][j] = lk_fmax3(m[s][j], c0.x, c0.y);
+                                    m[s][j] = lk_fmax3(m[s][j], c1.x, c1.y);
+                                }
                             }
                         }
 #pragma unroll
                         for (int s = 0; s < LK_NSQ; ++s)
-                            *reinterpret_cast<float2 *>(&sm.part[pb][warp][s][2 * lane]) = make_float2(m0[s], m1[s]);
+                            *reinterpret_cast<float4 *>(po + s * LK_NC) = make_float4(m[s][0], m[s][1], m[s][2], m[s][3]);
                     }
+                    LK_TRACE(2);
+                }
+                // (part[g] is free again by then: group g's next exchange, which the wait above needs, is pushed after its finals)
+                lk_bar_arrive(LK_BAR_PART + g, LK_THREADS);
+            }
+        }
+    } else {
+        // ================================ FINAL warps: thread = (sequence fs of the group, output state fc) ============
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LK_REGS_FINAL));
+        const int ft = tid - LK_FINAL, fwarp = ft >> 5;
+        const int fs = ft / LK_NC, fc = ft % LK_NC;
+        const int gcol = col0 + fc;
+        const bool need_m = (p.rowmax != nullptr);
+        auto frame_of = [&](int t) { return (DIR == 0) ? t : T - 1 - t; };
+        auto prefetch = [&](int t) {
+            if (t < T) {
+                const int f = frame_of(t);
+#pragma unroll
+                for (int g = 0; g < LK_NG; ++g) {
+                    if (g >= n_groups) continue;
+                    const int sq = seq0 + g * LK_NSQ + fs;
+                    const bool okk = sq < B && gcol < K;
+                    lk_cp_async4(&sm.eraw[g][t % LK_PF][ft], p.emis + ((size_t)(okk ? sq : 0) * T + f) * K + (okk ? gcol : 0));
+                    if (need_m) lk_cp_async4(&sm.mraw[g][t % LK_PF][ft], p.rowmax + (size_t)(sq < B ? sq : 0) * T + f);
                 }
             }
-            LK_TRACE(2);
-            __syncthreads();
-            LK_TRACE(4);
+            lk_cp_commit();
+        };
+        for (int t = 0; t < LK_PF - 1; ++t) prefetch(t);
+        int ksum_g[LK_NG] = {0, 0};                          // running power-of-two exponent per group
+        float *ws_l = (DIR == 0) ? p.ws_la : p.ws_lb;
 
-            if (fg == g) {
-                const int f = frame_of(t);
+        for (int t = 0; t < T; ++t) {
+            const int cur = t & 1, prv = cur ^ 1;
+            prefetch(t + LK_PF - 1);
+            lk_cp_wait<LK_PF - 1>();                         // this step's emissions have landed (own slots only)
+            const int f = frame_of(t);
+#pragma unroll
+            for (int g = 0; g < LK_NG; ++g) {
+                if (g >= n_groups) continue;
                 const int fseq = seq0 + g * LK_NSQ + fs;
                 const bool f_ok = fseq < B && gcol < K;
                 const float raw = sm.eraw[g][t % LK_PF][ft];
                 const float mf = need_m ? sm.mraw[g][t % LK_PF][ft] : 0.f;
-                float wv, pre = 0.f;                         // wv: the value pushed to the cluster
+                float bq = 0.f, lb = 0.f;                    // emission: probability form (fb) / log form (viterbi)
                 if (!VIT) {
-                    float bq;                                // emission in probability form
                     if (p.mode == HMMB200_EMIS_PROB_FLOOR) bq = raw + p.eps;
                     else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) bq = expf(raw) + p.eps;
                     else bq = expf(raw - mf) + ((p.mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? p.eps : 0.f);
                     if (!f_ok) bq = 0.f;
+                } else {                                     // the reference's formula per input kind
+                    if (p.mode == HMMB200_EMIS_LOG) lb = raw;
+                    else if (p.mode == HMMB200_EMIS_PROB_FLOOR) lb = logf(raw + p.eps);
+                    else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) lb = logf(expf(raw) + p.eps);
+                    else lb = logf(expf(raw - mf) + p.eps);
+                }
+                if (t > 0) {
+                    lk_bar_sync(LK_BAR_PART + g, LK_THREADS);                           // all k-slice partials are in part[g]
+                    if (ok) ok = lk_mbar_wait(&sm.bar[g][prv], ((t - 1) >> 1) & 1);     // the previous vector (its maxima) is visible
+                }
+                LK_TRACE(4);
+                float wv, pre = 0.f;                         // wv: the value pushed to the cluster
+                if (!VIT) {
                     float acc, r = 1.f;
                     if (t == 0) {
                         acc = (DIR == 0) ? (f_ok ? __ldg(p.init + gcol) : 0.f) : (f_ok ? 1.f : 0.f);
                     } else {
-                        float a4[4] = {0.f, 0.f, 0.f, 0.f};  // fixed summation order: deterministic
+                        float a4[4];                         // fixed summation order: deterministic
 #pragma unroll
-                        for (int w = 0; w < LK_NW; ++w)
-                            if (w < nkw) a4[w & 3] += sm.part[pb][w][fs][fc];
+                        for (int w = 0; w < LK_NSL; ++w) {
+                            const float x = sm.part[g][w][fs][fc];
+                            a4[w & 3] = (w < 4) ? x : a4[w & 3] + x;
+                        }
                         acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
                         // power-of-two normaliser from the largest entry of the previous vector (all CTAs' local maxima)
                         float m = 0.f;
 #pragma unroll
                         for (int q = 0; q < LK_CSMAX; ++q) {
                             const float2 y = *reinterpret_cast<const float2 *>(&sm.vec[g][prv][q][fs][LK_NC]);
-                            m = fmaxf(m, fmaxf(y.x, y.y));
+                            m = lk_fmax3(m, y.x, y.y);
                         }
                         const unsigned eb = __float_as_uint(m) >> 23;
-                        ksum_own += (int)eb - 127;
+                        ksum_g[g] += (int)eb - 127;
                         r = __uint_as_float((254u - eb) << 23);
                     }
                     pre = acc * r;                           // beta_t (scaled) for the backward sweep
                     wv = acc * (bq * r);
                 } else {
-                    float lb;                                // log emission, the reference's formula per input kind
-                    if (p.mode == HMMB200_EMIS_LOG) lb = raw;
-                    else if (p.mode == HMMB200_EMIS_PROB_FLOOR) lb = logf(raw + p.eps);
-                    else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) lb = logf(expf(raw) + p.eps);
-                    else lb = logf(expf(raw - mf) + p.eps);
                     float acc;
                     if (t == 0) {
                         acc = f_ok ? __ldg(p.init + gcol) : -INFINITY;
                     } else {
-                        float a4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+                        float a4[4];
 #pragma unroll
-                        for (int w = 0; w < LK_NW; ++w)
-                            if (w < nkw) a4[w & 3] = fmaxf(a4[w & 3], sm.part[pb][w][fs][fc]);
+                        for (int w = 0; w < LK_NSL; ++w) {
+                            const float x = sm.part[g][w][fs][fc];
+                            a4[w & 3] = (w < 4) ? x : fmaxf(a4[w & 3], x);
+                        }
                         acc = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
                     }
                     wv = f_ok ? __fadd_rn(acc, lb) : -INFINITY;   // delta_t = max_i(..) + log b_t  (hmm.py:168)
@@ -334,35 +377,23 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                 }
                 LK_TRACE(5);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async-proxy reads
-                asm volatile("bar.sync %0, %1;" ::"r"(1 + g), "n"(LK_FINAL) : "memory");   // this group's 256 final threads only
+                lk_bar_sync(LK_BAR_FINAL, LK_FINAL);
                 LK_TRACE(6);
                 // (the bulk copy is a per-warp uniform-datapath instruction: one destination per final warp)
                 if (lane == 0 && fwarp < CS)
                     lk_bulk_push(lk_mapa(lk_smem_u32(&sm.vec[g][cur][rank][0][0]), fwarp), lk_smem_u32(&sm.stage[g][cur][0][0]),
                                  BLOCK_BYTES, lk_mapa(lk_smem_u32(&sm.bar[g][cur]), fwarp));
                 LK_TRACE(7);
-                // ---- results to HBM and log-scale bookkeeping: after the push, off the step's critical path ----------
+                // ---- results to HBM: after the push, off the step's critical path.  The log scale goes out as the integer
+                // exponent; lk_logscale_kernel turns it into log units (and adds the per-frame maxima) in double afterwards.
                 if (f_ok) {
                     const size_t o = ((size_t)fseq * T + f) * K + gcol;
                     if (VIT) p.delta[o] = wv;
                     else if (DIR == 0) p.ws_a[o] = wv;
                     else p.ws_b[o] = pre;
                 }
-                if (!VIT && rank == 0 && fc == 0 && fseq < B) {
-                    double ms = sm.msum[g][fs];
-                    if (DIR == 0) {
-                        if (add_m) ms += (double)mf;
-                        const float la = (float)(ms + 0.69314718055994530942 * (double)ksum_own);
-                        p.ws_la[(size_t)fseq * T + f] = la;
-                        if (t == T - 1) sm.la_last[g][fs] = la;
-                    } else {
-                        p.ws_lb[(size_t)fseq * T + f] = (float)(ms + 0.69314718055994530942 * (double)ksum_own);
-                        if (add_m) ms += (double)mf;
-                    }
-                    if (add_m) sm.msum[g][fs] = ms;
-                }
+                if (!VIT && rank == 0 && fc == 0 && fseq < B) ws_l[(size_t)fseq * T + f] = __int_as_float(ksum_g[g]);
             }
-            pb ^= 1;
         }
     }
 
@@ -378,11 +409,41 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
             for (int k = lane; k < K; k += 32) tot += sm.vec[g][(T - 1) & 1][k / LK_NC][s][k % LK_NC];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(FULL_MASK, tot, o);
-            if (lane == 0) p.loglik[sq] = sm.la_last[g][s] + logf(tot);
+            if (lane == 0) p.loglik[sq] = logf(tot);         // lk_logscale_kernel adds the last frame's log scale
         }
     }
     if (!ok && p.err != nullptr) atomicExch(p.err, 1);
     cluster.sync();
+}
+
+// ----------------------------------------------------------------------------------------------------------------------
+// log scales (one warp per sequence): the sweeps leave the running power-of-two exponent k_t as an integer; this turns it
+// into log units, la_t = k_t ln 2 + sum of the per-frame maxima divided out so far (inclusive for the forward sweep,
+// exclusive for the backward one), in double, and adds the last forward scale to the log-likelihood.
+// ----------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) lk_logscale_kernel(float *ws_l, const float *rowmax, int T, int dir, int add_m, float *loglik) {
+    const int sq = blockIdx.x, lane = threadIdx.x;
+    float *l = ws_l + (size_t)sq * T;
+    const float *rm = rowmax + (size_t)sq * T;
+    double carry = 0.0;
+    for (int t0 = 0; t0 < T; t0 += 32) {
+        const int t = t0 + lane;
+        const int f = dir ? T - 1 - t : t;
+        const double m = (add_m && t < T) ? (double)rm[f] : 0.0;
+        double x = m;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double y = __shfl_up_sync(FULL_MASK, x, o);
+            if (lane >= o) x += y;
+        }
+        if (t < T) {
+            const double ms = carry + (dir ? x - m : x);
+            const float v = (float)(ms + 0.69314718055994530942 * (double)__float_as_int(l[f]));
+            l[f] = v;
+            if (loglik != nullptr && t == T - 1) loglik[sq] += v;
+        }
+        carry += __shfl_sync(FULL_MASK, x, 31);
+    }
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -605,11 +666,16 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
         if (int rc = check_launch("lk_rowmax_kernel")) return rc;
         p.rowmax = rowmax;
     }
+    const int add_m = (emis_mode == HMMB200_EMIS_LOG) || (emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR && add_rowmax);
     if (int rc = lk_launch<LK_FWD>(p, s)) return rc;
+    lk_logscale_kernel<<<(unsigned)B, 32, 0, s>>>(p.ws_la, rowmax, T, 0, add_m, loglik);
+    if (int rc = check_launch("lk_logscale_kernel")) return rc;
     if (gamma || fwd_prob || bwd_prob || log_alpha || log_beta) {
         LkParams q = p;
         q.loglik = nullptr;
         if (int rc = lk_launch<LK_BWD>(q, s)) return rc;
+        lk_logscale_kernel<<<(unsigned)B, 32, 0, s>>>(p.ws_lb, rowmax, T, 1, add_m, nullptr);
+        if (int rc = check_launch("lk_logscale_kernel")) return rc;
         LkCombineParams c;
         c.ws_a = p.ws_a; c.ws_b = p.ws_b; c.ws_la = p.ws_la; c.ws_lb = p.ws_lb; c.n_frames = (int64_t)n; c.K = K;
         c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
