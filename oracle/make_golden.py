@@ -52,6 +52,7 @@ def core(ref):
         ll = hmm.compute_likelihood(obs)
         out.update({f"{tag}_P": _np(P), f"{tag}_obs": _np(obs),
                     f"{tag}_log_P": _np(hmm.log_P), f"{tag}_log_p0": _np(hmm.log_p0),
+                    f"{tag}_log_obs": _np(torch.log(obs + 1e-8)),   # hmm.py:152, on the generating machine's ATen
                     f"{tag}_posterior": _np(post), f"{tag}_forward": _np(fwd), f"{tag}_backward": _np(bwd),
                     f"{tag}_states": _np(states), f"{tag}_log_delta": _np(delta), f"{tag}_likelihood": _np(ll)})
         if p0 is not None:
@@ -248,6 +249,7 @@ def largek(ref):
         post, fwd, bwd = hmm.forward_backward(obs)
         states, delta = hmm.viterbi_decode(obs)
         out.update({f"{tag}_P": _np(P), f"{tag}_obs": _np(obs), f"{tag}_log_P": _np(hmm.log_P), f"{tag}_log_p0": _np(hmm.log_p0),
+                    f"{tag}_log_obs": _np(torch.log(obs + 1e-8)),   # hmm.py:152, on the generating machine's ATen
                     f"{tag}_posterior": _np(post), f"{tag}_forward": _np(fwd), f"{tag}_backward": _np(bwd),
                     f"{tag}_states": _np(states), f"{tag}_log_delta": _np(delta),
                     f"{tag}_likelihood": _np(hmm.compute_likelihood(obs))})

@@ -34,7 +34,7 @@ namespace cg = cooperative_groups;
 
 namespace hmmb200 {
 
-constexpr int LK_NSQ = 4;                       // sequences per group
+constexpr int LK_NSQ_MAX = 4;                   // sequences per group: 4, or 3 when that spreads one wave of clusters over more SMs
 constexpr int LK_NG = 2;                        // independent sequence groups per cluster (software-pipelined)
 constexpr int LK_NC = 64;                       // output states per CTA
 constexpr int LK_KS = 64;                       // source states per compute warp (k-slice) = one CTA's block of the vector
@@ -50,7 +50,7 @@ constexpr int LK_BAR_PART = 1;                  // named barriers 1 + g: partial
 constexpr int LK_BAR_FINAL = 1 + LK_NG;         // the 256 final threads, between staging and the push
 constexpr int LK_BLK = LK_NC + 4;               // floats per (CTA, sequence) block: 64 states + 2 local maxima + pad (272 B)
 constexpr int LK_CSMAX = LK_KMAX / LK_NC;       // 8 CTAs per cluster at most (portable cluster size)
-constexpr int LK_FINAL = LK_NSQ * LK_NC;        // 256 final threads: (sequence, output state)
+constexpr int LK_FINAL = LK_NSQ_MAX * LK_NC;    // 256 final threads: (sequence, output state); the last 64 idle when NSQ = 3
 constexpr int LK_PF = 8;                        // emission prefetch distance in steps
 
 enum { LK_FWD = 0, LK_BWD = 1, LK_VIT = 2 };
@@ -125,10 +125,11 @@ __device__ __forceinline__ void lk_cp_commit() { asm volatile("cp.async.commit_g
 template <int N>
 __device__ __forceinline__ void lk_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int NSQ>
 struct LkSmem {
-    float vec[LK_NG][2][LK_CSMAX][LK_NSQ][LK_BLK];   // the exchanged state vector: one block per source CTA, double-buffered
-    float part[LK_NG][LK_NSL][LK_NSQ][LK_NC];        // per-k-slice partial sums, one buffer per group
-    float stage[LK_NG][2][LK_NSQ][LK_BLK];           // this CTA's new block before it is pushed (double-buffered)
+    float vec[LK_NG][2][LK_CSMAX][NSQ][LK_BLK];   // the exchanged state vector: one block per source CTA, double-buffered
+    float part[LK_NG][LK_NSL][NSQ][LK_NC];        // per-k-slice partial sums, one buffer per group
+    float stage[LK_NG][2][NSQ][LK_BLK];           // this CTA's new block before it is pushed (double-buffered)
     float eraw[LK_NG][LK_PF][LK_FINAL];              // prefetched emissions, one slot per final thread
     float mraw[LK_NG][LK_PF][LK_FINAL];              // prefetched per-frame max
     uint64_t bar[LK_NG][2];
@@ -141,7 +142,7 @@ __device__ long long lk_trace_buf[8 * 8];
         if (p.trace && g == 0 && blockIdx.x == 0 && (tid & (LK_FINAL - 1)) == 0 && t >= 64 && t < 72) lk_trace_buf[(t - 64) * 8 + (slot)] = clock64(); \
     } while (0)
 
-// One cluster = CS CTAs x LK_NG groups of LK_NSQ sequences.  The groups are independent recursions that share the CTA's
+// One cluster = CS CTAs x LK_NG groups of NSQ (3 or 4) sequences.  The groups are independent recursions that share the CTA's
 // register-resident slab of P.  Warp roles (register budgets moved between them with setmaxnreg):
 //   warps 0-7  COMPUTE: warp w keeps P[64w..64w+63][the CTA's 64 output states] (128 registers per thread: 4 output
 //              states x 32 source states per lane) and, per
@@ -154,10 +155,10 @@ __device__ long long lk_trace_buf[8 * 8];
 __device__ __forceinline__ void lk_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void lk_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int MODE>
+template <int MODE, int NSQ>
 __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     extern __shared__ __align__(16) uint8_t lk_smem_raw[];
-    LkSmem &sm = *reinterpret_cast<LkSmem *>(lk_smem_raw);
+    LkSmem<NSQ> &sm = *reinterpret_cast<LkSmem<NSQ> *>(lk_smem_raw);
     constexpr bool VIT = (MODE == LK_VIT);
     constexpr int DIR = (MODE == LK_BWD) ? 1 : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -165,14 +166,14 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int cluster_id = blockIdx.x / CS;
-    const int seq0 = cluster_id * (LK_NSQ * LK_NG);
+    const int seq0 = cluster_id * (NSQ * LK_NG);
     const int col0 = rank * LK_NC;
     const float PADV = VIT ? -INFINITY : 0.f;
-    const int n_groups = min(LK_NG, (B - seq0 + LK_NSQ - 1) / LK_NSQ);   // groups of this cluster that hold sequences
+    const int n_groups = min(LK_NG, (B - seq0 + NSQ - 1) / NSQ);   // groups of this cluster that hold sequences
 
-    for (int i = tid; i < LK_NG * 2 * LK_CSMAX * LK_NSQ * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
-    for (int i = tid; i < LK_NG * 2 * LK_NSQ * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
-    for (int i = tid; i < LK_NG * LK_NSL * LK_NSQ * LK_NC; i += LK_THREADS) (&sm.part[0][0][0][0])[i] = PADV;   // idle k-slices: neutral element
+    for (int i = tid; i < LK_NG * 2 * LK_CSMAX * NSQ * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
+    for (int i = tid; i < LK_NG * 2 * NSQ * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
+    for (int i = tid; i < LK_NG * LK_NSL * NSQ * LK_NC; i += LK_THREADS) (&sm.part[0][0][0][0])[i] = PADV;   // idle k-slices: neutral element
     if (tid == 0) {
 #pragma unroll
         for (int g = 0; g < LK_NG; ++g) { lk_mbar_init(&sm.bar[g][0], 1); lk_mbar_init(&sm.bar[g][1], 1); }
@@ -181,7 +182,7 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     cluster.sync();                                          // every CTA's mbarriers exist before anyone pushes
 
     // bytes every receiver gets per step and group: one [NSQ][BLK] block from each of the CS CTAs
-    constexpr uint32_t BLOCK_BYTES = LK_NSQ * LK_BLK * sizeof(float);
+    constexpr uint32_t BLOCK_BYTES = NSQ * LK_BLK * sizeof(float);
     const uint32_t tx_bytes = (uint32_t)CS * BLOCK_BYTES;
     bool ok = true;
 
@@ -223,15 +224,15 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                     const float *v = &sm.vec[g][prv][warp][0][hw * LK_KH];             // states 64w.. = CTA w's block
                     float *po = &sm.part[g][2 * warp + hw][0][c4];
                     if (!VIT) {
-                        float2 acc[LK_NSQ][4];
+                        float2 acc[NSQ][4];
 #pragma unroll
-                        for (int s = 0; s < LK_NSQ; ++s)
+                        for (int s = 0; s < NSQ; ++s)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) acc[s][j] = make_float2(0.f, 0.f);
 #pragma unroll
                         for (int kk = 0; kk < LK_KH; kk += 4) {
 #pragma unroll
-                            for (int s = 0; s < LK_NSQ; ++s) {
+                            for (int s = 0; s < NSQ; ++s) {
                                 const float4 x = *reinterpret_cast<const float4 *>(v + s * LK_BLK + kk);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) acc[s][j] = lk_ffma2(make_float2(x.x, x.y), Pj[j][kk / 2], acc[s][j]);
@@ -240,19 +241,19 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                             }
                         }
 #pragma unroll
-                        for (int s = 0; s < LK_NSQ; ++s)
+                        for (int s = 0; s < NSQ; ++s)
                             *reinterpret_cast<float4 *>(po + s * LK_NC) = make_float4(acc[s][0].x + acc[s][0].y, acc[s][1].x + acc[s][1].y,
                                                                                       acc[s][2].x + acc[s][2].y, acc[s][3].x + acc[s][3].y);
                     } else {
-                        float m[LK_NSQ][4];
+                        float m[NSQ][4];
 #pragma unroll
-                        for (int s = 0; s < LK_NSQ; ++s)
+                        for (int s = 0; s < NSQ; ++s)
 #pragma unroll
                             for (int j = 0; j < 4; ++j) m[s][j] = -INFINITY;
 #pragma unroll
                         for (int kk = 0; kk < LK_KH; kk += 4) {
 #pragma unroll
-                            for (int s = 0; s < LK_NSQ; ++s) {
+                            for (int s = 0; s < NSQ; ++s) {
                                 const float4 x = *reinterpret_cast<const float4 *>(v + s * LK_BLK + kk);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                             }
                         }
 #pragma unroll
-                        for (int s = 0; s < LK_NSQ; ++s)
+                        for (int s = 0; s < NSQ; ++s)
                             *reinterpret_cast<float4 *>(po + s * LK_NC) = make_float4(m[s][0], m[s][1], m[s][2], m[s][3]);
                     }
                     LK_TRACE(2);
@@ -277,17 +278,18 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
         // ================================ FINAL warps: thread = (sequence fs of the group, output state fc) ============
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(LK_REGS_FINAL));
         const int ft = tid - LK_FINAL, fwarp = ft >> 5;
-        const int fs = ft / LK_NC, fc = ft % LK_NC;
+        const bool valid = ft < NSQ * LK_NC;                 // (whole warps: NSQ = 3 leaves final warps 6, 7 with the barriers only)
+        const int fs = valid ? ft / LK_NC : 0, fc = ft % LK_NC;
         const int gcol = col0 + fc;
         const bool need_m = (p.rowmax != nullptr);
         auto frame_of = [&](int t) { return (DIR == 0) ? t : T - 1 - t; };
         auto prefetch = [&](int t) {
-            if (t < T) {
+            if (t < T && valid) {
                 const int f = frame_of(t);
 #pragma unroll
                 for (int g = 0; g < LK_NG; ++g) {
                     if (g >= n_groups) continue;
-                    const int sq = seq0 + g * LK_NSQ + fs;
+                    const int sq = seq0 + g * NSQ + fs;
                     const bool okk = sq < B && gcol < K;
                     lk_cp_async4(&sm.eraw[g][t % LK_PF][ft], p.emis + ((size_t)(okk ? sq : 0) * T + f) * K + (okk ? gcol : 0));
                     if (need_m) lk_cp_async4(&sm.mraw[g][t % LK_PF][ft], p.rowmax + (size_t)(sq < B ? sq : 0) * T + f);
@@ -307,8 +309,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
 #pragma unroll
             for (int g = 0; g < LK_NG; ++g) {
                 if (g >= n_groups) continue;
-                const int fseq = seq0 + g * LK_NSQ + fs;
-                const bool f_ok = fseq < B && gcol < K;
+                const int fseq = seq0 + g * NSQ + fs;
+                const bool f_ok = valid && fseq < B && gcol < K;
                 const float raw = sm.eraw[g][t % LK_PF][ft];
                 const float mf = need_m ? sm.mraw[g][t % LK_PF][ft] : 0.f;
                 float bq = 0.f, lb = 0.f;                    // emission: probability form (fb) / log form (viterbi)
@@ -370,8 +372,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                     wv = f_ok ? __fadd_rn(acc, lb) : -INFINITY;   // delta_t = max_i(..) + log b_t  (hmm.py:168)
                 }
                 // ---- push the block: stage in shared memory, then ONE bulk DSMEM copy per CTA of the cluster --------
-                sm.stage[g][cur][fs][fc] = wv;
-                if (!VIT) {
+                if (valid) sm.stage[g][cur][fs][fc] = wv;
+                if (!VIT && valid) {
                     const float lmax = __uint_as_float(__reduce_max_sync(FULL_MASK, __float_as_uint(wv)));   // wv >= 0
                     if (lane == 0) sm.stage[g][cur][fs][LK_NC + (fwarp & 1)] = lmax;
                 }
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                     else if (DIR == 0) p.ws_a[o] = wv;
                     else p.ws_b[o] = pre;
                 }
-                if (!VIT && rank == 0 && fc == 0 && fseq < B) ws_l[(size_t)fseq * T + f] = __int_as_float(ksum_g[g]);
+                if (!VIT && rank == 0 && fc == 0 && valid && fseq < B) ws_l[(size_t)fseq * T + f] = __int_as_float(ksum_g[g]);
             }
         }
     }
@@ -402,8 +404,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     for (int g = 0; g < LK_NG; ++g)
         if (g < n_groups && ok) ok = lk_mbar_wait(&sm.bar[g][(T - 1) & 1], ((T - 1) >> 1) & 1);
     __syncthreads();
-    if (MODE == LK_FWD && p.loglik != nullptr && rank == 0 && warp < LK_NG * LK_NSQ) {
-        const int g = warp / LK_NSQ, s = warp % LK_NSQ, sq = seq0 + warp;
+    if (MODE == LK_FWD && p.loglik != nullptr && rank == 0 && warp < LK_NG * NSQ) {
+        const int g = warp / NSQ, s = warp % NSQ, sq = seq0 + warp;
         if (sq < B) {
             float tot = 0.f;
             for (int k = lane; k < K; k += 32) tot += sm.vec[g][(T - 1) & 1][k / LK_NC][s][k % LK_NC];
@@ -620,13 +622,34 @@ static int lk_cluster_size(int K) {
     return cs;                                               // 1, 2, 4 or 8
 }
 
-template <int MODE>
-static int lk_launch(const LkParams &p, cudaStream_t s) {
-    auto kern = lk_sweep_kernel<MODE>;
-    const size_t smem = sizeof(LkSmem);
+// Sequences per group: 3 when one wave of clusters still covers the batch (more clusters = more SMs on a latency-bound
+// sweep: B = 64 runs on 11 clusters = 88 SMs instead of 8 = 64), otherwise 4 (fewer waves).
+template <int MODE, int NSQ>
+static int lk_max_clusters(int cs) {
+    static int cache[LK_CSMAX + 1] = {0};
+    if (cache[cs] > 0) return cache[cs];
+    auto kern = lk_sweep_kernel<MODE, NSQ>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem<NSQ>));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
+    cfg.blockDim = dim3(LK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(LkSmem<NSQ>);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
+    return cache[cs] = n;
+}
+
+template <int MODE, int NSQ>
+static int lk_launch_nsq(const LkParams &p, cudaStream_t s) {
+    auto kern = lk_sweep_kernel<MODE, NSQ>;
+    const size_t smem = sizeof(LkSmem<NSQ>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K smem opt-in: %s", cudaGetErrorString(e));
-    const int n_clusters = (p.B + LK_NSQ * LK_NG - 1) / (LK_NSQ * LK_NG);
+    const int n_clusters = (p.B + NSQ * LK_NG - 1) / (NSQ * LK_NG);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * p.CS), 1, 1);
     cfg.blockDim = dim3(LK_THREADS, 1, 1);
@@ -642,6 +665,15 @@ static int lk_launch(const LkParams &p, cudaStream_t s) {
     e = cudaLaunchKernelEx(&cfg, kern, p);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K sweep launch: %s", cudaGetErrorString(e));
     return check_launch("lk_sweep_kernel");
+}
+
+template <int MODE>
+static int lk_launch(const LkParams &p, cudaStream_t s) {
+    const int clusters3 = (p.B + 3 * LK_NG - 1) / (3 * LK_NG);
+    bool three = clusters3 <= lk_max_clusters<MODE, 3>(p.CS);
+    if (const char *f = getenv("HMMB200_LK_NSQ")) three = (f[0] == '3');   // tests force either variant
+    if (three) return lk_launch_nsq<MODE, 3>(p, s);
+    return lk_launch_nsq<MODE, 4>(p, s);
 }
 
 int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, int add_rowmax, const float *trans_prob,
@@ -721,20 +753,8 @@ int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const floa
 }  // namespace hmmb200
 
 HMMB200_EXPORT int hmmb200_debug_lk_max_clusters(int cs) {
-    using namespace hmmb200;
-    auto kern = lk_sweep_kernel<LK_FWD>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
-    cfg.blockDim = dim3(LK_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = sizeof(LkSmem);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    int n = -1;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
-    return e == cudaSuccess ? n : -(int)e;
+    if (cs < 1 || cs > hmmb200::LK_CSMAX) return -1;
+    return hmmb200::lk_max_clusters<hmmb200::LK_FWD, 4>(cs);
 }
 
 HMMB200_EXPORT int hmmb200_debug_lk_trace(long long *host64) {
