@@ -23,6 +23,8 @@
 // count IS its latency: packed fp32x2 FMAs/adds, 3-input max, no per-step branches, 4x unrolled (fits the L0 I-cache).
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace hmmb200 {
 
 constexpr int CH = 64;          // frames per pipeline chunk
@@ -32,6 +34,7 @@ constexpr int MAXNS = 8;        // sequences per warp at G = 4
 constexpr int MR_BUFS = 2 * NB; // log-scale ring depth: loaders run up to NB chunks ahead of the drainer's read
 constexpr int BAR_FULL = 1;     // named barriers BAR_FULL + b, BAR_DONE + b  (0 is __syncthreads)
 constexpr int BAR_DONE = 1 + NB;
+enum { SC_FULL = 0, SC_APPLY = 1, SC_ESTIMATE = 2 };   // fb consumer: what a step does about the power-of-two normaliser
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -244,8 +247,17 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
         k_cur = (int)eb - 127;
         r_cur = __uint_as_float((254u - eb) << 23);
     };
-    // one time step: w <- (sum_i prev[i] * M[i]) * (b~ * r) ; the pad lane carries (float)ksum instead
-    auto step = [&](int u, float bqv) {
+    // one time step: w <- (sum_i prev[i] * M[i]) * (b~ * r) ; the pad lane carries (float)ksum instead.
+    // The normaliser costs a third of the step's instructions (max tree, exponent arithmetic), and the step's
+    // instruction count is its latency, so inside the 4x unrolled loop only every other step derives one:
+    //   SC_APPLY     applies the pending scale, derives none;
+    //   SC_ESTIMATE  applies none (r = 1 folds away), derives the next one from the vector it has just read back;
+    //   SC_FULL      both (loop remainders).
+    // Powers of two are exact, so posteriors do not depend on where the scales fall; three steps of lag are far from
+    // underflow even on floored frames (1e-8 per step).
+    auto step = [&](auto sc_tag, int u, float bqv) {
+        constexpr int SC = decltype(sc_tag)::value;
+        constexpr bool APPLY = (SC != SC_ESTIMATE), EST = (SC != SC_APPLY);
         float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
         float v[KP];
 #pragma unroll
@@ -257,23 +269,28 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
         }
         const float2 s2 = fadd2(acc_a, acc_b);
         const float acc = s2.x + s2.y;
-        const float mb = bqv * r_cur;
-        ksum += k_cur;
+        const float mb = APPLY ? bqv * r_cur : bqv;
+        if (APPLY) ksum += k_cur;
         const float padf = pad_lane ? (float)ksum : 0.f;
         const float w = fmaf(acc, mb, padf);
-        if (DIR == 1) bp2[u * 32] = acc * r_cur;
+        if (DIR == 1) bp2[u * 32] = APPLY ? acc * r_cur : acc;
         wp[u * 32] = w;
         if (!PAD && j == 0) ep[u * MAXNS] = ksum;
-        if (NS == 1) {
-            set_scale(__reduce_max_sync(FULL_MASK, lane_ok ? __float_as_uint(w) : 0u));
-        } else {
-            // scale the new vector by what the previous one needed, times the growth r_cur already applied to it
-            const float vm = max_tree<KP>(v) * r_cur;
-            set_scale(__float_as_uint(vm));
+        if (EST) {
+            if (NS == 1) {
+                set_scale(__reduce_max_sync(FULL_MASK, lane_ok ? __float_as_uint(w) : 0u));
+            } else {
+                // scale the new vector by what the previous one needed, times the growth r_cur already applied to it
+                const float vm = APPLY ? max_tree<KP>(v) * r_cur : max_tree<KP>(v);
+                set_scale(__float_as_uint(vm));
+            }
         }
         prev = reinterpret_cast<const float4 *>(wp + u * 32 - j);
         __syncwarp();
     };
+    using ScFull = std::integral_constant<int, SC_FULL>;
+    using ScApply = std::integral_constant<int, SC_APPLY>;
+    using ScEstimate = std::integral_constant<int, SC_ESTIMATE>;
 
     const int nch = (T + CH - 1) / CH;
     for (int c = 0; c < nch; ++c) {
@@ -301,10 +318,12 @@ __device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, 
             float bq[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) bq[i] = btb[(u + i) * BT_PITCH];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) step(u + i, bq[i]);
+            step(ScApply{}, u, bq[0]);
+            step(ScEstimate{}, u + 1, bq[1]);
+            step(ScApply{}, u + 2, bq[2]);
+            step(ScEstimate{}, u + 3, bq[3]);
         }
-        for (; u < nf; ++u) step(u, btb[u * BT_PITCH]);
+        for (; u < nf; ++u) step(ScFull{}, u, btb[u * BT_PITCH]);
         bar_arrive(BAR_DONE + b, FB_THREADS);
     }
 }
