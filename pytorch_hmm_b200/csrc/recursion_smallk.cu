@@ -523,6 +523,70 @@ __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
     }
 }
 
+// Coalesced form for K % 4 == 0: a warp finishes 32 consecutive frames = 32 * KV float4 pieces, lane l taking pieces
+// l, l + 32, ... -- every load and store instruction covers 512 contiguous bytes (with one thread per frame the 32 lanes
+// of an instruction sit K * 4 bytes apart: three times the L1 wavefronts and partial-sector stores at K = 12).  The
+// per-piece dot products meet in a warp-private shared-memory row; each frame's normaliser is their sum in piece order,
+// so a frame's posterior does not depend on its position in the batch (sharding-independent, like the kernel above).
+template <int KV>
+__global__ void __launch_bounds__(256) fb_combine_warp_kernel(CombineParams p) {
+    __shared__ float zs[8][32 * KV];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t n_blocks = (p.n_frames + 31) / 32;
+    float *z = zs[wib];
+    for (int64_t blk = (int64_t)blockIdx.x * 8 + wib; blk < n_blocks; blk += (int64_t)gridDim.x * 8) {
+        const int64_t f0 = blk * 32;
+        const int nf = (int)((p.n_frames - f0 < 32) ? (p.n_frames - f0) : 32);
+        const int npieces = nf * KV;
+        const float4 *pa = reinterpret_cast<const float4 *>(p.ws_a) + f0 * KV;
+        const float4 *pb = reinterpret_cast<const float4 *>(p.ws_b) + f0 * KV;
+        float4 xa[KV], xb[KV];
+#pragma unroll
+        for (int j = 0; j < KV; ++j) {
+            const int idx = lane + 32 * j;
+            const bool ok = idx < npieces;
+            xa[j] = ok ? __ldcs(pa + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            xb[j] = ok ? __ldcs(pb + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float la_l = (lane < nf) ? __ldcs(p.ws_la + f0 + lane) : 0.f;
+        const float lb_l = (lane < nf) ? __ldcs(p.ws_lb + f0 + lane) : 0.f;
+#pragma unroll
+        for (int j = 0; j < KV; ++j) {
+            float d = __fmul_rn(xa[j].x, xb[j].x);
+            d = __fmaf_rn(xa[j].y, xb[j].y, d);
+            d = __fmaf_rn(xa[j].z, xb[j].z, d);
+            d = __fmaf_rn(xa[j].w, xb[j].w, d);
+            z[lane + 32 * j] = d;
+        }
+        __syncwarp();
+        const float ea_l = expf(la_l), eb_l = expf(lb_l);
+#pragma unroll
+        for (int j = 0; j < KV; ++j) {
+            const int idx = lane + 32 * j;
+            const bool ok = idx < npieces;
+            const int fr = ok ? idx / KV : 0;
+            float Z = z[fr * KV];
+#pragma unroll
+            for (int q = 1; q < KV; ++q) Z = __fadd_rn(Z, z[fr * KV + q]);
+            const float inv = 1.f / Z;
+            const float ea = __shfl_sync(FULL_MASK, ea_l, fr), eb = __shfl_sync(FULL_MASK, eb_l, fr);
+            const float la = __shfl_sync(FULL_MASK, la_l, fr), lb = __shfl_sync(FULL_MASK, lb_l, fr);
+            if (!ok) continue;
+            const float4 x = xa[j], y = xb[j];
+            const int64_t o = f0 * KV + idx;
+            auto g = [&](float u, float v) { return __fmul_rn(__fmul_rn(u, v), inv); };
+            if (p.gamma) __stcs(reinterpret_cast<float4 *>(p.gamma) + o, make_float4(g(x.x, y.x), g(x.y, y.y), g(x.z, y.z), g(x.w, y.w)));
+            if (p.fwd) __stcs(reinterpret_cast<float4 *>(p.fwd) + o, make_float4(x.x * ea, x.y * ea, x.z * ea, x.w * ea));
+            if (p.bwd) __stcs(reinterpret_cast<float4 *>(p.bwd) + o, make_float4(y.x * eb, y.y * eb, y.z * eb, y.w * eb));
+            if (p.log_alpha) __stcs(reinterpret_cast<float4 *>(p.log_alpha) + o,
+                                    make_float4(logf(x.x) + la, logf(x.y) + la, logf(x.z) + la, logf(x.w) + la));
+            if (p.log_beta) __stcs(reinterpret_cast<float4 *>(p.log_beta) + o,
+                                   make_float4(logf(y.x) + lb, logf(y.y) + lb, logf(y.z) + lb, logf(y.w) + lb));
+        }
+        __syncwarp();                                        // the row of partial dots is reused by the next block
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // Viterbi
 // ----------------------------------------------------------------------------------------------------------
@@ -861,15 +925,16 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
         const unsigned blocks = (unsigned)((n + (size_t)threads * COMBINE_FPT - 1) / ((size_t)threads * COMBINE_FPT));
         auto al16 = [](const void *q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
         const bool vec = K % 4 == 0 && al16(gamma) && al16(fwd_prob) && al16(bwd_prob) && al16(log_alpha) && al16(log_beta);
+        const unsigned wblocks = (unsigned)((n + 255) / 256);   // one 32-frame block per warp, 8 warps per CTA
         switch (vec ? K / 4 : 0) {
-            case 1: fb_combine_kernel<4, 1><<<blocks, threads, 0, s>>>(c); break;
-            case 2: fb_combine_kernel<4, 2><<<blocks, threads, 0, s>>>(c); break;
-            case 3: fb_combine_kernel<4, 3><<<blocks, threads, 0, s>>>(c); break;
-            case 4: fb_combine_kernel<4, 4><<<blocks, threads, 0, s>>>(c); break;
-            case 5: fb_combine_kernel<4, 5><<<blocks, threads, 0, s>>>(c); break;
-            case 6: fb_combine_kernel<4, 6><<<blocks, threads, 0, s>>>(c); break;
-            case 7: fb_combine_kernel<4, 7><<<blocks, threads, 0, s>>>(c); break;
-            case 8: fb_combine_kernel<4, 8><<<blocks, threads, 0, s>>>(c); break;
+            case 1: fb_combine_warp_kernel<1><<<wblocks, threads, 0, s>>>(c); break;
+            case 2: fb_combine_warp_kernel<2><<<wblocks, threads, 0, s>>>(c); break;
+            case 3: fb_combine_warp_kernel<3><<<wblocks, threads, 0, s>>>(c); break;
+            case 4: fb_combine_warp_kernel<4><<<wblocks, threads, 0, s>>>(c); break;
+            case 5: fb_combine_warp_kernel<5><<<wblocks, threads, 0, s>>>(c); break;
+            case 6: fb_combine_warp_kernel<6><<<wblocks, threads, 0, s>>>(c); break;
+            case 7: fb_combine_warp_kernel<7><<<wblocks, threads, 0, s>>>(c); break;
+            case 8: fb_combine_warp_kernel<8><<<wblocks, threads, 0, s>>>(c); break;
             default: fb_combine_kernel<1, 1><<<blocks, threads, 0, s>>>(c); break;
         }
         if (int rc = check_launch("fb_combine_kernel")) return rc;
