@@ -36,7 +36,7 @@ BYTES_PER_FRAME = 4 * FEAT + 4 * K_STATES * 4 + 8          # x i
 METRIC = "frames/sec forward-backward+Viterbi (K=12,T=2000,B=256)"
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
 NCU_TRAFFIC_SRC = "profiles/r01_ncu_full_summary.md"
-NCU_TRAFFIC = {"gmm_emission_tc_kernel": 175.0e6, "fb_sweep_kernel": 29.6e6, "fb_combine_kernel": 99.2e6, "viterbi_kernel": 24.7e6}
+NCU_TRAFFIC = {"gmm_emission_tc_kernel": 175.8e6, "fb_sweep_kernel": 30.0e6, "fb_combine_kernel": 73.4e6, "viterbi_kernel": 24.7e6}
 
 
 def measured_peaks():
@@ -341,7 +341,9 @@ def run_gpu_arm(args, rank, world, local_rank):
                 "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()},
                 "note": "the recursion kernels are bound by the latency of T dependent steps, not by HBM (DESIGN.md 4.2); "
                         "per-kernel fractions: " + ", ".join(
-                            f"{k} {alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak:.3f}" for k in alg_bytes),
+                            f"{k} {alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak:.3f}" for k in alg_bytes)
+                        + " (fb_combine = the posterior kernel fb_combine_warp_kernel, timed as fb minus the sweeps; its inputs are"
+                          " still in L2 from the sweeps and its outputs are written back after it ends, so its figure can exceed the HBM peak)",
                 "path": {"bytes_per_frame": BYTES_PER_FRAME, "achieved": value / world * BYTES_PER_FRAME / 1e9,
                          "frac": value / world * BYTES_PER_FRAME / 1e9 / peak}}
 
