@@ -2,7 +2,8 @@
 //
 //   fb_sweep_kernel     forward and backward sweeps (blockIdx.y = direction), scaled-probability space.
 //                       Replaces the per-time-step ATen launches of pytorch_hmm/hmm.py:95-117.
-//   fb_combine_kernel   posterior / exp(log alpha) / exp(log beta) from the two scaled sweeps (hmm.py:120-128).
+//   fb_combine_warp_kernel / fb_combine_kernel   posterior / exp(log alpha) / exp(log beta) from the two scaled sweeps
+//                       (hmm.py:120-128): coalesced warp-per-32-frames form for K % 4 == 0, scalar form otherwise.
 //   viterbi_kernel      max-plus recursion, packed uint8 backpointers in shared memory, chunk-parallel on-device
 //                       traceback (hmm.py:159-178; mixture_gaussian.py:312-336).
 //
@@ -449,76 +450,30 @@ struct CombineParams {
     float *gamma, *fwd, *bwd, *log_alpha, *log_beta;
 };
 
-// Each thread finishes COMBINE_FPT frames (idx, idx + stride, ...) and issues all of their loads before the first use: the
-// kernel is a pure stream (2 x K floats in, 3 x K floats out per frame) and needs bytes in flight, not arithmetic.
+// Scalar form (K not a multiple of 4, or unaligned outputs): one thread per frame, COMBINE_FPT frames per thread.
+// Explicit fused / rounded operations in a fixed order: a frame's result must not depend on how the batch was sharded.
 constexpr int COMBINE_FPT = 2;
 
-template <int VEC, int KV>
 __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int K = p.K;
-    if (VEC == 4) {
-        // KV = K / 4 vector pieces per frame (compile-time: registers)
-        float4 xa[COMBINE_FPT][KV], xb[COMBINE_FPT][KV];
-        float la[COMBINE_FPT], lb[COMBINE_FPT];
-#pragma unroll
-        for (int f = 0; f < COMBINE_FPT; ++f) {
-            const int64_t idx = idx0 + f * stride;
-            const bool ok = idx < p.n_frames;
-            const int64_t i = ok ? idx : 0;
-#pragma unroll
-            for (int q = 0; q < KV; ++q) {
-                xa[f][q] = __ldcs(reinterpret_cast<const float4 *>(p.ws_a + i * K) + q);
-                xb[f][q] = __ldcs(reinterpret_cast<const float4 *>(p.ws_b + i * K) + q);
-            }
-            la[f] = __ldcs(p.ws_la + i); lb[f] = __ldcs(p.ws_lb + i);
-        }
-#pragma unroll
-        for (int f = 0; f < COMBINE_FPT; ++f) {
-            const int64_t idx = idx0 + f * stride;
-            if (idx >= p.n_frames) continue;
-            // explicit fused / rounded operations in a fixed order: the result of a frame must not depend on which unrolled
-            // copy (f) it lands in, i.e. on how the batch was sharded
-            float2 z2 = make_float2(0.f, 0.f);            // explicit packed FMAs: same instruction sequence in every copy
-#pragma unroll
-            for (int q = 0; q < KV; ++q) {
-                z2 = ffma2(make_float2(xa[f][q].x, xa[f][q].y), make_float2(xb[f][q].x, xb[f][q].y), z2);
-                z2 = ffma2(make_float2(xa[f][q].z, xa[f][q].w), make_float2(xb[f][q].z, xb[f][q].w), z2);
-            }
-            const float Z = __fadd_rn(z2.x, z2.y);
-            const float inv = 1.f / Z, ea = expf(la[f]), eb = expf(lb[f]);
-            auto g = [&](float u, float v) { return u * v * inv; };   // products only: nothing to contract, packs as f32x2
-#pragma unroll
-            for (int q = 0; q < KV; ++q) {
-                const float4 x = xa[f][q], y = xb[f][q];
-                if (p.gamma) __stcs(reinterpret_cast<float4 *>(p.gamma + idx * K) + q, make_float4(g(x.x, y.x), g(x.y, y.y), g(x.z, y.z), g(x.w, y.w)));
-                if (p.fwd) __stcs(reinterpret_cast<float4 *>(p.fwd + idx * K) + q, make_float4(x.x * ea, x.y * ea, x.z * ea, x.w * ea));
-                if (p.bwd) __stcs(reinterpret_cast<float4 *>(p.bwd + idx * K) + q, make_float4(y.x * eb, y.y * eb, y.z * eb, y.w * eb));
-                if (p.log_alpha) __stcs(reinterpret_cast<float4 *>(p.log_alpha + idx * K) + q,
-                                        make_float4(logf(x.x) + la[f], logf(x.y) + la[f], logf(x.z) + la[f], logf(x.w) + la[f]));
-                if (p.log_beta) __stcs(reinterpret_cast<float4 *>(p.log_beta + idx * K) + q,
-                                       make_float4(logf(y.x) + lb[f], logf(y.y) + lb[f], logf(y.z) + lb[f], logf(y.w) + lb[f]));
-            }
-        }
-    } else {
-        for (int f = 0; f < COMBINE_FPT; ++f) {
-            const int64_t idx = idx0 + f * stride;
-            if (idx >= p.n_frames) continue;
-            const float *a = p.ws_a + idx * K, *b = p.ws_b + idx * K;
-            const float la = p.ws_la[idx], lb = p.ws_lb[idx];
-            const float ea = expf(la), eb = expf(lb);
-            float Z = 0.f;
-            for (int k = 0; k < K; ++k) Z = fmaf(a[k], b[k], Z);
-            const float inv = __fdiv_rn(1.f, Z);
-            for (int k = 0; k < K; ++k) {
-                float x = a[k], y = b[k];
-                if (p.gamma) p.gamma[idx * K + k] = __fmul_rn(__fmul_rn(x, y), inv);
-                if (p.fwd) p.fwd[idx * K + k] = x * ea;
-                if (p.bwd) p.bwd[idx * K + k] = y * eb;
-                if (p.log_alpha) p.log_alpha[idx * K + k] = logf(x) + la;
-                if (p.log_beta) p.log_beta[idx * K + k] = logf(y) + lb;
-            }
+    for (int f = 0; f < COMBINE_FPT; ++f) {
+        const int64_t idx = idx0 + f * stride;
+        if (idx >= p.n_frames) continue;
+        const float *a = p.ws_a + idx * K, *b = p.ws_b + idx * K;
+        const float la = p.ws_la[idx], lb = p.ws_lb[idx];
+        const float ea = expf(la), eb = expf(lb);
+        float Z = 0.f;
+        for (int k = 0; k < K; ++k) Z = fmaf(a[k], b[k], Z);
+        const float inv = __fdiv_rn(1.f, Z);
+        for (int k = 0; k < K; ++k) {
+            float x = a[k], y = b[k];
+            if (p.gamma) p.gamma[idx * K + k] = __fmul_rn(__fmul_rn(x, y), inv);
+            if (p.fwd) p.fwd[idx * K + k] = x * ea;
+            if (p.bwd) p.bwd[idx * K + k] = y * eb;
+            if (p.log_alpha) p.log_alpha[idx * K + k] = logf(x) + la;
+            if (p.log_beta) p.log_beta[idx * K + k] = logf(y) + lb;
         }
     }
 }
@@ -527,7 +482,7 @@ __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
 // l, l + 32, ... -- every load and store instruction covers 512 contiguous bytes (with one thread per frame the 32 lanes
 // of an instruction sit K * 4 bytes apart: three times the L1 wavefronts and partial-sector stores at K = 12).  The
 // per-piece dot products meet in a warp-private shared-memory row; each frame's normaliser is their sum in piece order,
-// so a frame's posterior does not depend on its position in the batch (sharding-independent, like the kernel above).
+// so a frame's posterior does not depend on its position in the batch (sharding-independent).
 template <int KV>
 __global__ void __launch_bounds__(256) fb_combine_warp_kernel(CombineParams p) {
     __shared__ float zs[8][32 * KV];
@@ -935,7 +890,7 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
             case 6: fb_combine_warp_kernel<6><<<wblocks, threads, 0, s>>>(c); break;
             case 7: fb_combine_warp_kernel<7><<<wblocks, threads, 0, s>>>(c); break;
             case 8: fb_combine_warp_kernel<8><<<wblocks, threads, 0, s>>>(c); break;
-            default: fb_combine_kernel<1, 1><<<blocks, threads, 0, s>>>(c); break;
+            default: fb_combine_kernel<<<blocks, threads, 0, s>>>(c); break;
         }
         if (int rc = check_launch("fb_combine_kernel")) return rc;
     }
