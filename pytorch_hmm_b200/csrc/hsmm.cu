@@ -372,9 +372,12 @@ __device__ __forceinline__ double warp_max_d(double v) {
     return v;
 }
 
+// KT / DT: compile-time K and max_duration for the shapes worth specialising (0 = run-time): the transition and duration
+// loops then unroll, and the independent ring updates of a step overlap instead of queueing behind loop control.
+template <int KT, int DT>
 __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
     extern __shared__ __align__(16) double smem_d[];
-    const int K = p.K, Dm = p.Dm, T = p.T;
+    const int K = KT > 0 ? KT : p.K, Dm = DT > 0 ? DT : p.Dm, T = p.T;
     double *ring = smem_d;                      // [Dm][K]  Bg (forward) / bend (backward), slot t % Dm
     double *bt_r = ring + Dm * K;               // [Dm][K]  b~ of the last Dm frames
     double *durc = bt_r + Dm * K;               // [Dm][K]  dur(s,d) * c(s)
@@ -449,6 +452,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
             if (t == 0) bg = p.logpi ? exp((double)p.logpi[s]) : 1.0;
             else {
                 double g0 = 0.0, g1 = 0.0;
+#pragma unroll
                 for (int sp = 0; sp + 1 < K; sp += 2) {
                     if (sp != s) g0 = fma(vec[sp], A_s[sp * K + s], g0);
                     if (sp + 1 != s) g1 = fma(vec[sp + 1], A_s[(sp + 1) * K + s], g1);
@@ -462,8 +466,9 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
             double e0 = 0.0;
             int st = cur - r;                               // slot of duration d = 1 + r: (t - d + 1) % Dm
             if (st < 0) st += Dm;
-            const int nd = min(Dm, t + 1);
-            for (int d = 1 + r; d <= nd; d += LPS) {
+            // (slots of segments that would begin before frame 0 still hold their initial zeros: no bound on t needed)
+#pragma unroll
+            for (int d = 1 + r; d <= Dm; d += LPS) {
                 const double r0 = ring[st * K + s] * bq;
                 ring[st * K + s] = r0;
                 e0 = fma(r0, durc[(d - 1) * K + s], e0);
@@ -525,6 +530,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
             const double bq = (double)expf(ft - m);
             if (t < T - 1) {
                 double g0 = 0.0, g1 = 0.0;
+#pragma unroll
                 for (int sn = 0; sn + 1 < K; sn += 2) {
                     if (sn != s) g0 = fma(A_s[s * K + sn], vec[sn], g0);
                     if (sn + 1 != s) g1 = fma(A_s[s * K + sn + 1], vec[sn + 1], g1);
@@ -539,8 +545,8 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
             double b0 = 0.0;
             int en = cur + r;                               // slot of duration d = 1 + r: (t + d - 1) % Dm
             if (en >= Dm) en -= Dm;
-            const int nd = min(Dm, T - t);
-            for (int d = 1 + r; d <= nd; d += LPS) {
+#pragma unroll
+            for (int d = 1 + r; d <= Dm; d += LPS) {          // (segments ending after frame T-1: zeros, as above)
                 const double q0 = ring[en * K + s] * bq;
                 ring[en * K + s] = q0;
                 b0 = fma(q0, durc[(d - 1) * K + s], b0);
@@ -666,8 +672,9 @@ HMMB200_EXPORT int hmmb200_hsmm_forward_backward_f32(const float *frame_logp, co
     if (int rc = require_sm100()) return rc;
     const size_t smem = ((size_t)3 * Dm * K + (size_t)K * K + K) * sizeof(double) + (size_t)HSF_PF * 32 * (8 + 8 + 4) + HSF_PF * 4 + 64;
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_forward_backward: max_duration too large");
+    const bool spec = (K == 10 && Dm == 20);                // BASELINE config 4 (HSMMLayer defaults of the reference's factory)
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(hsmm_fb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(hsmm_fb_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_forward_backward smem opt-in: %s", cudaGetErrorString(e));
     }
     const size_t n = (size_t)B * T;
@@ -680,6 +687,7 @@ HMMB200_EXPORT int hmmb200_hsmm_forward_backward_f32(const float *frame_logp, co
     p.ws_M = (double *)w;  w += n * sizeof(double);
     p.ws_pend = (float *)w; w += n * K * sizeof(float);
     p.ws_k = (int *)w;
-    hsmm_fb_kernel<<<B, 32, smem, (cudaStream_t)stream>>>(p);
+    if (spec) hsmm_fb_kernel<10, 20><<<B, 32, smem, (cudaStream_t)stream>>>(p);
+    else hsmm_fb_kernel<0, 0><<<B, 32, smem, (cudaStream_t)stream>>>(p);
     return check_launch("hsmm_fb_kernel");
 }
