@@ -479,7 +479,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
         }
         e = group_sum(e);
         __syncwarp();                                       // every lane has read E(t-1,.)
-        bg *= rescale(e, kf);
+        if ((t & 7) == 7) bg *= rescale(e, kf);              // drift is checked every 8th frame: doubles have the headroom
         if (lead) {
             vec[s] = e;
             p.ws_E[(base + t) * K + s] = e;
@@ -557,7 +557,7 @@ __global__ void __launch_bounds__(32) hsmm_fb_kernel(HsmmFbParams p) {
         }
         bb = group_sum(bb);
         __syncwarp();                                       // every lane has read bbeg(t+1,.)
-        be *= rescale(bb, kb);
+        if ((t & 7) == 0) be *= rescale(bb, kb);
         if (lead) {
             vec[s] = bb;
             const size_t o = (base + t) * K + s;
