@@ -164,7 +164,7 @@ def run_reference_arm(args, rank):
     fps, dt = time_cpu_port(model, x, args.steps, args.warmup)
     cores = torch.get_num_threads()
     sample = f"{bs} of {BATCH} sequences x T={SEQ} per step (op-for-op torch port of the reference, all host threads)"
-    print(json.dumps({
+    emit_result({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -172,7 +172,7 @@ def run_reference_arm(args, rank):
                    "B": BATCH, "T": SEQ, "K": K_STATES, "C": N_MIX, "D": FEAT},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -401,10 +401,23 @@ def run_gpu_arm(args, rank, world, local_rank):
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
                                     "sample": f"{bs} of {BATCH} sequences x T={SEQ}, 1 warm-up + 3 timed passes of oracle/ref_port.py "
                                               f"({dt:.2f} s per pass)"}
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+_REAL_STDOUT_FD = None
+
+
+def emit_result(line: dict):
+    """Print the result line on the process's real stdout (see main)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(2, 1)
 
 
 def main():
@@ -417,6 +430,12 @@ def main():
     ap.add_argument("--e2e-shard", type=int, default=32, help="utterances per in-flight shard on the host path")
     ap.add_argument("--e2e-streams", type=int, default=4)
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: until it is printed, file descriptor 1 points at stderr so that
+    # native libraries (NCCL prints its version banner on stdout at communicator creation) cannot add lines to it
+    sys.stdout.flush()
+    global _REAL_STDOUT_FD
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
