@@ -174,16 +174,20 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     for (int i = tid; i < LK_NG * 2 * LK_CSMAX * NSQ * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
     for (int i = tid; i < LK_NG * 2 * NSQ * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
     for (int i = tid; i < LK_NG * LK_NSL * NSQ * LK_NC; i += LK_THREADS) (&sm.part[0][0][0][0])[i] = PADV;   // idle k-slices: neutral element
+    // bytes every receiver gets per step and group: one [NSQ][BLK] block from each of the CS CTAs
+    constexpr uint32_t BLOCK_BYTES = NSQ * LK_BLK * sizeof(float);
+    const uint32_t tx_bytes = (uint32_t)CS * BLOCK_BYTES;
     if (tid == 0) {
 #pragma unroll
         for (int g = 0; g < LK_NG; ++g) { lk_mbar_init(&sm.bar[g][0], 1); lk_mbar_init(&sm.bar[g][1], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // step 0 is armed here: the final warps push it without waiting for the compute warps (no product at t = 0),
+        // so nothing else orders this expect_tx before their complete_tx
+#pragma unroll
+        for (int g = 0; g < LK_NG; ++g)
+            if (g < n_groups) lk_mbar_expect_tx(&sm.bar[g][0], tx_bytes);
     }
-    cluster.sync();                                          // every CTA's mbarriers exist before anyone pushes
-
-    // bytes every receiver gets per step and group: one [NSQ][BLK] block from each of the CS CTAs
-    constexpr uint32_t BLOCK_BYTES = NSQ * LK_BLK * sizeof(float);
-    const uint32_t tx_bytes = (uint32_t)CS * BLOCK_BYTES;
+    cluster.sync();                                          // every CTA's mbarriers exist (and are armed) before anyone pushes
     bool ok = true;
 
     if (warp < LK_NWC) {
@@ -215,8 +219,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
             for (int g = 0; g < LK_NG; ++g) {
                 if (g >= n_groups) continue;
                 LK_TRACE(0);
+                if (t == 0) continue;                        // step 0 has no product (and was armed at set-up)
                 if (tid == 0) lk_mbar_expect_tx(&sm.bar[g][cur], tx_bytes);
-                if (t == 0) continue;                        // step 0 has no product
                 // (idle warps wait too: nobody may arrive on the named barrier twice within one of its phases)
                 if (ok) ok = lk_mbar_wait(&sm.bar[g][prv], ((t - 1) >> 1) & 1);   // after a time-out: drain without waiting
                 LK_TRACE(1);
