@@ -6,17 +6,20 @@
 //   lk_traceback_kernel       arg-max + backpointers recomputed on the path     (hmm.py:167, :174-178)
 //   lk_combine_kernel         posterior / exp(log alpha) / exp(log beta)        (hmm.py:120-128)
 //   lk_rowmax_kernel          per-frame max_k of the log-emissions (scaling of the LOG emission modes)
+//   lk_logscale_kernel        integer scale exponents of a sweep -> log units (double), log-likelihood
 //
 // Why a cluster: one step is a [n_seq, K] x [K, K] product followed by a dependency on ALL K results, T times.  A K = 512
 // fp32 matrix is 1 MB: it fits in no single SM, and re-reading it from L2 every step (1 MB x 4000 steps x 64 sequences)
 // would make the sweep L2-bound.  So the CS CTAs of a cluster each own NC = 64 output states: their [K, 64] slab of P lives
-// in REGISTERS (64 per thread: warp w holds source states 32w..32w+31, lane l the two output states 2l, 2l+1), read
-// from HBM exactly once.  Per step a warp multiplies its 32-state slice of the previous vector (broadcast LDS.128 from
-// shared memory) into the slab with packed FFMA2, the 16 slices are summed through shared memory, the 256 "final"
-// threads apply emission and scaling, and the new 64-state slice is pushed to every CTA of the cluster with
-// st.async (DSMEM store + mbarrier complete_tx): the receiver's mbarrier flips exactly when all CS slices have landed,
-// so there is no cluster-wide barrier on the critical path, only the data's own arrival.  The vector is double-buffered;
-// a sender can never run more than one step ahead of a receiver because it needs the receiver's slice to do so.
+// in the REGISTERS of 8 compute warps (128 per thread: warp w holds source states 64w..64w+63, each half-warp 32 of them,
+// each lane 4 output states), read from HBM exactly once.  Per step a compute warp multiplies its slice of the previous
+// vector (broadcast LDS.128 from shared memory) into the slab with packed FFMA2; 8 final warps add the 16 partial sums,
+// apply emission and scaling, and push the CTA's new 64-state block to every CTA of the cluster with ONE bulk DSMEM copy
+// per destination (cp.async.bulk + mbarrier complete_tx): the receiver's mbarrier flips exactly when all CS blocks have
+// landed, so there is no cluster-wide barrier on the critical path, only the data's own arrival.  The vector is
+// double-buffered; a sender can never run more than one step ahead of a receiver because it needs the receiver's block to
+// do so.  Two independent groups of sequences alternate on the slab so that one group's finals and exchange overlap the
+// other group's product (see lk_sweep_kernel).
 //
 // Scaling (forward/backward): every step is multiplied by 2^-k, k = exponent of the previous vector's largest entry
 // (each CTA ships its local maxima with its slice), exact power-of-two scaling with integer bookkeeping -- the same
