@@ -62,14 +62,23 @@ def lib_path() -> str:
 
 
 def load(build_if_missing: bool = True):
-    """Returns the loaded CDLL; builds it in-tree first when it is missing or stale and nvcc is available."""
+    """Returns the loaded CDLL.  The in-tree library is (re)built first when it is missing or was built from other sources
+    than the ones in the tree (content hash recorded at build time) and nvcc is available; a stale library that cannot be
+    rebuilt is an error -- argument-layout drift between header and binary must never be loaded silently."""
     global _lib
     with _lock:
         if _lib is not None:
             return _lib
         path = lib_path()
-        if build_if_missing and (not os.path.exists(path) or os.environ.get("HMMB200_REBUILD") == "1"):
-            path = _build.build_library(force=os.environ.get("HMMB200_REBUILD") == "1")
+        in_tree = path == _build.lib_path()
+        force = os.environ.get("HMMB200_REBUILD") == "1"
+        if in_tree and build_if_missing and (force or _build.is_stale(path)):
+            import shutil
+            if shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc"):
+                path = _build.build_library(force=True)
+            elif os.path.exists(path):
+                raise RuntimeError(f"{path} was built from different sources than the tree holds and nvcc is not available "
+                                   "to rebuild it")
         if not os.path.exists(path):
             raise RuntimeError(f"{path} is missing: build it with `python -m pytorch_hmm_b200.build` "
                                "(pytorch_hmm_b200 has no CPU fallback)")

@@ -90,6 +90,8 @@ class BaumWelch:
         self.var_floor = var_floor
         self.stats = torch.zeros(stats_size(self.K, self.C, self.D), dtype=torch.float64, device=self.dev)
         self._packed = None
+        self._buf = None
+        self._n_frames = self._n_seqs = 0
 
     @classmethod
     def from_layer(cls, layer, **kw) -> "BaumWelch":
@@ -104,42 +106,58 @@ class BaumWelch:
     def reset(self):
         self.stats.zero_()
         self._packed = None
+        self._n_frames = self._n_seqs = 0
 
     def _pack(self):
         if self._packed is None:
             self._packed = ops.gmm_pack(self.p.means, torch.log(self.p.vars), 1.0, torch.log(self.p.weights))
+            self._trans = self.p.trans.float().contiguous()
+            self._init = self.p.init.float().contiguous()
         return self._packed
 
+    def _buffers(self, B: int, T: int):
+        """Per-shape scratch, allocated once: log b, per-component values, posteriors, log-likelihoods, sweep workspace."""
+        if self._buf is None or self._buf[0] != (B, T):
+            K, C, dev = self.K, self.C, self.dev
+            self._buf = ((B, T), torch.empty(B, T, K, device=dev), torch.empty(B, T, K * C, device=dev),
+                         {"gamma": torch.empty(B, T, K, device=dev), "loglik": torch.empty(B, device=dev)},
+                         ops.fb_workspace(B, T, K, dev))
+        return self._buf[1:]
+
     def e_step(self, x: torch.Tensor) -> torch.Tensor:
-        """x [B,T,D] (this rank's utterances).  Adds to self.stats; returns the batch's per-sequence log-likelihoods."""
+        """x [B,T,D] (this rank's utterances).  Adds to self.stats; returns the batch's per-sequence log-likelihoods (a view
+        of reused scratch: copy it if it must outlive the next call).  Everything is enqueued on the current stream; nothing
+        is allocated after the first batch of a shape and no host scalar crosses to the device."""
         x = x.to(self.dev).float().contiguous()
         B, T, D = x.shape
         K, C = self.K, self.C
         lib = _lib.load()
         packed = self._pack()
-        logb = torch.empty(B, T, K, dtype=torch.float32, device=self.dev)
-        comp = torch.empty(B, T, K * C, dtype=torch.float32, device=self.dev)
-        ws = ops.fb_workspace(B, T, K, self.dev)
+        logb, comp, out, ws = self._buffers(B, T)
         with torch.cuda.device(self.dev):          # log b and the per-component values in one pass over x
             ops._check(lib.hmmb200_gmm_emission_components_f32(ops._p(x), ops._p(packed), B * T, K, C, D, ops._p(logb), ops._p(comp),
                                                                ops._stream(self.dev)), "hmmb200_gmm_emission_components_f32")
-        r = ops.forward_backward(logb, ops.EMIS_LOG, self.p.trans, self.p.init, want=("gamma",), workspace=ws)
-        trans = self.p.trans.float().contiguous()
+        # method="sweep": the accumulate kernel reads the scaled alpha / beta the sweeps leave in `ws`; the time-parallel scan
+        # (which "auto" would pick for long utterances at small batch) keeps its own workspace and never writes them
+        r = ops.forward_backward(logb, ops.EMIS_LOG, self._trans, self._init, want=("gamma",), out=out, workspace=ws, method="sweep")
         with torch.cuda.device(self.dev):
             ops._check(lib.hmmb200_bw_accumulate_f32(ops._p(x), ops._p(comp), ops._p(logb), ops._p(r["gamma"]), ops._p(logb),
-                                                     ops.EMIS_LOG, 0.0, ops._p(trans), ops._p(ws), B, T, K, C, D,
+                                                     ops.EMIS_LOG, 0.0, ops._p(self._trans), ops._p(ws), B, T, K, C, D,
                                                      ops._p(self.stats), ops._stream(self.dev)), "hmmb200_bw_accumulate_f32")
         ex = stats_slices(K, C, D)["extra"]
-        self.stats[ex] += torch.stack([r["loglik"].double().sum(), torch.tensor(float(B * T), dtype=torch.float64, device=self.dev),
-                                       torch.tensor(float(B), dtype=torch.float64, device=self.dev)])
+        self.stats[ex.start] += r["loglik"].double().sum()
+        self._n_frames += B * T
+        self._n_seqs += B
         return r["loglik"]
 
     def m_step(self) -> float:
         """All-reduce the statistics, update the parameters (identically on every rank); returns the mean log-likelihood
         per frame over ALL ranks' data for the parameters the E-step used."""
-        all_reduce_stats(self.stats)
-        ex = self.stats[stats_slices(self.K, self.C, self.D)["extra"]]
-        ll_per_frame = float(ex[0] / ex[1])
+        ex = stats_slices(self.K, self.C, self.D)["extra"]
+        self.stats[ex.start + 1:ex.stop] = torch.tensor([float(self._n_frames), float(self._n_seqs)], dtype=torch.float64)
+        all_reduce_stats(self.stats)                 # one collective per EM iteration, enqueued behind the last statistics kernel
+        exv = self.stats[ex]
+        ll_per_frame = float(exv[0] / exv[1])
         self.p = m_step_from_stats(self.stats, self.K, self.C, self.D, self.var_floor).to(self.dev)
         self.reset()
         return ll_per_frame

@@ -26,30 +26,35 @@ struct EmisParams {
 };
 
 // packed layout: float4 prm[D][NP] = (s_{2p}, s_{2p+1}, nms_{2p}, nms_{2p+1}); then float cst[2*NP].
-__global__ void gmm_pack_kernel(const float *means, const float *log_vars, float scale, const float *logw,
-                                int KC, int D, int NP, float *packed) {
-    const int kc = blockIdx.x * blockDim.x + threadIdx.x;
+// One warp per component slot (lanes over the dimensions; the double-precision exp per element is the cost).
+__global__ void __launch_bounds__(32) gmm_pack_kernel(const float *means, const float *log_vars, float scale, const float *logw,
+                                                      int KC, int D, int NP, float *packed) {
+    const int kc = blockIdx.x, lane = threadIdx.x;
     if (kc >= 2 * NP) return;
     float *cst = packed + (size_t)D * NP * 4;
     const int pr = kc >> 1, hi = kc & 1;
     if (kc >= KC) {
-        for (int d = 0; d < D; ++d) {
+        for (int d = lane; d < D; d += 32) {
             packed[((size_t)d * NP + pr) * 4 + hi] = 0.f;
             packed[((size_t)d * NP + pr) * 4 + 2 + hi] = 0.f;
         }
-        cst[kc] = -INFINITY;
+        if (lane == 0) cst[kc] = -INFINITY;
         return;
     }
     double sum_lv = 0.0;
-    for (int d = 0; d < D; ++d) {
+    for (int d = lane; d < D; d += 32) {
         const double lv = (double)scale * (double)log_vars[(size_t)kc * D + d];
         const double s = exp(-0.5 * lv);
         packed[((size_t)d * NP + pr) * 4 + hi] = (float)s;
         packed[((size_t)d * NP + pr) * 4 + 2 + hi] = (float)(-(double)means[(size_t)kc * D + d] * s);
         sum_lv += lv;
     }
-    const double lw = logw ? (double)logw[kc] : 0.0;
-    cst[kc] = (float)(lw - 0.5 * (sum_lv + (double)D * 1.8378770664093454835606594728112));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum_lv += __shfl_xor_sync(FULL_MASK, sum_lv, o);
+    if (lane == 0) {
+        const double lw = logw ? (double)logw[kc] : 0.0;
+        cst[kc] = (float)(lw - 0.5 * (sum_lv + (double)D * 1.8378770664093454835606594728112));
+    }
 }
 
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -245,8 +250,7 @@ HMMB200_EXPORT int hmmb200_gmm_pack_f32(const float *means, const float *log_var
     if (!log_weights && C != 1) return set_error(HMMB200_EINVAL, "gmm_pack: log_weights may be NULL only when C == 1");
     if (int rc = require_sm100()) return rc;
     const int KC = K * C, NP = (KC + 1) / 2;
-    const int threads = 64, blocks = (2 * NP + threads - 1) / threads;
-    gmm_pack_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(means, log_vars, log_var_scale, log_weights, KC, D, NP, packed);
+    gmm_pack_kernel<<<2 * NP, 32, 0, (cudaStream_t)stream>>>(means, log_vars, log_var_scale, log_weights, KC, D, NP, packed);
     if (int rc = check_launch("gmm_pack_kernel")) return rc;
     if (tc_shape_ok(K, C, D))
         return launch_pack_tc(means, log_vars, log_var_scale, log_weights, K, C, D, packed + fp32_section_floats(K, C, D),

@@ -138,12 +138,17 @@ struct LkSmem {
     uint64_t bar[LK_NG][2];
 };
 
-// timing trace (debug aid, tools/lk_trace.py): clock64 at the phase boundaries of steps 64..71 of CTA 0, thread 0, group 0
+// timing trace (debug builds only, -DHMMB200_DEBUG_HOOKS; tools/lk_trace.py): clock64 at the phase boundaries of steps 64..71 of
+// CTA 0, thread 0, group 0.  Release builds carry no device globals, no environment look-ups and no debug exports.
+#ifdef HMMB200_DEBUG_HOOKS
 __device__ long long lk_trace_buf[8 * 8];
 #define LK_TRACE(slot)                                                                          \
     do {                                                                                        \
         if (p.trace && g == 0 && blockIdx.x == 0 && (tid & (LK_FINAL - 1)) == 0 && t >= 64 && t < 72) lk_trace_buf[(t - 64) * 8 + (slot)] = clock64(); \
     } while (0)
+#else
+#define LK_TRACE(slot) do { } while (0)
+#endif
 
 // One cluster = CS CTAs x LK_NG groups of NSQ (3 or 4) sequences.  The groups are independent recursions that share the CTA's
 // register-resident slab of P.  Warp roles (register budgets moved between them with setmaxnreg):
@@ -674,11 +679,25 @@ static int lk_launch_nsq(const LkParams &p, cudaStream_t s) {
     return check_launch("lk_sweep_kernel");
 }
 
+// An exchange wait that timed out (never in a correct run) leaves the sweep's outputs undefined: make that visible to a caller
+// who does not look at the flag -- NaN log-likelihoods / scores and a -1 first state per sequence.
+__global__ void lk_poison_kernel(const int *err, int B, int T, float *loglik, float *score, int64_t *states) {
+    if (*err == 0) return;
+    const float nan = __int_as_float(0x7fc00000);
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+        if (loglik) loglik[b] = nan;
+        if (score) score[b] = nan;
+        if (states) states[(size_t)b * T] = -1;
+    }
+}
+
 template <int MODE>
 static int lk_launch(const LkParams &p, cudaStream_t s) {
     const int clusters3 = (p.B + 3 * LK_NG - 1) / (3 * LK_NG);
     bool three = clusters3 <= lk_max_clusters<MODE, 3>(p.CS);
-    if (const char *f = getenv("HMMB200_LK_NSQ")) three = (f[0] == '3');   // tests force either variant
+#ifdef HMMB200_DEBUG_HOOKS
+    if (const char *f = getenv("HMMB200_LK_NSQ")) three = (f[0] == '3');   // debug builds can force either variant
+#endif
     if (three) return lk_launch_nsq<MODE, 3>(p, s);
     return lk_launch_nsq<MODE, 4>(p, s);
 }
@@ -698,7 +717,9 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
     float *rowmax = (float *)w; w += lk_align256(n * sizeof(float));
     p.err = (int *)w;
     cudaMemsetAsync(p.err, 0, sizeof(int), s);
+#ifdef HMMB200_DEBUG_HOOKS
     p.trace = getenv("HMMB200_LK_TRACE") != nullptr;
+#endif
     p.loglik = loglik;
     if (emis_mode == HMMB200_EMIS_LOG || emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR) {
         lk_rowmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(emis, (int64_t)n, K, rowmax);
@@ -720,6 +741,10 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
         c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
         lk_combine_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(c);
         if (int rc = check_launch("lk_combine_kernel")) return rc;
+    }
+    if (loglik != nullptr) {
+        lk_poison_kernel<<<1, 256, 0, s>>>(p.err, B, T, loglik, nullptr, nullptr);
+        if (int rc = check_launch("lk_poison_kernel")) return rc;
     }
     return HMMB200_OK;
 }
@@ -752,13 +777,15 @@ int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const floa
         const unsigned blocks = (unsigned)((n_warps + 7) / 8);
         if (K <= 256) lk_psi_kernel<uint8_t><<<blocks, 256, 0, s>>>(p.delta, log_trans, B, T, K, (uint8_t *)psi);
         else lk_psi_kernel<uint16_t><<<blocks, 256, 0, s>>>(p.delta, log_trans, B, T, K, (uint16_t *)psi);
-        return check_launch("lk_psi_kernel");
+        if (int rc = check_launch("lk_psi_kernel")) return rc;
     }
-    return HMMB200_OK;
+    lk_poison_kernel<<<1, 256, 0, s>>>(p.err, B, T, nullptr, score, states);
+    return check_launch("lk_poison_kernel");
 }
 
 }  // namespace hmmb200
 
+#ifdef HMMB200_DEBUG_HOOKS
 HMMB200_EXPORT int hmmb200_debug_lk_max_clusters(int cs) {
     if (cs < 1 || cs > hmmb200::LK_CSMAX) return -1;
     return hmmb200::lk_max_clusters<hmmb200::LK_FWD, 4>(cs);
@@ -767,3 +794,4 @@ HMMB200_EXPORT int hmmb200_debug_lk_max_clusters(int cs) {
 HMMB200_EXPORT int hmmb200_debug_lk_trace(long long *host64) {
     return (int)cudaMemcpyFromSymbol(host64, hmmb200::lk_trace_buf, sizeof(long long) * 64);
 }
+#endif

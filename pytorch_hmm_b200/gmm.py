@@ -17,6 +17,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from ._cache import DerivedCache
 
 
 class MixtureGaussianHMMLayer(nn.Module):
@@ -29,6 +30,7 @@ class MixtureGaussianHMMLayer(nn.Module):
         self.max_sequence_length = max_sequence_length
         self.eps = 1e-8
         self.log_eps = math.log(self.eps)
+        self._derived = DerivedCache()          # kernel operands, re-derived only when a parameter changes
         S, Cn, D = num_states, num_components, feature_dim
         if learnable_transitions:
             self.transition_logits = nn.Parameter(torch.randn(S, S) * 0.1)
@@ -72,8 +74,29 @@ class MixtureGaussianHMMLayer(nn.Module):
         return self.log_vars
 
     def _packed(self) -> torch.Tensor:
-        logw = self._safe_log(F.softmax(self.mixture_weights_logits, dim=-1))       # mixture_gaussian.py:178-179
-        return ops.gmm_pack(self.means, self._diag_log_vars(), 1.0, logw)
+        """Packed emission parameters (pack kernels + softmax / clamp / log run once per parameter update, not per call)."""
+        def make():
+            logw = self._safe_log(F.softmax(self.mixture_weights_logits, dim=-1))   # mixture_gaussian.py:178-179
+            return ops.gmm_pack(self.means, self._diag_log_vars(), 1.0, logw)
+        return self._derived.get("packed", (self.means, self.log_vars, self.mixture_weights_logits), make)
+
+    def _packed_tc(self):
+        """(packed, tc_known).  The setup-time query synchronises the stream once per parameter update, so it is only made
+        for inference calls; training steps (parameters change every call) take the two-launch dispatch instead."""
+        packed = self._packed()
+        if torch.is_grad_enabled() and self.training:
+            return packed, False
+        tc = self._derived.get("tc_known", (packed,), lambda: ops.gmm_pack_on_tensor_cores(
+            packed, self.num_states, self.num_components, self.feature_dim))
+        return packed, tc
+
+    def _log_transitions(self) -> torch.Tensor:
+        src = self.transition_logits if self.learnable_transitions else self.transition_matrix
+        return self._derived.get("log_trans", (src,), lambda: self._safe_log(self.get_transition_matrix()).contiguous())
+
+    def _prior(self, dev) -> torch.Tensor:
+        S = self.num_states
+        return self._derived.get(f"prior@{dev}", (), lambda: torch.full((S,), -math.log(S), dtype=torch.float32, device=dev))
 
     def get_observation_log_probs(self, observations: torch.Tensor) -> torch.Tensor:
         """(B,T,D) -> (B,T,S) log-likelihood under each state's GMM (mixture_gaussian.py:157-198)."""
@@ -81,8 +104,9 @@ class MixtureGaussianHMMLayer(nn.Module):
             warnings.warn(f"Sequence length {observations.shape[1]} exceeds recommended maximum "
                           f"{self.max_sequence_length}. Consider chunked processing.")
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
-        out = ops.gmm_emission(observations.detach().to(dev), self._packed(), self.num_states, self.num_components,
-                               self.feature_dim)
+        packed, tc = self._packed_tc()
+        out = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, self.num_components,
+                               self.feature_dim, tc_known=tc)
         return out if observations.device == out.device else out.to(observations.device)
 
     def _viterbi_decode(self, obs_log_probs: torch.Tensor, log_transitions: torch.Tensor
@@ -90,7 +114,7 @@ class MixtureGaussianHMMLayer(nn.Module):
         """(B,T,S) raw log-emissions -> (states int64 (B,T), final_scores (B,))  (mixture_gaussian.py:290-338)."""
         dev = ops.require_cuda(obs_log_probs.device if obs_log_probs.is_cuda else None)
         S = obs_log_probs.shape[-1]
-        prior = torch.full((S,), -math.log(S), dtype=torch.float32, device=dev)
+        prior = self._prior(dev) if S == self.num_states else torch.full((S,), -math.log(S), dtype=torch.float32, device=dev)
         r = ops.viterbi(obs_log_probs.detach().to(dev), ops.EMIS_LOG, log_transitions.detach().to(dev), prior,
                         want_delta=False, want_score=True)
         st, sc = r["states"], r["score"]
@@ -101,12 +125,13 @@ class MixtureGaussianHMMLayer(nn.Module):
     def forward(self, observations: torch.Tensor, return_log_probs: bool = False
                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
-        logb = ops.gmm_emission(observations.detach().to(dev), self._packed(), self.num_states, self.num_components,
-                                self.feature_dim)
-        log_trans = self._safe_log(self.get_transition_matrix())                     # mixture_gaussian.py:357
-        states, scores = self._viterbi_decode(logb, log_trans)
+        packed, tc = self._packed_tc()
+        logb = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, self.num_components,
+                                self.feature_dim, tc_known=tc)
+        states, scores = self._viterbi_decode(logb, self._log_transitions())         # mixture_gaussian.py:357
         if return_log_probs and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # value: the kernel's score, bit for bit; gradient: along the decoded path
+            log_trans = self._safe_log(self.get_transition_matrix())
             ps = self._path_score(observations.to(dev), states, log_trans)
             scores = scores.detach() + (ps - ps.detach())
         if observations.device != states.device:

@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from ._cache import DerivedCache
 
 
 class HSMMLayer(nn.Module):
@@ -51,6 +52,11 @@ class HSMMLayer(nn.Module):
         else:
             self.register_buffer("duration_means", torch.ones(S) * 10.0)
         self.register_buffer("duration_range", torch.arange(min_duration, max_duration + 1, dtype=torch.float))
+        self._derived = DerivedCache()          # packed emission parameters and log tables, re-derived when a parameter changes
+
+    def _duration_sources(self):
+        names = ("duration_shape", "duration_rate", "duration_lambda", "duration_scale", "duration_concentration", "duration_means")
+        return [getattr(self, n) for n in names if hasattr(self, n)]
 
     # -- host-side tables (O(K * Dmax), same formulas as the reference) -------------------------------------
     def get_transition_matrix(self) -> torch.Tensor:
@@ -84,14 +90,17 @@ class HSMMLayer(nn.Module):
     def get_observation_log_probs(self, observations: torch.Tensor) -> torch.Tensor:
         """(B,T,D) -> (B,T,S) single diagonal Gaussian per state (hsmm.py:181-206) on the emission kernel."""
         dev = self._cuda()
-        packed = ops.gmm_pack(self.observation_means, self.observation_log_vars, 1.0, None)
+        packed = self._derived.get("packed", (self.observation_means, self.observation_log_vars),
+                                   lambda: ops.gmm_pack(self.observation_means, self.observation_log_vars, 1.0, None))
         out = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, 1, self.feature_dim)
         return out if observations.device == out.device else out.to(observations.device)
 
     def _tables(self, dev):
-        log_dur = torch.log(self.get_duration_probabilities().detach() + self.eps)           # hsmm.py:227
-        log_trans = torch.log(self.get_transition_matrix().detach() + self.eps)              # hsmm.py:229
-        return log_dur.to(dev), log_trans.to(dev)
+        def make():
+            log_dur = torch.log(self.get_duration_probabilities().detach() + self.eps)       # hsmm.py:227
+            log_trans = torch.log(self.get_transition_matrix().detach() + self.eps)          # hsmm.py:229
+            return log_dur.to(dev).contiguous(), log_trans.to(dev).contiguous()
+        return self._derived.get(f"tables@{dev}", [self.transition_logits] + self._duration_sources(), make)
 
     def viterbi_decode_hsmm(self, observations: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         """(B,T,D) -> (states int64 (B,T), scores (B,))  (hsmm.py:208-243)."""
@@ -198,14 +207,18 @@ class SemiMarkovHMM(nn.Module):
         self.observation_means = nn.Parameter(torch.randn(num_states, observation_dim))
         self.observation_logvars = nn.Parameter(torch.zeros(num_states, observation_dim))
         self.observation_model_type = observation_model
+        self._derived = DerivedCache()
 
     def _frame_terms(self, observations: torch.Tensor, dev):
         """Per-frame quadratic term q[t][s] = -0.5 sum_d (x-mu)^2/var and the per-SEGMENT constant
         c[s] = -0.5 sum log var - 0.5 D log 2pi (counted once per segment, semi_markov.py:422-424)."""
-        packed = ops.gmm_pack(self.observation_means, self.observation_logvars, 1.0, None)
+        def make():
+            packed = ops.gmm_pack(self.observation_means, self.observation_logvars, 1.0, None)
+            const = (-0.5 * self.observation_logvars.detach().sum(-1)
+                     - 0.5 * self.observation_dim * math.log(2 * math.pi)).to(dev).float()
+            return packed, const
+        packed, const = self._derived.get(f"packed@{dev}", (self.observation_means, self.observation_logvars), make)
         logb = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, 1, self.observation_dim)
-        const = (-0.5 * self.observation_logvars.detach().sum(-1)
-                 - 0.5 * self.observation_dim * math.log(2 * math.pi)).to(dev).float()
         return logb - const, const
 
     def _tables(self, dev):

@@ -19,6 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
+from ._cache import DerivedCache
 from .core import HMMPyTorch, EPS
 from .transitions import create_left_to_right_matrix, create_transition_matrix
 
@@ -132,6 +133,11 @@ class GaussianHMMLayer(nn.Module):
             self.log_scales = nn.Parameter(torch.zeros(num_states, 1))
         else:
             raise ValueError(f"Unknown covariance_type: {covariance_type}")
+        self._derived = DerivedCache()          # packed emission parameters, re-packed only when means / log_scales change
+
+    def _packed(self) -> torch.Tensor:
+        return self._derived.get("packed", (self.means, self.log_scales),
+                                 lambda: ops.gmm_pack(self.means, self._diag_log_scales(), 2.0, None))
 
     def _diag_log_scales(self) -> torch.Tensor:
         """[K, D] log sigma for every covariance type: the reference's 'full' branch reads only the diagonal of its
@@ -145,14 +151,12 @@ class GaussianHMMLayer(nn.Module):
     def _compute_gaussian_log_probs(self, observations: torch.Tensor) -> torch.Tensor:
         """(B,T,D) -> (B,T,K) log N(x | mu_k, diag(exp(2 log_scales_k)))  (emission kernel)."""
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
-        packed = ops.gmm_pack(self.means, self._diag_log_scales(), 2.0, None)
-        out = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, 1, self.feature_dim)
+        out = ops.gmm_emission(observations.detach().to(dev), self._packed(), self.num_states, 1, self.feature_dim)
         return out if observations.device == out.device else out.to(observations.device)
 
     def _posteriors(self, observations: torch.Tensor, want):
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
-        packed = ops.gmm_pack(self.means, self._diag_log_scales(), 2.0, None)
-        logb = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, 1, self.feature_dim)
+        logb = ops.gmm_emission(observations.detach().to(dev), self._packed(), self.num_states, 1, self.feature_dim)
         hmm = self.hmm_layer._get_hmm()
         trans, init = hmm._effective_probs(dev)
         mode = ops.EMIS_LOG_NORM_FLOOR if self.normalize_emissions else ops.EMIS_LOG_EXP_FLOOR

@@ -44,7 +44,8 @@ def test_e_step_statistics_vs_float64_oracle(hm, B, T, K, C, D):
     ref = c_oracle.bw_stats_f64(x, comp, np.log(P32), np.log(p32))
     sl = bw.stats_slices(K, C, D)
     np.testing.assert_allclose(ll.double().sum().item(), ref["loglik"], rtol=1e-5)
-    np.testing.assert_allclose(stats[sl["extra"]], [ref["loglik"], B * T, B], rtol=1e-5)
+    np.testing.assert_allclose(stats[sl["extra"]][0], ref["loglik"], rtol=1e-5)
+    assert (tr._n_frames, tr._n_seqs) == (B * T, B)              # written into the statistics vector by m_step()
     # 1e-4 relative on every statistic (atol for entries that are numerically zero)
     np.testing.assert_allclose(stats[sl["gamma1"]], ref["gamma1"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(stats[sl["xi"]].reshape(K, K), ref["xi"], rtol=1e-4, atol=1e-5)
@@ -54,6 +55,30 @@ def test_e_step_statistics_vs_float64_oracle(hm, B, T, K, C, D):
     np.testing.assert_allclose(stats[sl["occ"]].sum(), B * T, rtol=1e-5)
     if T > 1:
         np.testing.assert_allclose(stats[sl["xi"]].sum(), B * (T - 1), rtol=1e-5)
+
+
+def test_e_step_long_utterances_use_the_sweep_workspace(hm):
+    """T >= 8192 at small batch is where ops.forward_backward(method="auto") switches to the time-parallel scan, which does not
+    leave the scaled alpha / beta in the caller's workspace: the E-step must pin the sweep.  xi and the
+    occupancies against the float64 oracle."""
+    from pytorch_hmm_b200 import baum_welch as bw
+    B, T, K, C, D = 2, 8300, 5, 2, 8
+    assert hm.ops.use_time_parallel_scan(B, T, K)
+    x, means, var, w, P, p0 = _problem(41, B, T, K, C, D)
+    f32 = lambda a: torch.from_numpy(np.asarray(a, np.float32))
+    tr = bw.BaumWelch(bw.GMMHMMParams(f32(P), f32(p0), f32(w), f32(means), f32(var)))
+    ll = tr.e_step(torch.from_numpy(x))
+    stats = tr.stats.cpu().numpy()
+    m32, v32, w32, P32, p32 = (np.asarray(a, np.float32).astype(np.float64) for a in (means, var, w, P, p0))
+    comp = np.log(w32)[None, None] - 0.5 * (((x[:, :, None, None, :].astype(np.float64) - m32[None, None]) ** 2 / v32[None, None]).sum(-1)
+                                            + np.log(v32).sum(-1)[None, None] + D * np.log(2 * np.pi))
+    ref = c_oracle.bw_stats_f64(x, comp, np.log(P32), np.log(p32))
+    sl = bw.stats_slices(K, C, D)
+    assert np.isfinite(stats).all()
+    np.testing.assert_allclose(ll.double().sum().item(), ref["loglik"], rtol=1e-5)
+    np.testing.assert_allclose(stats[sl["xi"]].reshape(K, K), ref["xi"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(stats[sl["occ"]].reshape(K, C), ref["occ"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(stats[sl["xi"]].sum(), B * (T - 1), rtol=1e-5)
 
 
 def test_em_increases_likelihood_and_recovers_structure(hm):

@@ -151,12 +151,11 @@ def test_largek_config5_slice_properties(hm):
     assert np.array_equal(r["score"].cpu().numpy(), sc)
 
 
-@pytest.mark.parametrize("nsq", ["3", "4"])
-@pytest.mark.parametrize("K,T,B", [(512, 24, 13), (200, 30, 7), (64, 17, 1)])
-def test_largek_both_group_sizes(hm, monkeypatch, nsq, K, T, B):
-    """The sweeps run 3 or 4 sequences per group (chosen from the batch size: recursion_largek.cu lk_launch); force each
-    variant on ragged batches: Viterbi bit-exact, posteriors / log-likelihood within 1e-4 of float64."""
-    monkeypatch.setenv("HMMB200_LK_NSQ", nsq)
+# (K, T, B): B <= 90 at K = 512 (8-CTA clusters, at most 15 co-resident) runs 3 sequences per group, larger batches 4
+@pytest.mark.parametrize("K,T,B", [(512, 24, 13), (200, 30, 7), (64, 17, 1), (512, 12, 97), (512, 9, 200), (384, 11, 131)])
+def test_largek_both_group_sizes(hm, K, T, B):
+    """The sweeps run 3 or 4 sequences per group (chosen from the batch size: recursion_largek.cu lk_launch); ragged batches on
+    either side of the switch: Viterbi bit-exact, posteriors / log-likelihood within 1e-4 of float64."""
     rng = np.random.default_rng(9100 + K + B)
     logb = (rng.standard_normal((B, T, K)) * 3.0 - 20.0).astype(np.float32)
     P = rng.random((K, K)).astype(np.float32) ** 3 + 0.01

@@ -1,5 +1,6 @@
 """Phase timeline (clock64) of the large-K forward sweep, CTA 0, steps 64..71.  Debug aid."""
 import ctypes, os, sys
+os.environ["HMMB200_DEBUG_BUILD"] = "1"      # the trace hooks exist in debug builds only (libhmm_b200_dbg.so)
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["HMMB200_LK_TRACE"] = "1"

@@ -1,5 +1,6 @@
 """Dumps the role hand-off timeline of the tcgen05 emission kernel (CTA 0, first tiles).  Debug aid."""
 import ctypes, os, sys
+os.environ["HMMB200_DEBUG_BUILD"] = "1"      # the trace hooks exist in debug builds only (libhmm_b200_dbg.so)
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ["HMMB200_TC_DBG"] = str(8 | int(os.environ.get("TC_EXTRA", "0")))
