@@ -34,9 +34,17 @@ if ROOT not in sys.path:
 K_STATES, N_MIX, FEAT, BATCH, SEQ = 12, 4, 80, 256, 2000
 BYTES_PER_FRAME = 4 * FEAT + 4 * K_STATES * 4 + 8          # x in; posterior, forward, backward, log_delta + int64 state out
 METRIC = "frames/sec forward-backward+Viterbi (K=12,T=2000,B=256)"
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this workload
-NCU_TRAFFIC_SRC = "profiles/r01_ncu_full_summary.md"
-NCU_TRAFFIC = {"gmm_emission_tc_kernel": 175.8e6, "fb_sweep_kernel": 30.0e6, "fb_combine_kernel": 73.4e6, "viterbi_kernel": 24.7e6}
+# dram__bytes_read.sum + dram__bytes_write.sum per launch come from the committed `ncu --set full` capture of this workload
+# (a profiler run cannot be part of a timed run): profiles/ncu_traffic.json, written from the capture by tools/ncu_traffic.py
+NCU_TRAFFIC_SRC = "profiles/ncu_traffic.json"
+
+
+def ncu_traffic():
+    try:
+        with open(os.path.join(ROOT, NCU_TRAFFIC_SRC)) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def measured_peaks():
@@ -137,40 +145,82 @@ def cpu_port_step(model, x):
                                       log_P, log_p0, log_trans)
 
 
-def time_cpu_port(model, x_sample, steps, warmup):
+CHUNK = 32            # sequences per CPU pass: B=256 is run as 8 x B=32 (sequences are independent, so chunking is exact;
+                      # the [B,T,S,C,D] temporaries of the reference need ~27 GB at B=256)
+
+
+def host_ram_gb():
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemTotal"):
+                    return round(int(ln.split()[1]) / 1048576.0, 1)
+    except Exception:
+        pass
+    return None
+
+
+def cpu_port_batch(model, x, n_chunks):
+    """One CPU step = the first n_chunks chunks of 32 sequences of the B=256 batch (8 chunks = the full configuration)."""
+    for c in range(n_chunks):
+        cpu_port_step(model, x[c * CHUNK:(c + 1) * CHUNK])
+
+
+def pick_threads(model, x):
+    """time the reference with all host threads and with one, quote the faster (the recursion is
+    dispatch-bound, the emission is not)."""
+    best = None
+    for nt in sorted({os.cpu_count() or 1, 1}, reverse=True):
+        torch.set_num_threads(nt)
+        cpu_port_step(model, x[:8])                                   # warm
+        t0 = time.perf_counter(); cpu_port_step(model, x[:CHUNK]); dt = time.perf_counter() - t0
+        if best is None or dt < best[1]:
+            best = (nt, dt)
+    torch.set_num_threads(best[0])
+    return best
+
+
+def time_cpu_port(model, x, n_chunks, steps, warmup):
     for _ in range(warmup):
-        cpu_port_step(model, x_sample)
+        cpu_port_batch(model, x, n_chunks)
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu_port_step(model, x_sample)
+        cpu_port_batch(model, x, n_chunks)
     dt = (time.perf_counter() - t0) / max(steps, 1)
-    return x_sample.shape[0] * x_sample.shape[1] / dt, dt
+    return n_chunks * CHUNK * SEQ / dt, dt
+
+
+def cpu_sample_text(n_chunks, threads, chunk_s):
+    full = n_chunks * CHUNK == BATCH
+    return (f"{n_chunks} x {CHUNK} = {n_chunks * CHUNK} of {BATCH} sequences x T={SEQ} per step"
+            + (" (the full configuration, chunked: sequences are independent)" if full else " (bounded sample)")
+            + f"; oracle/ref_port.py = op-for-op torch port of the reference, pinned bit-identical to it by tests/test_oracle_golden.py; "
+              f"{threads} thread(s) (faster of all-threads / 1 thread); {chunk_s:.2f} s per {CHUNK}-sequence chunk; host RAM {host_ram_gb()} GB")
 
 
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
     model = make_model()
-    # bounded sample: the recursion is dispatch-bound, so keep the per-step cost ~1-2 s and the whole run in minutes
-    budget_s = 150.0
-    bs = 32
-    x = make_frames(model, bs, SEQ, 2001)
-    t0 = time.perf_counter(); cpu_port_step(model, x[:8]); probe = time.perf_counter() - t0
-    per_step = probe * 2.5                                   # B=32 costs roughly 2-3x the B=8 probe
-    while bs > 4 and per_step * (args.steps + args.warmup) > budget_s:
-        bs //= 2; per_step *= 0.6
-    x = x[:bs].contiguous()
-    fps, dt = time_cpu_port(model, x, args.steps, args.warmup)
-    cores = torch.get_num_threads()
-    sample = f"{bs} of {BATCH} sequences x T={SEQ} per step (op-for-op torch port of the reference, all host threads)"
+    x = make_frames(model, BATCH, SEQ, 2001)
+    threads, chunk_s = pick_threads(model, x)
+    # the full configuration (8 chunks per step) when the whole run fits ~4 minutes, else as many chunks per step as do
+    budget_s = 240.0
+    n_chunks = BATCH // CHUNK
+    while n_chunks > 1 and n_chunks * chunk_s * (args.steps + args.warmup) > budget_s:
+        n_chunks //= 2
+    steps, warmup = args.steps, args.warmup
+    fps, dt = time_cpu_port(model, x, n_chunks, steps, warmup)
+    sample = cpu_sample_text(n_chunks, threads, chunk_s)
     emit_result({
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: mixture_gaussian K=12, 4 mixtures, D=80, B=256, T=2000 (CPU arm runs a bounded sample)",
-                   "B": BATCH, "T": SEQ, "K": K_STATES, "C": N_MIX, "D": FEAT},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": "configs[1]: mixture_gaussian K=12, 4 mixtures, D=80, B=256, T=2000 (CPU arm: 8 chunks of 32 sequences "
+                               "per step when the run fits the time budget, else a bounded sample)",
+                   "B": BATCH, "T": SEQ, "K": K_STATES, "C": N_MIX, "D": FEAT, "same_config": n_chunks * CHUNK == BATCH,
+                   "host_ram_gb": host_ram_gb()},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
 
@@ -181,7 +231,7 @@ def run_reference_arm(args, rank):
 class Headline:
     """Device-side state of the headline step, through the public engine / ops of pytorch_hmm_b200."""
 
-    def __init__(self, model, dev, shard=None, n_streams=1, host_io=False):
+    def __init__(self, model, dev, shard=None, n_streams=1, host_io=False, fused=True):
         import pytorch_hmm_b200 as hm
         from pytorch_hmm_b200.engine import HMMInferenceEngine
         self.hm, self.dev = hm, dev
@@ -189,7 +239,7 @@ class Headline:
         self.layer.load_state_dict({k: v.to(dev) for k, v in model.items()})
         self.layer.eval()
         self.eng = HMMInferenceEngine(self.layer, BATCH, SEQ, shard=shard or BATCH, n_streams=n_streams, device=dev,
-                                      host_io=host_io)
+                                      host_io=host_io, fused=fused)
         e = self.eng
         self.logb = e.slots[0].logb
         self.launches_per_step = e.kernels_per_shard * e.n_shards
@@ -212,6 +262,14 @@ class Headline:
         self.hm.ops.viterbi(self.logb, self.hm.ops.EMIS_LOG, e.log_trans, e.prior,
                             out={"states": o["states"], "delta": o["log_delta"], "score": o["score"]},
                             workspace=e.slots[0].vit_ws)
+
+    def fused(self, want=("gamma", "fwd", "bwd")):
+        e, o = self.eng, self.eng.out
+        out = {"loglik": o["loglik"], "states": o["states"], "delta": o["log_delta"], "score": o["score"]}
+        if want:
+            out.update({"gamma": o["posterior"], "fwd": o["forward"], "bwd": o["backward"]})
+        self.hm.ops.forward_backward_viterbi(self.logb, self.hm.ops.EMIS_LOG_NORM_FLOOR, self.hm.ops.EMIS_LOG, e.trans, e.init,
+                                             e.log_trans, e.prior, want=want, out=out, workspace=e.slots[0].fused_ws)
 
     def step(self, x):
         self.eng.run_device(x)
@@ -259,6 +317,174 @@ def pin_to_gpu_numa_node(local_rank):
         return f"numa: not pinned ({type(exc).__name__})"
 
 
+# ------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configs, short blocks (driver-visible numbers; each is a few launches)
+# ------------------------------------------------------------------------------------------------------------
+def _ms(fn, it=3, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    return event_ms(fn, it)
+
+
+def extra_config1(dev):
+    """configs[0]: HMMPyTorch left-to-right K=10, D=80 diag-Gaussian, forward_backward + viterbi_decode, B=32, T=1000."""
+    import pytorch_hmm_b200 as hm
+    K, D, B, T = 10, 80, 32, 1000
+    torch.manual_seed(1001)
+    g = hm.GaussianHMMLayer(K, D, normalize_emissions=True).to(dev).eval()
+    P = hm.create_left_to_right_matrix(K, 0.7)
+    path = (torch.arange(T) * K // T).expand(B, T)
+    x = (g.means.detach().cpu()[path] + torch.randn(B, T, D)).to(dev)
+    hmm = hm.HMMPyTorch(P, None, device=str(dev))
+    trans, init = hmm._effective_probs(dev)
+    logP, logp0 = hmm.log_P.to(dev), hmm.log_p0.to(dev)
+
+    def step():
+        logb = g._compute_gaussian_log_probs(x)
+        hm.ops.forward_backward_viterbi(logb, hm.ops.EMIS_LOG_NORM_FLOOR, hm.ops.EMIS_LOG_NORM_FLOOR, trans, init, logP, logp0,
+                                        want=("gamma", "fwd", "bwd"))
+    ms = _ms(step, it=20, warm=3)
+    return {"config": "configs[0]: K=10 left-to-right, D=80 diag-Gaussian, B=32, T=1000 (emission + forward_backward + viterbi_decode)",
+            "ms_per_step": ms, "frames_per_s": B * T / (ms * 1e-3)}
+
+
+def extra_config4(dev):
+    """configs[3]: HSMM K=10, max_duration=20, D=80, B=128, T=2000, duration-augmented forward-backward (+ explicit-duration Viterbi)."""
+    import warnings
+    import pytorch_hmm_b200 as hm
+    K, Dm, D, B, T = 10, 20, 80, 128, 2000
+    torch.manual_seed(4001)
+    m = hm.HSMMLayer(K, D, duration_distribution="gamma", max_duration=Dm).to(dev).eval()
+    with torch.no_grad():
+        m.observation_means.mul_(10.0)
+    x = torch.randn(B, T, D, device=dev) + m.observation_means.detach()[torch.randint(0, K, (B, T), device=dev)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        logb = m.get_observation_log_probs(x)
+        log_dur, log_trans = m._tables(dev)
+        e_ms = _ms(lambda: m.get_observation_log_probs(x))
+        fb_ms = _ms(lambda: hm.ops.hsmm_forward_backward(logb, log_dur, log_trans))
+        v_ms = _ms(lambda: hm.ops.hsmm_viterbi(logb, log_dur, log_trans, sum_order=0))
+    return {"config": "configs[3]: HSMM K=10, Dmax=20, D=80, B=128, T=2000", "emission_ms": e_ms, "forward_backward_ms": fb_ms,
+            "viterbi_ms": v_ms, "frames_per_s_fb_plus_viterbi": B * T / ((e_ms + fb_ms + v_ms) * 1e-3)}
+
+
+def extra_config5(dev):
+    """configs[4]: K=512 ergodic, B=64, T=4000: forward_backward + viterbi_decode on softmax(randn) observations."""
+    import pytorch_hmm_b200 as hm
+    K, B, T = 512, 64, 4000
+    torch.manual_seed(5001)
+    P = hm.create_transition_matrix(K, "ergodic")
+    hmm = hm.HMMPyTorch(P, None, device=str(dev))
+    obs = torch.softmax(torch.randn(B, T, K, device=dev), dim=-1)
+    trans, init = hmm._effective_probs(dev)
+    n = (B, T, K)
+    out = {k: torch.empty(n, device=dev) for k in ("gamma", "fwd", "bwd", "delta")}
+    out.update({"loglik": torch.empty(B, device=dev), "states": torch.empty(B, T, dtype=torch.int64, device=dev),
+                "score": torch.empty(B, device=dev)})
+    ws = hm.ops.fb_viterbi_workspace(B, T, K, dev)
+    logP, logp0 = hmm.log_P.to(dev), hmm.log_p0.to(dev)
+
+    def step():
+        hm.ops.forward_backward_viterbi(obs, hm.ops.EMIS_PROB_FLOOR, hm.ops.EMIS_PROB_FLOOR, trans, init, logP, logp0,
+                                        want=("gamma", "fwd", "bwd"), out=out, workspace=ws)
+    ms = _ms(step, it=3, warm=1)
+    return {"config": "configs[4]: K=512 ergodic, B=64, T=4000 (forward_backward + viterbi_decode)", "ms_per_step": ms,
+            "frames_per_s": B * T / (ms * 1e-3)}
+
+
+def _hash_uniform(idx: torch.Tensor, salt: int) -> torch.Tensor:
+    """Counter-based uniform(0,1) from an int64 index tensor (splitmix64 finaliser): a pure function of (index, salt), so every
+    sharding of the utterance list sees bit-identical data whatever the rank."""
+    z = idx + (salt * 0x9E3779B97F4A7C15 & 0x7FFFFFFFFFFFFFFF)
+    z = (z ^ (z >> 30)) * (-4658895280553007687)              # 0xBF58476D1CE4E5B9 as int64
+    z = (z ^ (z >> 27)) * (-7723592293110705685)              # 0x94D049BB133111EB as int64
+    z = z ^ (z >> 31)
+    # bits 10..62 (the arithmetic shifts above leave the sign bit clear)
+    return ((z >> 10) & ((1 << 53) - 1)).double().mul_(1.0 / (1 << 53)).float().clamp_(1e-7, 1.0 - 1e-7)
+
+
+def bw_utterances(model, u_lo: int, u_hi: int, T: int, dev) -> torch.Tensor:
+    """Utterances [u_lo, u_hi) of the config-3 corpus, generated ON THE DEVICE as a function of the utterance id only:
+    the state changes every 8 frames (hashed), the mixture component per frame (hashed), Gaussian noise by Box-Muller."""
+    K, C, D = K_STATES, N_MIX, FEAT
+    n = u_hi - u_lo
+    u = torch.arange(u_lo, u_hi, device=dev, dtype=torch.int64).view(n, 1)
+    t = torch.arange(T, device=dev, dtype=torch.int64).view(1, T)
+    st = (_hash_uniform(u * 1_000_003 + t // 8, 1) * K).long().clamp_(max=K - 1)
+    cp = (_hash_uniform(u * 1_000_003 + t, 2) * C).long().clamp_(max=C - 1)
+    base = (u * T + t).view(n, T, 1) * D + torch.arange(D, device=dev, dtype=torch.int64).view(1, 1, D)
+    z = torch.sqrt(-2.0 * torch.log(_hash_uniform(base, 3))) * torch.cos(6.283185307179586 * _hash_uniform(base, 4))
+    means, lv = model["means"].to(dev), model["log_vars"].to(dev)
+    return (means[st, cp] + torch.exp(0.5 * lv[st, cp]) * z).contiguous()
+
+
+def extra_baum_welch(dev, rank, world, n_utts, iters=3, batch=256):
+    """configs[2]: Baum-Welch EM over n_utts synthetic utterances (K=12, C=4, D=80, T=2000), utterances sharded contiguously
+    across ranks, ONE all-reduce of the sufficient statistics (7 888 doubles) per EM iteration."""
+    import torch.distributed as dist
+    from pytorch_hmm_b200 import baum_welch as bw
+    model = make_model(3001)
+    lo, hi = bw.shard_range(n_utts, rank, world)
+    batches = [bw_utterances(model, s, min(hi, s + batch), SEQ, dev) for s in range(lo, hi, batch)]
+    K, C, D = K_STATES, N_MIX, FEAT
+    g = torch.Generator().manual_seed(3001)
+    start = bw.GMMHMMParams(torch.softmax(model["transition_logits"], -1), torch.full((K,), 1.0 / K),
+                            torch.softmax(model["mixture_weights_logits"], -1),
+                            model["means"] + 0.05 * torch.randn(K, C, D, generator=g), torch.ones(K, C, D))
+    tr = bw.BaumWelch(start, device=dev)
+    hist, times, ar_us = [], [], []
+    for it in range(iters + 1):                                    # iteration 0 warms the kernels up and is not reported
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, m, e = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        s.record()
+        for xb in batches:
+            tr.e_step(xb)
+        m.record()
+        ll = tr.m_step()                                           # all-reduce (NCCL) + closed-form update on every rank
+        e.record(); e.synchronize()
+        t_all = torch.tensor([s.elapsed_time(e), m.elapsed_time(e)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+        if it > 0:
+            hist.append(ll); times.append(float(t_all[0]) * 1e-3); ar_us.append(float(t_all[1]) * 1e3)
+    return {"config": f"configs[2]: Baum-Welch EM, {n_utts} utterances x T={SEQ}, K=12, C=4, D=80, utterance-sharded x{world}",
+            "utterances": n_utts, "frames_per_iteration": n_utts * SEQ, "iterations_timed": iters,
+            "frames_per_s_per_iter": [n_utts * SEQ / t for t in times], "ms_per_iteration": [t * 1e3 for t in times],
+            "allreduce_plus_mstep_us": ar_us, "loglik_per_frame": hist,
+            "collective": "one all_reduce(SUM) of 7 888 float64 per EM iteration (NCCL)" if world > 1 else "none at N=1",
+            "data": "generated on the device as a function of the utterance id only (counter-based hash), resident in HBM"}
+
+
+def copies_only_ms(he, x_host, outs_host, n, barrier):
+    """The platform bound of the end-to-end step: the SAME pinned-host <-> device copies on the same shards and streams with no
+    kernel in between."""
+    eng = he.eng
+
+    def step(i):
+        main = eng._fan_out()
+        for sh in range(eng.n_shards):
+            slot = eng.slots[sh % eng.n_streams]
+            lo, hi = sh * eng.shard, min(eng.B, (sh + 1) * eng.shard)
+            with torch.cuda.stream(slot.stream):
+                slot.x[:hi - lo].copy_(x_host[lo:hi], non_blocking=True)
+                for name, dst in outs_host[i & 1].items():
+                    dst[lo:hi].copy_(eng.out[name][lo:hi], non_blocking=True)
+    for i in range(2):
+        step(i)
+    eng.join(); torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(n):
+        step(i)
+    eng.join()
+    barrier()
+    return (time.perf_counter() - t0) * 1e3 / n
+
+
 def run_gpu_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -270,20 +496,30 @@ def run_gpu_arm(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     model = make_model()
     x_host = make_frames(model, BATCH, SEQ, 2001 + 7919 * rank).pin_memory()     # this rank's shard of utterances
-    x = x_host.to(dev, non_blocking=True)
-    h = Headline(model, dev)
+    # two device-resident input batches, alternated by the timed loop: no step can find its own x in L2 from the step before
+    xs = [x_host.to(dev, non_blocking=True), x_host.flip(0).contiguous().to(dev)]
+    x = xs[0]
+    h = Headline(model, dev, fused=not args.unfused)
     torch.cuda.synchronize()
-    # one pass = one CUDA-graph launch (emission, then forward-backward || Viterbi on two streams); falls back to
-    # eager stream launches if capture is refused
-    graph = None
+    # one pass = one CUDA-graph launch (emission -> fused forward + backward + Viterbi -> posteriors); eager stream launches if
+    # capture is refused
+    graphs = None
     if not args.no_graph:
         try:
-            graph = h.eng.capture_device(x)
+            graphs = [h.eng.capture_device(xi) for xi in xs]
         except Exception as exc:                                  # noqa: BLE001
             print(f"bench.py: CUDA-graph capture failed ({exc}); timing eager launches", file=sys.stderr)
-            graph = None
+            graphs = None
             torch.cuda.synchronize()
-    step = (lambda: graph.replay()) if graph is not None else (lambda: h.step(x))
+    counter = [0]
+
+    def step():
+        i = counter[0] & 1
+        counter[0] += 1
+        if graphs is not None:
+            graphs[i].replay()
+        else:
+            h.step(xs[i])
 
     def barrier():
         if world > 1:
@@ -295,7 +531,7 @@ def run_gpu_arm(args, rank, world, local_rank):
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
-    # ---- timed region: K steps, inputs resident in HBM; x (164 MB) + logb + outputs exceed the 126 MB L2 ----
+    # ---- timed region: K steps, inputs resident in HBM; x (164 MB, two alternating batches) + logb + outputs exceed the 126 MB L2 ----
     barrier()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
@@ -321,35 +557,38 @@ def run_gpu_arm(args, rank, world, local_rank):
     it = max(10, min(args.steps, 50))
     k_ms = {
         "gmm_emission_tc_kernel": event_ms(lambda: h.emission(x), it),
-        "fb_sweep_kernel": event_ms(lambda: h.fb(want=()), it),
-        "fb_sweep_kernel+fb_combine_kernel": event_ms(lambda: h.fb(), it),
-        "viterbi_kernel": event_ms(lambda: h.vit(), it),
+        "fb_viterbi_kernel": event_ms(lambda: h.fused(want=()), it),
+        "fb_viterbi_kernel+fb_combine_kernel": event_ms(lambda: h.fused(), it),
+        "fb_sweep_kernel (stand-alone)": event_ms(lambda: h.fb(want=()), it),
+        "viterbi_kernel (stand-alone)": event_ms(lambda: h.vit(), it),
     }
-    k_ms["fb_combine_kernel"] = max(k_ms["fb_sweep_kernel+fb_combine_kernel"] - k_ms["fb_sweep_kernel"], 0.0)
+    k_ms["fb_combine_kernel"] = max(k_ms["fb_viterbi_kernel+fb_combine_kernel"] - k_ms["fb_viterbi_kernel"], 0.0)
     frames = BATCH * SEQ
     alg_bytes = {   # algorithmic bytes per launch (per-frame figure x frames per launch), DESIGN.md "Kernels"
         "gmm_emission_tc_kernel": (4 * FEAT + 4 * K_STATES) * frames,
-        "fb_sweep_kernel": (4 * K_STATES + 2 * (4 * K_STATES + 4)) * frames,
+        # log b in (once: the forward and Viterbi loaders hit the same lines), scaled alpha / beta + log-scales out, delta + int64 state out
+        "fb_viterbi_kernel": (4 * K_STATES + 2 * (4 * K_STATES + 4) + 4 * K_STATES + 8) * frames,
         "fb_combine_kernel": (2 * (4 * K_STATES + 4) + 3 * 4 * K_STATES) * frames,
-        "viterbi_kernel": (4 * K_STATES + 4 * K_STATES + 8) * frames,
     }
     dom = max(alg_bytes, key=lambda k: k_ms[k])
     peak, peak_src = measured_peaks()
     achieved = alg_bytes[dom] / (k_ms[dom] * 1e-3) / 1e9
+    traffic = ncu_traffic()
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC.get(dom), "traffic_source": NCU_TRAFFIC_SRC, "peak_source": peak_src,
+                "traffic": traffic.get(dom), "traffic_source": NCU_TRAFFIC_SRC, "peak_source": peak_src,
                 "kernel_ms": {k: round(v, 4) for k, v in k_ms.items()},
-                "note": "the recursion kernels are bound by the latency of T dependent steps, not by HBM (DESIGN.md 4.2); "
+                "note": "the recursion kernel is bound by the latency of T dependent steps, not by HBM (DESIGN.md 4.2); "
                         "per-kernel fractions: " + ", ".join(
-                            f"{k} {alg_bytes[k] / (k_ms[k] * 1e-3) / 1e9 / peak:.3f}" for k in alg_bytes)
-                        + " (fb_combine = the posterior kernel fb_combine_warp_kernel, timed as fb minus the sweeps; its inputs are"
-                          " still in L2 from the sweeps and its outputs are written back after it ends, so its figure can exceed the HBM peak)",
+                            f"{k} {alg_bytes[k] / (max(k_ms[k], 1e-6) * 1e-3) / 1e9 / peak:.3f}" for k in alg_bytes)
+                        + " (fb_combine = the posterior kernel fb_combine_warp_kernel, timed as the fused pass minus the recursion kernel; its"
+                          " inputs are still in L2 from the sweeps and its outputs are written back after it ends, so its figure can exceed"
+                          " the HBM peak)",
                 "path": {"bytes_per_frame": BYTES_PER_FRAME, "achieved": value / world * BYTES_PER_FRAME / 1e9,
                          "frac": value / world * BYTES_PER_FRAME / 1e9 / peak}}
 
     # ---- end to end: pinned host buffers in, pinned host buffers out, copies inside the timed region.  The public
     #      engine shards the batch over 4 streams so that H2D, kernels and D2H of different shards overlap. ----
-    he = Headline(model, dev, shard=args.e2e_shard, n_streams=args.e2e_streams, host_io=True)
+    he = Headline(model, dev, shard=args.e2e_shard, n_streams=args.e2e_streams, host_io=True, fused=not args.unfused)
     names = ("posterior", "forward", "backward", "log_delta", "states")
     outs_host = [{k: torch.empty(he.eng.out[k].shape, dtype=he.eng.out[k].dtype).pin_memory() for k in names} for _ in range(2)]
     h2d = x_host.numel() * 4
@@ -374,10 +613,35 @@ def run_gpu_arm(args, rank, world, local_rank):
     e2e = {"value": world * BATCH * SEQ / (e2e_ms * 1e-3), "unit": "frames/s", "ms_per_step": e2e_ms,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e,
            "api": f"HMMInferenceEngine.run_host (shard={he.eng.shard}, streams={he.eng.n_streams})", "host": numa_note}
-    # spot check: the pipelined host path returns what the single-pass device path computed
+    # spot check: the pipelined host path returns what the single-pass device path computed for the same batch
     torch.cuda.synchronize()
+    h.step(xs[0]); torch.cuda.synchronize()
     same = all(torch.equal(outs_host[(n_e2e - 1) & 1][k], h.eng.out[k].cpu()) for k in names)
     e2e["matches_device_pass"] = bool(same)
+    # the platform's bound for this step: the same copies, same shards, same streams, no kernels (all ranks at once)
+    cb = copies_only_ms(he, x_host, outs_host, n_e2e, barrier)
+    if world > 1:
+        t = torch.tensor([cb], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); cb = float(t.item())
+    e2e["copy_bound_ms"] = cb
+    e2e["copy_bound_note"] = (f"copies only ({h2d / 1e6:.0f} MB in + {d2h / 1e6:.0f} MB out per step and rank, {world} rank(s) at once): "
+                              f"{(h2d + d2h) * world / (cb * 1e-3) / 1e9:.1f} GB/s aggregate pinned-memory DMA; e2e step / bound = {e2e_ms / cb:.2f}")
+    del he, outs_host
+    torch.cuda.empty_cache()
+
+    extra = {}
+    if not args.skip_extras:
+        try:
+            extra["baum_welch"] = extra_baum_welch(dev, rank, world, args.bw_utts, iters=args.bw_iters)
+        except Exception as exc:                                  # noqa: BLE001
+            extra["baum_welch"] = {"error": f"{type(exc).__name__}: {exc}"}
+        torch.cuda.empty_cache()
+        if rank == 0:
+            for name, fn in (("config1", extra_config1), ("config4", extra_config4), ("config5", extra_config5)):
+                try:
+                    extra[name] = fn(dev)
+                except Exception as exc:                          # noqa: BLE001
+                    extra[name] = {"error": f"{type(exc).__name__}: {exc}"}
+                torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
@@ -387,20 +651,26 @@ def run_gpu_arm(args, rank, world, local_rank):
             "config": {"workload": "configs[1]: create_speech_hmm mixture_gaussian K=12, 4 mixtures, D=80, B=256, T=2000 "
                                    "(GMM emission -> forward_backward + viterbi_decode), B=256 per GPU",
                        "B": BATCH, "T": SEQ, "K": K_STATES, "C": N_MIX, "D": FEAT, "parallelism": f"utterance-sharded x{world}",
-                       "l2": "no flush: per-step inputs+outputs (164 MB x, 25 MB log b, 102 MB outputs) exceed the 126 MB L2"},
+                       "l2": "no flush: per-step inputs+outputs (164 MB x, 25 MB log b, 102 MB outputs) exceed the 126 MB L2, and the "
+                             "timed loop alternates two resident input batches"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": h.launches_per_step * args.steps, "roofline": roofline,
         }
-        line["config"]["launch"] = "cuda-graph replay per step" if not args.no_graph else "eager stream launches"
+        line["config"]["launch"] = "cuda-graph replay per step" if graphs is not None else "eager stream launches"
+        line["config"]["kernels_per_step"] = ("gmm_emission_tc_kernel, fb_viterbi_kernel, fb_combine_warp_kernel" if not args.unfused
+                                              else "gmm_emission_tc_kernel, fb_sweep_kernel, fb_combine_warp_kernel, viterbi_kernel")
+        if extra:
+            line["extra"] = extra
         if world == 1:
             if _ORIG_AFFINITY:
                 os.sched_setaffinity(0, _ORIG_AFFINITY)          # the CPU baseline gets every host core again
-            torch.set_num_threads(os.cpu_count() or 1)
-            bs = 32
-            xs = x_host[:bs].clone()
-            fps, dt = time_cpu_port(model, xs, 3, 1)
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
-                                    "sample": f"{bs} of {BATCH} sequences x T={SEQ}, 1 warm-up + 3 timed passes of oracle/ref_port.py "
-                                              f"({dt:.2f} s per pass)"}
+            xc = x_host.clone()
+            threads, chunk_s = pick_threads(model, xc)
+            n_chunks = BATCH // CHUNK                            # the full configuration when one warm-up + two timed passes fit ~30 s
+            while n_chunks > 1 and 3 * n_chunks * chunk_s > 30.0:
+                n_chunks //= 2
+            fps, dt = time_cpu_port(model, xc, n_chunks, 2, 1)
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                                    "sample": cpu_sample_text(n_chunks, threads, chunk_s) + f"; 1 warm-up + 2 timed steps of {dt:.2f} s"}
         emit_result(line)
     if world > 1:
         dist.barrier()
@@ -429,6 +699,10 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a CUDA-graph replay")
     ap.add_argument("--e2e-shard", type=int, default=32, help="utterances per in-flight shard on the host path")
     ap.add_argument("--e2e-streams", type=int, default=4)
+    ap.add_argument("--unfused", action="store_true", help="forward-backward and Viterbi as separate kernels on two streams (A/B)")
+    ap.add_argument("--skip-extras", action="store_true", help="only the headline configuration (no configs 0/2/3/4 blocks)")
+    ap.add_argument("--bw-utts", type=int, default=65536, help="utterances of the Baum-Welch block (BASELINE configs[2]: 64 k)")
+    ap.add_argument("--bw-iters", type=int, default=2)
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: until it is printed, file descriptor 1 points at stderr so that
     # native libraries (NCCL prints its version banner on stdout at communicator creation) cannot add lines to it

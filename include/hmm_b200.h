@@ -127,6 +127,48 @@ int    hmmb200_viterbi_f32(const float *emis, int emis_mode, float floor_eps,
                            void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Forward-backward AND Viterbi on the same emissions in one pass (K <= 32: ONE launch hosting the forward sweep, the backward
+ * sweep and the Viterbi recursion of a group of sequences in one CTA, each chain on its own SM sub-partition; other shapes: the two
+ * entry points above, back to back).
+ *   replaces  the whole-batch pass the reference times: hmm.forward_backward(obs) then hmm.viterbi_decode(obs)
+ *             pytorch_hmm/examples/benchmark.py:120-196; HMMLayer.forward train / eval, pytorch_hmm/hmm_layer.py:119-131
+ *   The two recursions may read `emis` differently (fb_mode / vit_mode): HMMPyTorch semantics on max-normalised probabilities for
+ *   the posteriors and MixtureGaussianHMMLayer._viterbi_decode on the raw log-emissions is the BASELINE configs[1] step.
+ *   Arguments and outputs as for hmmb200_forward_backward_f32 and hmmb200_viterbi_f32 (same NULL rules).
+ *   flags: HMMB200_FUSED_PDL -- launch with programmatic stream serialisation: the kernel's set-up overlaps the tail of the
+ *     preceding kernel on `stream` (normally the emission kernel writing `emis`); the caller promises that this preceding kernel
+ *     writes none of trans_prob / init_prob / log_trans / log_init.
+ *   workspace: hmmb200_fb_viterbi_workspace_bytes(B, T, K) bytes.
+ * --------------------------------------------------------------------------------------------------------- */
+#define HMMB200_FUSED_PDL 1
+size_t hmmb200_fb_viterbi_workspace_bytes(int B, int T, int K);
+int    hmmb200_fb_viterbi_f32(const float *emis, int fb_mode, int vit_mode, float floor_eps, int add_rowmax,
+                              const float *trans_prob, const float *init_prob,
+                              const float *log_trans, const float *log_init, int B, int T, int K,
+                              float *gamma, float *fwd_prob, float *bwd_prob, float *log_alpha, float *log_beta,
+                              float *loglik, float *delta, void *psi, int64_t *states, float *score,
+                              void *workspace, size_t workspace_bytes, int flags, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Recursions with TIME-VARYING transitions (K <= 32): the NeuralHMM form of the path.
+ *   replaces  NeuralHMM._forward_algorithm / _backward_algorithm    pytorch_hmm/neural.py:403-461
+ *             NeuralHMM.viterbi_decode (recursion + backtrack)       pytorch_hmm/neural.py:463-511
+ *   log_emis [B,T,K] log-emissions, used as they are (no floor).  Slice t of the [B,T,K,K] transition tensor carries frame t to
+ *   frame t+1 (neural.py:424, :448, :490); slice T-1 is never read.  Forward-backward takes PROBABILITIES trans_prob =
+ *   exp(log_transition_probs) and init_prob [K] (the recursion runs in scaled-probability space); Viterbi takes the logs.
+ *   Outputs and NULL rules as for the fixed-transition entry points; forward-backward workspace: hmmb200_fb_workspace_bytes(B,T,K);
+ *   Viterbi workspace: hmmb200_tv_viterbi_workspace_bytes (0 when the backpointers fit in shared memory).
+ * --------------------------------------------------------------------------------------------------------- */
+int    hmmb200_tv_forward_backward_f32(const float *log_emis, const float *trans_prob, const float *init_prob,
+                                       int B, int T, int K, float *gamma, float *fwd_prob, float *bwd_prob,
+                                       float *log_alpha, float *log_beta, float *loglik,
+                                       void *workspace, size_t workspace_bytes, void *stream);
+size_t hmmb200_tv_viterbi_workspace_bytes(int B, int T, int K);
+int    hmmb200_tv_viterbi_f32(const float *log_emis, const float *log_trans, const float *log_init,
+                              int B, int T, int K, float *delta, void *psi, int64_t *states, float *score,
+                              void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Explicit-duration (semi-Markov) recursions.
  *   hmmb200_hsmm_viterbi_f32 replaces  HSMMLayer._viterbi_decode_single      pytorch_hmm/hsmm.py:245-354
  *                                      SemiMarkovHMM.viterbi_decode          pytorch_hmm/semi_markov.py:455-570
@@ -200,6 +242,19 @@ int    hmmb200_bw_accumulate_f32(const float *x, const float *comp, const float 
 int    hmmb200_xi_sum_f32(const float *emis, int emis_mode, float floor_eps, const float *trans_prob,
                           const void *fb_workspace, const float *seq_weights, int B, int T, int K,
                           double *xi, double *gamma1, void *stream);
+
+/* Backward pass of a loss on the POSTERIORS (HMMLayer.forward in training mode feeding a loss; the supervised cross-entropy of
+ * HMMLayer.compute_loss, pytorch_hmm/hmm_layer.py:161-167): with grad_gamma = dL/dgamma [B,T,K] and the forward pass's gamma and
+ * workspace, writes dL/d log b [B,T,K] and ADDS dL/d log P [K,K], dL/d log p0 [K] (double; either may be NULL).  K <= 32. */
+int    hmmb200_posterior_backward_f32(const float *emis, int emis_mode, float floor_eps, const float *trans_prob,
+                                      const void *fb_workspace, const float *gamma, const float *grad_gamma,
+                                      int B, int T, int K, float *grad_logb, double *grad_logP, double *grad_logp0, void *stream);
+
+/* Weighted Gaussian-mixture statistics alone: with weight[n,K] per (frame, state) and r = exp(comp - logb) the component
+ * responsibilities,  occ[K,C] += sum_n weight r,  sx[K,C,D] += sum_n weight r x,  sxx[K,C,D] += sum_n weight r x^2  (double).
+ * With weight = dL/d log b these are the sufficient statistics of the emission kernel's backward pass (d/d mu, d/d log var, d/d log w). */
+int    hmmb200_gmm_stats_f32(const float *x, const float *comp, const float *logb, const float *weight, int64_t n_frames,
+                             int K, int C, int D, double *occ, double *sx, double *sxx, void *stream);
 
 #ifdef __cplusplus
 }

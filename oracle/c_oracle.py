@@ -121,3 +121,22 @@ def greedy_decode_f32(logb, logA, prev_state=-1):
     lib().orc_greedy_decode_f32(_p(logb, C.c_float), _p(logA, C.c_float), T, K, int(prev_state),
                                 _p(states, C.c_int64), _p(scores, C.c_float))
     return states, scores
+
+
+def tv_viterbi_f32(logb, logT, logp0):
+    """NeuralHMM Viterbi with time-varying transitions (neural.py:463-511): logT [B,T,K,K], slice t carries frame t -> t+1."""
+    logb, logT, logp0 = _f32(logb), _f32(logT), _f32(logp0)
+    B, T, K = logb.shape
+    delta = np.empty((B, T, K), np.float32); psi = np.empty((B, T, K), np.int32); states = np.empty((B, T), np.int64)
+    lib().orc_tv_viterbi_f32(_p(logb, C.c_float), _p(logT, C.c_float), _p(logp0, C.c_float), B, T, K,
+                             _p(delta, C.c_float), _p(psi, C.c_int32), _p(states, C.c_int64))
+    return states, delta, psi
+
+
+def tv_forward_backward_f64(logb, logT, logp0):
+    logb, logT, logp0 = _f64(logb), _f64(logT), _f64(logp0)
+    B, T, K = logb.shape
+    la = np.empty((B, T, K)); lb = np.empty((B, T, K)); g = np.empty((B, T, K)); ll = np.empty((B,))
+    lib().orc_tv_forward_backward_f64(_p(logb, C.c_double), _p(logT, C.c_double), _p(logp0, C.c_double), B, T, K,
+                                      _p(la, C.c_double), _p(lb, C.c_double), _p(g, C.c_double), _p(ll, C.c_double))
+    return la, lb, g, ll

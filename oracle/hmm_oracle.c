@@ -14,6 +14,8 @@
  *   orc_hsmm_backward_f64      no reference (new); matching beta recursion, checked by brute force in tests
  *   orc_bw_stats_f64           docs/01_hmm_theory.md:196-227       (Baum-Welch sufficient statistics)
  *   orc_greedy_decode_f32      pytorch_hmm/streaming.py:292-308    (per-frame greedy argmax chain)
+ *   orc_tv_viterbi_f32         pytorch_hmm/neural.py:463-511       (NeuralHMM Viterbi, time-varying transitions)
+ *   orc_tv_forward_backward_f64 pytorch_hmm/neural.py:403-461      (NeuralHMM forward / backward, in double)
  *
  * Parity status: pinned.  tests/test_oracle_golden.py checks these against fixtures produced by
  * importing the real reference (oracle/make_golden.py -> the .npz fixtures under tests/golden).
@@ -456,4 +458,78 @@ ORC_API void orc_greedy_decode_f32(const float *logb, const float *logA, int T, 
         }
         s = arg; states[t] = arg; if (scores) scores[t] = best;
     }
+}
+
+
+/* ------------------------------------------------------------------------------------------
+ * NeuralHMM recursions: log-emissions used as they are, a [K,K] log-transition slice per frame.
+ * neural.py:487-499: log_delta[0] = log_init + log_obs[0]; for t >= 1 the slice t-1 carries t-1 -> t:
+ *   (m, psi_t[j]) = max_i(log_delta[t-1][i] + logT[t-1][i][j]) (first index), log_delta[t][j] = m + log_obs[t][j]
+ * neural.py:502-506: s_{T-1} = argmax (first index); s_t = psi_{t+1}[s_{t+1}].
+ * ------------------------------------------------------------------------------------------ */
+ORC_API void orc_tv_viterbi_f32(const float *logb, const float *logT, const float *logp0, int B, int T, int K,
+                                float *delta, int32_t *psi, int64_t *states) {
+    for (int b = 0; b < B; ++b) {
+        const float *lb = logb + (size_t)b * T * K;
+        const float *lt = logT + (size_t)b * T * K * K;
+        float *dl = delta + (size_t)b * T * K;
+        int32_t *ps = psi + (size_t)b * T * K;
+        for (int j = 0; j < K; ++j) { dl[j] = logp0[j] + lb[j]; ps[j] = 0; }
+        for (int t = 1; t < T; ++t) {
+            const float *sl = lt + (size_t)(t - 1) * K * K;
+            for (int j = 0; j < K; ++j) {
+                float best = -INFINITY; int arg = 0;
+                for (int i = 0; i < K; ++i) {
+                    float c = dl[(size_t)(t - 1) * K + i] + sl[(size_t)i * K + j];
+                    if (c > best) { best = c; arg = i; }
+                }
+                dl[(size_t)t * K + j] = best + lb[(size_t)t * K + j];
+                ps[(size_t)t * K + j] = arg;
+            }
+        }
+        int s = 0; float bv = dl[(size_t)(T - 1) * K];
+        for (int j = 1; j < K; ++j) if (dl[(size_t)(T - 1) * K + j] > bv) { bv = dl[(size_t)(T - 1) * K + j]; s = j; }
+        states[(size_t)b * T + T - 1] = s;
+        for (int t = T - 1; t >= 1; --t) { s = ps[(size_t)t * K + s]; states[(size_t)b * T + t - 1] = s; }
+    }
+}
+
+/* neural.py:417-431 (forward: slice t-1 into frame t) and :441-459 (backward: slice t out of frame t), posterior :396-399 */
+ORC_API void orc_tv_forward_backward_f64(const double *logb, const double *logT, const double *logp0, int B, int T, int K,
+                                         double *log_alpha, double *log_beta, double *gamma, double *loglik) {
+    double *tmp = (double *)malloc(sizeof(double) * (size_t)K);
+    for (int b = 0; b < B; ++b) {
+        const double *lb = logb + (size_t)b * T * K;
+        const double *lt = logT + (size_t)b * T * K * K;
+        double *la = log_alpha + (size_t)b * T * K, *lbe = log_beta + (size_t)b * T * K, *g = gamma + (size_t)b * T * K;
+        for (int j = 0; j < K; ++j) la[j] = logp0[j] + lb[j];
+        for (int t = 1; t < T; ++t) {
+            const double *sl = lt + (size_t)(t - 1) * K * K;
+            for (int j = 0; j < K; ++j) {
+                double acc = -INFINITY;
+                for (int i = 0; i < K; ++i) acc = lse2(acc, la[(size_t)(t - 1) * K + i] + sl[(size_t)i * K + j]);
+                la[(size_t)t * K + j] = acc + lb[(size_t)t * K + j];
+            }
+        }
+        for (int i = 0; i < K; ++i) lbe[(size_t)(T - 1) * K + i] = 0.0;
+        for (int t = T - 2; t >= 0; --t) {
+            const double *sl = lt + (size_t)t * K * K;
+            for (int i = 0; i < K; ++i) {
+                double acc = -INFINITY;
+                for (int j = 0; j < K; ++j) acc = lse2(acc, sl[(size_t)i * K + j] + lb[(size_t)(t + 1) * K + j] + lbe[(size_t)(t + 1) * K + j]);
+                lbe[(size_t)t * K + i] = acc;
+            }
+        }
+        for (int t = 0; t < T; ++t) {
+            double z = -INFINITY;
+            for (int k = 0; k < K; ++k) { tmp[k] = la[(size_t)t * K + k] + lbe[(size_t)t * K + k]; z = lse2(z, tmp[k]); }
+            for (int k = 0; k < K; ++k) g[(size_t)t * K + k] = exp(tmp[k] - z);
+        }
+        if (loglik) {
+            double z = -INFINITY;
+            for (int k = 0; k < K; ++k) z = lse2(z, la[(size_t)(T - 1) * K + k]);
+            loglik[b] = z;
+        }
+    }
+    free(tmp);
 }

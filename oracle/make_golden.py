@@ -256,12 +256,41 @@ def largek(ref):
     np.savez_compressed(os.path.join(OUT, "largek.npz"), **out)
 
 
+def neural(ref):
+    """NeuralHMM (neural.py:355-519).  The observation / transition networks are torch modules outside the
+    path; the fixture stores THEIR outputs (log-emissions, per-frame transition probabilities) as inputs of the recursion and the
+    class's own forward / viterbi_decode / compute_likelihood results."""
+    from pytorch_hmm.neural import NeuralHMM
+    import torch.nn.functional as F
+    out = {}
+    for tag, K, D, ctx, B, T, seed in (("tv", 6, 8, 4, 3, 40, 7101), ("static", 5, 8, 0, 2, 25, 7102), ("tv12", 12, 10, 6, 2, 300, 7103)):
+        torch.manual_seed(seed)
+        m = NeuralHMM(num_states=K, observation_dim=D, context_dim=ctx, hidden_dim=16)
+        m.eval()
+        x = torch.randn(B, T, D)
+        c = torch.randn(B, T, ctx) if ctx > 0 else None
+        with torch.no_grad():
+            post, fwd, bwd = m(x, c)
+            states, delta = m.viterbi_decode(x, c)
+            ll = m.compute_likelihood(x, c)
+            log_obs = m.observation_model(x)
+            if ctx > 0:
+                log_trans = torch.log(m.transition_model(c) + 1e-8)
+            else:
+                log_trans = torch.log(F.softmax(m.transition_matrix, dim=1) + 1e-8)
+            log_init = torch.log(F.softmax(m.initial_logits, dim=0) + 1e-8)
+        out.update({f"{tag}_log_obs": _np(log_obs), f"{tag}_log_trans": _np(log_trans), f"{tag}_log_init": _np(log_init),
+                    f"{tag}_posterior": _np(post), f"{tag}_forward": _np(fwd), f"{tag}_backward": _np(bwd),
+                    f"{tag}_states": _np(states), f"{tag}_log_delta": _np(delta), f"{tag}_likelihood": _np(ll)})
+    np.savez_compressed(os.path.join(OUT, "neural.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = _import_reference()
     torch.set_num_threads(1)
     sections = {"core": core, "gaussian": gaussian, "mixture": mixture, "hsmm": hsmm, "semimarkov": semimarkov,
-                "streaming": streaming, "largek": largek}
+                "streaming": streaming, "largek": largek, "neural": neural}
     only = [a for a in sys.argv[1:] if a in sections or a == "segsum"]        # e.g. `make_golden.py largek`
     for name, fn in sections.items():
         if not only or name in only:

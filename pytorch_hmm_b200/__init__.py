@@ -8,6 +8,7 @@ from .layers import HMMLayer, GaussianHMMLayer
 from .gmm import MixtureGaussianHMMLayer
 from .hsmm_layer import HSMMLayer, SemiMarkovHMM, DurationModel
 from .stream import StreamingHMMProcessor, StreamingResult
+from .neural import NeuralHMMRecursion
 from .transitions import create_transition_matrix, create_left_to_right_matrix
 from . import ops
 
@@ -54,5 +55,5 @@ class ModelFactory:
 
 
 __all__ = ["HMM", "HMMPyTorch", "HMMLayer", "GaussianHMMLayer", "MixtureGaussianHMMLayer", "HSMMLayer", "SemiMarkovHMM",
-           "DurationModel", "StreamingHMMProcessor", "StreamingResult", "create_speech_hmm", "ModelFactory",
+           "DurationModel", "StreamingHMMProcessor", "StreamingResult", "NeuralHMMRecursion", "create_speech_hmm", "ModelFactory",
            "create_transition_matrix", "create_left_to_right_matrix", "ops"]

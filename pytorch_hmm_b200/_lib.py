@@ -36,6 +36,18 @@ SIGNATURES = {
     "hmmb200_viterbi_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hmmb200_viterbi_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
                                       c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),
+    "hmmb200_fb_viterbi_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hmmb200_fb_viterbi_f32": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_float, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
+                                         c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         c_ptr, C.c_size_t, C.c_int, c_ptr]),
+    "hmmb200_tv_forward_backward_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr,
+                                                  c_ptr, C.c_size_t, c_ptr]),
+    "hmmb200_tv_viterbi_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "hmmb200_tv_viterbi_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr,
+                                         c_ptr, C.c_size_t, c_ptr]),
+    "hmmb200_posterior_backward_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
+                                                 c_ptr, c_ptr, c_ptr, c_ptr]),
+    "hmmb200_gmm_stats_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr]),
     "hmmb200_hsmm_viterbi_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "hmmb200_hsmm_viterbi_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                            c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

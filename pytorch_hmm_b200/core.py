@@ -81,6 +81,12 @@ class HMMPyTorch(HMM):
         B, T, K = obs.shape
         assert K == self.K, f"Observation dim {K} must match model states {self.K}"
         dev = self._cuda()
+        from . import autograd as ag
+        if ag.needs_grad(observations, self.log_P, self.log_p0) and self.K <= 32:
+            # training callers (HMMLayer.forward in training mode, the supervised loss of hmm_layer.py:161-167): the posterior
+            # carries its gradient w.r.t. the observations and log_P / log_p0 (csrc/autograd_kernels.cu)
+            g, f, b = ag.hmm_posteriors(obs, self.log_P, self.log_p0, ops.EMIS_PROB_FLOOR, EPS)
+            return self._back(g), self._back(f), self._back(b)
         trans, init = self._effective_probs(dev)
         r = ops.forward_backward(obs.detach().to(dev), ops.EMIS_PROB_FLOOR, trans, init, eps=EPS)
         return self._back(r["gamma"]), self._back(r["fwd"]), self._back(r["bwd"])

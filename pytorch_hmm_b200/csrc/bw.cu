@@ -231,6 +231,30 @@ static int launch_xi(const float *emis, int mode, float eps, const float *trans,
     return launch_xi_kp<32>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, xi, gamma1, s);
 }
 
+static int launch_gmm_stats(const float *x, const float *comp, const float *logb, const float *gamma, int64_t n, int K, int C, int D,
+                            double *occ, double *sx, double *sxx, cudaStream_t s) {
+    const int KCp = (K * C + BW_TC - 1) / BW_TC * BW_TC, Dp = (D + BW_TD - 1) / BW_TD * BW_TD;
+    size_t smem = (size_t)BW_F * (KCp + 2 * Dp) * sizeof(float);
+    smem = smem > 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float) ? smem : 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float);   // also the fold buffer
+    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "gmm_stats: K*C + D too large");
+    if (smem > 48 * 1024) cudaFuncSetAttribute(bw_gmm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t n_tiles = (n + BW_F - 1) / BW_F;
+    const int ndg = Dp / BW_TD, ncg_all = KCp / BW_TC;
+    if (ndg > 512) return set_error(HMMB200_EUNSUPPORTED, "gmm_stats: D = %d too large", D);
+    int gy = 1;                                                     // slices of the component groups (<= 512 cells per CTA)
+    while (((ncg_all + gy - 1) / gy) * ndg > 512) ++gy;
+    const int cells = ((ncg_all + gy - 1) / gy) * ndg;
+    int FG = 512 / cells;                                           // frame sub-sequences per tile: up to 512 threads per CTA
+    FG = FG < 1 ? 1 : (FG > 8 ? 8 : FG);
+    const int threads = (cells * FG + 31) & ~31;                   // whole warps (the staging loops are warp-per-row)
+    dim3 grid((unsigned)min((int64_t)sms, n_tiles), (unsigned)gy);      // one CTA per SM (128 registers x ~480 threads)
+    bw_gmm_stats_kernel<<<grid, threads, smem, s>>>(x, comp, logb, gamma, n, K, C, D, FG, occ, sx, sxx);
+    return check_launch("bw_gmm_stats_kernel");
+}
+
 }  // namespace hmmb200
 
 using namespace hmmb200;
@@ -284,26 +308,16 @@ HMMB200_EXPORT int hmmb200_bw_accumulate_f32(const float *x, const float *comp, 
     const float *ws_a = (const float *)fb_workspace;
     const float *ws_b = (const float *)((const uint8_t *)fb_workspace + al(n * K * sizeof(float)));
     if (int rc = launch_xi(emis, emis_mode, floor_eps, trans_prob, ws_a, ws_b, nullptr, B, T, K, xi, gamma1, s)) return rc;
-    const int KCp = (K * C + BW_TC - 1) / BW_TC * BW_TC, Dp = (D + BW_TD - 1) / BW_TD * BW_TD;
-    size_t smem = (size_t)BW_F * (KCp + 2 * Dp) * sizeof(float);
-    smem = smem > 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float) ? smem : 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float);   // also the fold buffer
-    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: K*C + D too large");
-    if (smem > 48 * 1024) cudaFuncSetAttribute(bw_gmm_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t n_tiles = ((int64_t)n + BW_F - 1) / BW_F;
-    const int ndg = Dp / BW_TD, ncg_all = KCp / BW_TC;
-    if (ndg > 512) return set_error(HMMB200_EUNSUPPORTED, "bw_accumulate: D = %d too large", D);
-    int gy = 1;                                                     // slices of the component groups (<= 512 cells per CTA)
-    while (((ncg_all + gy - 1) / gy) * ndg > 512) ++gy;
-    const int cells = ((ncg_all + gy - 1) / gy) * ndg;
-    int FG = 512 / cells;                                           // frame sub-sequences per tile: up to 512 threads per CTA
-    FG = FG < 1 ? 1 : (FG > 8 ? 8 : FG);
-    const int threads = (cells * FG + 31) & ~31;                   // whole warps (the staging loops are warp-per-row)
-    dim3 grid((unsigned)min((int64_t)sms, n_tiles), (unsigned)gy);      // one CTA per SM (128 registers x ~480 threads)
-    bw_gmm_stats_kernel<<<grid, threads, smem, s>>>(x, comp, logb, gamma, (int64_t)n, K, C, D, FG, occ, sx, sxx);
-    return check_launch("bw_gmm_stats_kernel");
+    return launch_gmm_stats(x, comp, logb, gamma, (int64_t)n, K, C, D, occ, sx, sxx, s);
+}
+
+HMMB200_EXPORT int hmmb200_gmm_stats_f32(const float *x, const float *comp, const float *logb, const float *weight, int64_t n_frames,
+                                         int K, int C, int D, double *occ, double *sx, double *sxx, void *stream) {
+    if (n_frames < 0 || K <= 0 || C <= 0 || D <= 0) return set_error(HMMB200_EINVAL, "gmm_stats: bad shape");
+    if (n_frames == 0) return HMMB200_OK;
+    if (!x || !comp || !logb || !weight || !occ || !sx || !sxx) return set_error(HMMB200_EINVAL, "gmm_stats: null argument");
+    if (int rc = require_sm100()) return rc;
+    return launch_gmm_stats(x, comp, logb, weight, n_frames, K, C, D, occ, sx, sxx, (cudaStream_t)stream);
 }
 
 // Weighted transition / initial-state statistics alone: xi[i][j] += sum_b w_b sum_t xi_t(i,j), gamma1[k] += sum_b w_b gamma_0(k).

@@ -218,6 +218,9 @@ template <bool WITH_COMP, int CT>
 __global__ void __launch_bounds__(TC_THREADS, 1) gmm_emission_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int D = p.D, DP = p.DP, NP = p.NP, K = p.K, C = p.C, KC = p.KC;
+    // A dependent kernel launched with programmatic stream serialisation (the fused recursion kernel) may be scheduled as soon as
+    // SMs free up: its set-up then overlaps this kernel's last tiles; it waits for this grid's completion before reading log b.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.tc[0] == 0.f) return;                                   // parameters outside the fp16 range: fp32 kernel runs instead
     const int NBOX = (D + TC_BOXW - 1) / TC_BOXW;                 // TMA boxes per tile
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

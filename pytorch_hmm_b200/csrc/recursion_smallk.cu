@@ -22,746 +22,9 @@
 // previous step's largest entry (one REDUX; exact; integer exponent bookkeeping), so alpha = a * 2^ksum * exp(sum m).
 // A lone warp issues roughly one instruction every ~4-5 cycles on a dependent chain, so the consumer's instruction
 // count IS its latency: packed fp32x2 FMAs/adds, 3-input max, no per-step branches, 4x unrolled (fits the L0 I-cache).
-#include "common.cuh"
-
-#include <type_traits>
+#include "recursion_smallk.cuh"
 
 namespace hmmb200 {
-
-constexpr int CH = 64;          // frames per pipeline chunk
-constexpr int NB = 2;           // ring buffers
-constexpr int BT_PITCH = 33;    // floats per frame row of the emission ring (32 lanes + 1 pad)
-constexpr int MAXNS = 8;        // sequences per warp at G = 4
-constexpr int MR_BUFS = 2 * NB; // log-scale ring depth: loaders run up to NB chunks ahead of the drainer's read
-constexpr int BAR_FULL = 1;     // named barriers BAR_FULL + b, BAR_DONE + b  (0 is __syncthreads)
-constexpr int BAR_DONE = 1 + NB;
-enum { SC_FULL = 0, SC_APPLY = 1, SC_ESTIMATE = 2 };   // fb consumer: what a step does about the power-of-two normaliser
-
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// Blackwell packed fp32 pairs (one issue slot for two IEEE round-to-nearest operations) and 3-input max.
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b);
-    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c), rd;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    return *reinterpret_cast<float2 *>(&rd);
-}
-__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
-    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-    return *reinterpret_cast<float2 *>(&rd);
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) {
-    float d;
-    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
-    return d;
-}
-// exact maximum of N values as a 3-ary tree (order-independent, so bit-identical to any other order)
-template <int N>
-__device__ __forceinline__ float max_tree(float (&x)[N]) {
-    if constexpr (N == 1) {
-        return x[0];
-    } else if constexpr (N == 2) {
-        return fmaxf(x[0], x[1]);
-    } else {
-        constexpr int M = (N + 2) / 3;
-        float y[M];
-#pragma unroll
-        for (int i = 0; i < M; ++i) {
-            if (3 * i + 2 < N) y[i] = fmax3(x[3 * i], x[3 * i + 1], x[3 * i + 2]);
-            else if (3 * i + 1 < N) y[i] = fmaxf(x[3 * i], x[3 * i + 1]);
-            else y[i] = x[3 * i];
-        }
-        return max_tree<M>(y);
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// per-frame emission transforms (helper side; one lane holds the K values of one frame)
-// ----------------------------------------------------------------------------------------------------------
-// scaled-probability form for forward/backward: b~ and the log-scale m divided out of the frame
-template <int KP>
-__device__ __forceinline__ void row_to_scaled(int mode, float eps, int K, float (&e)[KP], float &m) {
-    m = 0.f;
-    if (mode == HMMB200_EMIS_PROB_FLOOR) {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? e[k] + eps : 0.f;
-    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? expf(e[k]) + eps : 0.f;
-    } else {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) if (k < K) mx = fmaxf(mx, e[k]);
-        if (!(mx > -INFINITY)) mx = 0.f;                     // all states impossible: keep the frame finite
-        const float add = (mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? expf(e[k] - mx) + add : 0.f;
-        m = mx;
-    }
-}
-
-// log form for Viterbi (fp32, the reference's formula for each input kind)
-template <int KP>
-__device__ __forceinline__ void row_to_log(int mode, float eps, int K, float (&e)[KP]) {
-    if (mode == HMMB200_EMIS_LOG) return;
-    if (mode == HMMB200_EMIS_PROB_FLOOR) {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? logf(e[k] + eps) : 0.f;
-    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? logf(expf(e[k]) + eps) : 0.f;
-    } else {
-        float mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) if (k < K) mx = fmaxf(mx, e[k]);
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = (k < K) ? logf(expf(e[k] - mx) + eps) : 0.f;
-    }
-}
-
-// Loader-warp loop: stream this CTA's NS sequences from HBM one chunk (CH frames) ahead of the consumer, transform each
-// frame (scaled-probability form for forward/backward, log form for Viterbi) and publish the per-lane values in bt[b]
-// (and the per-frame log-scale in mraw[b]).  NL loader warps split the frames; lane (sub, q) of loader `lw` handles
-// FL = CH/G/NL consecutive frames of sequence `sub`.  Raw values for chunk c+1 are already in flight (registers)
-// while chunk c is converted, so no HBM latency is exposed.
-template <int G, int KP, int DIR, bool SCALED, int NL>
-__device__ __forceinline__ void loader_loop(const float *emis, int mode, float eps, int B, int T, int K, int lw,
-                                            float *bt, float *mraw, int n_bar) {
-    constexpr int NS = 32 / G, FPL = CH / G, FL = FPL / NL;
-    static_assert(FPL % NL == 0 && FL >= 1, "loader split");
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / G, q = lane % G;
-    const int seq = blockIdx.x * NS + sub;
-    const bool seq_ok = seq < B;
-    const int nch = (T + CH - 1) / CH;
-    const int u_base = q * FPL + lw * FL;
-
-    float cur[FL][KP], nxt[FL][KP];
-    auto fetch = [&](int c, float (&dst)[FL][KP]) {
-#pragma unroll
-        for (int i = 0; i < FL; ++i) {
-            const int n = c * CH + u_base + i;
-            const bool ok = seq_ok && n < T;
-            const int f = (DIR == 0) ? n : T - 1 - n;
-            const float *row = emis + ((size_t)(ok ? seq : 0) * T + (ok ? f : 0)) * K;
-#pragma unroll
-            for (int k = 0; k < KP; ++k) dst[i][k] = (ok && k < K) ? __ldg(row + k) : 0.f;
-        }
-    };
-    fetch(0, cur);
-    for (int c = 0; c < nch; ++c) {
-        const int b = c % NB;
-        if (c + 1 < nch) fetch(c + 1, nxt);
-        if (c >= NB) bar_sync(BAR_DONE + b, n_bar);          // consumer is done reading bt[b] (chunk c - NB)
-        float *btb = bt + (size_t)b * CH * BT_PITCH;
-#pragma unroll
-        for (int i = 0; i < FL; ++i) {
-            const int u = u_base + i;
-            const bool ok = seq_ok && (c * CH + u) < T;
-            float m = 0.f;
-            if (SCALED) row_to_scaled<KP>(mode, eps, K, cur[i], m);
-            else row_to_log<KP>(mode, eps, K, cur[i]);
-            float *dst = btb + u * BT_PITCH + sub * G;
-#pragma unroll
-            for (int k = 0; k < G; ++k) {
-                float v = 0.f;
-                if (k < KP) v = (ok && k < K) ? cur[i][k] : 0.f;
-                dst[k] = v;
-            }
-            if (SCALED) mraw[((size_t)(c % MR_BUFS) * CH + u) * MAXNS + sub] = ok ? m : 0.f;
-        }
-        bar_arrive(BAR_FULL + b, n_bar);
-#pragma unroll
-        for (int i = 0; i < FL; ++i)
-#pragma unroll
-            for (int k = 0; k < KP; ++k) cur[i][k] = nxt[i][k];
-    }
-    for (int c = max(0, nch - NB); c < nch; ++c) bar_sync(BAR_DONE + (c % NB), n_bar);
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// forward / backward sweeps
-// ----------------------------------------------------------------------------------------------------------
-struct FbParams {
-    const float *emis;
-    int mode;
-    float eps;
-    int add_rowmax;
-    const float *trans;   // [K,K] effective probabilities
-    const float *init;    // [K]
-    int B, T, K;
-    float *ws_a, *ws_b;   // [B,T,K] scaled alpha / beta
-    float *ws_la, *ws_lb; // [B,T]   log scale: alpha = a * exp(la), beta = b * exp(lb)
-    float *loglik;        // [B] or null
-};
-
-constexpr int FB_NL = 2;                                   // loader warps
-constexpr int FB_ND = 2;                                   // drainer warps
-constexpr int FB_THREADS = 32 * (1 + FB_NL + FB_ND);
-constexpr size_t FB_SMEM_BT = (size_t)NB * CH * BT_PITCH * sizeof(float);
-constexpr size_t FB_SMEM_WR = (size_t)NB * CH * 32 * sizeof(float);
-constexpr size_t FB_SMEM_ER = (size_t)NB * CH * MAXNS * sizeof(int);
-constexpr size_t FB_SMEM_MR = (size_t)MR_BUFS * CH * MAXNS * sizeof(float);
-constexpr size_t FB_SMEM_BYTES = FB_SMEM_MR + FB_SMEM_BT + 2 * FB_SMEM_WR + FB_SMEM_ER;
-
-// DIR 0: alpha_t(j) = (sum_i alpha_{t-1}(i) P(i,j)) b_t(j)                         (hmm.py:98-101)
-// DIR 1: beta_t(i)  = sum_j P(i,j) b_{t+1}(j) beta_{t+1}(j)                         (hmm.py:113-117)
-// Both are  w <- (sum_i w_prev(i) * M[i]) * b~ * r  on w = alpha (DIR 0) or w = beta .* b~ (DIR 1), M = the lane's
-// column (DIR 0) / row (DIR 1) of P, r = 2^-k from the previous step's sum.
-template <int G, int KP, int DIR, bool PAD>
-__device__ __forceinline__ void fb_consumer(const FbParams &p, const float *bt, float *wr, float *br, int *er) {
-    constexpr int NS = 32 / G;
-    const int lane = threadIdx.x & 31;
-    const int sub = lane / G, j = lane % G;
-    const int seq = blockIdx.x * NS + sub;
-    const int K = p.K, T = p.T;
-    const bool lane_ok = seq < p.B && j < K;
-    // PAD (KP < G): the last lane of each group owns no state and its ring slot is never read back by the recursion;
-    // it publishes the running exponent there, so the bookkeeping costs no extra store.  Otherwise lane 0 writes
-    // it to the `er` ring.
-    const bool pad_lane = PAD && (j == G - 1);
-
-    float2 M2[KP / 2];
-#pragma unroll
-    for (int i = 0; i < KP / 2; ++i) {
-        float v0 = 0.f, v1 = 0.f;
-        if (lane_ok && 2 * i < K) v0 = (DIR == 0) ? __ldg(p.trans + (2 * i) * K + j) : __ldg(p.trans + j * K + 2 * i);
-        if (lane_ok && 2 * i + 1 < K) v1 = (DIR == 0) ? __ldg(p.trans + (2 * i + 1) * K + j) : __ldg(p.trans + j * K + 2 * i + 1);
-        M2[i] = make_float2(v0, v1);
-    }
-    const float pi = (DIR == 0 && lane_ok) ? __ldg(p.init + j) : 0.f;
-
-    float r_cur = 1.f;
-    int k_cur = 0, ksum = 0;
-    const float4 *prev = reinterpret_cast<const float4 *>(wr + sub * G);
-    float *wp = wr, *bp2 = br;
-    int *ep = er;
-
-    // Power-of-two normaliser r = 2^-k for the NEXT step, from the exponent of the largest entry (exact scaling,
-    // integer bookkeeping).  One sequence per warp: a single REDUX over the new vector.  Several sequences per warp:
-    // a REDUX with per-group masks takes a slow divergent path, so each lane instead reduces the previous vector it
-    // has just read back (3-input max tree, no cross-lane traffic; one more step of lag, which is harmless).
-    auto set_scale = [&](unsigned mx) {
-        const unsigned eb = mx >> 23;
-        k_cur = (int)eb - 127;
-        r_cur = __uint_as_float((254u - eb) << 23);
-    };
-    // one time step: w <- (sum_i prev[i] * M[i]) * (b~ * r) ; the pad lane carries (float)ksum instead.
-    // The normaliser costs a third of the step's instructions (max tree, exponent arithmetic), and the step's
-    // instruction count is its latency, so inside the 4x unrolled loop only every other step derives one:
-    //   SC_APPLY     applies the pending scale, derives none;
-    //   SC_ESTIMATE  applies none (r = 1 folds away), derives the next one from the vector it has just read back;
-    //   SC_FULL      both (loop remainders).
-    // Powers of two are exact, so posteriors do not depend on where the scales fall; three steps of lag are far from
-    // underflow even on floored frames (1e-8 per step).
-    auto step = [&](auto sc_tag, int u, float bqv) {
-        constexpr int SC = decltype(sc_tag)::value;
-        constexpr bool APPLY = (SC != SC_ESTIMATE), EST = (SC != SC_APPLY);
-        float2 acc_a = make_float2(0.f, 0.f), acc_b = make_float2(0.f, 0.f);
-        float v[KP];
-#pragma unroll
-        for (int i4 = 0; i4 < KP / 4; ++i4) {
-            const float4 t = prev[i4];
-            acc_a = ffma2(make_float2(t.x, t.y), M2[2 * i4], acc_a);
-            acc_b = ffma2(make_float2(t.z, t.w), M2[2 * i4 + 1], acc_b);
-            v[4 * i4 + 0] = t.x; v[4 * i4 + 1] = t.y; v[4 * i4 + 2] = t.z; v[4 * i4 + 3] = t.w;
-        }
-        const float2 s2 = fadd2(acc_a, acc_b);
-        const float acc = s2.x + s2.y;
-        const float mb = APPLY ? bqv * r_cur : bqv;
-        if (APPLY) ksum += k_cur;
-        const float padf = pad_lane ? (float)ksum : 0.f;
-        const float w = fmaf(acc, mb, padf);
-        if (DIR == 1) bp2[u * 32] = APPLY ? acc * r_cur : acc;
-        wp[u * 32] = w;
-        if (!PAD && j == 0) ep[u * MAXNS] = ksum;
-        if (EST) {
-            if (NS == 1) {
-                set_scale(__reduce_max_sync(FULL_MASK, lane_ok ? __float_as_uint(w) : 0u));
-            } else {
-                // scale the new vector by what the previous one needed, times the growth r_cur already applied to it
-                const float vm = APPLY ? max_tree<KP>(v) * r_cur : max_tree<KP>(v);
-                set_scale(__float_as_uint(vm));
-            }
-        }
-        prev = reinterpret_cast<const float4 *>(wp + u * 32 - j);
-        __syncwarp();
-    };
-    using ScFull = std::integral_constant<int, SC_FULL>;
-    using ScApply = std::integral_constant<int, SC_APPLY>;
-    using ScEstimate = std::integral_constant<int, SC_ESTIMATE>;
-
-    const int nch = (T + CH - 1) / CH;
-    for (int c = 0; c < nch; ++c) {
-        const int b = c % NB;
-        bar_sync(BAR_FULL + b, FB_THREADS);
-        const int nf = min(CH, T - c * CH);
-        const float *btb = bt + (size_t)b * CH * BT_PITCH + lane;
-        wp = wr + (size_t)b * CH * 32 + lane;
-        bp2 = br + (size_t)b * CH * 32 + lane;
-        ep = er + (size_t)b * CH * MAXNS + sub;
-        int u = 0;
-        if (c == 0) {
-            // step 0: alpha_0 = p0 .* b_0 (hmm.py:92)  /  beta_{T-1} = 1 (hmm.py:107)
-            const float b0 = btb[0];
-            const float w = (DIR == 0) ? pi * b0 : (lane_ok ? b0 : 0.f);
-            if (DIR == 1) bp2[0] = lane_ok ? 1.f : 0.f;
-            wp[0] = w;                                       // pad lane: ksum = 0
-            if (!PAD && j == 0) ep[0] = 0;
-            if (NS == 1) set_scale(__reduce_max_sync(FULL_MASK, lane_ok ? __float_as_uint(w) : 0u));
-            prev = reinterpret_cast<const float4 *>(wp - j);
-            __syncwarp();
-            u = 1;
-        }
-        for (; u + 4 <= nf; u += 4) {
-            float bq[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) bq[i] = btb[(u + i) * BT_PITCH];
-            step(ScApply{}, u, bq[0]);
-            step(ScEstimate{}, u + 1, bq[1]);
-            step(ScApply{}, u + 2, bq[2]);
-            step(ScEstimate{}, u + 3, bq[3]);
-        }
-        for (; u < nf; ++u) step(ScFull{}, u, btb[u * BT_PITCH]);
-        bar_arrive(BAR_DONE + b, FB_THREADS);
-    }
-}
-
-// Drainer warp: trails the consumer by NB chunks; copies the scaled vectors from the ring to HBM with coalesced
-// stores and turns the exponent / log-scale bookkeeping into the per-frame log scale la (alpha = a * exp(la)).
-template <int G, int KP, int DIR, bool PAD>
-__device__ __forceinline__ void fb_drainer(const FbParams &p, const float *wr, const float *br, const int *er,
-                                           const float *mraw, int dw) {
-    constexpr int NS = 32 / G;
-    static_assert(CH == 64, "the log-scale scan assumes two frames per lane");
-    const int lane = threadIdx.x & 31;
-    const int K = p.K, T = p.T, B = p.B;
-    const bool add_m = (p.mode == HMMB200_EMIS_LOG) || (p.mode == HMMB200_EMIS_LOG_NORM_FLOOR && p.add_rowmax);
-    const int nch = (T + CH - 1) / CH;
-    float *ws = (DIR == 0) ? p.ws_a : p.ws_b;
-    float *wsl = (DIR == 0) ? p.ws_la : p.ws_lb;
-    const float *src_ring = (DIR == 0) ? wr : br;
-    double carry[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) carry[s] = 0.0;
-    // running exponent published by the consumer: pad slot of the w ring (PAD) or the er ring
-    auto ksum_at = [&](int b, int u, int s) -> double {
-        return PAD ? (double)wr[((size_t)b * CH + u) * 32 + s * G + (G - 1)] : (double)er[((size_t)b * CH + u) * MAXNS + s];
-    };
-
-    auto drain = [&](int c, int b) {
-        const int nf = min(CH, T - c * CH);
-        const int n_lo = c * CH;
-        const int f_lo = (DIR == 0) ? n_lo : T - n_lo - nf;          // lowest frame index of the chunk
-        constexpr int R = 32 / G;                                    // frame rows covered per warp iteration
-        const int rr = lane / G, k = lane % G;
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int sq = blockIdx.x * NS + s;
-            if (sq < B) {
-                const float *src = src_ring + (size_t)b * CH * 32 + s * G;
-                float *dst = ws + ((size_t)sq * T + f_lo) * K;
-                // rows are interleaved over the FB_ND drainer warps
-#pragma unroll 4
-                for (int fl0 = dw * R; fl0 < nf; fl0 += R * FB_ND) {
-                    const int fl = fl0 + rr;
-                    if (fl < nf && k < K) {
-                        const int u = (DIR == 0) ? fl : nf - 1 - fl;
-                        dst[(size_t)fl * K + k] = src[u * 32 + k];
-                    }
-                }
-                if ((s % FB_ND) != dw) continue;                     // the log-scale of sequence s belongs to one drainer
-                // log scale: prefix of the per-frame m (inclusive for alpha, exclusive for beta) + ln2 * exponent
-                const int u0 = 2 * lane, u1 = 2 * lane + 1;
-                const double m0 = add_m ? (double)mraw[((size_t)(c % MR_BUFS) * CH + u0) * MAXNS + s] : 0.0;
-                const double m1 = add_m ? (double)mraw[((size_t)(c % MR_BUFS) * CH + u1) * MAXNS + s] : 0.0;
-                double x = m0 + m1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double y = __shfl_up_sync(FULL_MASK, x, o);
-                    if (lane >= o) x += y;
-                }
-                const double pre0 = carry[s] + (x - m1);             // inclusive prefix at u0
-                const double pre1 = carry[s] + x;                    // inclusive prefix at u1
-                carry[s] += __shfl_sync(FULL_MASK, x, 31);
-                const double l0 = ((DIR == 0) ? pre0 : pre0 - m0) + 0.69314718055994530942 * ksum_at(b, u0, s);
-                const double l1 = ((DIR == 0) ? pre1 : pre1 - m1) + 0.69314718055994530942 * ksum_at(b, u1, s);
-                float *dl = wsl + (size_t)sq * T;
-                if (u0 < nf) dl[(DIR == 0) ? n_lo + u0 : T - 1 - (n_lo + u0)] = (float)l0;
-                if (u1 < nf) dl[(DIR == 0) ? n_lo + u1 : T - 1 - (n_lo + u1)] = (float)l1;
-                if (DIR == 0 && p.loglik != nullptr && c == nch - 1) {
-                    const int ul = (T - 1) - n_lo;                   // last frame: loglik = la + log(sum_k a)
-                    if (u0 == ul || u1 == ul) {
-                        const float *v = wr + ((size_t)b * CH + ul) * 32 + s * G;
-                        float tot = 0.f;
-                        for (int kk = 0; kk < K; ++kk) tot += v[kk];
-                        p.loglik[sq] = (float)(((u0 == ul) ? l0 : l1) + (double)logf(tot));
-                    }
-                }
-            }
-        }
-    };
-
-    for (int c = 0; c < nch; ++c) {
-        const int b = c % NB;
-        if (c >= NB) {
-            bar_sync(BAR_DONE + b, FB_THREADS);
-            drain(c - NB, b);
-        }
-        bar_arrive(BAR_FULL + b, FB_THREADS);                        // ring buffer b drained: consumer may overwrite it
-    }
-    for (int c = max(0, nch - NB); c < nch; ++c) {
-        const int b = c % NB;
-        bar_sync(BAR_DONE + b, FB_THREADS);
-        drain(c, b);
-    }
-}
-
-template <int G, int KP, int DIR, bool PAD>
-__device__ __forceinline__ void fb_roles(const FbParams &p, uint8_t *smem) {
-    float *mraw = reinterpret_cast<float *>(smem);
-    float *bt = reinterpret_cast<float *>(smem + FB_SMEM_MR);
-    float *wr = reinterpret_cast<float *>(smem + FB_SMEM_MR + FB_SMEM_BT);
-    float *br = reinterpret_cast<float *>(smem + FB_SMEM_MR + FB_SMEM_BT + FB_SMEM_WR);
-    int *er = reinterpret_cast<int *>(smem + FB_SMEM_MR + FB_SMEM_BT + 2 * FB_SMEM_WR);
-    const int warp = threadIdx.x >> 5;
-    if (warp == 0) fb_consumer<G, KP, DIR, PAD>(p, bt, wr, br, er);
-    else if (warp <= FB_NL) loader_loop<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, warp - 1, bt, mraw, FB_THREADS);
-    else fb_drainer<G, KP, DIR, PAD>(p, wr, br, er, mraw, warp - 1 - FB_NL);
-}
-
-template <int G, int KP>
-__global__ void __launch_bounds__(FB_THREADS) fb_sweep_kernel(FbParams p) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    constexpr bool PAD = KP < G;
-    if (blockIdx.y == 0) fb_roles<G, KP, 0, PAD>(p, smem);
-    else fb_roles<G, KP, 1, PAD>(p, smem);
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// combine: gamma = a.*b / sum, fwd = a*exp(la), bwd = b*exp(lb)           (hmm.py:120-128)
-// ----------------------------------------------------------------------------------------------------------
-struct CombineParams {
-    const float *ws_a, *ws_b, *ws_la, *ws_lb;
-    int64_t n_frames;
-    int K;
-    float *gamma, *fwd, *bwd, *log_alpha, *log_beta;
-};
-
-// Scalar form (K not a multiple of 4, or unaligned outputs): one thread per frame, COMBINE_FPT frames per thread.
-// Explicit fused / rounded operations in a fixed order: a frame's result must not depend on how the batch was sharded.
-constexpr int COMBINE_FPT = 2;
-
-__global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t idx0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int K = p.K;
-    for (int f = 0; f < COMBINE_FPT; ++f) {
-        const int64_t idx = idx0 + f * stride;
-        if (idx >= p.n_frames) continue;
-        const float *a = p.ws_a + idx * K, *b = p.ws_b + idx * K;
-        const float la = p.ws_la[idx], lb = p.ws_lb[idx];
-        const float ea = expf(la), eb = expf(lb);
-        float Z = 0.f;
-        for (int k = 0; k < K; ++k) Z = fmaf(a[k], b[k], Z);
-        const float inv = __fdiv_rn(1.f, Z);
-        for (int k = 0; k < K; ++k) {
-            float x = a[k], y = b[k];
-            if (p.gamma) p.gamma[idx * K + k] = __fmul_rn(__fmul_rn(x, y), inv);
-            if (p.fwd) p.fwd[idx * K + k] = x * ea;
-            if (p.bwd) p.bwd[idx * K + k] = y * eb;
-            if (p.log_alpha) p.log_alpha[idx * K + k] = logf(x) + la;
-            if (p.log_beta) p.log_beta[idx * K + k] = logf(y) + lb;
-        }
-    }
-}
-
-// Coalesced form for K % 4 == 0: a warp finishes 32 consecutive frames = 32 * KV float4 pieces, lane l taking pieces
-// l, l + 32, ... -- every load and store instruction covers 512 contiguous bytes (with one thread per frame the 32 lanes
-// of an instruction sit K * 4 bytes apart: three times the L1 wavefronts and partial-sector stores at K = 12).  The
-// per-piece dot products meet in a warp-private shared-memory row; each frame's normaliser is their sum in piece order,
-// so a frame's posterior does not depend on its position in the batch (sharding-independent).
-template <int KV>
-__global__ void __launch_bounds__(256) fb_combine_warp_kernel(CombineParams p) {
-    __shared__ float zs[8][32 * KV];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t n_blocks = (p.n_frames + 31) / 32;
-    float *z = zs[wib];
-    for (int64_t blk = (int64_t)blockIdx.x * 8 + wib; blk < n_blocks; blk += (int64_t)gridDim.x * 8) {
-        const int64_t f0 = blk * 32;
-        const int nf = (int)((p.n_frames - f0 < 32) ? (p.n_frames - f0) : 32);
-        const int npieces = nf * KV;
-        const float4 *pa = reinterpret_cast<const float4 *>(p.ws_a) + f0 * KV;
-        const float4 *pb = reinterpret_cast<const float4 *>(p.ws_b) + f0 * KV;
-        float4 xa[KV], xb[KV];
-#pragma unroll
-        for (int j = 0; j < KV; ++j) {
-            const int idx = lane + 32 * j;
-            const bool ok = idx < npieces;
-            xa[j] = ok ? __ldcs(pa + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-            xb[j] = ok ? __ldcs(pb + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        const float la_l = (lane < nf) ? __ldcs(p.ws_la + f0 + lane) : 0.f;
-        const float lb_l = (lane < nf) ? __ldcs(p.ws_lb + f0 + lane) : 0.f;
-#pragma unroll
-        for (int j = 0; j < KV; ++j) {
-            float d = __fmul_rn(xa[j].x, xb[j].x);
-            d = __fmaf_rn(xa[j].y, xb[j].y, d);
-            d = __fmaf_rn(xa[j].z, xb[j].z, d);
-            d = __fmaf_rn(xa[j].w, xb[j].w, d);
-            z[lane + 32 * j] = d;
-        }
-        __syncwarp();
-        const float ea_l = expf(la_l), eb_l = expf(lb_l);
-#pragma unroll
-        for (int j = 0; j < KV; ++j) {
-            const int idx = lane + 32 * j;
-            const bool ok = idx < npieces;
-            const int fr = ok ? idx / KV : 0;
-            float Z = z[fr * KV];
-#pragma unroll
-            for (int q = 1; q < KV; ++q) Z = __fadd_rn(Z, z[fr * KV + q]);
-            const float inv = 1.f / Z;
-            const float ea = __shfl_sync(FULL_MASK, ea_l, fr), eb = __shfl_sync(FULL_MASK, eb_l, fr);
-            const float la = __shfl_sync(FULL_MASK, la_l, fr), lb = __shfl_sync(FULL_MASK, lb_l, fr);
-            if (!ok) continue;
-            const float4 x = xa[j], y = xb[j];
-            const int64_t o = f0 * KV + idx;
-            auto g = [&](float u, float v) { return __fmul_rn(__fmul_rn(u, v), inv); };
-            if (p.gamma) __stcs(reinterpret_cast<float4 *>(p.gamma) + o, make_float4(g(x.x, y.x), g(x.y, y.y), g(x.z, y.z), g(x.w, y.w)));
-            if (p.fwd) __stcs(reinterpret_cast<float4 *>(p.fwd) + o, make_float4(x.x * ea, x.y * ea, x.z * ea, x.w * ea));
-            if (p.bwd) __stcs(reinterpret_cast<float4 *>(p.bwd) + o, make_float4(y.x * eb, y.y * eb, y.z * eb, y.w * eb));
-            if (p.log_alpha) __stcs(reinterpret_cast<float4 *>(p.log_alpha) + o,
-                                    make_float4(logf(x.x) + la, logf(x.y) + la, logf(x.z) + la, logf(x.w) + la));
-            if (p.log_beta) __stcs(reinterpret_cast<float4 *>(p.log_beta) + o,
-                                   make_float4(logf(y.x) + lb, logf(y.y) + lb, logf(y.z) + lb, logf(y.w) + lb));
-        }
-        __syncwarp();                                        // the row of partial dots is reused by the next block
-    }
-}
-
-// ----------------------------------------------------------------------------------------------------------
-// Viterbi
-// ----------------------------------------------------------------------------------------------------------
-struct VitParams {
-    const float *emis;
-    int mode;
-    float eps;
-    const float *log_trans, *log_init;
-    int B, T, K;
-    float *delta;        // [B,T,K] or null
-    uint8_t *psi_out;    // [B,T,K] or null
-    int64_t *states;     // [B,T]
-    float *score;        // [B] or null
-    uint8_t *psi_ws;     // [B,T,G] global fallback when the backpointers do not fit in shared memory
-    int psi_in_smem;
-    int chunk;           // traceback chunk length L
-    int n_chunks;        // ceil((T-1)/L)
-};
-
-constexpr int VIT_NL = 2;                                  // loader warps
-constexpr int VIT_ND = 5;                                  // drainer warps (delta store + backpointers)
-constexpr int VIT_THREADS = 32 * (1 + VIT_NL + VIT_ND);
-constexpr size_t VIT_SMEM_BT = (size_t)NB * CH * BT_PITCH * sizeof(float);
-constexpr size_t VIT_SMEM_DR = (size_t)NB * CH * 32 * sizeof(float);
-constexpr size_t VIT_SMEM_CARRY = 2 * 32 * sizeof(float);
-constexpr size_t VIT_SMEM_PIPE = VIT_SMEM_BT + VIT_SMEM_DR + VIT_SMEM_CARRY;
-
-// Shared-memory layout (bytes), NS sequences per CTA:
-//   [bt ring][delta ring][carry][psi: NS*T*G if psi_in_smem][st: NS*T][exit: NS*n_chunks*G][entry: NS*n_chunks][final]
-template <int G, int KP>
-__global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
-    constexpr int NS = 32 / G;
-    extern __shared__ __align__(16) uint8_t smem[];
-    const int K = p.K, T = p.T, B = p.B;
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int seq_base = blockIdx.x * NS;
-
-    float *bt = reinterpret_cast<float *>(smem);
-    float *dr = reinterpret_cast<float *>(smem + VIT_SMEM_BT);
-    float *carry = reinterpret_cast<float *>(smem + VIT_SMEM_BT + VIT_SMEM_DR);
-    uint8_t *psi_s = smem + VIT_SMEM_PIPE;
-    size_t off = VIT_SMEM_PIPE + (p.psi_in_smem ? (size_t)NS * T * G : 0);
-    uint8_t *st_s = smem + off;            off += (size_t)NS * T;
-    uint8_t *exit_s = smem + off;          off += (size_t)NS * p.n_chunks * G;
-    uint8_t *entry_s = smem + off;         off += (size_t)NS * p.n_chunks;
-    off = (off + 15) & ~(size_t)15;
-    int *final_s = reinterpret_cast<int *>(smem + off);
-
-    const int sub = lane / G, j = lane % G;
-    const int seq = seq_base + sub;
-    const bool seq_ok = seq < B;
-    const bool lane_ok = seq_ok && j < K;
-    const int nch = (T + CH - 1) / CH;
-
-    // every warp keeps the lane's transition column: the consumer for the recursion, the helpers for psi.
-    // Lanes that own no state hold -inf, so their delta stays -inf without any select on the chain.
-    float2 M2[KP / 2];
-#pragma unroll
-    for (int i = 0; i < KP / 2; ++i) {
-        const float v0 = (lane_ok && 2 * i < K) ? __ldg(p.log_trans + (2 * i) * K + j) : -INFINITY;
-        const float v1 = (lane_ok && 2 * i + 1 < K) ? __ldg(p.log_trans + (2 * i + 1) * K + j) : -INFINITY;
-        M2[i] = make_float2(v0, v1);
-    }
-    // c[i] = delta_prev[i] + logP[i][j] as packed IEEE adds (bit-identical to scalar adds)
-    auto candidates = [&](const float4 *pv, float (&cv)[KP]) {
-#pragma unroll
-        for (int i4 = 0; i4 < KP / 4; ++i4) {
-            const float4 t = pv[i4];
-            const float2 lo = fadd2(make_float2(t.x, t.y), M2[2 * i4]);
-            const float2 hi = fadd2(make_float2(t.z, t.w), M2[2 * i4 + 1]);
-            cv[4 * i4 + 0] = lo.x; cv[4 * i4 + 1] = lo.y; cv[4 * i4 + 2] = hi.x; cv[4 * i4 + 3] = hi.y;
-        }
-    };
-
-    if (warp == 0) {
-        // ---------------- consumer: delta_t(j) = max_i(delta_{t-1}(i) + logP(i,j)) + log b_t(j) --------------
-        const float li = lane_ok ? __ldg(p.log_init + j) : -INFINITY;
-        float d = -INFINITY;
-        const float4 *prev = reinterpret_cast<const float4 *>(dr + sub * G);
-        float *dp = dr;
-        auto step = [&](int u, float eqv) {
-            float cv[KP];
-            candidates(prev, cv);
-            d = __fadd_rn(max_tree<KP>(cv), eqv);
-            dp[u * 32] = d;
-            prev = reinterpret_cast<const float4 *>(dp + u * 32 - j);
-            __syncwarp();
-        };
-        for (int c = 0; c < nch; ++c) {
-            const int b = c % NB;
-            bar_sync(BAR_FULL + b, VIT_THREADS);
-            const int nf = min(CH, T - c * CH);
-            const float *btb = bt + (size_t)b * CH * BT_PITCH + lane;
-            dp = dr + (size_t)b * CH * 32 + lane;
-            int u = 0;
-            if (c == 0) {
-                d = __fadd_rn(li, btb[0]);                  // delta_0 = log_p0 + log b_0 (hmm.py:159)
-                dp[0] = d;
-                prev = reinterpret_cast<const float4 *>(dp - j);
-                __syncwarp();
-                u = 1;
-            }
-            for (; u + 4 <= nf; u += 4) {
-                float eq[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) eq[i] = btb[(u + i) * BT_PITCH];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) step(u + i, eq[i]);
-            }
-            for (; u < nf; ++u) step(u, btb[u * BT_PITCH]);
-            bar_arrive(BAR_DONE + b, VIT_THREADS);
-        }
-        // final state: first index of the maximum (hmm.py:174)
-        float bv = lane_ok ? d : -INFINITY;
-        int bi = j;
-#pragma unroll
-        for (int o = G / 2; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(FULL_MASK, bv, o, G);
-            const int oi = __shfl_xor_sync(FULL_MASK, bi, o, G);
-            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-        }
-        if (j == 0) {
-            final_s[sub] = (bi < K) ? bi : 0;
-            if (seq_ok && p.score) p.score[seq] = bv;
-        }
-    } else if (warp <= VIT_NL) {
-        // ---------------- loaders: emission feed -----------------------------------------------------------
-        loader_loop<G, KP, 0, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, warp - 1, bt, nullptr, VIT_THREADS);
-    } else {
-        // ---------------- drainers: delta store and backpointers, NB chunks behind the consumer ------------
-        const int hw = warp - 1 - VIT_NL;
-        const int seq_c = seq_ok ? seq : B - 1;
-        auto drain = [&](int c, int b) {
-            const int nf = min(CH, T - c * CH);
-            const float *drb = dr + (size_t)b * CH * 32;
-            for (int u = hw; u < nf; u += VIT_ND) {
-                const int n = c * CH + u;
-                const float dv = drb[u * 32 + lane];
-                if (lane_ok && p.delta) p.delta[((size_t)seq * T + n) * K + j] = dv;
-                // backpointer: lowest index attaining max_i(delta_{n-1}(i) + logP(i,j))  (torch.max tie rule, hmm.py:167),
-                // recomputed from the stored delta vector with the same fp32 adds as the consumer; psi_0 = 0.
-                const float4 *pv = reinterpret_cast<const float4 *>(
-                    (u > 0) ? (drb + (u - 1) * 32 + sub * G) : (carry + ((c - 1) & 1) * 32 + sub * G));
-                float cv[KP];
-                candidates(pv, cv);
-                const float best = max_tree<KP>(cv);
-                unsigned eqm = 1u << (KP - 1);                       // keeps the index in range if everything is NaN
-#pragma unroll
-                for (int i = 0; i < KP - 1; ++i) eqm |= (cv[i] == best) ? (1u << i) : 0u;
-                const int arg = (n > 0) ? (__ffs(eqm) - 1) : 0;
-                if (lane_ok && p.psi_out) p.psi_out[((size_t)seq * T + n) * K + j] = (uint8_t)arg;
-                if (p.psi_in_smem) psi_s[((size_t)sub * T + n) * G + j] = (uint8_t)arg;
-                else if (seq_ok) p.psi_ws[((size_t)seq_c * T + n) * G + j] = (uint8_t)arg;
-                if (u == nf - 1) carry[(c & 1) * 32 + lane] = dv;
-            }
-        };
-        for (int c = 0; c < nch; ++c) {
-            const int b = c % NB;
-            if (c >= NB) {
-                bar_sync(BAR_DONE + b, VIT_THREADS);
-                drain(c - NB, b);
-            }
-            bar_arrive(BAR_FULL + b, VIT_THREADS);              // ring buffer b drained: consumer may overwrite it
-        }
-        for (int c = max(0, nch - NB); c < nch; ++c) {
-            const int b = c % NB;
-            bar_sync(BAR_DONE + b, VIT_THREADS);
-            drain(c, b);
-        }
-        if (!p.psi_in_smem) __threadfence_block();
-    }
-    __syncthreads();
-
-    // ---------------- chunk-parallel traceback: all threads --------------------------------------------
-    // chunk c covers t in [1 + c*L, min(T-1, (c+1)*L)]; following psi from its top frame to its bottom frame
-    // maps the state at t_hi to the state at t_lo - 1.
-    const int L = p.chunk, nC = p.n_chunks;
-    auto psi_at = [&](int s_sub, int s_seq, int t, int s) -> int {
-        return p.psi_in_smem ? psi_s[((size_t)s_sub * T + t) * G + s] : p.psi_ws[((size_t)s_seq * T + t) * G + s];
-    };
-    // phase A: exit state for every (sequence, chunk, entry state)
-    for (int task = tid; task < NS * nC * K; task += VIT_THREADS) {
-        const int e = task % K, c = (task / K) % nC, s_sub = task / (K * nC);
-        const int s_seq = min(seq_base + s_sub, B - 1);
-        const int t_lo = 1 + c * L, t_hi = min(T - 1, t_lo + L - 1);
-        int s = e;
-        for (int t = t_hi; t >= t_lo; --t) s = psi_at(s_sub, s_seq, t, s);
-        exit_s[((size_t)s_sub * nC + c) * G + e] = (uint8_t)s;
-    }
-    __syncthreads();
-    // phase B: the true entry state of every chunk (serial over chunks, one thread per sequence)
-    if (tid < NS) {
-        int s = final_s[tid];
-        st_s[(size_t)tid * T + (T - 1)] = (uint8_t)s;
-        for (int c = nC - 1; c >= 0; --c) {
-            entry_s[(size_t)tid * nC + c] = (uint8_t)s;
-            s = exit_s[((size_t)tid * nC + c) * G + s];
-        }
-    }
-    __syncthreads();
-    // phase C: re-walk every chunk from its true entry state, recording the path
-    for (int task = tid; task < NS * nC; task += VIT_THREADS) {
-        const int c = task % nC, s_sub = task / nC;
-        const int s_seq = min(seq_base + s_sub, B - 1);
-        const int t_lo = 1 + c * L, t_hi = min(T - 1, t_lo + L - 1);
-        int s = entry_s[(size_t)s_sub * nC + c];
-        for (int t = t_hi; t >= t_lo; --t) {
-            s = psi_at(s_sub, s_seq, t, s);
-            st_s[(size_t)s_sub * T + (t - 1)] = (uint8_t)s;
-        }
-    }
-    __syncthreads();
-    // phase D: coalesced int64 store
-    for (int i = tid; i < NS * T; i += VIT_THREADS) {
-        const int s_sub = i / T, t = i % T;
-        const int s_seq = seq_base + s_sub;
-        if (s_seq < B) p.states[(size_t)s_seq * T + t] = (int64_t)st_s[i];
-    }
-}
 
 // ----------------------------------------------------------------------------------------------------------
 // host-side dispatch
@@ -774,28 +37,6 @@ static int launch_fb(const FbParams &p, cudaStream_t s) {
     dim3 grid((p.B + NS - 1) / NS, 2);
     fb_sweep_kernel<G, KP><<<grid, FB_THREADS, FB_SMEM_BYTES, s>>>(p);
     return check_launch("fb_sweep_kernel");
-}
-
-static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
-
-static size_t vit_smem_bytes(int NS, int T, int G, int nC, bool psi_in_smem) {
-    size_t off = VIT_SMEM_PIPE + (psi_in_smem ? (size_t)NS * T * G : 0);
-    off += (size_t)NS * T + (size_t)NS * nC * G + (size_t)NS * nC;
-    off = (off + 15) & ~(size_t)15;
-    return off + NS * sizeof(int) * 2;
-}
-
-static void vit_plan(int T, int G, int &L, int &nC, bool &psi_in_smem, size_t &smem) {
-    const int NS = 32 / G;
-    L = 64;
-    if (T - 1 > 64 * 1024) L = (T - 1 + 1023) / 1024;
-    nC = (T <= 1) ? 0 : (T - 1 + L - 1) / L;
-    psi_in_smem = true;
-    smem = vit_smem_bytes(NS, T, G, nC, true);
-    if (smem > 200 * 1024) {
-        psi_in_smem = false;
-        smem = vit_smem_bytes(NS, T, G, nC, false);
-    }
 }
 
 template <int G, int KP>
@@ -814,21 +55,8 @@ static int launch_vit(VitParams p, cudaStream_t s) {
     return check_launch("viterbi_kernel");
 }
 
-#define DISPATCH_GK(FN, K, ...)                                                           \
-    do {                                                                                  \
-        const int kp_ = pad4(K);                                                          \
-        if (kp_ <= 4) return FN<4, 4>(__VA_ARGS__);                                       \
-        if (kp_ <= 8) return FN<8, 8>(__VA_ARGS__);                                       \
-        if (kp_ <= 12) return FN<16, 12>(__VA_ARGS__);                                    \
-        if (kp_ <= 16) return FN<16, 16>(__VA_ARGS__);                                    \
-        if (kp_ <= 20) return FN<32, 20>(__VA_ARGS__);                                    \
-        if (kp_ <= 24) return FN<32, 24>(__VA_ARGS__);                                    \
-        if (kp_ <= 28) return FN<32, 28>(__VA_ARGS__);                                    \
-        return FN<32, 32>(__VA_ARGS__);                                                   \
-    } while (0)
-
-static int dispatch_fb(const FbParams &p, cudaStream_t s) { DISPATCH_GK(launch_fb, p.K, p, s); }
-static int dispatch_vit(const VitParams &p, cudaStream_t s) { DISPATCH_GK(launch_vit, p.K, p, s); }
+static int dispatch_fb(const FbParams &p, cudaStream_t s) { HMMB200_DISPATCH_GK(launch_fb, p.K, p, s); }
+static int dispatch_vit(const VitParams &p, cudaStream_t s) { HMMB200_DISPATCH_GK(launch_vit, p.K, p, s); }
 
 }  // namespace hmmb200
 
@@ -869,30 +97,14 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
     p.ws_b = (float *)w;  w += align256(n * K * sizeof(float));
     p.ws_la = (float *)w; w += align256(n * sizeof(float));
     p.ws_lb = (float *)w;
-    p.loglik = loglik;
+    p.loglik = loglik; p.pdl = 0;
     if (int rc = dispatch_fb(p, s)) return rc;
     if (gamma || fwd_prob || bwd_prob || log_alpha || log_beta) {
         CombineParams c;
         c.ws_a = p.ws_a; c.ws_b = p.ws_b; c.ws_la = p.ws_la; c.ws_lb = p.ws_lb;
         c.n_frames = (int64_t)n; c.K = K;
         c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
-        const int threads = 256;
-        const unsigned blocks = (unsigned)((n + (size_t)threads * COMBINE_FPT - 1) / ((size_t)threads * COMBINE_FPT));
-        auto al16 = [](const void *q) { return q == nullptr || ((uintptr_t)q & 15) == 0; };
-        const bool vec = K % 4 == 0 && al16(gamma) && al16(fwd_prob) && al16(bwd_prob) && al16(log_alpha) && al16(log_beta);
-        const unsigned wblocks = (unsigned)((n + 255) / 256);   // one 32-frame block per warp, 8 warps per CTA
-        switch (vec ? K / 4 : 0) {
-            case 1: fb_combine_warp_kernel<1><<<wblocks, threads, 0, s>>>(c); break;
-            case 2: fb_combine_warp_kernel<2><<<wblocks, threads, 0, s>>>(c); break;
-            case 3: fb_combine_warp_kernel<3><<<wblocks, threads, 0, s>>>(c); break;
-            case 4: fb_combine_warp_kernel<4><<<wblocks, threads, 0, s>>>(c); break;
-            case 5: fb_combine_warp_kernel<5><<<wblocks, threads, 0, s>>>(c); break;
-            case 6: fb_combine_warp_kernel<6><<<wblocks, threads, 0, s>>>(c); break;
-            case 7: fb_combine_warp_kernel<7><<<wblocks, threads, 0, s>>>(c); break;
-            case 8: fb_combine_warp_kernel<8><<<wblocks, threads, 0, s>>>(c); break;
-            default: fb_combine_kernel<<<blocks, threads, 0, s>>>(c); break;
-        }
-        if (int rc = check_launch("fb_combine_kernel")) return rc;
+        if (int rc = launch_combine(c, s)) return rc;
     }
     return HMMB200_OK;
 }
@@ -925,6 +137,6 @@ HMMB200_EXPORT int hmmb200_viterbi_f32(const float *emis, int emis_mode, float f
     VitParams p;
     p.emis = emis; p.mode = emis_mode; p.eps = floor_eps; p.log_trans = log_trans; p.log_init = log_init;
     p.B = B; p.T = T; p.K = K; p.delta = delta; p.psi_out = psi; p.states = states; p.score = score;
-    p.psi_ws = (uint8_t *)workspace; p.psi_in_smem = 1; p.chunk = 64; p.n_chunks = 0;
+    p.psi_ws = (uint8_t *)workspace; p.psi_in_smem = 1; p.chunk = 64; p.n_chunks = 0; p.pdl = 0;
     return dispatch_vit(p, (cudaStream_t)stream);
 }

@@ -39,16 +39,20 @@ class _Slot:
         self.logb = torch.empty(bs, T, K, device=dev)
         self.fb_ws = ops.fb_workspace(bs, T, K, dev)
         self.vit_ws = ops.viterbi_workspace(bs, T, K, dev)
+        self.fused_ws = ops.fb_viterbi_workspace(bs, T, K, dev)
         self.x = torch.empty(bs, T, D, device=dev) if staged else None
         self.done = torch.cuda.Event()
 
 
 class HMMInferenceEngine:
     def __init__(self, layer, batch: int, seq_len: int, shard: int = 64, n_streams: int = 4,
-                 device: Optional[torch.device] = None, host_io: bool = False):
+                 device: Optional[torch.device] = None, host_io: bool = False, fused: bool = True, pdl: bool = True):
         """layer: a MixtureGaussianHMMLayer (its parameters are packed once here; call refresh() after an update).
         batch/seq_len: the shape of one pass.  shard: utterances per in-flight shard.  host_io: also allocate the
-        per-slot device staging for x so that run_host() can take pinned host tensors."""
+        per-slot device staging for x so that run_host() can take pinned host tensors.
+        fused: forward sweep, backward sweep and Viterbi of a shard in ONE launch (hmmb200_fb_viterbi_f32) instead of two
+        kernels on two streams.  pdl: that launch may overlap the tail of the emission kernel (programmatic dependent launch)."""
+        self.fused, self.pdl = bool(fused), bool(pdl)
         self.dev = ops.require_cuda(device if device is not None else (layer.means.device if layer.means.is_cuda else None))
         self.layer = layer
         self.K, self.C, self.D = layer.num_states, layer.num_components, layer.feature_dim
@@ -66,7 +70,8 @@ class HMMInferenceEngine:
             "states": torch.empty(self.B, self.T, dtype=torch.int64, device=self.dev),
             "score": torch.empty(self.B, device=self.dev), "loglik": torch.empty(self.B, device=self.dev)}
         self._fork = torch.cuda.Event()
-        self.kernels_per_shard = 4 if self.tc_known else 5   # gmm_emission_tc (+ the fp32 kernel when unknown), fb_sweep, fb_combine, viterbi
+        # gmm_emission_tc (+ the fp32 kernel when unknown), then fb_viterbi + fb_combine (fused) or fb_sweep, fb_combine, viterbi
+        self.kernels_per_shard = (1 if self.tc_known else 2) + (2 if self.fused else 3)
 
     def refresh(self):
         """Re-derive the kernel operands from the layer's parameters (O(K^2 + K*C*D), host side: SURVEY H4)."""
@@ -87,6 +92,15 @@ class HMMInferenceEngine:
         logb = slot.logb[:n]
         o = self.out
         ops.gmm_emission(x_sh, self.packed, self.K, self.C, self.D, out=logb, tc_known=self.tc_known)
+        if self.fused:
+            ops.forward_backward_viterbi(
+                logb, ops.EMIS_LOG_NORM_FLOOR, ops.EMIS_LOG, self.trans, self.init, self.log_trans, self.prior,
+                want=("gamma", "fwd", "bwd"),
+                out={"gamma": o["posterior"][lo:hi], "fwd": o["forward"][lo:hi], "bwd": o["backward"][lo:hi],
+                     "loglik": o["loglik"][lo:hi], "states": o["states"][lo:hi], "delta": o["log_delta"][lo:hi],
+                     "score": o["score"][lo:hi]},
+                workspace=slot.fused_ws, pdl=self.pdl and self.tc_known)
+            return
         slot.ev_emis.record(slot.stream)
         with torch.cuda.stream(slot.aux):
             slot.aux.wait_event(slot.ev_emis)

@@ -104,6 +104,11 @@ class MixtureGaussianHMMLayer(nn.Module):
             warnings.warn(f"Sequence length {observations.shape[1]} exceeds recommended maximum "
                           f"{self.max_sequence_length}. Consider chunked processing.")
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
+        from . import autograd as ag
+        if ag.needs_grad(observations, self.means, self.log_vars, self.mixture_weights_logits):
+            # training callers: differentiable w.r.t. means, log_vars, the mixture logits and x (autograd._GMMEmission)
+            logw = self._safe_log(F.softmax(self.mixture_weights_logits, dim=-1))
+            return ag.gmm_log_probs(observations, self.means, self._diag_log_vars(), logw, 1.0)
         packed, tc = self._packed_tc()
         out = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, self.num_components,
                                self.feature_dim, tc_known=tc)

@@ -149,8 +149,12 @@ class GaussianHMMLayer(nn.Module):
         return self.log_scales
 
     def _compute_gaussian_log_probs(self, observations: torch.Tensor) -> torch.Tensor:
-        """(B,T,D) -> (B,T,K) log N(x | mu_k, diag(exp(2 log_scales_k)))  (emission kernel)."""
+        """(B,T,D) -> (B,T,K) log N(x | mu_k, diag(exp(2 log_scales_k)))  (emission kernel; differentiable w.r.t. means,
+        log_scales and the observations when gradients are being recorded)."""
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
+        from . import autograd as ag
+        if ag.needs_grad(observations, self.means, self.log_scales):
+            return ag.gmm_log_probs(observations, self.means, self._diag_log_scales(), None, 2.0)
         out = ops.gmm_emission(observations.detach().to(dev), self._packed(), self.num_states, 1, self.feature_dim)
         return out if observations.device == out.device else out.to(observations.device)
 
@@ -163,6 +167,13 @@ class GaussianHMMLayer(nn.Module):
         return logb, mode, hmm, trans, init
 
     def forward(self, observations: torch.Tensor) -> torch.Tensor:
+        from . import autograd as ag
+        mode = ops.EMIS_LOG_NORM_FLOOR if self.normalize_emissions else ops.EMIS_LOG_EXP_FLOOR
+        if (self.hmm_layer.training or not self.hmm_layer.viterbi_inference) and self.num_states <= 32 and \
+                ag.needs_grad(observations, *self.parameters()):
+            hmm = self.hmm_layer._get_hmm()                               # differentiable log_P / log_p0 (hmm_layer.py:73-89)
+            post, _, _ = ag.hmm_posteriors(self._compute_gaussian_log_probs(observations), hmm.log_P, hmm.log_p0, mode, EPS)
+            return post if observations.device == post.device else post.to(observations.device)
         logb, mode, hmm, trans, init = self._posteriors(observations, ("gamma",))
         if self.hmm_layer.training or not self.hmm_layer.viterbi_inference:
             r = ops.forward_backward(logb, mode, trans, init, eps=EPS, want=("gamma",))
@@ -174,9 +185,20 @@ class GaussianHMMLayer(nn.Module):
         return post if observations.device == post.device else post.to(observations.device)
 
     def compute_loss(self, observations: torch.Tensor) -> torch.Tensor:
+        """Negative mean log-likelihood (hmm_layer.py:342-359).  The VALUE is the reference's saturating formula
+        logsumexp_k log(exp(log alpha_{T-1,k}) + 1e-8) (hmm.py:203-206); the GRADIENT (w.r.t. means, log_scales, the transition and
+        initial logits) is that of the true log-likelihood damped by the saturation factor sum_k alpha_k / sum_k (alpha_k + 1e-8) --
+        the reference's own gradient wherever no state is floored (it is identically zero once exp(alpha) has underflowed)."""
+        from . import autograd as ag
         logb, mode, hmm, trans, init = self._posteriors(observations, ("fwd",))
         r = ops.forward_backward(logb, mode, trans, init, eps=EPS, want=("fwd",))
-        ll = torch.logsumexp(torch.log(r["fwd"][:, -1] + EPS), dim=-1)       # hmm.py:206 via hmm_layer.py:358
+        last = r["fwd"][:, -1]
+        ll = torch.logsumexp(torch.log(last + EPS), dim=-1)                   # hmm.py:206 via hmm_layer.py:358
+        if self.num_states <= 32 and ag.needs_grad(observations, *self.parameters()):
+            logb_d = self._compute_gaussian_log_probs(observations)          # differentiable emission (means, log_scales, x)
+            true_ll = ag.hmm_log_likelihood(logb_d, hmm.log_P, hmm.log_p0, mode, EPS).to(ll.device)
+            sat = (last.sum(-1) / (last + EPS).sum(-1)).detach()
+            ll = ll.detach() + sat * (true_ll - true_ll.detach())
         out = -ll.mean()
         return out if observations.device == out.device else out.to(observations.device)
 

@@ -200,6 +200,104 @@ def viterbi(emis: torch.Tensor, mode: int, log_trans: torch.Tensor, log_init: to
     return res
 
 
+def tv_forward_backward(log_emis: torch.Tensor, trans_prob: torch.Tensor, init_prob: torch.Tensor,
+                        want=("gamma", "fwd", "bwd"), out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None) -> dict:
+    """Forward-backward with time-varying transitions (NeuralHMM form): log_emis [B,T,K] log-emissions, trans_prob [B,T,K,K]
+    probabilities (slice t: frame t -> t+1), init_prob [K].  Same result dict as forward_backward()."""
+    dev = require_cuda(log_emis.device)
+    e = _f32c(log_emis, dev)
+    B, T, K = e.shape
+    tp, ip = _f32c(trans_prob, dev), _f32c(init_prob, dev)
+    if tuple(tp.shape) != (B, T, K, K):
+        raise ValueError(f"trans_prob must be [B,T,K,K] = {(B, T, K, K)}, got {tuple(tp.shape)}")
+    lib = _lib.load()
+    res = {} if out is None else out
+    for name in ("gamma", "fwd", "bwd", "log_alpha", "log_beta"):
+        if name in want and name not in res:
+            res[name] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    if "loglik" not in res:
+        res["loglik"] = torch.empty(B, dtype=torch.float32, device=dev)
+    ws_bytes = lib.hmmb200_fb_workspace_bytes(B, T, K)
+    ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_tv_forward_backward_f32(_p(e), _p(tp), _p(ip), B, T, K, _p(res.get("gamma")), _p(res.get("fwd")),
+                                                   _p(res.get("bwd")), _p(res.get("log_alpha")), _p(res.get("log_beta")),
+                                                   _p(res["loglik"]), _p(ws), ws_bytes, _stream(dev)), "hmmb200_tv_forward_backward_f32")
+    return res
+
+
+def tv_viterbi(log_emis: torch.Tensor, log_trans: torch.Tensor, log_init: torch.Tensor, want_delta: bool = True,
+               want_psi: bool = False, want_score: bool = True) -> dict:
+    """Viterbi with time-varying transitions: log_trans [B,T,K,K] (slice t: frame t -> t+1) -> states / delta / psi / score."""
+    dev = require_cuda(log_emis.device)
+    e = _f32c(log_emis, dev)
+    B, T, K = e.shape
+    lt, li = _f32c(log_trans, dev), _f32c(log_init, dev)
+    if tuple(lt.shape) != (B, T, K, K):
+        raise ValueError(f"log_trans must be [B,T,K,K] = {(B, T, K, K)}, got {tuple(lt.shape)}")
+    lib = _lib.load()
+    res = {"states": torch.empty(B, T, dtype=torch.int64, device=dev)}
+    if want_delta:
+        res["delta"] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    if want_psi:
+        res["psi"] = torch.empty(B, T, K, dtype=torch.uint8, device=dev)
+    if want_score:
+        res["score"] = torch.empty(B, dtype=torch.float32, device=dev)
+    n = lib.hmmb200_tv_viterbi_workspace_bytes(B, T, K)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_tv_viterbi_f32(_p(e), _p(lt), _p(li), B, T, K, _p(res.get("delta")), _p(res.get("psi")), _p(res["states"]),
+                                          _p(res.get("score")), _p(ws), n, _stream(dev)), "hmmb200_tv_viterbi_f32")
+    return res
+
+
+FUSED_PDL = 1
+
+
+def fb_viterbi_workspace(B: int, T: int, K: int, dev) -> torch.Tensor:
+    n = _lib.load().hmmb200_fb_viterbi_workspace_bytes(B, T, K)
+    return torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+
+
+def forward_backward_viterbi(emis: torch.Tensor, fb_mode: int, vit_mode: int, trans_prob: torch.Tensor, init_prob: torch.Tensor,
+                             log_trans: torch.Tensor, log_init: torch.Tensor, eps: float = EPS, add_rowmax: bool = False,
+                             want=("gamma", "fwd", "bwd"), want_delta: bool = True, want_psi: bool = False, want_score: bool = True,
+                             out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None, pdl: bool = False) -> dict:
+    """Forward-backward and Viterbi on the same emissions in one pass (hmmb200_fb_viterbi_f32: one launch for K <= 32).
+    Returns the union of forward_backward()'s and viterbi()'s dicts.  pdl: the kernel may overlap the tail of the previous
+    kernel on the stream (the emission kernel that writes `emis`); only pass True when that kernel writes none of the tables."""
+    dev = require_cuda(emis.device)
+    emis = _f32c(emis, dev)
+    B, T, K = emis.shape
+    trans_prob, init_prob = _f32c(trans_prob, dev), _f32c(init_prob, dev)
+    log_trans, log_init = _f32c(log_trans, dev), _f32c(log_init, dev)
+    lib = _lib.load()
+    res = {} if out is None else out
+    for name in ("gamma", "fwd", "bwd", "log_alpha", "log_beta"):
+        if name in want and name not in res:
+            res[name] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    if "loglik" not in res:
+        res["loglik"] = torch.empty(B, dtype=torch.float32, device=dev)
+    if "states" not in res:
+        res["states"] = torch.empty(B, T, dtype=torch.int64, device=dev)
+    if want_delta and "delta" not in res:
+        res["delta"] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+    if want_psi and "psi" not in res:
+        res["psi"] = torch.empty(B, T, K, dtype=torch.uint8 if K <= 256 else torch.int16, device=dev)
+    if want_score and "score" not in res:
+        res["score"] = torch.empty(B, dtype=torch.float32, device=dev)
+    ws_bytes = lib.hmmb200_fb_viterbi_workspace_bytes(B, T, K)
+    ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.hmmb200_fb_viterbi_f32(
+            _p(emis), int(fb_mode), int(vit_mode), float(eps), int(bool(add_rowmax)), _p(trans_prob), _p(init_prob),
+            _p(log_trans), _p(log_init), B, T, K,
+            _p(res.get("gamma")), _p(res.get("fwd")), _p(res.get("bwd")), _p(res.get("log_alpha")), _p(res.get("log_beta")),
+            _p(res["loglik"]), _p(res.get("delta")), _p(res.get("psi")), _p(res["states"]), _p(res.get("score")),
+            _p(ws), ws_bytes, FUSED_PDL if pdl else 0, _stream(dev)), "hmmb200_fb_viterbi_f32")
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------
 # explicit-duration (semi-Markov) recursions
 # ------------------------------------------------------------------------------------------------------

@@ -354,3 +354,58 @@ def test_errors_and_edges(hm):
     r = hm.ops.viterbi(torch.empty(0, 5, 3).cuda(), hm.ops.EMIS_LOG, torch.zeros(3, 3).cuda(), torch.zeros(3).cuda())
     assert r["states"].shape == (0, 5)
     assert lib.hmmb200_device_check(-1) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# fused forward + backward + Viterbi launch (hmmb200_fb_viterbi_f32)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,T,B", [(1, 3, 2), (3, 1, 1), (4, 70, 9), (7, 129, 3), (8, 64, 5), (12, 500, 7), (12, 2000, 5), (16, 257, 3),
+                                   (17, 90, 2), (24, 65, 3), (32, 130, 2), (12, 6000, 3), (40, 20, 3)])
+@pytest.mark.parametrize("pdl", [False, True])
+def test_fused_fb_viterbi_equals_the_separate_passes(hm, K, T, B, pdl):
+    """One launch (three chains in one CTA) must reproduce the stand-alone kernels bit for bit: same device code, same operation
+    order.  T = 6000 exceeds the shared-memory budget for the backpointers beside the sweeps and K = 40 is a large-K shape: both take
+    the entry point's two-pass route.  Also against the oracles: Viterbi bit-exact, posteriors 1e-4 of float64."""
+    rng = np.random.default_rng(4200 + K * 3 + T)
+    l = (rng.standard_normal((B, T, K)) * 5.0 - 60.0).astype(np.float32)
+    l[rng.random((B, T, K)) < 0.1] = np.float32(-200.0)
+    P = rng.random((K, K)) + 0.02
+    P /= P.sum(1, keepdims=True)
+    p0 = np.full(K, 1.0 / K)
+    Pe, p0e = (P + 1e-8).astype(np.float32), (p0 + 1e-8).astype(np.float32)
+    logP, logp0 = np.log(Pe).astype(np.float32), np.log(p0e).astype(np.float32)
+    e = _dev(l)
+    sep_f = hm.ops.forward_backward(e, hm.ops.EMIS_LOG_NORM_FLOOR, _dev(Pe), _dev(p0e), want=("gamma", "fwd", "bwd", "log_alpha", "log_beta"),
+                                    method="sweep")
+    sep_v = hm.ops.viterbi(e, hm.ops.EMIS_LOG, _dev(logP), _dev(logp0), want_delta=True, want_psi=True)
+    r = hm.ops.forward_backward_viterbi(e, hm.ops.EMIS_LOG_NORM_FLOOR, hm.ops.EMIS_LOG, _dev(Pe), _dev(p0e), _dev(logP), _dev(logp0),
+                                        want=("gamma", "fwd", "bwd", "log_alpha", "log_beta"), want_psi=True, pdl=pdl)
+    for k in ("gamma", "fwd", "bwd", "log_alpha", "log_beta", "loglik"):
+        assert torch.equal(r[k], sep_f[k]), k
+    for k in ("states", "delta", "psi", "score"):
+        assert torch.equal(r[k], sep_v[k]), k
+    st, dl, psi, sc = c_oracle.viterbi_f32(l, logP, logp0)
+    assert np.array_equal(r["states"].cpu().numpy(), st) and np.array_equal(r["delta"].cpu().numpy(), dl)
+    log_obs = np.log(np.exp(l - l.max(-1, keepdims=True)).astype(np.float32) + np.float32(1e-8)).astype(np.float64)
+    _, _, gam, ll = c_oracle.forward_backward_f64(log_obs, np.log(Pe.astype(np.float64)), np.log(p0e.astype(np.float64)))
+    np.testing.assert_allclose(r["gamma"].cpu().numpy(), gam, rtol=max(RTOL, 3e-4 if T > 1000 else RTOL), atol=1e-7)
+    np.testing.assert_allclose(r["loglik"].cpu().numpy(), ll, rtol=RTOL, atol=1e-4)
+
+
+def test_fused_fb_viterbi_mixed_modes_and_optional_outputs(hm):
+    """Posteriors on floored probabilities + Viterbi on the same probabilities (HMMPyTorch's two calls), with outputs left out."""
+    rng = np.random.default_rng(77)
+    K, T, B = 10, 333, 6
+    obs = rng.random((B, T, K)).astype(np.float32)
+    obs[rng.random((B, T, K)) < 0.2] = 0.0
+    P = rng.random((K, K)) + 0.05
+    P /= P.sum(1, keepdims=True)
+    Pe, p0e = (P + 1e-8).astype(np.float32), np.full(K, 1.0 / K + 1e-8, np.float32)
+    logP, logp0 = np.log(Pe).astype(np.float32), np.log(p0e).astype(np.float32)
+    e = _dev(obs)
+    r = hm.ops.forward_backward_viterbi(e, hm.ops.EMIS_PROB_FLOOR, hm.ops.EMIS_PROB_FLOOR, _dev(Pe), _dev(p0e), _dev(logP), _dev(logp0),
+                                        want=("gamma",), want_delta=False, want_score=False)
+    f = hm.ops.forward_backward(e, hm.ops.EMIS_PROB_FLOOR, _dev(Pe), _dev(p0e), want=("gamma",))
+    v = hm.ops.viterbi(e, hm.ops.EMIS_PROB_FLOOR, _dev(logP), _dev(logp0), want_delta=False, want_score=False)
+    assert torch.equal(r["gamma"], f["gamma"]) and torch.equal(r["loglik"], f["loglik"]) and torch.equal(r["states"], v["states"])
+    assert "delta" not in r and "score" not in r

@@ -235,3 +235,22 @@ def test_oracle_pinned_at_large_k(golden):
         _, _, gam, _ = c_oracle.forward_backward_f64(log_obs.astype(np.float64), g[f"{tag}_log_P"].astype(np.float64),
                                                       g[f"{tag}_log_p0"].astype(np.float64))
         np.testing.assert_allclose(gam, g[f"{tag}_posterior"], rtol=1e-4, atol=1e-7)
+
+
+def test_neural_oracle_vs_reference_golden(golden):
+    """orc_tv_viterbi_f32 / orc_tv_forward_backward_f64 restate NeuralHMM's recursions (neural.py:403-511): bit-identical Viterbi,
+    posteriors to the reference's fp32 rounding (1e-3 absolute at T = 300), on the real class's outputs."""
+    from oracle import c_oracle
+    g = golden("neural")
+    for tag in ("tv", "tv12"):
+        st, dl, psi = c_oracle.tv_viterbi_f32(g[f"{tag}_log_obs"], g[f"{tag}_log_trans"], g[f"{tag}_log_init"])
+        assert np.array_equal(st, g[f"{tag}_states"]) and np.array_equal(dl, g[f"{tag}_log_delta"])
+        la, lb, gam, ll = c_oracle.tv_forward_backward_f64(g[f"{tag}_log_obs"], g[f"{tag}_log_trans"], g[f"{tag}_log_init"])
+        np.testing.assert_allclose(gam, g[f"{tag}_posterior"], atol=1e-3)
+        np.testing.assert_allclose(np.exp(la), g[f"{tag}_forward"], rtol=1e-3, atol=1e-37)
+        np.testing.assert_allclose(np.exp(lb), g[f"{tag}_backward"], rtol=1e-3, atol=1e-37)
+        sat = np.log(np.sum(np.exp(la[:, -1]) + 1e-8, axis=-1))
+        np.testing.assert_allclose(sat, g[f"{tag}_likelihood"], rtol=1e-4)
+    # the static-transition case is the fixed-matrix recursion on log-emissions
+    st, dl, psi, sc = c_oracle.viterbi_f32(g["static_log_obs"], g["static_log_trans"], g["static_log_init"])
+    assert np.array_equal(st, g["static_states"]) and np.array_equal(dl, g["static_log_delta"])
