@@ -490,6 +490,7 @@ def run_gpu_arm(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; pytorch_hmm_b200 has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
+    torch.set_grad_enabled(False)                                 # inference and EM statistics only: no autograd graphs
     numa_note = pin_to_gpu_numa_node(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:

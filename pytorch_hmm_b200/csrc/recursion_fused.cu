@@ -48,7 +48,9 @@ struct FusedParams {
     int dbg;              // debug builds only: bit 0 warp layout, bits 4-6 skip the forward / backward / Viterbi pipeline (timing experiments)
 };
 
-constexpr size_t FU_SMEM_F = FbSmem<0>::BYTES, FU_SMEM_B = FbSmem<1>::BYTES;
+// shared-memory layout: [forward sweep][backward sweep][raw stage asc (forward)][raw stage desc (backward)][raw stage asc (Viterbi)][Viterbi]
+template <bool PAD> __host__ __device__ constexpr size_t fu_smem_f() { return FbSmem<0, PAD>::BYTES; }
+template <bool PAD> __host__ __device__ constexpr size_t fu_smem_b() { return FbSmem<1, PAD>::BYTES; }
 
 template <int G, int KP>
 __global__ void __launch_bounds__(FU_THREADS, 1) fb_viterbi_kernel(const __grid_constant__ FusedParams p) {
@@ -58,16 +60,25 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fb_viterbi_kernel(const __grid_
 #ifdef HMMB200_DEBUG_HOOKS
     if (p.dbg & 1) fused_role<1>(threadIdx.x >> 5, pipe, role);
     else fused_role<0>(threadIdx.x >> 5, pipe, role);
-    if ((p.dbg >> 4) & (1 << pipe)) return;
 #else
     fused_role<0>(threadIdx.x >> 5, pipe, role);
 #endif
+    constexpr size_t OFF_B = fu_smem_f<PAD>(), OFF_RAW = OFF_B + fu_smem_b<PAD>();
+    const size_t raw = p.fb.bulk ? raw_stage_bytes(p.fb.K, 32 / G) : 0;
+    const RawStage rs_f(smem + OFF_RAW, p.fb.K), rs_b(smem + OFF_RAW + raw, p.fb.K), rs_v(smem + OFF_RAW + 2 * raw, p.fb.K);
+    if (p.fb.bulk) {
+        if (threadIdx.x == 0) { rs_f.init(FB_NL); rs_b.init(FB_NL); rs_v.init(VIT_NL); }
+        __syncthreads();
+    }
+#ifdef HMMB200_DEBUG_HOOKS
+    if ((p.dbg >> 4) & (1 << pipe)) return;                         // timing experiments: leave a pipeline out
+#endif
     if (pipe == 0) {
-        fb_roles<G, KP, 0, PAD>(p.fb, smem, role, PipeBars{1, 3, FB_THREADS});
+        fb_roles<G, KP, 0, PAD>(p.fb, smem, role, PipeBars{1, 3, FB_THREADS}, rs_f);
     } else if (pipe == 1) {
-        fb_roles<G, KP, 1, PAD>(p.fb, smem + FU_SMEM_F, role, PipeBars{5, 7, FB_THREADS});
+        fb_roles<G, KP, 1, PAD>(p.fb, smem + OFF_B, role, PipeBars{5, 7, FB_THREADS}, rs_b);
     } else {
-        vit_roles<G, KP>(p.vit, smem + FU_SMEM_F + FU_SMEM_B, role, role * 32 + (int)(threadIdx.x & 31), PipeBars{9, 11, VIT_THREADS},
+        vit_roles<G, KP>(p.vit, smem + OFF_RAW + 3 * raw, role, role * 32 + (int)(threadIdx.x & 31), PipeBars{9, 11, VIT_THREADS}, rs_v,
                          [] { bar_sync(13, VIT_THREADS); });
     }
 }
@@ -76,7 +87,10 @@ template <int G, int KP>
 static int launch_fused(FusedParams p, int pdl, cudaStream_t s) {
     constexpr int NS = 32 / G;
     bool in_smem; size_t vsmem;
-    const size_t budget = 227 * 1024 - FU_SMEM_F - FU_SMEM_B;
+    constexpr bool PAD = KP < G;
+    p.fb.bulk = p.vit.bulk = bulk_feed_ok(p.fb.emis, p.fb.T, p.fb.K) ? 1 : 0;
+    const size_t fixed = fu_smem_f<PAD>() + fu_smem_b<PAD>() + (p.fb.bulk ? 3 * raw_stage_bytes(p.fb.K, NS) : 0);
+    const size_t budget = 227 * 1024 - fixed;
     vit_plan(p.vit.T, G, p.vit.chunk, p.vit.n_chunks, in_smem, vsmem, budget);
     if (!in_smem || vsmem > budget) return 1;                       // backpointers do not fit beside the sweeps: caller runs the separate kernels
     p.vit.psi_in_smem = 1;
@@ -84,8 +98,9 @@ static int launch_fused(FusedParams p, int pdl, cudaStream_t s) {
     p.dbg = 0;
 #ifdef HMMB200_DEBUG_HOOKS
     if (const char *e = getenv("HMMB200_FUSED_DBG")) p.dbg = atoi(e);
+    if (p.dbg & 2) p.fb.bulk = p.vit.bulk = 0;                     // bit 1: per-lane global loads instead of the bulk-copy feed (A/B timing)
 #endif
-    const size_t smem = FU_SMEM_F + FU_SMEM_B + vsmem;
+    const size_t smem = fixed + vsmem;
     static bool done[64];                                           // per-device function attribute, set once (idempotent)
     int dev = 0;
     cudaGetDevice(&dev);

@@ -30,12 +30,14 @@ namespace hmmb200 {
 // host-side dispatch
 // ----------------------------------------------------------------------------------------------------------
 template <int G, int KP>
-static int launch_fb(const FbParams &p, cudaStream_t s) {
+static int launch_fb(FbParams p, cudaStream_t s) {
     constexpr int NS = 32 / G;
-    cudaError_t e = cudaFuncSetAttribute(fb_sweep_kernel<G, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB_SMEM_BYTES);
+    p.bulk = bulk_feed_ok(p.emis, p.T, p.K) ? 1 : 0;
+    const size_t smem = FB_SMEM_BYTES + (p.bulk ? raw_stage_bytes(p.K, NS) : 0);
+    cudaError_t e = cudaFuncSetAttribute(fb_sweep_kernel<G, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "fb smem opt-in: %s", cudaGetErrorString(e));
     dim3 grid((p.B + NS - 1) / NS, 2);
-    fb_sweep_kernel<G, KP><<<grid, FB_THREADS, FB_SMEM_BYTES, s>>>(p);
+    fb_sweep_kernel<G, KP><<<grid, FB_THREADS, smem, s>>>(p);
     return check_launch("fb_sweep_kernel");
 }
 
@@ -43,9 +45,12 @@ template <int G, int KP>
 static int launch_vit(VitParams p, cudaStream_t s) {
     constexpr int NS = 32 / G;
     bool in_smem; size_t smem;
-    vit_plan(p.T, G, p.chunk, p.n_chunks, in_smem, smem);
+    p.bulk = bulk_feed_ok(p.emis, p.T, p.K) ? 1 : 0;
+    const size_t raw = p.bulk ? raw_stage_bytes(p.K, NS) : 0;
+    vit_plan(p.T, G, p.chunk, p.n_chunks, in_smem, smem, 200 * 1024 - raw);
     p.psi_in_smem = in_smem ? 1 : 0;
-    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "viterbi: T=%d too long for the traceback tables", p.T);
+    if (smem > 200 * 1024 - raw) return set_error(HMMB200_EUNSUPPORTED, "viterbi: T=%d too long for the traceback tables", p.T);
+    smem += raw;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(viterbi_kernel<G, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "viterbi smem opt-in: %s", cudaGetErrorString(e));
@@ -113,7 +118,8 @@ HMMB200_EXPORT size_t hmmb200_viterbi_workspace_bytes(int B, int T, int K) {
     if (B <= 0 || T <= 0 || K <= 0) return 0;
     if (K > 32) return largek_shape_ok(K) ? largek_viterbi_workspace_bytes(B, T, K) : 0;
     int G = group_lanes(K), L, nC; bool in_smem; size_t smem;
-    vit_plan(T, G, L, nC, in_smem, smem);
+    // (the launch may also carve the raw emission stage out of the same budget: plan with it, so that the query never under-reports)
+    vit_plan(T, G, L, nC, in_smem, smem, 200 * 1024 - raw_stage_bytes(K, 32 / G));
     return in_smem ? 0 : (size_t)B * T * G;
 }
 

@@ -50,6 +50,58 @@ __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.ar
 // tail, everything after it sees the predecessor's memory.  A no-op when the kernel was launched the ordinary way.
 __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- raw emission stage: chunks of the [B,T,K] emission tensor land in shared memory by bulk asynchronous copies ----------------
+// A chunk of CH frames of one sequence is CH*K*4 contiguous bytes in HBM.  Reading it with per-lane loads (lane = frame) costs one
+// L1 wavefront per lane and per value -- ~770 wavefronts per loader warp and chunk, and the SM's single load/store FIFO is what the
+// latency-critical consumer warps' shared-memory round trips queue in.  One cp.async.bulk per (sequence, chunk) moves the same
+// bytes without occupying that FIFO at all; its arrival is counted on an mbarrier (transaction bytes); NR chunks are in flight.
+constexpr int NR = 2;
+__device__ __forceinline__ uint32_t sk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sk_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sk_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sk_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sk_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "SKWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"      // suspends: a waiting warp burns no issue slots
+        "@p bra SKDONE_%=;\n\t"
+        "bra SKWAIT_%=;\n\t"
+        "SKDONE_%=:\n\t"
+        "}" ::"r"(sk_smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+__device__ __forceinline__ void sk_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(sk_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(sk_smem_u32(bar)) : "memory");
+}
+// floats of one (buffer, sequence) block: CH*K values + 16 floats of padding so that the blocks of the two sequences of a warp sit
+// 16 banks apart; 16-byte aligned for any K
+__host__ __device__ inline int raw_seq_floats(int K) { return CH * K + 16 + ((4 - (CH * K) % 4) % 4); }
+__host__ __device__ inline size_t raw_stage_bytes(int K, int NS) { return 64 + (size_t)NR * NS * raw_seq_floats(K) * sizeof(float); }
+struct RawStage {
+    uint64_t *full, *empty;   // [NR] each: bytes of the chunk have landed / every reader warp has copied its frames out
+    float *buf;               // [NR][NS][raw_seq_floats(K)]
+    int seq_floats;
+    __device__ RawStage() : full(nullptr), empty(nullptr), buf(nullptr), seq_floats(0) {}
+    __device__ RawStage(uint8_t *smem, int K) {
+        full = reinterpret_cast<uint64_t *>(smem);
+        empty = full + NR;
+        buf = reinterpret_cast<float *>(smem + 64);
+        seq_floats = raw_seq_floats(K);
+    }
+    __device__ void init(int reader_warps) const {               // ONE thread, before a CTA-wide barrier
+        for (int i = 0; i < NR; ++i) { sk_mbar_init(full + i, 1); sk_mbar_init(empty + i, reader_warps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+};
+
 // Blackwell packed fp32 pairs (one issue slot for two IEEE round-to-nearest operations) and 3-input max.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
     unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b);
@@ -157,7 +209,8 @@ __device__ __forceinline__ void loader_loop(const float *emis, int mode, float e
             const int f = (DIR == 0) ? n : T - 1 - n;
             const float *row = emis + ((size_t)(ok ? seq : 0) * T + (ok ? f : 0)) * K;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) dst[i][k] = (ok && k < K) ? __ldg(row + k) : 0.f;
+            // (ld.global.cg, not the read-only path: an invariant load could be hoisted above griddepcontrol.wait by the compiler)
+            for (int k = 0; k < KP; ++k) dst[i][k] = (ok && k < K) ? __ldcg(row + k) : 0.f;
         }
     };
     fetch(0, cur);
@@ -191,6 +244,84 @@ __device__ __forceinline__ void loader_loop(const float *emis, int mode, float e
     for (int c = max(0, nch - NB); c < nch; ++c) bar_sync(pb.done0 + (c % NB), pb.n);
 }
 
+// Same role with the chunks arriving in the raw stage by bulk copies (lane 0 of loader 0 issues them NR chunks ahead; needs every
+// chunk start and size to be a multiple of 16 bytes: (T*K) % 4 == 0 and a 16-byte aligned tensor).  Lane (sub, q) of loader `lw`
+// takes the frames u = q + G*(lw*FL + i) of the chunk: neighbouring lanes read neighbouring frame rows (conflict-free 16-byte
+// shared-memory loads at K = 12) and write neighbouring rows of the emission ring.
+template <int G, int KP, int DIR, bool SCALED, int NL>
+__device__ __forceinline__ void loader_loop_bulk(const float *emis, int mode, float eps, int B, int T, int K, int lw,
+                                                 float *bt, float *mraw, PipeBars pb, RawStage rs) {
+    constexpr int NS = 32 / G, FPL = CH / G, FL = FPL / NL;
+    static_assert(FPL % NL == 0 && FL >= 1, "loader split");
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / G, q = lane % G;
+    const int seq0 = blockIdx.x * NS;
+    const bool seq_ok = seq0 + sub < B;
+    const int nch = (T + CH - 1) / CH;
+    const bool issuer = (lw == 0 && lane == 0);
+    const int n_seq = min(NS, B - seq0);
+    auto issue = [&](int c) {                                        // chunk c (sweep order) -> raw buffer c % NR
+        const int rb = c % NR;
+        const int nf = min(CH, T - c * CH);
+        const int f_lo = (DIR == 0) ? c * CH : T - c * CH - nf;      // lowest frame of the chunk: the block is frames f_lo .. f_lo+nf-1
+        const uint32_t bytes = (uint32_t)nf * K * sizeof(float);
+        sk_mbar_expect_tx(rs.full + rb, bytes * n_seq);
+        for (int s = 0; s < n_seq; ++s)
+            sk_bulk_g2s(rs.buf + (size_t)(rb * NS + s) * rs.seq_floats, emis + ((size_t)(seq0 + s) * T + f_lo) * K, bytes, rs.full + rb);
+    };
+    if (issuer) for (int c = 0; c < min(NR, nch); ++c) issue(c);
+    for (int c = 0; c < nch; ++c) {
+        const int b = c % NB, rb = c % NR;
+        const int nf = min(CH, T - c * CH);
+        sk_mbar_wait(rs.full + rb, (c / NR) & 1);
+        float cur[FL][KP];
+#pragma unroll
+        for (int i = 0; i < FL; ++i) {
+            const int u = q + G * (lw * FL + i);
+            const bool ok = seq_ok && u < nf;
+            const int row = ok ? ((DIR == 0) ? u : nf - 1 - u) : 0;
+            const float *src = rs.buf + (size_t)(rb * NS + sub) * rs.seq_floats + (size_t)row * K;
+            if ((KP % 4) == 0 && (K % 4) == 0) {
+#pragma unroll
+                for (int k4 = 0; k4 < KP / 4; ++k4) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok && 4 * k4 < K) v = *reinterpret_cast<const float4 *>(src + 4 * k4);
+                    cur[i][4 * k4] = v.x; cur[i][4 * k4 + 1] = v.y; cur[i][4 * k4 + 2] = v.z; cur[i][4 * k4 + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < KP; ++k) cur[i][k] = (ok && k < K) ? src[k] : 0.f;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) sk_mbar_arrive(rs.empty + rb);                // this warp has its frames of raw[rb] in registers
+        if (issuer && c + NR < nch) {
+            sk_mbar_wait(rs.empty + rb, (c / NR) & 1);               // ... and so have the other loader warps: refill the buffer
+            issue(c + NR);
+        }
+        if (c >= NB) bar_sync(pb.done0 + b, pb.n);                   // consumer is done reading bt[b] (chunk c - NB)
+        float *btb = bt + (size_t)b * CH * BT_PITCH;
+#pragma unroll
+        for (int i = 0; i < FL; ++i) {
+            const int u = q + G * (lw * FL + i);
+            const bool ok = seq_ok && u < nf;
+            float m = 0.f;
+            if (SCALED) row_to_scaled<KP>(mode, eps, K, cur[i], m);
+            else row_to_log<KP>(mode, eps, K, cur[i]);
+            float *dst = btb + u * BT_PITCH + sub * G;
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                float v = 0.f;
+                if (k < KP) v = (ok && k < K) ? cur[i][k] : 0.f;
+                dst[k] = v;
+            }
+            if (SCALED) mraw[((size_t)(c % MR_BUFS) * CH + u) * MAXNS + sub] = ok ? m : 0.f;
+        }
+        bar_arrive(pb.full0 + b, pb.n);
+    }
+    for (int c = max(0, nch - NB); c < nch; ++c) bar_sync(pb.done0 + (c % NB), pb.n);
+}
+
 // ----------------------------------------------------------------------------------------------------------
 // forward / backward sweeps
 // ----------------------------------------------------------------------------------------------------------
@@ -206,6 +337,7 @@ struct FbParams {
     float *ws_la, *ws_lb; // [B,T]   log scale: alpha = a * exp(la), beta = b * exp(lb)
     float *loglik;        // [B] or null
     int pdl;              // launched with programmatic stream serialisation: wait for the previous kernel before touching its data
+    int bulk;             // emission chunks arrive by bulk asynchronous copies (16-byte aligned tensor, (T*K) % 4 == 0)
 };
 
 constexpr int FB_NL = 2;                                   // loader warps
@@ -430,12 +562,13 @@ __device__ __forceinline__ void fb_drainer(const FbParams &p, const float *wr, c
     }
 }
 
-// One sweep's shared-memory carve-up (the forward sweep has no `br` ring: DIR 0 never touches it).
-template <int DIR>
+// One sweep's shared-memory carve-up (the forward sweep has no `br` ring: DIR 0 never touches it; with a pad lane -- K < group
+// width -- the running exponent travels in the w ring and there is no `er` ring either).
+template <int DIR, bool PAD = false>
 struct FbSmem {
     float *mraw, *bt, *wr, *br;
     int *er;
-    static constexpr size_t BYTES = FB_SMEM_MR + FB_SMEM_BT + FB_SMEM_WR + (DIR == 1 ? FB_SMEM_WR : 0) + FB_SMEM_ER;
+    static constexpr size_t BYTES = FB_SMEM_MR + FB_SMEM_BT + FB_SMEM_WR + (DIR == 1 ? FB_SMEM_WR : 0) + (PAD ? 0 : FB_SMEM_ER);
     __device__ explicit FbSmem(uint8_t *smem) {
         mraw = reinterpret_cast<float *>(smem);
         bt = reinterpret_cast<float *>(smem + FB_SMEM_MR);
@@ -447,13 +580,14 @@ struct FbSmem {
 
 // role: 0 consumer, 1 .. FB_NL loaders, FB_NL + 1 .. FB_NL + FB_ND drainers
 template <int G, int KP, int DIR, bool PAD>
-__device__ __forceinline__ void fb_roles(const FbParams &p, uint8_t *smem, int role, PipeBars pb) {
-    FbSmem<DIR> s(smem);
+__device__ __forceinline__ void fb_roles(const FbParams &p, uint8_t *smem, int role, PipeBars pb, RawStage rs) {
+    FbSmem<DIR, PAD> s(smem);
     if (role == 0) {
         fb_consumer<G, KP, DIR, PAD>(p, s.bt, s.wr, s.br, s.er, pb);       // (touches no global memory a predecessor writes)
     } else if (role <= FB_NL) {
         if (p.pdl) grid_dependency_wait();
-        loader_loop<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, role - 1, s.bt, s.mraw, pb);
+        if (p.bulk) loader_loop_bulk<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, role - 1, s.bt, s.mraw, pb, rs);
+        else loader_loop<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, role - 1, s.bt, s.mraw, pb);
     } else {
         if (p.pdl) grid_dependency_wait();
         fb_drainer<G, KP, DIR, PAD>(p, s.wr, s.br, s.er, s.mraw, role - 1 - FB_NL, pb);
@@ -465,8 +599,13 @@ __global__ void __launch_bounds__(FB_THREADS) fb_sweep_kernel(FbParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr bool PAD = KP < G;
     const PipeBars pb = {BAR_FULL, BAR_DONE, FB_THREADS};
-    if (blockIdx.y == 0) fb_roles<G, KP, 0, PAD>(p, smem, threadIdx.x >> 5, pb);
-    else fb_roles<G, KP, 1, PAD>(p, smem, threadIdx.x >> 5, pb);
+    const RawStage rs(smem + FB_SMEM_BYTES, p.K);                  // (bulk-copy feed only; unused bytes otherwise)
+    if (p.bulk) {
+        if (threadIdx.x == 0) rs.init(FB_NL);
+        __syncthreads();
+    }
+    if (blockIdx.y == 0) fb_roles<G, KP, 0, PAD>(p, smem, threadIdx.x >> 5, pb, rs);
+    else fb_roles<G, KP, 1, PAD>(p, smem, threadIdx.x >> 5, pb, rs);
 }
 
 // ----------------------------------------------------------------------------------------------------------
@@ -589,6 +728,7 @@ struct VitParams {
     int chunk;           // traceback chunk length L
     int n_chunks;        // ceil((T-1)/L)
     int pdl;             // launched with programmatic stream serialisation: wait for the previous kernel before touching its data
+    int bulk;            // emission chunks arrive by bulk asynchronous copies (16-byte aligned tensor, (T*K) % 4 == 0)
 };
 
 constexpr int VIT_NL = 2;                                  // loader warps
@@ -606,8 +746,10 @@ constexpr size_t VIT_SMEM_PIPE = VIT_SMEM_BT + VIT_SMEM_DR + VIT_SMEM_CARRY;
 // `sync_all` synchronises exactly these VIT_THREADS threads (__syncthreads in the stand-alone kernel, a named barrier when the
 // pipeline shares its CTA with the forward / backward sweeps).
 template <int G, int KP, typename SyncAll>
-__device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int role, int vtid, PipeBars pb, SyncAll sync_all) {
+__device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int role, int vtid, PipeBars pb, RawStage rs, SyncAll sync_all) {
     constexpr int NS = 32 / G;
+    constexpr bool NIB = G <= 16;                         // backpointers < 16: two per byte in shared memory
+    constexpr int PSI_ROW = NIB ? G / 2 : G;              // bytes per (sequence, frame) of the shared-memory table
     const int K = p.K, T = p.T, B = p.B;
     const int lane = threadIdx.x & 31;
     const int seq_base = blockIdx.x * NS;
@@ -616,7 +758,7 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
     float *dr = reinterpret_cast<float *>(smem + VIT_SMEM_BT);
     float *carry = reinterpret_cast<float *>(smem + VIT_SMEM_BT + VIT_SMEM_DR);
     uint8_t *psi_s = smem + VIT_SMEM_PIPE;
-    size_t off = VIT_SMEM_PIPE + (p.psi_in_smem ? (size_t)NS * T * G : 0);
+    size_t off = VIT_SMEM_PIPE + (p.psi_in_smem ? (size_t)NS * T * PSI_ROW : 0);
     uint8_t *st_s = smem + off;            off += (size_t)NS * T;
     uint8_t *exit_s = smem + off;          off += (size_t)NS * p.n_chunks * G;
     uint8_t *entry_s = smem + off;         off += (size_t)NS * p.n_chunks;
@@ -703,7 +845,8 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
     } else if (role <= VIT_NL) {
         // ---------------- loaders: emission feed -----------------------------------------------------------
         if (p.pdl) grid_dependency_wait();
-        loader_loop<G, KP, 0, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, role - 1, bt, nullptr, pb);
+        if (p.bulk) loader_loop_bulk<G, KP, 0, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, role - 1, bt, nullptr, pb, rs);
+        else loader_loop<G, KP, 0, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, role - 1, bt, nullptr, pb);
     } else {
         // ---------------- drainers: delta store and backpointers, NB chunks behind the consumer ------------
         const int hw = role - 1 - VIT_NL;
@@ -728,8 +871,14 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
                 for (int i = 0; i < KP - 1; ++i) eqm |= (cv[i] == best) ? (1u << i) : 0u;
                 const int arg = (n > 0) ? (__ffs(eqm) - 1) : 0;
                 if (lane_ok && p.psi_out) p.psi_out[((size_t)seq * T + n) * K + j] = (uint8_t)arg;
-                if (p.psi_in_smem) psi_s[((size_t)sub * T + n) * G + j] = (uint8_t)arg;
-                else if (seq_ok) p.psi_ws[((size_t)seq_c * T + n) * G + j] = (uint8_t)arg;
+                if (p.psi_in_smem) {
+                    if (NIB) {                                           // lanes (j, j + 1) share a byte: low nibble = even state
+                        const int hi = __shfl_down_sync(FULL_MASK, arg, 1);
+                        if ((j & 1) == 0) psi_s[((size_t)sub * T + n) * PSI_ROW + (j >> 1)] = (uint8_t)(arg | (hi << 4));
+                    } else {
+                        psi_s[((size_t)sub * T + n) * PSI_ROW + j] = (uint8_t)arg;
+                    }
+                } else if (seq_ok) p.psi_ws[((size_t)seq_c * T + n) * G + j] = (uint8_t)arg;
                 if (u == nf - 1) carry[(c & 1) * 32 + lane] = dv;
             }
         };
@@ -755,7 +904,9 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
     // maps the state at t_hi to the state at t_lo - 1.
     const int L = p.chunk, nC = p.n_chunks;
     auto psi_at = [&](int s_sub, int s_seq, int t, int s) -> int {
-        return p.psi_in_smem ? psi_s[((size_t)s_sub * T + t) * G + s] : p.psi_ws[((size_t)s_seq * T + t) * G + s];
+        if (!p.psi_in_smem) return p.psi_ws[((size_t)s_seq * T + t) * G + s];
+        if (NIB) return (psi_s[((size_t)s_sub * T + t) * PSI_ROW + (s >> 1)] >> ((s & 1) * 4)) & 15;
+        return psi_s[((size_t)s_sub * T + t) * PSI_ROW + s];
     };
     // phase A: exit state for every (sequence, chunk, entry state)
     for (int task = vtid; task < NS * nC * K; task += VIT_THREADS) {
@@ -801,12 +952,18 @@ template <int G, int KP>
 __global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const PipeBars pb = {BAR_FULL, BAR_DONE, VIT_THREADS};
-    vit_roles<G, KP>(p, smem, threadIdx.x >> 5, threadIdx.x, pb, [] { __syncthreads(); });
+    const RawStage rs(smem, p.K);                                  // the raw stage leads the layout (bulk-copy feed only)
+    const size_t raw = p.bulk ? raw_stage_bytes(p.K, 32 / G) : 0;
+    if (p.bulk) {
+        if (threadIdx.x == 0) rs.init(VIT_NL);
+        __syncthreads();
+    }
+    vit_roles<G, KP>(p, smem + raw, threadIdx.x >> 5, threadIdx.x, pb, rs, [] { __syncthreads(); });
 }
 
 // shared-memory bytes of one Viterbi pipeline and its traceback plan (chunk length L, number of chunks, where psi lives)
 inline size_t vit_smem_bytes(int NS, int T, int G, int nC, bool psi_in_smem) {
-    size_t off = VIT_SMEM_PIPE + (psi_in_smem ? (size_t)NS * T * G : 0);
+    size_t off = VIT_SMEM_PIPE + (psi_in_smem ? (size_t)NS * T * (G <= 16 ? G / 2 : G) : 0);
     off += (size_t)NS * T + (size_t)NS * nC * G + (size_t)NS * nC;
     off = (off + 15) & ~(size_t)15;
     return off + NS * sizeof(int) * 2;
@@ -839,6 +996,8 @@ inline void vit_plan(int T, int G, int &L, int &nC, bool &psi_in_smem, size_t &s
     } while (0)
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+// every chunk of every sequence starts and ends on a 16-byte boundary: the bulk-copy feed applies
+inline bool bulk_feed_ok(const float *emis, int T, int K) { return (((uintptr_t)emis) & 15) == 0 && ((size_t)T * K) % 4 == 0; }
 
 // posterior / exp(log alpha) / exp(log beta) from the scaled sweeps left in the workspace
 inline int launch_combine(const CombineParams &c, cudaStream_t s) {

@@ -110,7 +110,8 @@ class HSMMLayer(nn.Module):
         if observations.shape[1] > 1000:
             warnings.warn(f"Long sequence ({observations.shape[1]} frames) may cause memory issues in HSMM decoding.")
         dev = self._cuda()
-        logb = self.get_observation_log_probs(observations.to(dev))
+        with torch.no_grad():                                        # decoding: the emission kernel alone, no autograd bookkeeping
+            logb = self.get_observation_log_probs(observations.to(dev))
         states, scores = self._viterbi_from_log_probs(logb)
         if observations.device != states.device:
             states, scores = states.to(observations.device), scores.to(observations.device)
@@ -131,7 +132,8 @@ class HSMMLayer(nn.Module):
         log(A + 1e-8) transitions without self loops, no prior on the first segment), sums instead of maxima.
         (B,T,D) -> (posterior (B,T,S) = P(state_t = s | x), log_likelihood (B,))."""
         dev = self._cuda()
-        logb = self.get_observation_log_probs(observations.to(dev))
+        with torch.no_grad():
+            logb = self.get_observation_log_probs(observations.to(dev))
         log_dur, log_trans = self._tables(dev)
         r = ops.hsmm_forward_backward(logb, log_dur, log_trans)
         g, ll = r["gamma"], r["total"]

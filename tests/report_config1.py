@@ -4,6 +4,7 @@ import argparse, json, os, sys, time
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # repo root
 import pytorch_hmm_b200 as hm
+torch.set_grad_enabled(False)
 
 K, D, B, T = 10, 80, 32, 1000
 ap = argparse.ArgumentParser(); ap.add_argument("--cpu", action="store_true"); a = ap.parse_args()

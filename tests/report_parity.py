@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__)))) 
 import pytorch_hmm_b200 as hm
 from oracle import c_oracle, ref_port
 import bench
+torch.set_grad_enabled(False)
 
 K, C, D, B, T = 12, 4, 80, 16, 2000
 model = bench.make_model()

@@ -99,7 +99,7 @@ def test_gaussian_hmm_layer(hm):
     assert post.shape == (2, 30, 5) and torch.allclose(post.sum(-1), torch.ones(2, 30, device="cuda"), atol=1e-5)
     assert torch.isfinite(g.compute_loss(x))
     for cov in ("diag", "spherical", "full"):
-        lp = hm.GaussianHMMLayer(4, 6, covariance_type=cov).cuda()._compute_gaussian_log_probs(torch.randn(2, 7, 6).cuda())
+        lp = hm.GaussianHMMLayer(4, 6, covariance_type=cov).cuda()._compute_gaussian_log_probs(torch.randn(2, 7, 6).cuda()).detach()
         assert lp.shape == (2, 7, 4) and torch.isfinite(lp).all()
 
 
@@ -110,7 +110,7 @@ def test_mixture_layer_properties(hm):
     x = torch.randn(4, 50, 20).cuda()
     states, none = m(x)
     assert none is None and states.shape == (4, 50) and (states >= 0).all() and (states < 5).all()
-    lp = m.get_observation_log_probs(x)
+    lp = m.get_observation_log_probs(x).detach()
     assert lp.shape == (4, 50, 5) and torch.isfinite(lp).all() and (lp <= 0).all()            # :110-121
     A = m.get_transition_matrix()
     assert (A >= 0).all() and (A <= 1).all() and torch.allclose(A.sum(1), torch.ones(5, device="cuda"), atol=1e-6)

@@ -170,7 +170,10 @@ def test_posterior_gradients_vs_float64_autograd(hm, K, T, B, mode):
     np.testing.assert_allclose(gam.detach().cpu().numpy(), gam64.detach().numpy(), rtol=1e-4, atol=1e-7)
     # 1e-3 relative on the gradients (fp32 kernels vs float64 autograd), absolute floor for entries that are numerically zero
     np.testing.assert_allclose(x.grad.cpu().numpy(), a.grad.numpy(), rtol=1e-3, atol=2e-5)
-    np.testing.assert_allclose(y.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=5e-5)
+    if T > 1:                                                        # (a single frame never touches the transition matrix)
+        np.testing.assert_allclose(y.grad.cpu().numpy(), b.grad.numpy(), rtol=1e-3, atol=5e-5)
+    else:
+        assert float(y.grad.abs().max()) == 0.0
     np.testing.assert_allclose(z.grad.cpu().numpy(), c.grad.numpy(), rtol=1e-3, atol=2e-5)
 
 

@@ -92,7 +92,7 @@ def test_config1_full_shape(hm):
     P = hm.create_left_to_right_matrix(K, 0.7)
     path = (torch.arange(T) * K // T).expand(B, T)
     x = (g.means.detach().cpu()[path] + torch.randn(B, T, D)).cuda()
-    logb = g._compute_gaussian_log_probs(x)
+    logb = g._compute_gaussian_log_probs(x).detach()
     ref_logb = c_oracle.gmm_emission_f64(x.cpu().numpy(), g.means.detach().cpu().numpy(), g.log_scales.detach().cpu().numpy(),
                                          2.0, None)
     np.testing.assert_allclose(logb.cpu().numpy(), ref_logb, rtol=1e-5, atol=1e-4)
@@ -173,7 +173,7 @@ def test_config4_full_shape_hsmm(hm):
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        logb = m.get_observation_log_probs(x)
+        logb = m.get_observation_log_probs(x).detach()
         states, scores = m._viterbi_from_log_probs(logb)
         gamma, ll = m.forward_backward(x)
     torch.cuda.synchronize()

@@ -209,7 +209,7 @@ def test_gaussian_emission_vs_golden(hm, golden):
     layer = hm.GaussianHMMLayer(10, 80).cuda()
     with torch.no_grad():
         layer.means.copy_(torch.from_numpy(g["means"])); layer.log_scales.copy_(torch.from_numpy(g["log_scales"]))
-    lp = layer._compute_gaussian_log_probs(torch.from_numpy(g["x"]).cuda())
+    lp = layer._compute_gaussian_log_probs(torch.from_numpy(g["x"]).cuda()).detach()
     # fp32 emission: 1e-5 relative (|l| ~ 100-200, i.e. ~1e-3 nats absolute)
     np.testing.assert_allclose(lp.cpu().numpy(), g["log_probs"], rtol=1e-5)
 
@@ -223,7 +223,7 @@ def test_mixture_layer_vs_golden(hm, golden, tag):
         m.mixture_weights_logits.copy_(torch.from_numpy(g[f"{tag}_mixture_weights_logits"]))
         m.transition_logits.copy_(torch.from_numpy(g[f"{tag}_transition_logits"]))
     x = torch.from_numpy(g[f"{tag}_x"]).cuda()
-    logb = m.get_observation_log_probs(x)
+    logb = m.get_observation_log_probs(x).detach()
     np.testing.assert_allclose(logb.cpu().numpy(), g[f"{tag}_logb"], rtol=1e-5)
     states, scores = m(x, return_log_probs=True)
     assert states.dtype == torch.int64
@@ -315,7 +315,7 @@ def test_hmm_layer_vs_golden(hm, golden):
         hl.log_initial_logits.copy_(torch.from_numpy(g["hl_log_initial_logits"]))
     x = torch.from_numpy(g["hl_x"]).cuda()
     hl.train()
-    np.testing.assert_allclose(hl(x).cpu().numpy(), g["hl_post_train"], rtol=RTOL, atol=1e-7)
+    np.testing.assert_allclose(hl(x).detach().cpu().numpy(), g["hl_post_train"], rtol=RTOL, atol=1e-7)
     hl.eval()
     post, align = hl(x, return_alignment=True)
     assert np.array_equal(align.cpu().numpy(), g["hl_alignment"])

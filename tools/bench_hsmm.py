@@ -3,6 +3,7 @@ import json, os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pytorch_hmm_b200 as hm
+torch.set_grad_enabled(False)
 
 K, Dm, D, B, T = 10, 20, 80, 128, 2000
 torch.manual_seed(4001)

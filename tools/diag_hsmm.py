@@ -3,6 +3,7 @@ import os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pytorch_hmm_b200 as hm
+torch.set_grad_enabled(False)
 from oracle import c_oracle
 
 K, D, Dm = 10, 80, 20

@@ -3,6 +3,7 @@ import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pytorch_hmm_b200 as hm
+torch.set_grad_enabled(False)
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
