@@ -89,8 +89,9 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
     float *ring = smem_h;                       // [R][K][Dm]   delta for segments ending at te, slot te % R
     float *A_s = ring + (size_t)R * KD;         // [K][K]
     float *dur_s = A_s + K * K;                 // [K][Dm]
-    float *win = dur_s + KD;                    // [Dm][K]      frames t .. t+Dm-1 of f (ring, row `head` = frame t)
-    float *mx_s = win + KD;                     // [K]          max_d' prev[s'][d']
+    const int WR = Dm + 1;                      // window rows: frames t .. t+Dm-1 are read at step t, frame t+Dm lands in the spare row
+    float *win = dur_s + KD;                    // [Dm+1][K]    frames of f (ring, row `head` = frame t)
+    float *mx_s = win + (size_t)WR * K;         // [K]          max_d' prev[s'][d']
     int *arg_s = reinterpret_cast<int *>(mx_s + K);        // [K]   first d' (0-based) attaining it
     float *U_s = reinterpret_cast<float *>(arg_s + K);     // [K][K] fl(Mx[s'] + logA[s'][s])
     float *V_s = U_s + K * K;                   // [K]          max_{s' != s} U[s'][s]
@@ -105,9 +106,9 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
     for (int i = tid; i < R * KD; i += blockDim.x) ring[i] = -INFINITY;
     for (int i = tid; i < K * K; i += blockDim.x) A_s[i] = p.logA[i];
     for (int i = tid; i < KD; i += blockDim.x) dur_s[i] = p.logdur[i];
-    for (int i = tid; i < KD; i += blockDim.x) {                        // frames 0 .. Dm-1
+    for (int i = tid; i < WR * K; i += blockDim.x) {                    // frames 0 .. Dm-1 (the spare row is filled at step 0)
         const int fr = i / K, s = i % K;
-        win[i] = (fr < T) ? f[(size_t)fr * K + s] : 0.f;
+        win[i] = (fr < Dm && fr < T) ? f[(size_t)fr * K + s] : 0.f;
     }
     __syncthreads();
 
@@ -143,14 +144,14 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                 for (int q = 1; q < NQ; ++q) {
                     float x[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) { x[j] = win[r * K + s]; if (++r == Dm) r = 0; }
+                    for (int j = 0; j < 4; ++j) { x[j] = win[r * K + s]; if (++r == WR) r = 0; }
                     p0 = __fadd_rn(p0, x[0]); p1 = __fadd_rn(p1, x[1]); p2 = __fadd_rn(p2, x[2]); p3 = __fadd_rn(p3, x[3]);
                     tb[q * 4 + 0] = p0; tb[q * 4 + 1] = p1; tb[q * 4 + 2] = p2; tb[q * 4 + 3] = p3;
                 }
             } else {
                 float a = 0.f;
                 tb[0] = 0.f;
-                for (int d = 1; d <= Dm; ++d) { a = __fadd_rn(a, win[r * K + s]); if (++r == Dm) r = 0; tb[d] = a; }
+                for (int d = 1; d <= Dm; ++d) { a = __fadd_rn(a, win[r * K + s]); if (++r == WR) r = 0; tb[d] = a; }
             }
         }
         __syncthreads();
@@ -184,8 +185,8 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                         const int q = d >> 2;
                         float p0 = tb[q * 4];
                         int r = head + 4 * q;
-                        if (r >= Dm) r -= Dm;
-                        for (int i = 4 * q; i < d; ++i) { p0 = __fadd_rn(p0, win[r * K + s]); if (++r == Dm) r = 0; }
+                        if (r >= WR) r -= WR;
+                        for (int i = 4 * q; i < d; ++i) { p0 = __fadd_rn(p0, win[r * K + s]); if (++r == WR) r = 0; }
                         p0 = __fadd_rn(p0, tb[q * 4 + 1]);
                         p0 = __fadd_rn(p0, tb[q * 4 + 2]);
                         osum = __fadd_rn(p0, tb[q * 4 + 3]);
@@ -232,10 +233,15 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                 ring[(size_t)sc * KD + pr] = -INFINITY;
             }
         }
+        // slide the frame window: frame t + Dm goes into the spare row (the one that held frame t - 1), which no thread reads during
+        // this step; the barrier below orders it before the next step's prefix table.  (Round 1 slid the window AFTER the barrier
+        // into a row the next step reads at once: a race that showed up as wrong paths at B = 128.)
+        {
+            const int spare = (head == 0) ? WR - 1 : head - 1;
+            for (int s = tid; s < K; s += blockDim.x) win[spare * K + s] = (t + Dm < T) ? f[(size_t)(t + Dm) * K + s] : 0.f;
+        }
         __syncthreads();
-        // slide the frame window: row `head` (frame t) becomes frame t + Dm
-        for (int s = tid; s < K; s += blockDim.x) win[head * K + s] = (t + Dm < T) ? f[(size_t)(t + Dm) * K + s] : 0.f;
-        if (++head == Dm) head = 0;
+        if (++head == WR) head = 0;
         slot_prev = slot_t;
         if (++slot_t == R) slot_t = 0;
     }
@@ -618,7 +624,7 @@ HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float
     const size_t need = hmmb200_hsmm_viterbi_workspace_bytes(B, T, K, Dm);
     if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_viterbi: workspace %zu < %zu", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
-    const size_t smem = ((size_t)(Dm + 2) * K * Dm + 2 * (size_t)K * K + (size_t)2 * K * Dm + 4 * (size_t)K + (size_t)K * (Dm + 8)) * sizeof(float);
+    const size_t smem = ((size_t)(Dm + 2) * K * Dm + 2 * (size_t)K * K + (size_t)2 * K * Dm + 5 * (size_t)K + (size_t)K * (Dm + 8)) * sizeof(float);
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_viterbi: K=%d, max_duration=%d need %zu bytes of shared memory", K, Dm, smem);
     cudaError_t e = cudaFuncSetAttribute(hsmm_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_viterbi smem opt-in: %s", cudaGetErrorString(e));

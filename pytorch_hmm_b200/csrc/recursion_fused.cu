@@ -46,6 +46,7 @@ struct FusedParams {
     FbParams fb;
     VitParams vit;
     int dbg;              // debug builds only: bit 0 warp layout, bits 4-6 skip the forward / backward / Viterbi pipeline (timing experiments)
+    unsigned long long dbg_pm, dbg_rm;   // debug builds only: a warp map supplied at run time (2 / 3 bits per warp), 0 = none
 };
 
 // shared-memory layout: [forward sweep][backward sweep][raw stage asc (forward)][raw stage desc (backward)][raw stage asc (Viterbi)][Viterbi]
@@ -58,7 +59,10 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fb_viterbi_kernel(const __grid_
     constexpr bool PAD = KP < G;
     int pipe, role;
 #ifdef HMMB200_DEBUG_HOOKS
-    if (p.dbg & 1) fused_role<1>(threadIdx.x >> 5, pipe, role);
+    if (p.dbg_rm != 0ull) {
+        pipe = (int)((p.dbg_pm >> (2 * (threadIdx.x >> 5))) & 3);
+        role = (int)((p.dbg_rm >> (3 * (threadIdx.x >> 5))) & 7);
+    } else if (p.dbg & 1) fused_role<1>(threadIdx.x >> 5, pipe, role);
     else fused_role<0>(threadIdx.x >> 5, pipe, role);
 #else
     fused_role<0>(threadIdx.x >> 5, pipe, role);
@@ -95,8 +99,13 @@ static int launch_fused(FusedParams p, int pdl, cudaStream_t s) {
     if (!in_smem || vsmem > budget) return 1;                       // backpointers do not fit beside the sweeps: caller runs the separate kernels
     p.vit.psi_in_smem = 1;
     p.fb.pdl = p.vit.pdl = pdl;
-    p.dbg = 0;
+    p.dbg = 0; p.dbg_pm = p.dbg_rm = 0ull;
 #ifdef HMMB200_DEBUG_HOOKS
+    if (const char *e = getenv("HMMB200_FUSED_MAP")) {               // "pm,rm" as decimal integers
+        char *end = nullptr;
+        p.dbg_pm = strtoull(e, &end, 10);
+        if (end && *end == ',') p.dbg_rm = strtoull(end + 1, nullptr, 10);
+    }
     if (const char *e = getenv("HMMB200_FUSED_DBG")) p.dbg = atoi(e);
     if (p.dbg & 2) p.fb.bulk = p.vit.bulk = 0;                     // bit 1: per-lane global loads instead of the bulk-copy feed (A/B timing)
 #endif

@@ -24,6 +24,8 @@
 // count IS its latency: packed fp32x2 FMAs/adds, 3-input max, no per-step branches, 4x unrolled (fits the L0 I-cache).
 #include "recursion_smallk.cuh"
 
+#include <stdlib.h>
+
 namespace hmmb200 {
 
 // ----------------------------------------------------------------------------------------------------------
@@ -33,6 +35,9 @@ template <int G, int KP>
 static int launch_fb(FbParams p, cudaStream_t s) {
     constexpr int NS = 32 / G;
     p.bulk = bulk_feed_ok(p.emis, p.T, p.K) ? 1 : 0;
+#ifdef HMMB200_DEBUG_HOOKS
+    if (getenv("HMMB200_NO_BULK")) p.bulk = 0;
+#endif
     const size_t smem = FB_SMEM_BYTES + (p.bulk ? raw_stage_bytes(p.K, NS) : 0);
     cudaError_t e = cudaFuncSetAttribute(fb_sweep_kernel<G, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "fb smem opt-in: %s", cudaGetErrorString(e));
@@ -46,6 +51,9 @@ static int launch_vit(VitParams p, cudaStream_t s) {
     constexpr int NS = 32 / G;
     bool in_smem; size_t smem;
     p.bulk = bulk_feed_ok(p.emis, p.T, p.K) ? 1 : 0;
+#ifdef HMMB200_DEBUG_HOOKS
+    if (getenv("HMMB200_NO_BULK")) p.bulk = 0;
+#endif
     const size_t raw = p.bulk ? raw_stage_bytes(p.K, NS) : 0;
     vit_plan(p.T, G, p.chunk, p.n_chunks, in_smem, smem, 200 * 1024 - raw);
     p.psi_in_smem = in_smem ? 1 : 0;
