@@ -72,6 +72,15 @@ int    hmmb200_gmm_pack_on_tensor_cores(const float *packed, int K, int C, int D
 int    hmmb200_gmm_emission_tc_f32(const float *x, const float *packed, int64_t n_frames, int K, int C, int D,
                                    float *logb, void *stream);
 
+/* Full-covariance GMM emission.
+ *   replaces  MixtureGaussianHMMLayer._full_gaussian_log_probs   pytorch_hmm/mixture_gaussian.py:216-240
+ * The triangular solve L y = x - mu of the reference is folded into the parameters by the host (once per parameter update):
+ *   W [K*C, D, DP] = L^-1 per component, lower triangular, rows zero-padded to DP = (D + 3) & ~3 floats, 16-byte aligned;
+ *   cvec [K*C, D] = -W mu;   cst [K*C] = log w - 0.5 (log det + D log 2 pi).
+ *   x [n_frames, D] -> logb [n_frames, K] (the reference's private log-sum-exp over components), comp [n_frames, K*C] or NULL. */
+int    hmmb200_gmm_emission_full_f32(const float *x, const float *W, const float *cvec, const float *cst, int64_t n_frames,
+                                     int K, int C, int D, float *logb, float *comp, void *stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Forward-backward (K <= 32: warp-per-sequence sweeps; 32 < K <= 512: cluster kernels, BASELINE config 5).
  *   replaces  HMMPyTorch.forward_backward / compute_likelihood    pytorch_hmm/hmm.py:66-130, :186-211

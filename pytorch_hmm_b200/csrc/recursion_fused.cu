@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(FU_THREADS, 1) fb_viterbi_kernel(const __grid_
 #endif
     constexpr size_t OFF_B = fu_smem_f<PAD>(), OFF_RAW = OFF_B + fu_smem_b<PAD>();
     const size_t raw = p.fb.bulk ? raw_stage_bytes(p.fb.K, 32 / G) : 0;
-    const RawStage rs_f(smem + OFF_RAW, p.fb.K), rs_b(smem + OFF_RAW + raw, p.fb.K), rs_v(smem + OFF_RAW + 2 * raw, p.fb.K);
+    const RawStage rs_f(smem + OFF_RAW, p.fb.K, p.fb.bulk), rs_b(smem + OFF_RAW + raw, p.fb.K, p.fb.bulk), rs_v(smem + OFF_RAW + 2 * raw, p.fb.K, p.fb.bulk);
     if (p.fb.bulk) {
         if (threadIdx.x == 0) { rs_f.init(FB_NL); rs_b.init(FB_NL); rs_v.init(VIT_NL); }
         __syncthreads();
@@ -92,7 +92,7 @@ static int launch_fused(FusedParams p, int pdl, cudaStream_t s) {
     constexpr int NS = 32 / G;
     bool in_smem; size_t vsmem;
     constexpr bool PAD = KP < G;
-    p.fb.bulk = p.vit.bulk = bulk_feed_ok(p.fb.emis, p.fb.T, p.fb.K) ? 1 : 0;
+    p.fb.bulk = p.vit.bulk = bulk_feed_param(p.fb.emis, p.fb.T, p.fb.K);
     const size_t fixed = fu_smem_f<PAD>() + fu_smem_b<PAD>() + (p.fb.bulk ? 3 * raw_stage_bytes(p.fb.K, NS) : 0);
     const size_t budget = 227 * 1024 - fixed;
     vit_plan(p.vit.T, G, p.vit.chunk, p.vit.n_chunks, in_smem, vsmem, budget);

@@ -34,9 +34,9 @@ namespace hmmb200 {
 template <int G, int KP>
 static int launch_fb(FbParams p, cudaStream_t s) {
     constexpr int NS = 32 / G;
-    p.bulk = bulk_feed_ok(p.emis, p.T, p.K) ? 1 : 0;
+    p.bulk = bulk_feed_param(p.emis, p.T, p.K);
 #ifdef HMMB200_DEBUG_HOOKS
-    if (getenv("HMMB200_NO_BULK")) p.bulk = 0;
+    if (getenv("HMMB200_NO_BULK") || getenv("HMMB200_NO_BULK_FB")) p.bulk = 0;
 #endif
     const size_t smem = FB_SMEM_BYTES + (p.bulk ? raw_stage_bytes(p.K, NS) : 0);
     cudaError_t e = cudaFuncSetAttribute(fb_sweep_kernel<G, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -50,9 +50,9 @@ template <int G, int KP>
 static int launch_vit(VitParams p, cudaStream_t s) {
     constexpr int NS = 32 / G;
     bool in_smem; size_t smem;
-    p.bulk = bulk_feed_ok(p.emis, p.T, p.K) ? 1 : 0;
+    p.bulk = bulk_feed_param(p.emis, p.T, p.K);
 #ifdef HMMB200_DEBUG_HOOKS
-    if (getenv("HMMB200_NO_BULK")) p.bulk = 0;
+    if (getenv("HMMB200_NO_BULK") || getenv("HMMB200_NO_BULK_VIT")) p.bulk = 0;
 #endif
     const size_t raw = p.bulk ? raw_stage_bytes(p.K, NS) : 0;
     vit_plan(p.T, G, p.chunk, p.n_chunks, in_smem, smem, 200 * 1024 - raw);

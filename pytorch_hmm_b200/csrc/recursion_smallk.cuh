@@ -27,6 +27,7 @@
 // count IS its latency: packed fp32x2 FMAs/adds, 3-input max, no per-step branches, 4x unrolled (fits the L0 I-cache).
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <type_traits>
 
 namespace hmmb200 {
@@ -56,6 +57,7 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 // latency-critical consumer warps' shared-memory round trips queue in.  One cp.async.bulk per (sequence, chunk) moves the same
 // bytes without occupying that FIFO at all; its arrival is counted on an mbarrier (transaction bytes); NR chunks are in flight.
 constexpr int NR = 2;
+constexpr int RAW_REL_DEFAULT = 1;   // see loader_loop_bulk: how a reader warp releases a raw buffer
 __device__ __forceinline__ uint32_t sk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sk_mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sk_smem_u32(bar)), "r"(count) : "memory");
@@ -89,8 +91,14 @@ struct RawStage {
     uint64_t *full, *empty;   // [NR] each: bytes of the chunk have landed / every reader warp has copied its frames out
     float *buf;               // [NR][NS][raw_seq_floats(K)]
     int seq_floats;
-    __device__ RawStage() : full(nullptr), empty(nullptr), buf(nullptr), seq_floats(0) {}
-    __device__ RawStage(uint8_t *smem, int K) {
+    int rel;                  // how a reader warp releases a buffer (debug builds try the alternatives: p.bulk = 1 + 16 * rel)
+    __device__ RawStage() : full(nullptr), empty(nullptr), buf(nullptr), seq_floats(0), rel(1) {}
+    __device__ RawStage(uint8_t *smem, int K, int bulk) {
+#ifdef HMMB200_DEBUG_HOOKS
+        rel = bulk >> 4;
+#else
+        rel = RAW_REL_DEFAULT;
+#endif
         full = reinterpret_cast<uint64_t *>(smem);
         empty = full + NR;
         buf = reinterpret_cast<float *>(smem + 64);
@@ -293,8 +301,23 @@ __device__ __forceinline__ void loader_loop_bulk(const float *emis, int mode, fl
                 for (int k = 0; k < KP; ++k) cur[i][k] = (ok && k < K) ? src[k] : 0.f;
             }
         }
-        __syncwarp();
-        if (lane == 0) sk_mbar_arrive(rs.empty + rb);                // this warp has its frames of raw[rb] in registers
+        // Release raw[rb] only when the loads above have RETURNED: a shared-memory load that has merely been issued may still sit in
+        // the SM's load/store queue when the mbarrier arrive (a different unit) is performed, and the refill it permits would then
+        // overwrite rows that have not been read yet (seen as wrong Viterbi paths next to a kernel that keeps that queue busy).
+        // The vote below cannot be evaluated before every lane has all its values.
+        if (rs.rel == 1) {
+            float dep = 0.f;
+#pragma unroll
+            for (int i = 0; i < FL; ++i)
+#pragma unroll
+                for (int k = 0; k < KP; ++k) dep += cur[i][k];
+            const unsigned got = __ballot_sync(FULL_MASK, dep != 1.2345678e37f);
+            if (lane == 0 && got != 0x0badc0deu) sk_mbar_arrive(rs.empty + rb);
+        } else {
+            __syncwarp();
+            if (rs.rel == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (lane == 0) sk_mbar_arrive(rs.empty + rb);
+        }
         if (issuer && c + NR < nch) {
             sk_mbar_wait(rs.empty + rb, (c / NR) & 1);               // ... and so have the other loader warps: refill the buffer
             issue(c + NR);
@@ -599,7 +622,7 @@ __global__ void __launch_bounds__(FB_THREADS) fb_sweep_kernel(FbParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     constexpr bool PAD = KP < G;
     const PipeBars pb = {BAR_FULL, BAR_DONE, FB_THREADS};
-    const RawStage rs(smem + FB_SMEM_BYTES, p.K);                  // (bulk-copy feed only; unused bytes otherwise)
+    const RawStage rs(smem + FB_SMEM_BYTES, p.K, p.bulk);                  // (bulk-copy feed only; unused bytes otherwise)
     if (p.bulk) {
         if (threadIdx.x == 0) rs.init(FB_NL);
         __syncthreads();
@@ -952,7 +975,7 @@ template <int G, int KP>
 __global__ void __launch_bounds__(VIT_THREADS) viterbi_kernel(VitParams p) {
     extern __shared__ __align__(16) uint8_t smem[];
     const PipeBars pb = {BAR_FULL, BAR_DONE, VIT_THREADS};
-    const RawStage rs(smem, p.K);                                  // the raw stage leads the layout (bulk-copy feed only)
+    const RawStage rs(smem, p.K, p.bulk);                                // the raw stage leads the layout (bulk-copy feed only)
     const size_t raw = p.bulk ? raw_stage_bytes(p.K, 32 / G) : 0;
     if (p.bulk) {
         if (threadIdx.x == 0) rs.init(VIT_NL);
@@ -998,6 +1021,15 @@ inline void vit_plan(int T, int G, int &L, int &nC, bool &psi_in_smem, size_t &s
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // every chunk of every sequence starts and ends on a 16-byte boundary: the bulk-copy feed applies
 inline bool bulk_feed_ok(const float *emis, int T, int K) { return (((uintptr_t)emis) & 15) == 0 && ((size_t)T * K) % 4 == 0; }
+// value of the kernels' `bulk` parameter: 0 per-lane loads, else 1 + 16 * (release variant; only debug builds look at it)
+inline int bulk_feed_param(const float *emis, int T, int K) {
+    if (!bulk_feed_ok(emis, T, K)) return 0;
+    int rel = RAW_REL_DEFAULT;
+#ifdef HMMB200_DEBUG_HOOKS
+    if (const char *e = getenv("HMMB200_RAW_REL")) rel = atoi(e);
+#endif
+    return 1 + 16 * rel;
+}
 
 // posterior / exp(log alpha) / exp(log beta) from the scaled sweeps left in the workspace
 inline int launch_combine(const CombineParams &c, cudaStream_t s) {

@@ -3,8 +3,9 @@
 Parameter names (`transition_logits` / buffer `transition_matrix`, `mixture_weights_logits`, `means`, `log_vars`)
 and initialisation follow the reference (mixture_gaussian.py:58-105).  forward() = GMM emission kernel + Viterbi
 kernel on the RAW log-emissions with a uniform prior -log K and log(clamp(softmax(logits), 1e-8)) transitions
-(mixture_gaussian.py:312, :357).  Covariance types: 'diag', 'tied' and 'spherical' run on the diagonal kernel
-(the latter two are broadcast special cases); 'full' is outside the north-star path and raises.
+(mixture_gaussian.py:312, :357).  Covariance types: 'diag', 'tied' and 'spherical' run on the diagonal (tcgen05) kernel
+(the latter two are broadcast special cases); 'full' (Cholesky parameters, mixture_gaussian.py:88-117) runs on the
+triangular-contraction kernel csrc/emission_full.cu.
 """
 from __future__ import annotations
 
@@ -45,7 +46,11 @@ class MixtureGaussianHMMLayer(nn.Module):
         elif covariance_type == "spherical":
             self.log_vars = nn.Parameter(torch.zeros(S, Cn))
         elif covariance_type == "full":
-            raise NotImplementedError("covariance_type='full' is outside the B200 hot path (diag/tied/spherical only)")
+            # Cholesky parameterisation of the reference (mixture_gaussian.py:88-117): the lower triangle row by row, the diagonal
+            # entries are exponentiated; initialised to 0 with 0.1 on the diagonal
+            self.cholesky_params = nn.Parameter(torch.zeros(S, Cn, D * (D + 1) // 2))
+            with torch.no_grad():
+                self.cholesky_params[:, :, [i * (i + 1) // 2 + i for i in range(D)]] = 0.1
         else:
             raise ValueError(f"Unknown covariance_type: {covariance_type}")
 
@@ -64,6 +69,31 @@ class MixtureGaussianHMMLayer(nn.Module):
 
     def _safe_log(self, x: torch.Tensor) -> torch.Tensor:
         return torch.log(torch.clamp(x, min=self.eps))
+
+    def _get_cholesky_factors(self) -> torch.Tensor:
+        """[S,C,D,D] lower-triangular factors with exp() on the diagonal (mixture_gaussian.py:271-288)."""
+        S, Cn, D = self.num_states, self.num_components, self.feature_dim
+        L = torch.zeros(S * Cn, D, D, device=self.cholesky_params.device, dtype=self.cholesky_params.dtype)
+        idx = torch.tril_indices(D, D)
+        L[:, idx[0], idx[1]] = self.cholesky_params.view(S * Cn, -1)
+        d = torch.arange(D)
+        L[:, d, d] = torch.exp(L[:, d, d])
+        return L.view(S, Cn, D, D)
+
+    def _packed_full(self):
+        def make():
+            logw = self._safe_log(F.softmax(self.mixture_weights_logits, dim=-1))
+            return ops.gmm_pack_full(self.means, self._get_cholesky_factors(), logw, self.eps)
+        return self._derived.get("packed_full", (self.means, self.cholesky_params, self.mixture_weights_logits), make)
+
+    def _emission(self, observations: torch.Tensor, dev) -> torch.Tensor:
+        """log b on the emission kernels for the layer's covariance type (inference path: detached)."""
+        if self.covariance_type == "full":
+            return ops.gmm_emission_full(observations.detach().to(dev), self._packed_full(), self.num_states, self.num_components,
+                                         self.feature_dim)
+        packed, tc = self._packed_tc()
+        return ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, self.num_components, self.feature_dim,
+                                tc_known=tc)
 
     def _diag_log_vars(self) -> torch.Tensor:
         S, Cn, D = self.num_states, self.num_components, self.feature_dim
@@ -105,13 +135,11 @@ class MixtureGaussianHMMLayer(nn.Module):
                           f"{self.max_sequence_length}. Consider chunked processing.")
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
         from . import autograd as ag
-        if ag.needs_grad(observations, self.means, self.log_vars, self.mixture_weights_logits):
+        if self.covariance_type != "full" and ag.needs_grad(observations, self.means, self.log_vars, self.mixture_weights_logits):
             # training callers: differentiable w.r.t. means, log_vars, the mixture logits and x (autograd._GMMEmission)
             logw = self._safe_log(F.softmax(self.mixture_weights_logits, dim=-1))
             return ag.gmm_log_probs(observations, self.means, self._diag_log_vars(), logw, 1.0)
-        packed, tc = self._packed_tc()
-        out = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, self.num_components,
-                               self.feature_dim, tc_known=tc)
+        out = self._emission(observations, dev)
         return out if observations.device == out.device else out.to(observations.device)
 
     def _viterbi_decode(self, obs_log_probs: torch.Tensor, log_transitions: torch.Tensor
@@ -130,9 +158,7 @@ class MixtureGaussianHMMLayer(nn.Module):
     def forward(self, observations: torch.Tensor, return_log_probs: bool = False
                 ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
         dev = ops.require_cuda(self.means.device if self.means.is_cuda else None)
-        packed, tc = self._packed_tc()
-        logb = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, self.num_components,
-                                self.feature_dim, tc_known=tc)
+        logb = self._emission(observations, dev)
         states, scores = self._viterbi_decode(logb, self._log_transitions())         # mixture_gaussian.py:357
         if return_log_probs and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # value: the kernel's score, bit for bit; gradient: along the decoded path

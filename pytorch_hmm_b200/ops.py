@@ -101,6 +101,43 @@ def gmm_emission(x: torch.Tensor, packed: torch.Tensor, K: int, Cn: int, D: int,
     return out
 
 
+def gmm_pack_full(means: torch.Tensor, chol: torch.Tensor, log_weights: Optional[torch.Tensor], eps: float = 1e-8):
+    """Full-covariance operands from means [K,C,D], Cholesky factors L [K,C,D,D] (lower triangular, positive diagonal) and log mixture
+    weights [K,C] (or None): (W [K*C, D, DP], cvec [K*C, D], cst [K*C]) for gmm_emission_full.  Host-side derivation, O(K C D^3):
+    W = L^-1 by a triangular solve; log det = 2 sum log(diag L + eps) as the reference computes it (mixture_gaussian.py:232-233)."""
+    dev = require_cuda(means.device if means.is_cuda else None)
+    mu = _f32c(means.detach(), dev)
+    L = _f32c(chol.detach(), dev)
+    K, Cn, D = mu.shape
+    eye = torch.eye(D, device=dev, dtype=torch.float64).expand(K, Cn, D, D)
+    W = torch.linalg.solve_triangular(L.double(), eye, upper=False)                        # [K,C,D,D], lower triangular
+    cvec = -(W @ mu.double().unsqueeze(-1)).squeeze(-1)
+    log_det = 2.0 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1).double() + eps).sum(-1)
+    cst = -0.5 * (log_det + D * math.log(2.0 * math.pi))
+    if log_weights is not None:
+        cst = cst + _f32c(log_weights.detach(), dev).double()
+    DP = (D + 3) & ~3
+    Wp = torch.zeros(K * Cn, D, DP, dtype=torch.float32, device=dev)
+    Wp[:, :, :D] = torch.tril(W).reshape(K * Cn, D, D).float()
+    return Wp.contiguous(), cvec.reshape(K * Cn, D).float().contiguous(), cst.reshape(K * Cn).float().contiguous()
+
+
+def gmm_emission_full(x: torch.Tensor, packed_full, K: int, Cn: int, D: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x [..., D] (CUDA) -> log b [..., K] under full-covariance mixtures (operands from gmm_pack_full)."""
+    W, cvec, cst = packed_full
+    dev = W.device
+    x = _f32c(x, dev)
+    if x.shape[-1] != D:
+        raise ValueError(f"feature dim {x.shape[-1]} != {D}")
+    n = x.numel() // D
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (K,), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _check(_lib.load().hmmb200_gmm_emission_full_f32(_p(x), _p(W), _p(cvec), _p(cst), n, K, Cn, D, _p(out), None, _stream(dev)),
+               "hmmb200_gmm_emission_full_f32")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------
 # recursions
 # ------------------------------------------------------------------------------------------------------

@@ -23,13 +23,15 @@ def main():
     model = bench.make_model()
     g = torch.Generator().manual_seed(1)
     x = (torch.randn(args.batch, args.seq, bench.FEAT, generator=g)).to(dev)
+    torch.set_grad_enabled(False)
     h = bench.Headline(model, dev)
     for _ in range(args.steps):
-        h.step(x)
+        h.step(x)                                  # emission -> fused forward + backward + Viterbi -> posteriors
     torch.cuda.synchronize()
-    for name, fn in (("emission", lambda: h.emission(x)), ("fb", h.fb), ("fb_sweeps_only", lambda: h.fb(want=())),
-                     ("viterbi", h.vit)):
-        print(name, round(bench.event_ms(fn, 5), 4), "ms")
+    if os.environ.get("PROFILE_STANDALONE"):
+        for name, fn in (("emission", lambda: h.emission(x)), ("fused", h.fused), ("fb", h.fb), ("fb_sweeps_only", lambda: h.fb(want=())),
+                         ("viterbi", h.vit)):
+            print(name, round(bench.event_ms(fn, 5), 4), "ms")
 
 
 if __name__ == "__main__":
