@@ -265,6 +265,26 @@ int    hmmb200_posterior_backward_f32(const float *emis, int emis_mode, float fl
 int    hmmb200_gmm_stats_f32(const float *x, const float *comp, const float *logb, const float *weight, int64_t n_frames,
                              int K, int C, int D, double *occ, double *sx, double *sxx, void *stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Alignment utilities: CTC trellises and dynamic time warping.
+ *   replaces  ctc_forward_algorithm    pytorch_hmm/alignment/ctc.py:32-121   (direction 0: log alpha, log-likelihood)
+ *             ctc_backward_algorithm   pytorch_hmm/alignment/ctc.py:124-199  (direction 1: log beta)
+ *             compute_dtw_path         pytorch_hmm/alignment/dtw.py:47-153
+ * hmmb200_ctc_trellis_f32:
+ *   log_probs [T,B,C], targets [B,L] int64, input_lengths / target_lengths [B] int64 (all device pointers);
+ *   table [B,T,2L+1] or NULL (every element is written: -inf where the reference leaves its initial value);
+ *   loglik [B] or NULL (forward only).
+ * hmmb200_dtw_f32:
+ *   dist [n_pairs,N,M] -> cost [n_pairs,N,M]; dir_ws [n_pairs*N*M] bytes of scratch; path_i / path_j [n_pairs, N+M-1] int64
+ *   (the first path_len[p] entries of a row are the path from (0,0) to (N-1,M-1)); step_pattern 0 symmetric, 1 asymmetric,
+ *   2 rabiner_juang.  Costs, and therefore paths, are bit-identical to the reference's (fp32 adds and minima only).
+ * --------------------------------------------------------------------------------------------------------- */
+int    hmmb200_ctc_trellis_f32(int direction, const float *log_probs, const int64_t *targets, const int64_t *input_lengths,
+                               const int64_t *target_lengths, int blank, int T, int B, int C, int L,
+                               float *table, float *loglik, void *stream);
+int    hmmb200_dtw_f32(const float *dist, int n_pairs, int N, int M, int step_pattern, float *cost, void *dir_ws,
+                       int64_t *path_i, int64_t *path_j, int *path_len, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -285,12 +285,55 @@ def neural(ref):
     np.savez_compressed(os.path.join(OUT, "neural.npz"), **out)
 
 
+def alignment(ref):
+    """CTC forward / backward trellises (alignment/ctc.py:32-199) and DTW (alignment/dtw.py:47-153)."""
+    from pytorch_hmm.alignment.ctc import ctc_alignment_path, ctc_backward_algorithm, ctc_forward_algorithm
+    from pytorch_hmm.alignment.dtw import compute_distance_matrix, compute_dtw_path
+    out = {}
+    g = torch.Generator().manual_seed(6101)
+    # a: ragged batch (one full-length utterance, one short, one with an empty target, repeated labels)
+    T, B, C, L = 24, 4, 7, 5
+    lp = torch.log_softmax(2.0 * torch.randn(T, B, C, generator=g), dim=-1)
+    targets = torch.tensor([[1, 2, 2, 3, 6], [4, 4, 4, 1, 0], [0, 0, 0, 0, 0], [5, 1, 5, 1, 5]])
+    in_len = torch.tensor([24, 17, 9, 24])
+    tg_len = torch.tensor([5, 4, 0, 5])
+    # b: blank id in the middle of the alphabet, target that does not fit the utterance (log-likelihood -inf)
+    T2, B2, C2, L2 = 10, 2, 5, 6
+    lp2 = torch.log_softmax(torch.randn(T2, B2, C2, generator=g), dim=-1)
+    targets2 = torch.tensor([[0, 1, 3, 3, 4, 0], [1, 1, 1, 1, 1, 1]])
+    in_len2 = torch.tensor([10, 7])
+    tg_len2 = torch.tensor([6, 6])
+    for tag, args, blank in (("a", (lp, targets, in_len, tg_len), 0), ("b", (lp2, targets2, in_len2, tg_len2), 2)):
+        ll = ctc_forward_algorithm(*args, blank_id=blank)
+        lb = ctc_backward_algorithm(*args, blank_id=blank)
+        al = ctc_alignment_path(*args, blank_id=blank)
+        out.update({f"ctc_{tag}_log_probs": _np(args[0]), f"ctc_{tag}_targets": _np(args[1]), f"ctc_{tag}_input_lengths": _np(args[2]),
+                    f"ctc_{tag}_target_lengths": _np(args[3]), f"ctc_{tag}_blank": np.int64(blank), f"ctc_{tag}_loglik": _np(ll),
+                    f"ctc_{tag}_log_beta": _np(lb)})
+        for b, a in enumerate(al):
+            out[f"ctc_{tag}_align{b}"] = _np(a)
+    # torch's own CTC loss on (a): an independent check of the forward log-likelihood's value
+    flat = torch.cat([targets[b, : tg_len[b]] for b in range(B)])
+    out["ctc_a_torch_nll"] = _np(torch.nn.functional.ctc_loss(lp, flat, in_len, tg_len, blank=0, reduction="none"))
+    # DTW: euclidean distance matrices, the three step patterns; one matrix with exact ties (integers)
+    x, y = torch.randn(23, 6, generator=g), torch.randn(31, 6, generator=g)
+    d = compute_distance_matrix(x, y, "euclidean")
+    ties = torch.randint(0, 3, (17, 12), generator=g).float()
+    for tag, mat in (("rand", d), ("ties", ties)):
+        out[f"dtw_{tag}_dist"] = _np(mat)
+        for pat in ("symmetric", "asymmetric", "rabiner_juang"):
+            pi, pj, cost = compute_dtw_path(mat, pat)
+            out.update({f"dtw_{tag}_{pat}_path_i": _np(pi), f"dtw_{tag}_{pat}_path_j": _np(pj), f"dtw_{tag}_{pat}_cost": _np(cost)})
+    out["dtw_x"], out["dtw_y"] = _np(x), _np(y)
+    np.savez_compressed(os.path.join(OUT, "alignment.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = _import_reference()
     torch.set_num_threads(1)
     sections = {"core": core, "gaussian": gaussian, "mixture": mixture, "hsmm": hsmm, "semimarkov": semimarkov,
-                "streaming": streaming, "largek": largek, "neural": neural}
+                "streaming": streaming, "largek": largek, "neural": neural, "alignment": alignment}
     only = [a for a in sys.argv[1:] if a in sections or a == "segsum"]        # e.g. `make_golden.py largek`
     for name, fn in sections.items():
         if not only or name in only:

@@ -28,6 +28,8 @@ SIGNATURES = {
     "hmmb200_gmm_pack_on_tensor_cores": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, c_ptr]),
     "hmmb200_gmm_emission_tc_f32": (C.c_int, [c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr]),
     "hmmb200_gmm_emission_full_f32": (C.c_int, [c_ptr, c_ptr, c_ptr, c_ptr, C.c_int64, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "hmmb200_ctc_trellis_f32": (C.c_int, [C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr]),
+    "hmmb200_dtw_f32": (C.c_int, [c_ptr, C.c_int, C.c_int, C.c_int, C.c_int, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr]),
     "hmmb200_fb_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "hmmb200_forward_backward_f32": (C.c_int, [c_ptr, C.c_int, C.c_float, C.c_int, c_ptr, c_ptr, C.c_int, C.c_int, C.c_int,
                                                c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, c_ptr, C.c_size_t, c_ptr]),

@@ -2,13 +2,16 @@
 //
 // This is the whole-batch pass the reference times (examples/benchmark.py:120-196: forward_backward, then viterbi_decode, on the
 // same emissions) as one launch.  The three recursions are latency chains of T dependent steps each carried by a single
-// "consumer" warp (recursion_smallk.cuh); what a chain loses is issue slots taken by other warps on ITS scheduler.  As three
-// separate CTAs per SM (two sweep CTAs + one Viterbi CTA) every consumer is warp 0 of its CTA and the hardware is free to put all
-// three on one SM sub-partition; here the kernel owns the placement (warp w issues from sub-partition w % 4, highest warp id
-// first):
-//     warp 17 (SMSP 1) forward consumer      warp 16 (SMSP 0) backward consumer      warp 15 (SMSP 3) Viterbi consumer
-//     SMSP 2 (warps 2, 6, 10, 14): four of the five Viterbi drainers (the backpointer recomputation is the heaviest helper role)
-//     the other eleven helper warps (loaders, drainers) are spread over SMSPs 0, 1, 3 below their consumer's warp id.
+// "consumer" warp (recursion_smallk.cuh).  What a chain loses inside a busy SM is, in this order (ncu source-page samples on the
+// consumers' loops): INSTRUCTION FETCH -- with tens of KB of unrolled helper code streaming through the SM the consumers spent a
+// third of their samples in stall_no_inst, which is why the helper roles are written as small rolled loops -- and then issue slots
+// taken by other warps on the consumer's scheduler.  The kernel owns the placement (warp w issues from sub-partition w % 4):
+//     SMSP 1: forward consumer (warp 1), its two loaders, one of its drainers (+ one backward drainer)
+//     SMSP 2: backward consumer (warp 2), its two loaders, one of its drainers
+//     SMSP 3: Viterbi consumer (warp 3), its two loaders (+ one forward drainer)
+//     SMSP 0: the five Viterbi drainers (the backpointer recomputation is the heaviest helper role)
+// i.e. a consumer shares its scheduler -- and its 6 KB L0 instruction cache -- only with the small loops of its own pipeline.
+// Measured on the headline shape (tools/diag_layout.py, 7 placements): 0.126 ms, against 0.132 - 0.152 ms for the others.
 // Each pipeline keeps its own named barriers and shared-memory rings; the Viterbi traceback synchronises only the Viterbi warps, so
 // it runs while the sweeps finish.  Launched with programmatic stream serialisation the set-up (transition columns into registers,
 // ring carve-up) overlaps the tail of the emission kernel that produces the log-emissions.
@@ -25,11 +28,11 @@ static_assert(FU_WARPS == 18 && FB_NL == 2 && FB_ND == 2 && VIT_NL == 2 && VIT_N
 // warp -> (pipeline: 0 forward, 1 backward, 2 Viterbi; role within the pipeline: 0 consumer, then loaders, then drainers)
 template <int LAYOUT>
 __device__ __forceinline__ void fused_role(int warp, int &pipe, int &role) {
-    // LAYOUT 0: consumers on the three highest warp ids (SMSPs 1, 0, 3), Viterbi drainers 0-3 on SMSP 2
+    // LAYOUT 0: each consumer beside its own pipeline's helpers (SMSPs 1, 2, 3), the Viterbi drainers on SMSP 0
     // LAYOUT 1: consumers on the three lowest warp ids (SMSPs 0, 1, 2), Viterbi drainers 0-3 on SMSP 3
     //                          w0 w1 w2 w3 w4 w5 w6 w7 w8 w9 10 11 12 13 14 15 16 17
-    constexpr int PIPE0[18] = {0, 1, 2, 1, 0, 1, 2, 0, 2, 2, 2, 1, 2, 0, 2, 2, 1, 0};
-    constexpr int ROLE0[18] = {1, 1, 3, 2, 3, 3, 4, 4, 1, 2, 5, 4, 7, 2, 6, 0, 0, 0};
+    constexpr int PIPE0[18] = {2, 0, 1, 2, 2, 0, 1, 2, 2, 0, 1, 2, 2, 0, 1, 0, 2, 1};
+    constexpr int ROLE0[18] = {3, 0, 0, 0, 4, 1, 1, 1, 5, 2, 2, 2, 6, 3, 3, 4, 7, 4};
     constexpr int PIPE1[18] = {0, 1, 2, 2, 1, 0, 2, 2, 0, 2, 1, 2, 1, 0, 0, 2, 1, 2};
     constexpr int ROLE1[18] = {0, 0, 0, 3, 1, 1, 1, 4, 3, 2, 3, 5, 2, 2, 4, 6, 4, 7};
     unsigned long long pm = 0, rm = 0;

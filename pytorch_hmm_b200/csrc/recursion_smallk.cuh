@@ -252,13 +252,47 @@ __device__ __forceinline__ void loader_loop(const float *emis, int mode, float e
     for (int c = max(0, nch - NB); c < nch; ++c) bar_sync(pb.done0 + (c % NB), pb.n);
 }
 
+// scaled-probability form with the hardware exponential (ex2.approx, relative error 2^-22: far inside the 1e-4 contract of the
+// posteriors, and a fifth of the instructions of expf -- the helper warps' instruction footprint is what the consumers' instruction
+// fetches compete with, see the bulk loader below)
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+template <int KP>
+__device__ __forceinline__ void row_to_scaled_fast(int mode, float eps, int K, float (&e)[KP], float &m) {
+    m = 0.f;
+    if (mode == HMMB200_EMIS_PROB_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = e[k] + eps;
+    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = fast_exp(e[k]) + eps;
+    } else {
+        float t[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) t[k] = (k < K) ? e[k] : -INFINITY;
+        float mx = max_tree<KP>(t);
+        if (!(mx > -INFINITY)) mx = 0.f;                     // all states impossible: keep the frame finite
+        const float add = (mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = fast_exp(e[k] - mx) + add;
+        m = mx;
+    }
+}
+
 // Same role with the chunks arriving in the raw stage by bulk copies (lane 0 of loader 0 issues them NR chunks ahead; needs every
 // chunk start and size to be a multiple of 16 bytes: (T*K) % 4 == 0 and a 16-byte aligned tensor).  Lane (sub, q) of loader `lw`
 // takes the frames u = q + G*(lw*FL + i) of the chunk: neighbouring lanes read neighbouring frame rows (conflict-free 16-byte
 // shared-memory loads at K = 12) and write neighbouring rows of the emission ring.
-template <int G, int KP, int DIR, bool SCALED, int NL>
-__device__ __forceinline__ void loader_loop_bulk(const float *emis, int mode, float eps, int B, int T, int K, int lw,
-                                                 float *bt, float *mraw, PipeBars pb, RawStage rs) {
+// Written for a SMALL instruction footprint (one frame per trip of a rolled loop, hardware exponential, `dir` a run-time value so
+// that the forward and backward pipelines of a fused CTA run the same code): the three consumer warps of a fused CTA lose a third
+// of their issue slots to instruction-cache misses when the helper warps around them stream tens of KB of unrolled code
+// (ncu: stall_no_inst on the consumers' loops).
+template <int G, int KP, bool SCALED, int NL>
+__device__ __noinline__ void loader_loop_bulk(const float *emis, int mode, float eps, int B, int T, int K, int lw, int dir,
+                                              float *bt, float *mraw, PipeBars pb, RawStage rs) {
     constexpr int NS = 32 / G, FPL = CH / G, FL = FPL / NL;
     static_assert(FPL % NL == 0 && FL >= 1, "loader split");
     const int lane = threadIdx.x & 31;
@@ -271,74 +305,61 @@ __device__ __forceinline__ void loader_loop_bulk(const float *emis, int mode, fl
     auto issue = [&](int c) {                                        // chunk c (sweep order) -> raw buffer c % NR
         const int rb = c % NR;
         const int nf = min(CH, T - c * CH);
-        const int f_lo = (DIR == 0) ? c * CH : T - c * CH - nf;      // lowest frame of the chunk: the block is frames f_lo .. f_lo+nf-1
+        const int f_lo = (dir == 0) ? c * CH : T - c * CH - nf;      // lowest frame of the chunk: the block is frames f_lo .. f_lo+nf-1
         const uint32_t bytes = (uint32_t)nf * K * sizeof(float);
         sk_mbar_expect_tx(rs.full + rb, bytes * n_seq);
         for (int s = 0; s < n_seq; ++s)
             sk_bulk_g2s(rs.buf + (size_t)(rb * NS + s) * rs.seq_floats, emis + ((size_t)(seq0 + s) * T + f_lo) * K, bytes, rs.full + rb);
     };
     if (issuer) for (int c = 0; c < min(NR, nch); ++c) issue(c);
+    // the ring's columns K .. G-1 (lanes that own no state) are zero for the whole sweep: written once here, never again
+    // (each loader clears the rows it owns -- u in [lw*CH/NL, (lw+1)*CH/NL) of every ring buffer -- so no hand-off between loaders)
+    for (int b = 0; b < NB; ++b)
+        for (int e = lane; e < (CH / NL) * BT_PITCH; e += 32) bt[((size_t)b * CH + lw * (CH / NL)) * BT_PITCH + e] = 0.f;
+    __syncwarp();
+#pragma unroll 1
     for (int c = 0; c < nch; ++c) {
         const int b = c % NB, rb = c % NR;
         const int nf = min(CH, T - c * CH);
         sk_mbar_wait(rs.full + rb, (c / NR) & 1);
-        float cur[FL][KP];
-#pragma unroll
+        if (c >= NB) bar_sync(pb.done0 + b, pb.n);                   // consumer is done reading bt[b] (chunk c - NB)
+        float *btb = bt + (size_t)b * CH * BT_PITCH;
+#pragma unroll 1
         for (int i = 0; i < FL; ++i) {
             const int u = q + G * (lw * FL + i);
             const bool ok = seq_ok && u < nf;
-            const int row = ok ? ((DIR == 0) ? u : nf - 1 - u) : 0;
+            const int row = ok ? ((dir == 0) ? u : nf - 1 - u) : 0;
             const float *src = rs.buf + (size_t)(rb * NS + sub) * rs.seq_floats + (size_t)row * K;
+            float cur[KP];
             if ((KP % 4) == 0 && (K % 4) == 0) {
 #pragma unroll
                 for (int k4 = 0; k4 < KP / 4; ++k4) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok && 4 * k4 < K) v = *reinterpret_cast<const float4 *>(src + 4 * k4);
-                    cur[i][4 * k4] = v.x; cur[i][4 * k4 + 1] = v.y; cur[i][4 * k4 + 2] = v.z; cur[i][4 * k4 + 3] = v.w;
+                    if (4 * k4 < K) v = *reinterpret_cast<const float4 *>(src + 4 * k4);
+                    cur[4 * k4] = v.x; cur[4 * k4 + 1] = v.y; cur[4 * k4 + 2] = v.z; cur[4 * k4 + 3] = v.w;
                 }
             } else {
 #pragma unroll
-                for (int k = 0; k < KP; ++k) cur[i][k] = (ok && k < K) ? src[k] : 0.f;
+                for (int k = 0; k < KP; ++k) cur[k] = (k < K) ? src[k] : 0.f;
             }
-        }
-        // Release raw[rb] only when the loads above have RETURNED: a shared-memory load that has merely been issued may still sit in
-        // the SM's load/store queue when the mbarrier arrive (a different unit) is performed, and the refill it permits would then
-        // overwrite rows that have not been read yet (seen as wrong Viterbi paths next to a kernel that keeps that queue busy).
-        // The vote below cannot be evaluated before every lane has all its values.
-        if (rs.rel == 1) {
-            float dep = 0.f;
+            float m = 0.f;
+            if (SCALED) row_to_scaled_fast<KP>(mode, eps, K, cur, m);
+            else row_to_log<KP>(mode, eps, K, cur);
+            float *dst = btb + u * BT_PITCH + sub * G;
 #pragma unroll
-            for (int i = 0; i < FL; ++i)
-#pragma unroll
-                for (int k = 0; k < KP; ++k) dep += cur[i][k];
-            const unsigned got = __ballot_sync(FULL_MASK, dep != 1.2345678e37f);
-            if (lane == 0 && got != 0x0badc0deu) sk_mbar_arrive(rs.empty + rb);
-        } else {
-            __syncwarp();
-            if (rs.rel == 2) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            if (lane == 0) sk_mbar_arrive(rs.empty + rb);
+            for (int k = 0; k < KP; ++k) dst[k] = (ok && k < K) ? cur[k] : 0.f;
+            if (SCALED) mraw[((size_t)(c % MR_BUFS) * CH + u) * MAXNS + sub] = ok ? m : 0.f;
         }
+        // Release raw[rb].  Every load of the buffer has RETURNED by now (the stores above consumed the values and a warp issues in
+        // order); a reader that let the issuer refill the buffer while its loads were still queued read the next chunk's rows (seen
+        // as wrong paths next to a co-resident kernel).  The proxy fence orders these generic-proxy reads before the bulk copy's
+        // asynchronous-proxy writes.
+        __syncwarp();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (lane == 0) sk_mbar_arrive(rs.empty + rb);
         if (issuer && c + NR < nch) {
             sk_mbar_wait(rs.empty + rb, (c / NR) & 1);               // ... and so have the other loader warps: refill the buffer
             issue(c + NR);
-        }
-        if (c >= NB) bar_sync(pb.done0 + b, pb.n);                   // consumer is done reading bt[b] (chunk c - NB)
-        float *btb = bt + (size_t)b * CH * BT_PITCH;
-#pragma unroll
-        for (int i = 0; i < FL; ++i) {
-            const int u = q + G * (lw * FL + i);
-            const bool ok = seq_ok && u < nf;
-            float m = 0.f;
-            if (SCALED) row_to_scaled<KP>(mode, eps, K, cur[i], m);
-            else row_to_log<KP>(mode, eps, K, cur[i]);
-            float *dst = btb + u * BT_PITCH + sub * G;
-#pragma unroll
-            for (int k = 0; k < G; ++k) {
-                float v = 0.f;
-                if (k < KP) v = (ok && k < K) ? cur[i][k] : 0.f;
-                dst[k] = v;
-            }
-            if (SCALED) mraw[((size_t)(c % MR_BUFS) * CH + u) * MAXNS + sub] = ok ? m : 0.f;
         }
         bar_arrive(pb.full0 + b, pb.n);
     }
@@ -570,18 +591,14 @@ __device__ __forceinline__ void fb_drainer(const FbParams &p, const float *wr, c
         }
     };
 
-    for (int c = 0; c < nch; ++c) {
+#pragma unroll 1
+    for (int c = 0; c < nch + NB; ++c) {                             // (one call site of the drain body: instruction footprint)
         const int b = c % NB;
         if (c >= NB) {
             bar_sync(pb.done0 + b, pb.n);
             drain(c - NB, b);
         }
-        bar_arrive(pb.full0 + b, pb.n);                              // ring buffer b drained: consumer may overwrite it
-    }
-    for (int c = max(0, nch - NB); c < nch; ++c) {
-        const int b = c % NB;
-        bar_sync(pb.done0 + b, pb.n);
-        drain(c, b);
+        if (c < nch) bar_arrive(pb.full0 + b, pb.n);                 // ring buffer b drained: consumer may overwrite it
     }
 }
 
@@ -609,7 +626,7 @@ __device__ __forceinline__ void fb_roles(const FbParams &p, uint8_t *smem, int r
         fb_consumer<G, KP, DIR, PAD>(p, s.bt, s.wr, s.br, s.er, pb);       // (touches no global memory a predecessor writes)
     } else if (role <= FB_NL) {
         if (p.pdl) grid_dependency_wait();
-        if (p.bulk) loader_loop_bulk<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, role - 1, s.bt, s.mraw, pb, rs);
+        if (p.bulk) loader_loop_bulk<G, KP, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, role - 1, DIR, s.bt, s.mraw, pb, rs);
         else loader_loop<G, KP, DIR, true, FB_NL>(p.emis, p.mode, p.eps, p.B, p.T, p.K, role - 1, s.bt, s.mraw, pb);
     } else {
         if (p.pdl) grid_dependency_wait();
@@ -758,12 +775,15 @@ constexpr int VIT_NL = 2;                                  // loader warps
 constexpr int VIT_ND = 5;                                  // drainer warps (delta store + backpointers)
 constexpr int VIT_THREADS = 32 * (1 + VIT_NL + VIT_ND);
 constexpr size_t VIT_SMEM_BT = (size_t)NB * CH * BT_PITCH * sizeof(float);
-constexpr size_t VIT_SMEM_DR = (size_t)NB * CH * 32 * sizeof(float);
+constexpr int DR_PITCH = 36;                               // floats per frame row of the delta ring: 32 lanes + 4, so that the drainers'
+                                                           // 16-byte reads of DIFFERENT rows (lane = frame) fall on different banks
+constexpr size_t VIT_SMEM_DR = (size_t)NB * CH * DR_PITCH * sizeof(float);
 constexpr size_t VIT_SMEM_CARRY = 2 * 32 * sizeof(float);
-constexpr size_t VIT_SMEM_PIPE = VIT_SMEM_BT + VIT_SMEM_DR + VIT_SMEM_CARRY;
+constexpr size_t VIT_SMEM_MT = 32 * 32 * sizeof(float);    // transposed log-transition table of the drainers (KP x KP used)
+constexpr size_t VIT_SMEM_PIPE = VIT_SMEM_BT + VIT_SMEM_DR + VIT_SMEM_CARRY + VIT_SMEM_MT;
 
 // Shared-memory layout (bytes), NS sequences per CTA:
-//   [bt ring][delta ring][carry][psi: NS*T*G if psi_in_smem][st: NS*T][exit: NS*n_chunks*G][entry: NS*n_chunks][final]
+//   [bt ring][delta ring][carry][logP^T][psi: NS*T*G if psi_in_smem][st: NS*T][exit: NS*n_chunks*G][entry: NS*n_chunks][final]
 // vit_roles is the whole Viterbi pipeline of one group of NS sequences as seen by ONE warp: `role` 0 is the consumer, 1 .. VIT_NL
 // the loaders, above that the drainers; `vtid` in [0, VIT_THREADS) numbers the pipeline's threads for the traceback, and
 // `sync_all` synchronises exactly these VIT_THREADS threads (__syncthreads in the stand-alone kernel, a named barrier when the
@@ -780,6 +800,7 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
     float *bt = reinterpret_cast<float *>(smem);
     float *dr = reinterpret_cast<float *>(smem + VIT_SMEM_BT);
     float *carry = reinterpret_cast<float *>(smem + VIT_SMEM_BT + VIT_SMEM_DR);
+    float *mt = reinterpret_cast<float *>(smem + VIT_SMEM_BT + VIT_SMEM_DR + VIT_SMEM_CARRY);
     uint8_t *psi_s = smem + VIT_SMEM_PIPE;
     size_t off = VIT_SMEM_PIPE + (p.psi_in_smem ? (size_t)NS * T * PSI_ROW : 0);
     uint8_t *st_s = smem + off;            off += (size_t)NS * T;
@@ -824,8 +845,8 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
             float cv[KP];
             candidates(prev, cv);
             d = __fadd_rn(max_tree<KP>(cv), eqv);
-            dp[u * 32] = d;
-            prev = reinterpret_cast<const float4 *>(dp + u * 32 - j);
+            dp[u * DR_PITCH] = d;
+            prev = reinterpret_cast<const float4 *>(dp + u * DR_PITCH - j);
             __syncwarp();
         };
         for (int c = 0; c < nch; ++c) {
@@ -833,7 +854,7 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
             bar_sync(pb.full0 + b, pb.n);
             const int nf = min(CH, T - c * CH);
             const float *btb = bt + (size_t)b * CH * BT_PITCH + lane;
-            dp = dr + (size_t)b * CH * 32 + lane;
+            dp = dr + (size_t)b * CH * DR_PITCH + lane;
             int u = 0;
             if (c == 0) {
                 d = __fadd_rn(li, btb[0]);                  // delta_0 = log_p0 + log b_0 (hmm.py:159)
@@ -868,55 +889,110 @@ __device__ __forceinline__ void vit_roles(const VitParams &p, uint8_t *smem, int
     } else if (role <= VIT_NL) {
         // ---------------- loaders: emission feed -----------------------------------------------------------
         if (p.pdl) grid_dependency_wait();
-        if (p.bulk) loader_loop_bulk<G, KP, 0, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, role - 1, bt, nullptr, pb, rs);
+        if (p.bulk) loader_loop_bulk<G, KP, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, role - 1, 0, bt, nullptr, pb, rs);
         else loader_loop<G, KP, 0, false, VIT_NL>(p.emis, p.mode, p.eps, B, T, K, role - 1, bt, nullptr, pb);
     } else {
         // ---------------- drainers: delta store and backpointers, NB chunks behind the consumer ------------
+        // One LANE per (frame, sequence): the lane reads the frame's and the previous frame's delta vectors (conflict-free 16-byte
+        // loads thanks to DR_PITCH), recomputes all K arg-maxima against the transposed transition table in shared memory
+        // (uniform-address loads) with the consumer's own fp32 adds, and leaves with whole rows: K floats of delta (coalesced
+        // 16-byte stores), one packed backpointer row.  ~30 warp instructions per frame instead of ~90 with a lane per state.
         const int hw = role - 1 - VIT_NL;
-        const int seq_c = seq_ok ? seq : B - 1;
         if (p.pdl) grid_dependency_wait();                    // delta / psi outputs may still be read by the previous kernel's consumers
+        // every drainer warp fills the whole table with the same values (no cross-warp hand-off needed): mt[j][i] = logP[i][j]
+        for (int e = lane; e < KP * KP; e += 32) {
+            const int jj = e / KP, ii = e % KP;
+            mt[e] = (ii < K && jj < K) ? __ldg(p.log_trans + ii * K + jj) : -INFINITY;
+        }
+        __syncwarp();
+        const bool delta_vec = (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.delta) & 15) == 0);
         auto drain = [&](int c, int b) {
             const int nf = min(CH, T - c * CH);
-            const float *drb = dr + (size_t)b * CH * 32;
-            for (int u = hw; u < nf; u += VIT_ND) {
+            const float *drb = dr + (size_t)b * CH * DR_PITCH;
+            for (int task = hw * 32 + lane; task < nf * NS; task += VIT_ND * 32) {
+                const int u = task / NS, s = task % NS;
                 const int n = c * CH + u;
-                const float dv = drb[u * 32 + lane];
-                if (lane_ok && p.delta) p.delta[((size_t)seq * T + n) * K + j] = dv;
-                // backpointer: lowest index attaining max_i(delta_{n-1}(i) + logP(i,j))  (torch.max tie rule, hmm.py:167),
-                // recomputed from the stored delta vector with the same fp32 adds as the consumer; psi_0 = 0.
+                const int sq = seq_base + s;
+                const bool ok = sq < B;
                 const float4 *pv = reinterpret_cast<const float4 *>(
-                    (u > 0) ? (drb + (u - 1) * 32 + sub * G) : (carry + ((c - 1) & 1) * 32 + sub * G));
-                float cv[KP];
-                candidates(pv, cv);
-                const float best = max_tree<KP>(cv);
-                unsigned eqm = 1u << (KP - 1);                       // keeps the index in range if everything is NaN
+                    (u > 0) ? (drb + (u - 1) * DR_PITCH + s * G) : (carry + ((c - 1) & 1) * 32 + s * G));
+                float prev[KP];
 #pragma unroll
-                for (int i = 0; i < KP - 1; ++i) eqm |= (cv[i] == best) ? (1u << i) : 0u;
-                const int arg = (n > 0) ? (__ffs(eqm) - 1) : 0;
-                if (lane_ok && p.psi_out) p.psi_out[((size_t)seq * T + n) * K + j] = (uint8_t)arg;
-                if (p.psi_in_smem) {
-                    if (NIB) {                                           // lanes (j, j + 1) share a byte: low nibble = even state
-                        const int hi = __shfl_down_sync(FULL_MASK, arg, 1);
-                        if ((j & 1) == 0) psi_s[((size_t)sub * T + n) * PSI_ROW + (j >> 1)] = (uint8_t)(arg | (hi << 4));
-                    } else {
-                        psi_s[((size_t)sub * T + n) * PSI_ROW + j] = (uint8_t)arg;
+                for (int i4 = 0; i4 < KP / 4; ++i4) {
+                    const float4 t = pv[i4];
+                    prev[4 * i4] = t.x; prev[4 * i4 + 1] = t.y; prev[4 * i4 + 2] = t.z; prev[4 * i4 + 3] = t.w;
+                }
+                // backpointer of state j: lowest index attaining max_i(delta_{n-1}(i) + logP(i,j))  (torch.max tie rule, hmm.py:167),
+                // from the stored delta vector with the same fp32 adds as the consumer; psi_0 = 0.
+                // four states per trip of a rolled loop (small instruction footprint, see loader_loop_bulk): their backpointers leave
+                // as one 16-bit (nibbles) or 32-bit (bytes) piece of the row
+                uint8_t *row_s = psi_s + ((size_t)s * T + n) * PSI_ROW;
+                uint8_t *row_g = p.psi_in_smem ? nullptr : p.psi_ws + ((size_t)(ok ? sq : 0) * T + n) * G;
+                uint8_t *row_o = (ok && p.psi_out) ? p.psi_out + ((size_t)sq * T + n) * K : nullptr;
+#pragma unroll 1
+                for (int j4 = 0; j4 < KP / 4; ++j4) {
+                    uint32_t arg4[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const float4 *col = reinterpret_cast<const float4 *>(mt + (4 * j4 + r) * KP);
+                        float cv[KP];
+#pragma unroll
+                        for (int i4 = 0; i4 < KP / 4; ++i4) {
+                            const float4 m = col[i4];
+                            const float2 lo = fadd2(make_float2(prev[4 * i4], prev[4 * i4 + 1]), make_float2(m.x, m.y));
+                            const float2 hi = fadd2(make_float2(prev[4 * i4 + 2], prev[4 * i4 + 3]), make_float2(m.z, m.w));
+                            cv[4 * i4 + 0] = lo.x; cv[4 * i4 + 1] = lo.y; cv[4 * i4 + 2] = hi.x; cv[4 * i4 + 3] = hi.y;
+                        }
+                        const float best = max_tree<KP>(cv);
+                        uint32_t arg = KP - 1;                           // (stays in range if everything is NaN)
+#pragma unroll
+                        for (int i = KP - 2; i >= 0; --i) arg = (cv[i] == best) ? (uint32_t)i : arg;
+                        arg4[r] = (n > 0) ? arg : 0u;                    // psi_0 = 0
                     }
-                } else if (seq_ok) p.psi_ws[((size_t)seq_c * T + n) * G + j] = (uint8_t)arg;
-                if (u == nf - 1) carry[(c & 1) * 32 + lane] = dv;
+                    if (p.psi_in_smem) {
+                        if (NIB) *reinterpret_cast<uint16_t *>(row_s + 2 * j4) = (uint16_t)(arg4[0] | (arg4[1] << 4) | (arg4[2] << 8) | (arg4[3] << 12));
+                        else *reinterpret_cast<uint32_t *>(row_s + 4 * j4) = arg4[0] | (arg4[1] << 8) | (arg4[2] << 16) | (arg4[3] << 24);
+                    } else if (ok) {
+                        *reinterpret_cast<uint32_t *>(row_g + 4 * j4) = arg4[0] | (arg4[1] << 8) | (arg4[2] << 16) | (arg4[3] << 24);
+                    }
+                    if (row_o) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) if (4 * j4 + r < K) row_o[4 * j4 + r] = (uint8_t)arg4[r];
+                    }
+                }
+                // the frame's own delta vector: output row, and the carry for the first frame of the next chunk
+                const float4 *cvp = reinterpret_cast<const float4 *>(drb + u * DR_PITCH + s * G);
+                float4 cur[KP / 4];
+#pragma unroll
+                for (int i4 = 0; i4 < KP / 4; ++i4) cur[i4] = cvp[i4];
+                if (ok && p.delta) {
+                    float *dst = p.delta + ((size_t)sq * T + n) * K;
+                    if (delta_vec) {
+#pragma unroll
+                        for (int i4 = 0; i4 < KP / 4; ++i4) if (4 * i4 < K) reinterpret_cast<float4 *>(dst)[i4] = cur[i4];
+                    } else {
+#pragma unroll
+                        for (int i4 = 0; i4 < KP / 4; ++i4) {
+                            const float v[4] = {cur[i4].x, cur[i4].y, cur[i4].z, cur[i4].w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) if (4 * i4 + q < K) dst[4 * i4 + q] = v[q];
+                        }
+                    }
+                }
+                if (u == nf - 1) {
+                    float4 *cd = reinterpret_cast<float4 *>(carry + (c & 1) * 32 + s * G);
+#pragma unroll
+                    for (int i4 = 0; i4 < KP / 4; ++i4) cd[i4] = cur[i4];
+                }
             }
         };
-        for (int c = 0; c < nch; ++c) {
+        for (int c = 0; c < nch + NB; ++c) {                    // (one call site: the drain body is large)
             const int b = c % NB;
             if (c >= NB) {
                 bar_sync(pb.done0 + b, pb.n);
                 drain(c - NB, b);
             }
-            bar_arrive(pb.full0 + b, pb.n);                     // ring buffer b drained: consumer may overwrite it
-        }
-        for (int c = max(0, nch - NB); c < nch; ++c) {
-            const int b = c % NB;
-            bar_sync(pb.done0 + b, pb.n);
-            drain(c, b);
+            if (c < nch) bar_arrive(pb.full0 + b, pb.n);        // ring buffer b drained: consumer may overwrite it
         }
         if (!p.psi_in_smem) __threadfence_block();
     }

@@ -444,3 +444,41 @@ def new_forward_state(B: int, K: int, dev) -> dict:
     return {"alpha": torch.zeros(B, K, dtype=torch.float32, device=dev),
             "loglik": torch.zeros(B, dtype=torch.float64, device=dev),
             "started": torch.zeros(B, dtype=torch.int32, device=dev)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# alignment utilities (csrc/alignment.cu)
+# ------------------------------------------------------------------------------------------------------
+def ctc_trellis(direction: int, log_probs: torch.Tensor, targets: torch.Tensor, input_lengths: torch.Tensor,
+                target_lengths: torch.Tensor, blank: int, want_table: bool = True, want_loglik: bool = True):
+    """log_probs [T,B,C] (CUDA), targets [B,L], lengths [B] -> (table [B,T,2L+1] or None, loglik [B] or None).
+    direction 0: log alpha and the log-likelihood (ctc.py:32-121); 1: log beta (ctc.py:124-199)."""
+    dev = log_probs.device
+    lp = _f32c(log_probs, dev)
+    T, B, Cn = lp.shape
+    tg = targets.to(dev, torch.int64).contiguous()
+    L = tg.shape[1]
+    il = input_lengths.to(dev, torch.int64).contiguous()
+    tl = target_lengths.to(dev, torch.int64).contiguous()
+    table = torch.empty(B, T, 2 * L + 1, dtype=torch.float32, device=dev) if want_table else None
+    ll = torch.empty(B, dtype=torch.float32, device=dev) if (want_loglik and direction == 0) else None
+    with torch.cuda.device(dev):
+        _check(_lib.load().hmmb200_ctc_trellis_f32(direction, _p(lp), _p(tg), _p(il), _p(tl), int(blank), T, B, Cn, L, _p(table), _p(ll),
+                                                   _stream(dev)), "hmmb200_ctc_trellis_f32")
+    return table, ll
+
+
+def dtw(dist: torch.Tensor, step_pattern: int):
+    """dist [P,N,M] (CUDA) -> (cost [P,N,M], path_i [P,N+M-1], path_j [P,N+M-1], path_len [P] int32)."""
+    dev = dist.device
+    d = _f32c(dist, dev)
+    P, N, M = d.shape
+    cost = torch.empty_like(d)
+    dirs = torch.empty(P * N * M, dtype=torch.uint8, device=dev)
+    pi = torch.zeros(P, N + M - 1, dtype=torch.int64, device=dev)
+    pj = torch.zeros(P, N + M - 1, dtype=torch.int64, device=dev)
+    plen = torch.zeros(P, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _check(_lib.load().hmmb200_dtw_f32(_p(d), P, N, M, int(step_pattern), _p(cost), _p(dirs), _p(pi), _p(pj), _p(plen), _stream(dev)),
+               "hmmb200_dtw_f32")
+    return cost, pi, pj, plen

@@ -254,3 +254,36 @@ def test_neural_oracle_vs_reference_golden(golden):
     # the static-transition case is the fixed-matrix recursion on log-emissions
     st, dl, psi, sc = c_oracle.viterbi_f32(g["static_log_obs"], g["static_log_trans"], g["static_log_init"])
     assert np.array_equal(st, g["static_states"]) and np.array_equal(dl, g["static_log_delta"])
+
+
+# ------------------------------------------------------------------------------------------------
+# alignment utilities: oracle/alignment_port.py against the real reference's outputs
+# ------------------------------------------------------------------------------------------------
+def _finite_close(a, b, tol):
+    assert np.array_equal(np.isfinite(a), np.isfinite(b))
+    m = np.isfinite(b)
+    return np.all(np.abs(a[m] - b[m]) <= tol * np.maximum(1.0, np.abs(b[m])))
+
+
+def test_alignment_port_ctc_matches_reference(golden):
+    from oracle import alignment_port as ap
+    g = golden("alignment")
+    for tag in ("a", "b"):
+        args = (g[f"ctc_{tag}_log_probs"], g[f"ctc_{tag}_targets"], g[f"ctc_{tag}_input_lengths"], g[f"ctc_{tag}_target_lengths"],
+                int(g[f"ctc_{tag}_blank"]))
+        _, ll = ap.ctc_forward(*args)
+        assert _finite_close(ll, g[f"ctc_{tag}_loglik"], 1e-6), tag
+        assert _finite_close(ap.ctc_backward(*args), g[f"ctc_{tag}_log_beta"], 1e-6), tag
+    # the forward log-likelihood is minus torch's CTC loss (an implementation the reference does not share code with)
+    _, ll = ap.ctc_forward(g["ctc_a_log_probs"], g["ctc_a_targets"], g["ctc_a_input_lengths"], g["ctc_a_target_lengths"], 0)
+    assert np.allclose(-ll, g["ctc_a_torch_nll"], rtol=1e-6)
+
+
+def test_alignment_port_dtw_bit_identical(golden):
+    from oracle import alignment_port as ap
+    g = golden("alignment")
+    for tag in ("rand", "ties"):
+        for pat in ("symmetric", "asymmetric", "rabiner_juang"):
+            pi, pj, cost = ap.dtw(g[f"dtw_{tag}_dist"], pat)
+            assert np.array_equal(cost, g[f"dtw_{tag}_{pat}_cost"]), (tag, pat)
+            assert np.array_equal(pi, g[f"dtw_{tag}_{pat}_path_i"]) and np.array_equal(pj, g[f"dtw_{tag}_{pat}_path_j"]), (tag, pat)

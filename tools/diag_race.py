@@ -83,3 +83,8 @@ for rel in ("0", "1", "2"):
     run(f"rel={rel} viterbi bulk beside fb per-lane", True, {"HMMB200_RAW_REL": rel, "HMMB200_NO_BULK_FB": "1"})
     run(f"rel={rel} viterbi per-lane beside fb bulk", True, {"HMMB200_RAW_REL": rel, "HMMB200_NO_BULK_VIT": "1"})
     run_fused(f"rel={rel} fused kernel", {"HMMB200_RAW_REL": rel})
+
+# cost of the release variants (fused kernel, no posterior pass)
+for rel in ("1", "2", "1", "2"):
+    setenv({"HMMB200_RAW_REL": rel})
+    print(f"rel={rel} fused kernel {bench.event_ms(lambda: h.fused(want=()), 40):.4f} ms", flush=True)
