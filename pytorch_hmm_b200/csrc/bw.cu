@@ -31,73 +31,108 @@ __global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, con
     }
 }
 
-// one warp per (sequence, block of frames); lane j owns column j of xi.  KP = K padded to a multiple of 4 bounds the unrolled loops.
-template <int KP>
-__global__ void __launch_bounds__(128) bw_xi_kernel(const float *emis, int mode, float eps, const float *trans,
+// xi_t(i,j) = a_t(i) P(i,j) u_{t+1}(j) / Z_t,  u = b~ .* beta (scaled vectors from the fb workspace),  Z_t = sum_ij of the numerator.
+// One warp per (sequence, block of frames).  LPF lanes share a frame and split the K rows of xi (R = ceil(K / LPF) rows each), so a
+// warp works on 32 / LPF consecutive frames at once: the three input rows of those frames are contiguous in memory (coalesced), and a
+// lane spends 3 R KP multiply-adds per frame on R KP cells -- P(i,.) u(.) products, their row sums for Z, then one FMA per cell with
+// a(i) / Z -- instead of one warp-wide shuffle per row of every single frame.  KP = K padded to a multiple of 4.
+template <int KP, int LPF>
+__global__ void __launch_bounds__(384) bw_xi_kernel(const float *emis, int mode, float eps, const float *trans,
                                                     const float *ws_a, const float *ws_b, const float *wseq, int B, int T, int K,
                                                     int frames_per_warp, double *xi, double *gamma1) {
-    extern __shared__ double xi_s[];                       // [K*K] per CTA
-    for (int i = threadIdx.x; i < K * K; i += blockDim.x) xi_s[i] = 0.0;
+    extern __shared__ double xi_s[];                       // [K*K + K] per CTA: xi, gamma_0
+    constexpr int R = (KP + LPF - 1) / LPF, FPI = 32 / LPF;    // rows per lane, frames per warp iteration
+    double *g1_s = xi_s + K * K;
+    for (int i = threadIdx.x; i < K * K + K; i += blockDim.x) xi_s[i] = 0.0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int blocks_per_seq = (T - 1 + frames_per_warp - 1) / frames_per_warp;
-    const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp;
-    const bool ok = lane < K;
-    float col[KP];
+    const int fr = lane / LPF, part = lane % LPF;
+    const int blocks_per_seq = max((T - 1 + frames_per_warp - 1) / frames_per_warp, 1);
+    const int64_t n_tasks = (int64_t)B * blocks_per_seq;
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float Prow[R][KP], acc[R][KP];
 #pragma unroll
-    for (int i = 0; i < KP; ++i) col[i] = (ok && i < K) ? trans[i * K + lane] : 0.f;
-    float acc[KP];
+    for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int i = 0; i < KP; ++i) acc[i] = 0.f;
-    if (wid < (int64_t)B * max(blocks_per_seq, 1) && T > 1) {
-        const int b = (int)(wid / blocks_per_seq), blk = (int)(wid % blocks_per_seq);
-        const int t0 = blk * frames_per_warp, t1 = min(T - 1, t0 + frames_per_warp);
+        for (int j = 0; j < KP; ++j) {
+            const int i = part * R + r;
+            Prow[r][j] = (i < K && j < K) ? trans[i * K + j] : 0.f;
+            acc[r][j] = 0.f;
+        }
+    // Persistent warps: a warp walks tasks (sequence, block of frames) with its xi partial sums in registers and commits them ONCE;
+    // with a CTA per four tasks every one of the K*K global accumulators took ~2000 same-address atomics per call, which serialise
+    // in the L2 and were most of the kernel's time.
+    for (int64_t task = (int64_t)blockIdx.x * (blockDim.x >> 5) + warp; task < n_tasks; task += n_warps) {
+        const int b = (int)(task / blocks_per_seq), blk = (int)(task % blocks_per_seq);
         const float wb = wseq ? wseq[b] : 1.f;                 // per-sequence weight (autograd: d loss / d loglik_b)
-        for (int t = t0; t < t1; ++t) {
-            // u_j = b~_{t+1}(j) * beta_{t+1}(j)
-            float e = ok ? emis[((size_t)b * T + t + 1) * K + lane] : 0.f, bt;
-            if (mode == HMMB200_EMIS_PROB_FLOOR) bt = ok ? e + eps : 0.f;
-            else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) bt = ok ? expf(e) + eps : 0.f;
-            else {
-                float mx = ok ? e : -INFINITY;
+        if (T > 1) {
+            const int t0 = blk * frames_per_warp, t1 = min(T - 1, t0 + frames_per_warp);
+            for (int tb = t0; tb < t1; tb += FPI) {
+                const int t = tb + fr;
+                const bool live = t < t1;
+                const size_t row1 = ((size_t)b * T + (live ? t + 1 : t0 + 1)) * K, row0 = ((size_t)b * T + (live ? t : t0)) * K;
+                // u_j = b~_{t+1}(j) * beta_{t+1}(j)
+                float u[KP], bb[KP];
+                float mx = -INFINITY;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+                for (int j = 0; j < KP; ++j) { u[j] = (j < K) ? emis[row1 + j] : 0.f; bb[j] = (j < K) ? ws_b[row1 + j] : 0.f; }
+                float a[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { const int i = part * R + r; a[r] = (i < K) ? ws_a[row0 + i] : 0.f; }
+#pragma unroll
+                for (int j = 0; j < KP; ++j) if (j < K) mx = fmaxf(mx, u[j]);
                 if (!(mx > -INFINITY)) mx = 0.f;
-                bt = ok ? expf(e - mx) + ((mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f) : 0.f;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    float bt;
+                    if (mode == HMMB200_EMIS_PROB_FLOOR) bt = u[j] + eps;
+                    else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) bt = expf(u[j]) + eps;
+                    else bt = expf(u[j] - mx) + ((mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f);
+                    u[j] = (j < K) ? bt * bb[j] : 0.f;
+                }
+                float pu[R][KP], z = 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float rs = 0.f;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) { pu[r][j] = Prow[r][j] * u[j]; rs += pu[r][j]; }
+                    z = fmaf(a[r], rs, z);
+                }
+#pragma unroll
+                for (int o = LPF / 2; o > 0; o >>= 1) z += __shfl_xor_sync(FULL_MASK, z, o);
+                const float inv = (live && z > 0.f) ? wb / z : 0.f;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float sc = a[r] * inv;
+#pragma unroll
+                    for (int j = 0; j < KP; ++j) acc[r][j] = fmaf(sc, pu[r][j], acc[r][j]);
+                }
             }
-            const float u = ok ? bt * ws_b[((size_t)b * T + t + 1) * K + lane] : 0.f;
-            const float a = ok ? ws_a[((size_t)b * T + t) * K + lane] : 0.f;
-            float v[KP], cs = 0.f;
-#pragma unroll
-            for (int i = 0; i < KP; ++i) { v[i] = __shfl_sync(FULL_MASK, a, i) * col[i] * u; cs += v[i]; }
-            float Z = cs;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
-            const float inv = (Z > 0.f) ? wb / Z : 0.f;
-#pragma unroll
-            for (int i = 0; i < KP; ++i) acc[i] = fmaf(v[i], inv, acc[i]);
         }
         if (blk == 0 && gamma1 != nullptr) {               // gamma_0 = a_0 .* b_0 / sum
+            const bool ok = lane < K;
             const float g = ok ? ws_a[(size_t)b * T * K + lane] * ws_b[(size_t)b * T * K + lane] : 0.f;
             float Z = g;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
-            if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)(wb * g / Z));
+            if (ok && Z > 0.f) atomicAdd(g1_s + lane, (double)(wb * g / Z));
         }
-    } else if (T == 1 && wid < B && gamma1 != nullptr) {
-        const int b = (int)wid;
-        const float g = ok ? ws_a[(size_t)b * K + lane] * ws_b[(size_t)b * K + lane] : 0.f;
-        float Z = g;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
-        if (ok && Z > 0.f) atomicAdd(gamma1 + lane, (double)((wseq ? wseq[b] : 1.f) * g / Z));
     }
-    if (ok) {
+    // fold the frame groups of the warp (lanes that share `part`), then one shared-memory double add per cell and warp
 #pragma unroll
-        for (int i = 0; i < KP; ++i) if (i < K) atomicAdd(&xi_s[i * K + lane], (double)acc[i]);
-    }
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            float v = acc[r][j];
+#pragma unroll
+            for (int o = LPF; o < 32; o <<= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+            const int i = part * R + r;
+            if (fr == 0 && i < K && j < K && v != 0.f) atomicAdd(&xi_s[i * K + j], (double)v);
+        }
     __syncthreads();
     for (int i = threadIdx.x; i < K * K; i += blockDim.x) if (xi_s[i] != 0.0) atomicAdd(xi + i, xi_s[i]);
+    if (gamma1 != nullptr)
+        for (int i = threadIdx.x; i < K; i += blockDim.x) if (g1_s[i] != 0.0) atomicAdd(gamma1 + i, g1_s[i]);
 }
 
 // occ / sx / sxx are one [K*C, N] x [N, D] product (twice: with x and with x^2) over the N frames of the batch.  Per CTA a tile
@@ -211,13 +246,353 @@ __global__ void __launch_bounds__(512) bw_gmm_stats_kernel(const float *x, const
     }
 }
 
-template <int KP>
+// The same statistics with the tile feed taken off the compute warps (the form used when K*C % 4 == 0, D % 8 == 0 and the tensors are
+// 16-byte aligned, i.e. every BASELINE shape).  A tile of BW_F frames is FOUR contiguous byte ranges of the inputs (x, comp, gamma, log b
+// are dense [n, .] arrays): one thread moves them with cp.async.bulk into a BW_STAGES-deep shared-memory ring, completion counted on an
+// mbarrier per stage, so the HBM latency of tile t+2 hides behind the FMAs of tile t (the first version staged every tile with ordinary
+// loads between two block barriers: ~0.9 ms per 512 000 frames, eight times the FMA time).  Per tile: wait, turn comp into
+// w = gamma * exp(comp - log b) ([BW_F][K*C], 6 elements per thread), barrier, 4x8 register-tile FMAs straight from the raw x rows
+// (x^2 formed in registers), barrier, refill the stage.
+constexpr int BW_STAGES = 3;
+__device__ __forceinline__ uint32_t bw_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bw_mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bw_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bw_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bw_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bw_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "BWWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra BWDONE_%=;\n\t"
+        "bra BWWAIT_%=;\n\t"
+        "BWDONE_%=:\n\t"
+        "}" ::"r"(bw_smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+__device__ __forceinline__ void bw_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(bw_smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(bw_smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ float2 bw_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+__device__ __forceinline__ float2 bw_mul2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+__global__ void __launch_bounds__(512, 1) bw_gmm_stats_bulk_kernel(const float *x, const float *comp, const float *logb, const float *gamma,
+                                                                    int64_t n, int K, int C, int D, int FG, double *occ, double *sx, double *sxx) {
+    extern __shared__ __align__(16) float sm_bw[];
+    const int KC = K * C;
+    // ring stage: [x: F*D][comp: F*KC][gamma: F*K][logb: F*K] floats, every piece a multiple of 16 bytes (F = 64)
+    const int stage_floats = BW_F * (D + KC + 2 * K);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm_bw);                  // [BW_STAGES]
+    float *ring = sm_bw + 16;
+    float *w_s = ring + (size_t)BW_STAGES * stage_floats;                  // [BW_F][KC]
+    const int ndg = D / BW_TD, ncg = KC / BW_TC;
+    const int cells = ncg * ndg;
+    const int tid = threadIdx.x;
+    const int fg = tid / cells, cell = tid % cells;
+    // component group fastest: the lanes of a quarter-warp read ONE x address (broadcast) and consecutive 16-byte pieces of the w row,
+    // i.e. every 16-byte shared-memory load of the FMA loop is conflict-free (with the dim group fastest the x loads of neighbouring
+    // lanes sat 32 bytes apart: two-way bank conflicts, and the loop was bound by shared-memory wavefronts instead of FMAs)
+    const int gc = cell % ncg, gd = cell / ncg;
+    const bool live = fg < FG;
+    float2 ax[BW_TC][BW_TD / 2], axx[BW_TC][BW_TD / 2];
+    float aocc[BW_TC];
+#pragma unroll
+    for (int i = 0; i < BW_TC; ++i) {
+        aocc[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < BW_TD / 2; ++j) { ax[i][j] = make_float2(0.f, 0.f); axx[i][j] = make_float2(0.f, 0.f); }
+    }
+    const int64_t n_tiles = n / BW_F;                                      // full tiles only (the launcher sends the tail elsewhere)
+    const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](int64_t it) {                                         // this CTA's it-th tile -> stage it % BW_STAGES
+        const int64_t base = (blockIdx.x + it * gridDim.x) * BW_F;
+        float *st = ring + (size_t)(it % BW_STAGES) * stage_floats;
+        uint64_t *bar = full + (it % BW_STAGES);
+        const uint32_t bx = BW_F * D * 4, bc = BW_F * KC * 4, bk = BW_F * K * 4;
+        bw_mbar_expect_tx(bar, bx + bc + 2 * bk);
+        bw_bulk_g2s(st, x + base * D, bx, bar);
+        bw_bulk_g2s(st + BW_F * D, comp + base * KC, bc, bar);
+        bw_bulk_g2s(st + BW_F * (D + KC), gamma + base * K, bk, bar);
+        bw_bulk_g2s(st + BW_F * (D + KC + K), logb + base * K, bk, bar);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < BW_STAGES; ++i) bw_mbar_init(full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int64_t it = 0; it < min((int64_t)BW_STAGES, my_tiles); ++it) issue(it);
+    }
+    __syncthreads();
+    // element walk of the w pass without integer divisions in the loop: e = tid + i * blockDim  ->  (f, kc)
+    const int step_f = (int)blockDim.x / KC, step_kc = (int)blockDim.x % KC;
+    const float inv_c = 1.f / (float)C;
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const float *st = ring + (size_t)(it % BW_STAGES) * stage_floats;
+        bw_mbar_wait(full + (it % BW_STAGES), (uint32_t)((it / BW_STAGES) & 1));
+        const float *x_s = st, *c_s = st + BW_F * D, *g_s = st + BW_F * (D + KC), *l_s = st + BW_F * (D + KC + K);
+        {
+            int f = tid / KC, kc = tid % KC;
+            for (int e = tid; e < BW_F * KC; e += blockDim.x) {
+                const int k = __float2int_rz(((float)kc + 0.5f) * inv_c);
+                w_s[e] = g_s[f * K + k] * __expf(c_s[e] - l_s[f * K + k]);     // gamma_t(k) * responsibility(c | k)
+                f += step_f; kc += step_kc;
+                if (kc >= KC) { kc -= KC; ++f; }
+            }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll 2
+            for (int f = fg; f < BW_F; f += FG) {
+                const float4 w4 = *reinterpret_cast<const float4 *>(w_s + f * KC + gc * BW_TC);
+                const float4 xa = *reinterpret_cast<const float4 *>(x_s + f * D + gd * BW_TD);
+                const float4 xb = *reinterpret_cast<const float4 *>(x_s + f * D + gd * BW_TD + 4);
+                const float wv[BW_TC] = {w4.x, w4.y, w4.z, w4.w};
+                const float2 xv[BW_TD / 2] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
+                float2 qv[BW_TD / 2];
+#pragma unroll
+                for (int j = 0; j < BW_TD / 2; ++j) qv[j] = bw_mul2(xv[j], xv[j]);
+#pragma unroll
+                for (int i = 0; i < BW_TC; ++i) {
+                    aocc[i] += wv[i];
+                    const float2 ww = make_float2(wv[i], wv[i]);
+#pragma unroll
+                    for (int j = 0; j < BW_TD / 2; ++j) { ax[i][j] = bw_ffma2(ww, xv[j], ax[i][j]); axx[i][j] = bw_ffma2(ww, qv[j], axx[i][j]); }
+                }
+            }
+        }
+        __syncthreads();                                                   // every thread is done with the stage and with w_s
+        if (tid == 0 && it + BW_STAGES < my_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads above before the bulk copy's writes
+            issue(it + BW_STAGES);
+        }
+    }
+    // fold the FG frame sub-sequences inside the CTA, then one double atomic per statistic and CTA (as bw_gmm_stats_kernel)
+    constexpr int NACC = 2 * BW_TC * BW_TD + BW_TC;
+    float *fold = ring;
+    for (int r = 1; r < FG; ++r) {
+        __syncthreads();
+        float *slot = fold + (size_t)cell * NACC;
+        if (fg == r) {
+#pragma unroll
+            for (int i = 0; i < BW_TC; ++i) {
+                slot[2 * BW_TC * BW_TD + i] = aocc[i];
+#pragma unroll
+                for (int j = 0; j < BW_TD / 2; ++j) {
+                    slot[i * BW_TD + 2 * j] = ax[i][j].x; slot[i * BW_TD + 2 * j + 1] = ax[i][j].y;
+                    slot[BW_TC * BW_TD + i * BW_TD + 2 * j] = axx[i][j].x; slot[BW_TC * BW_TD + i * BW_TD + 2 * j + 1] = axx[i][j].y;
+                }
+            }
+        }
+        __syncthreads();
+        if (fg == 0) {
+#pragma unroll
+            for (int i = 0; i < BW_TC; ++i) {
+                aocc[i] += slot[2 * BW_TC * BW_TD + i];
+#pragma unroll
+                for (int j = 0; j < BW_TD / 2; ++j) {
+                    ax[i][j].x += slot[i * BW_TD + 2 * j]; ax[i][j].y += slot[i * BW_TD + 2 * j + 1];
+                    axx[i][j].x += slot[BW_TC * BW_TD + i * BW_TD + 2 * j]; axx[i][j].y += slot[BW_TC * BW_TD + i * BW_TD + 2 * j + 1];
+                }
+            }
+        }
+    }
+    if (fg != 0 || my_tiles == 0) return;
+#pragma unroll
+    for (int i = 0; i < BW_TC; ++i) {
+        const int kc = gc * BW_TC + i;
+        if (gd == 0) atomicAdd(occ + kc, (double)aocc[i]);
+#pragma unroll
+        for (int j = 0; j < BW_TD / 2; ++j) {
+            const int d = gd * BW_TD + 2 * j;
+            atomicAdd(sx + (size_t)kc * D + d, (double)ax[i][j].x);
+            atomicAdd(sx + (size_t)kc * D + d + 1, (double)ax[i][j].y);
+            atomicAdd(sxx + (size_t)kc * D + d, (double)axx[i][j].x);
+            atomicAdd(sxx + (size_t)kc * D + d + 1, (double)axx[i][j].y);
+        }
+    }
+}
+
+// The same [K*C, frames] x [frames, 2D] product on the tensor cores: mma.sync m16n8k8 TF32 with a 3-term hi/lo split
+// (hi = the value with its low 13 mantissa bits cleared, lo = value - hi, both exact; hi*hi + hi*lo + lo*hi leaves a relative error
+// of ~2^-21 per product), fp32 accumulators in registers over all the CTA's tiles.  The FMA form above peaks at 57 % of the fp32 pipe
+// (0.25 ms per 512 000 frames); this one needs a third of its instructions.  Same bulk-copy ring and w pass.
+//   16 warps = 4 frame groups (16 frames = 2 k-steps of a 64-frame tile each) x 4 column groups (x dims [0, D/2), [D/2, D), then the
+//   same two ranges of x^2); a warp holds MT x NTW accumulator tiles (MT = ceil(K*C / 16) <= 4, NTW = ceil(D / 16) <= 6) plus, in the
+//   first column group, one tile against a column of ones (the occupancies).
+__device__ __forceinline__ void bw_mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void bw_split(float v, uint32_t &hi, uint32_t &lo) {
+    hi = __float_as_uint(v) & 0xffffe000u;
+    lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+template <int MT, int NTW>
+__global__ void __launch_bounds__(512, 1) bw_gmm_stats_mma_kernel(const float *x, const float *comp, const float *logb, const float *gamma,
+                                                                   int64_t n, int K, int C, int D, double *occ, double *sx, double *sxx) {
+    extern __shared__ __align__(16) float sm_bw[];
+    const int KC = K * C;
+    constexpr int WP = MT * 16 + 8;                                        // w row pitch: the A-fragment loads (4 frames x 8 rows) are conflict-free
+    const int stage_floats = BW_F * (D + KC + 2 * K);
+    uint64_t *full = reinterpret_cast<uint64_t *>(sm_bw);
+    float *ring = sm_bw + 16;
+    float *w_s = ring + (size_t)BW_STAGES * stage_floats;                  // [BW_F][WP], columns KC .. WP-1 stay zero
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int fgp = warp >> 2, cgp = warp & 3;                             // frame group, column group
+    const bool sq = cgp >= 2;                                              // this warp's columns are x^2
+    const int nt_all = D / 8;                                              // n-tiles of x (and of x^2)
+    const int nt0 = (cgp & 1) * NTW;                                       // first n-tile of the warp within its half
+    float acc[MT][NTW][4], aocc[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) aocc[m][q] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NTW; ++j)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[m][j][q] = 0.f;
+    }
+    const int64_t n_tiles = n / BW_F;
+    const int64_t my_tiles = (n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto issue = [&](int64_t it) {
+        const int64_t base = (blockIdx.x + it * gridDim.x) * BW_F;
+        float *st = ring + (size_t)(it % BW_STAGES) * stage_floats;
+        uint64_t *bar = full + (it % BW_STAGES);
+        const uint32_t bx = BW_F * D * 4, bc = BW_F * KC * 4, bk = BW_F * K * 4;
+        bw_mbar_expect_tx(bar, bx + bc + 2 * bk);
+        bw_bulk_g2s(st, x + base * D, bx, bar);
+        bw_bulk_g2s(st + BW_F * D, comp + base * KC, bc, bar);
+        bw_bulk_g2s(st + BW_F * (D + KC), gamma + base * K, bk, bar);
+        bw_bulk_g2s(st + BW_F * (D + KC + K), logb + base * K, bk, bar);
+    };
+    if (tid == 0) {
+        for (int i = 0; i < BW_STAGES; ++i) bw_mbar_init(full + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int64_t it = 0; it < min((int64_t)BW_STAGES, my_tiles); ++it) issue(it);
+    }
+    for (int e = tid; e < BW_F * WP; e += blockDim.x) w_s[e] = 0.f;
+    __syncthreads();
+    const int step_f = (int)blockDim.x / KC, step_kc = (int)blockDim.x % KC;
+    const float inv_c = 1.f / (float)C;
+    const uint32_t one = __float_as_uint(1.f);
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const float *st = ring + (size_t)(it % BW_STAGES) * stage_floats;
+        bw_mbar_wait(full + (it % BW_STAGES), (uint32_t)((it / BW_STAGES) & 1));
+        const float *x_s = st, *c_s = st + BW_F * D, *g_s = st + BW_F * (D + KC), *l_s = st + BW_F * (D + KC + K);
+        {
+            int f = tid / KC, kc = tid % KC;
+            for (int e = tid; e < BW_F * KC; e += blockDim.x) {
+                const int k = __float2int_rz(((float)kc + 0.5f) * inv_c);
+                w_s[f * WP + kc] = g_s[f * K + k] * __expf(c_s[e] - l_s[f * K + k]);   // gamma_t(k) * responsibility(c | k)
+                f += step_f; kc += step_kc;
+                if (kc >= KC) { kc -= KC; ++f; }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < BW_F / 8 / 4; ++ks) {                        // this warp's k-steps (8 frames each) of the tile
+            const int f0 = (fgp * (BW_F / 8 / 4) + ks) * 8;
+            uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+                const float *wr = w_s + (f0 + t4) * WP + m * 16 + g;       // A(row = kc, col = frame) = w[frame][kc]
+                bw_split(wr[0], ah[m][0], al[m][0]);
+                bw_split(wr[8], ah[m][1], al[m][1]);
+                bw_split(wr[4 * WP], ah[m][2], al[m][2]);
+                bw_split(wr[4 * WP + 8], ah[m][3], al[m][3]);
+            }
+#pragma unroll
+            for (int j = 0; j < NTW; ++j) {
+                const int nt = nt0 + j;
+                if (nt < nt_all && nt < (cgp & 1) * NTW + NTW) {
+                    const float *xr = x_s + (f0 + t4) * D + nt * 8 + g;    // B(row = frame, col = dim) = x[frame][dim]
+                    float b0 = xr[0], b1 = xr[4 * D];
+                    if (sq) { b0 *= b0; b1 *= b1; }
+                    uint32_t bh[2], bl[2];
+                    bw_split(b0, bh[0], bl[0]);
+                    bw_split(b1, bh[1], bl[1]);
+#pragma unroll
+                    for (int m = 0; m < MT; ++m) {
+                        bw_mma_tf32(acc[m][j], ah[m], bh);
+                        bw_mma_tf32(acc[m][j], ah[m], bl);
+                        bw_mma_tf32(acc[m][j], al[m], bh);
+                    }
+                }
+            }
+            if (cgp == 0) {                                                 // occupancies: w^T x 1
+                const uint32_t b1v[2] = {one, one};
+#pragma unroll
+                for (int m = 0; m < MT; ++m) { bw_mma_tf32(aocc[m], ah[m], b1v); bw_mma_tf32(aocc[m], al[m], b1v); }
+            }
+        }
+        __syncthreads();                                                   // every thread is done with the stage and with w_s
+        if (tid == 0 && it + BW_STAGES < my_tiles) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(it + BW_STAGES);
+        }
+    }
+    if (my_tiles == 0) return;
+    // fold the four frame groups through shared memory (fp32), then one double atomic per statistic and CTA.
+    // accumulator element q of tile (m, j): row kc = 16 m + g + 8 (q >> 1), column d = 8 nt + 2 t4 + (q & 1)
+    float *fold = ring;                                                    // [MT*16][2*D + 1] floats
+    const int FW = 2 * D + 1;
+    for (int e = tid; e < MT * 16 * FW; e += blockDim.x) fold[e] = 0.f;
+    __syncthreads();
+    for (int r = 0; r < 4; ++r) {
+        if (fgp == r) {
+#pragma unroll
+            for (int m = 0; m < MT; ++m) {
+#pragma unroll
+                for (int j = 0; j < NTW; ++j) {
+                    const int nt = nt0 + j;
+                    if (nt < nt_all && nt < (cgp & 1) * NTW + NTW) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            fold[(m * 16 + g + 8 * (q >> 1)) * FW + (sq ? D : 0) + nt * 8 + 2 * t4 + (q & 1)] += acc[m][j][q];
+                    }
+                }
+                if (cgp == 0 && t4 == 0) {
+                    fold[(m * 16 + g) * FW + 2 * D] += aocc[m][0];
+                    fold[(m * 16 + g + 8) * FW + 2 * D] += aocc[m][2];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < KC * FW; e += blockDim.x) {
+        const int kc = e / FW, c = e % FW;
+        const double v = (double)fold[e];
+        if (c < D) atomicAdd(sx + (size_t)kc * D + c, v);
+        else if (c < 2 * D) atomicAdd(sxx + (size_t)kc * D + (c - D), v);
+        else atomicAdd(occ + kc, v);
+    }
+}
+
+template <int KP, int LPF>
 static int launch_xi_kp(const float *emis, int mode, float eps, const float *trans, const float *ws_a, const float *ws_b,
                         const float *wseq, int B, int T, int K, double *xi, double *gamma1, cudaStream_t s) {
-    const int fpw = 64, warps = 4;
+    const int fpw = 64, warps = 12;
     const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
-    const int64_t n_warps = (int64_t)B * blocks_per_seq;
-    bw_xi_kernel<KP><<<(unsigned)((n_warps + warps - 1) / warps), warps * 32, (size_t)K * K * sizeof(double), s>>>(
+    const int64_t n_tasks = (int64_t)B * blocks_per_seq;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t ctas = min((n_tasks + warps - 1) / warps, (int64_t)sms);
+    bw_xi_kernel<KP, LPF><<<(unsigned)ctas, warps * 32, (size_t)(K * K + K) * sizeof(double), s>>>(
         emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, fpw, xi, gamma1);
     return check_launch("bw_xi_kernel");
 }
@@ -225,14 +600,15 @@ static int launch_xi_kp(const float *emis, int mode, float eps, const float *tra
 static int launch_xi(const float *emis, int mode, float eps, const float *trans, const float *ws_a, const float *ws_b,
                      const float *wseq, int B, int T, int K, double *xi, double *gamma1, cudaStream_t s) {
     const int kp = pad4(K);
-#define XI_CASE(N) if (kp <= N) return launch_xi_kp<N>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, xi, gamma1, s)
-    XI_CASE(4); XI_CASE(8); XI_CASE(12); XI_CASE(16); XI_CASE(20); XI_CASE(24); XI_CASE(28);
+    // lanes per frame: the smallest power of two that leaves a lane at most ~48 cells of xi
+#define XI_CASE(N, L) if (kp <= N) return launch_xi_kp<N, L>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, xi, gamma1, s)
+    XI_CASE(4, 1); XI_CASE(8, 2); XI_CASE(12, 4); XI_CASE(16, 8); XI_CASE(20, 16); XI_CASE(24, 16); XI_CASE(28, 32);
 #undef XI_CASE
-    return launch_xi_kp<32>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, xi, gamma1, s);
+    return launch_xi_kp<32, 32>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, K, xi, gamma1, s);
 }
 
-static int launch_gmm_stats(const float *x, const float *comp, const float *logb, const float *gamma, int64_t n, int K, int C, int D,
-                            double *occ, double *sx, double *sxx, cudaStream_t s) {
+static int launch_gmm_stats_generic(const float *x, const float *comp, const float *logb, const float *gamma, int64_t n, int K, int C, int D,
+                                    double *occ, double *sx, double *sxx, cudaStream_t s) {
     const int KCp = (K * C + BW_TC - 1) / BW_TC * BW_TC, Dp = (D + BW_TD - 1) / BW_TD * BW_TD;
     size_t smem = (size_t)BW_F * (KCp + 2 * Dp) * sizeof(float);
     smem = smem > 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float) ? smem : 512 * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float);   // also the fold buffer
@@ -253,6 +629,61 @@ static int launch_gmm_stats(const float *x, const float *comp, const float *logb
     dim3 grid((unsigned)min((int64_t)sms, n_tiles), (unsigned)gy);      // one CTA per SM (128 registers x ~480 threads)
     bw_gmm_stats_kernel<<<grid, threads, smem, s>>>(x, comp, logb, gamma, n, K, C, D, FG, occ, sx, sxx);
     return check_launch("bw_gmm_stats_kernel");
+}
+
+static int launch_gmm_stats(const float *x, const float *comp, const float *logb, const float *gamma, int64_t n, int K, int C, int D,
+                            double *occ, double *sx, double *sxx, cudaStream_t s) {
+    const int KC = K * C;
+    auto al16 = [](const void *q) { return ((uintptr_t)q & 15) == 0; };
+    const int cells = (KC / BW_TC) * (D / BW_TD);
+    const size_t stage = (size_t)BW_F * (D + KC + 2 * K) * sizeof(float);
+    const size_t smem = 64 + BW_STAGES * stage + (size_t)BW_F * KC * sizeof(float);
+    const bool bulk = KC % BW_TC == 0 && D % BW_TD == 0 && cells >= 1 && cells <= 512 && n >= BW_F && smem <= 200 * 1024 &&
+                      BW_STAGES * stage >= (size_t)cells * (2 * BW_TC * BW_TD + BW_TC) * sizeof(float) &&
+                      al16(x) && al16(comp) && al16(logb) && al16(gamma);
+    if (!bulk) return launch_gmm_stats_generic(x, comp, logb, gamma, n, K, C, D, occ, sx, sxx, s);
+    static bool attr_done[64];
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(bw_gmm_stats_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "gmm_stats smem opt-in: %s", cudaGetErrorString(e));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    int FG = 512 / cells;
+    FG = FG < 1 ? 1 : (FG > 8 ? 8 : FG);
+    const int threads = (cells * FG + 31) & ~31;
+    const int64_t n_full = n / BW_F;
+    // tensor-core form when the register tiling covers the shape: K*C <= 64 rows (MT <= 4), D <= 96 (NTW <= 6)
+    const int MT = (KC + 15) / 16, NTW = (D / 8 + 1) / 2;
+    const size_t smem_mma = 64 + BW_STAGES * stage + (size_t)BW_F * (MT * 16 + 8) * sizeof(float);
+    const bool mma_ok = MT <= 4 && NTW <= 6 && smem_mma <= 200 * 1024 && BW_STAGES * stage >= (size_t)MT * 16 * (2 * D + 1) * sizeof(float);
+    bool launched = false;
+    if (mma_ok) {
+#define BW_MMA_CASE(M_, N_)                                                                                                            \
+        if (!launched && MT == M_ && NTW == N_) {                                                                                       \
+            cudaFuncSetAttribute(bw_gmm_stats_mma_kernel<M_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);             \
+            bw_gmm_stats_mma_kernel<M_, N_><<<(unsigned)min((int64_t)sms, n_full), 512, smem_mma, s>>>(x, comp, logb, gamma, n_full * BW_F, \
+                                                                                                    K, C, D, occ, sx, sxx);           \
+            launched = true;                                                                                                            \
+        }
+        BW_MMA_CASE(1, 1) BW_MMA_CASE(1, 2) BW_MMA_CASE(1, 3) BW_MMA_CASE(1, 4) BW_MMA_CASE(1, 5) BW_MMA_CASE(1, 6)
+        BW_MMA_CASE(2, 1) BW_MMA_CASE(2, 2) BW_MMA_CASE(2, 3) BW_MMA_CASE(2, 4) BW_MMA_CASE(2, 5) BW_MMA_CASE(2, 6)
+        BW_MMA_CASE(3, 1) BW_MMA_CASE(3, 2) BW_MMA_CASE(3, 3) BW_MMA_CASE(3, 4) BW_MMA_CASE(3, 5) BW_MMA_CASE(3, 6)
+        BW_MMA_CASE(4, 1) BW_MMA_CASE(4, 2) BW_MMA_CASE(4, 3) BW_MMA_CASE(4, 4) BW_MMA_CASE(4, 5) BW_MMA_CASE(4, 6)
+#undef BW_MMA_CASE
+    }
+    if (!launched)
+        bw_gmm_stats_bulk_kernel<<<(unsigned)min((int64_t)sms, n_full), threads, smem, s>>>(x, comp, logb, gamma, n_full * BW_F, K, C, D, FG,
+                                                                                          occ, sx, sxx);
+    if (int rc = check_launch("bw_gmm_stats_bulk_kernel")) return rc;
+    const int64_t tail = n - n_full * BW_F;                         // fewer than BW_F frames: the plain kernel
+    if (tail > 0) {
+        const int64_t o = n_full * BW_F;
+        return launch_gmm_stats_generic(x + o * D, comp + o * KC, logb + o * K, gamma + o * K, tail, K, C, D, occ, sx, sxx, s);
+    }
+    return HMMB200_OK;
 }
 
 }  // namespace hmmb200
