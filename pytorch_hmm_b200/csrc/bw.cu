@@ -13,7 +13,13 @@
 // Multi-GPU: each rank accumulates its shard; the host all-reduces the ~8 k doubles once per EM iteration (NCCL).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace hmmb200 {
+
+// bw_tc.cu: the statistics GEMM on tcgen05 (0 launched, 1 shape not covered, < 0 error)
+int launch_gmm_stats_tc(const float *x, const float *comp, const float *logb, const float *gamma, int64_t n_full, int K, int C, int D,
+                        double *occ, double *sx, double *sxx, cudaStream_t s);
 
 __global__ void __launch_bounds__(128) gmm_components_kernel(const float *x, const float *packed, int64_t n, int KC, int D,
                                                              int NP2, float *comp, const float *skip_if_one) {
@@ -660,7 +666,16 @@ static int launch_gmm_stats(const float *x, const float *comp, const float *logb
     const size_t smem_mma = 64 + BW_STAGES * stage + (size_t)BW_F * (MT * 16 + 8) * sizeof(float);
     const bool mma_ok = MT <= 4 && NTW <= 6 && smem_mma <= 200 * 1024 && BW_STAGES * stage >= (size_t)MT * 16 * (2 * D + 1) * sizeof(float);
     bool launched = false;
-    if (mma_ok) {
+    int path = 0;                                                   // 0 best available, 1 mma.sync, 2 CUDA-core FMAs (debug builds: A/B timing)
+#ifdef HMMB200_DEBUG_HOOKS
+    if (const char *e = getenv("HMMB200_STATS_PATH")) path = atoi(e);
+#endif
+    if (path == 0) {                                                // tcgen05 form (bw_tc.cu)
+        const int rc = launch_gmm_stats_tc(x, comp, logb, gamma, n_full * BW_F, K, C, D, occ, sx, sxx, s);
+        if (rc < 0) return rc;
+        launched = (rc == 0);
+    }
+    if (!launched && mma_ok && path <= 1) {
 #define BW_MMA_CASE(M_, N_)                                                                                                            \
         if (!launched && MT == M_ && NTW == N_) {                                                                                       \
             cudaFuncSetAttribute(bw_gmm_stats_mma_kernel<M_, N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);             \
