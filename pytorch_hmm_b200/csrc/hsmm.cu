@@ -13,7 +13,14 @@
 // uint8 backpointers go to a workspace in HBM and are walked by one thread at the end.  The DP ring has Dmax+2 slots.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace hmmb200 {
+
+// hsmm_fb.cu: the fp32 two-warp forward-backward (0 launched, 1 shape not covered, < 0 error) and its workspace
+size_t hsmm_fb2_workspace_bytes(int B, int T, int K);
+int launch_hsmm_fb2(const float *f, const float *segc, const float *logdur, const float *logA, const float *logpi, int B, int T, int K, int Dm,
+                    float *gamma, float *total, float *bbegin, float *bend, void *workspace, cudaStream_t s);
 
 struct HsmmVitParams {
     const float *f;        // [B,T,K] per-frame log-emission term
@@ -662,7 +669,9 @@ HMMB200_EXPORT int hmmb200_hsmm_forward_f32(const float *frame_logp, const float
 HMMB200_EXPORT size_t hmmb200_hsmm_fb_workspace_bytes(int B, int T, int K) {
     if (B <= 0 || T <= 0 || K <= 0) return 0;
     const size_t n = (size_t)B * T;
-    return n * K * (2 * sizeof(double) + sizeof(float)) + n * (sizeof(double) + sizeof(int)) + 64;
+    const size_t v1 = n * K * (2 * sizeof(double) + sizeof(float)) + n * (sizeof(double) + sizeof(int)) + 64;
+    const size_t v2 = hsmm_fb2_workspace_bytes(B, T, K);
+    return v1 > v2 ? v1 : v2;
 }
 
 HMMB200_EXPORT int hmmb200_hsmm_forward_backward_f32(const float *frame_logp, const float *seg_const, const float *log_dur,
@@ -676,6 +685,17 @@ HMMB200_EXPORT int hmmb200_hsmm_forward_backward_f32(const float *frame_logp, co
     const size_t need = hmmb200_hsmm_fb_workspace_bytes(B, T, K);
     if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_forward_backward: workspace %zu < %zu", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
+    {
+        bool v1 = false;
+#ifdef HMMB200_DEBUG_HOOKS
+        v1 = getenv("HMMB200_HSMM_FB_V1") != nullptr;            // A/B timing against the double-precision one-warp kernel
+#endif
+        if (!v1) {
+            const int rc = launch_hsmm_fb2(frame_logp, seg_const, log_dur, log_trans, log_init, B, T, K, Dm, gamma, total, beta_begin, beta_end,
+                                           workspace, (cudaStream_t)stream);
+            if (rc <= 0) return rc;                              // launched (0) or failed (< 0); 1 = shape for the general kernel below
+        }
+    }
     const size_t smem = ((size_t)3 * Dm * K + (size_t)K * K + K) * sizeof(double) + (size_t)HSF_PF * 32 * (8 + 8 + 4) + HSF_PF * 4 + 64;
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_forward_backward: max_duration too large");
     const bool spec = (K == 10 && Dm == 20);                // BASELINE config 4 (HSMMLayer defaults of the reference's factory)
