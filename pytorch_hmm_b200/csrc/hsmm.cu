@@ -119,32 +119,13 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
     }
     __syncthreads();
 
-    int head = 0, slot_prev = R - 1, slot_t = 0;                         // ring rows without integer division on the loop
-    for (int t = 0; t < T; ++t) {
-        const float *prev = ring + (size_t)slot_prev * KD;              // segments ending at t-1
-        // ---- phase A: Mx[s'] and its first arg-max (one warp per s'); prefix table of the frame window (one thread per s) ----
-        if (t > 0) {
-            for (int sp = warp; sp < K; sp += nwarps) {
-                float m = -INFINITY;
-                int mi = Dm;
-                for (int dp = lane; dp < Dm; dp += 32) {
-                    const float v = prev[sp * Dm + dp];
-                    if (v > m) { m = v; mi = dp; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float om = __shfl_xor_sync(FULL_MASK, m, o);
-                    const int oi = __shfl_xor_sync(FULL_MASK, mi, o);
-                    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
-                }
-                if (lane == 0) { mx_s[sp] = m; arg_s[sp] = (mi < Dm) ? mi : 0; }
-            }
-        }
-        // The segment sum seg(t,d,s) in ATen's order is four interleaved running sums plus a tail: the running sums depend on
-        // d only through q = d/4, so they are tabulated once per (t, s) and shared by the Dmax cells of the state.
-        for (int s = blockDim.x - 1 - tid; s < K; s += blockDim.x) {   // the LAST threads: they have no Mx work in warp 0
-            int r = head;
-            float *tb = tab + s * TABW;
+    // The segment sum seg(t,d,s) in ATen's order is four interleaved running sums plus a tail: the running sums depend on d only through
+    // q = d/4, so they are tabulated once per (t, s) and shared by the Dmax cells of the state.  The table of step t+1 only needs the
+    // frame window, so it is built DURING step t (two buffers) by threads that have no cell, off the step's critical path.
+    auto build_tab = [&](float *tbuf, int first_row) {                  // window rows first_row .. first_row + Dm - 1
+        for (int s = blockDim.x - 1 - tid; s < K; s += blockDim.x) {   // the LAST threads of the block
+            int r = first_row;
+            float *tb = tbuf + s * TABW;
             if (p.sum_order == 0) {
                 float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
                 tb[0] = 0.f; tb[1] = 0.f; tb[2] = 0.f; tb[3] = 0.f;
@@ -161,25 +142,65 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                 for (int d = 1; d <= Dm; ++d) { a = __fadd_rn(a, win[r * K + s]); if (++r == WR) r = 0; tb[d] = a; }
             }
         }
-        __syncthreads();
-        // ---- phase A2: U[s'][s] = fl(Mx[s'] + logA[s'][s]), then V[s] = max_{s' != s} U[s'][s] with its first arg-max ----
-        if (t > 0) {
-            for (int i = tid; i < K * K; i += blockDim.x) U_s[i] = __fadd_rn(mx_s[i / K], A_s[i]);
+    };
+    float *tab2 = tab + (size_t)K * TABW;                                // second table buffer
+    build_tab(tab, 0);
+    __syncthreads();
+
+    int head = 0, slot_prev = R - 1, slot_t = 0;                         // ring rows without integer division on the loop
+    for (int t = 0; t < T; ++t) {
+        const float *prev = ring + (size_t)slot_prev * KD;              // segments ending at t-1
+        const float *tabc = (t & 1) ? tab2 : tab;                        // this step's table; the other buffer receives step t+1's
+        // slide the frame window: frame t + Dm goes into the spare row (the one that held frame t - 1), which no cell reads during this
+        // step; the two barriers below order it before the table of step t+1 is built from it.
+        {
+            const int spare = (head == 0) ? WR - 1 : head - 1;
+            for (int s = tid; s < K; s += blockDim.x) win[spare * K + s] = (t + Dm < T) ? f[(size_t)(t + Dm) * K + s] : 0.f;
         }
-        __syncthreads();
         if (t > 0) {
-            for (int s = tid; s < K; s += blockDim.x) {
-                float v = -INFINITY;
-                int vi = -1;
-                for (int sp = 0; sp < K; ++sp) {
-                    if (sp == s) continue;
-                    const float u = U_s[sp * K + s];
-                    if (u > v) { v = u; vi = sp; }
+            // ---- phase A: Mx[s'] = max_d' prev[s'][d'] and its first arg-max (one warp per s') ----
+            for (int sp = warp; sp < K; sp += nwarps) {
+                float m = -INFINITY;
+                int mi = Dm;
+                for (int dp = lane; dp < Dm; dp += 32) {
+                    const float v = prev[sp * Dm + dp];
+                    if (v > m) { m = v; mi = dp; }
                 }
-                V_s[s] = v; varg_s[s] = vi;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float om = __shfl_xor_sync(FULL_MASK, m, o);
+                    const int oi = __shfl_xor_sync(FULL_MASK, mi, o);
+                    if (om > m || (om == m && oi < mi)) { m = om; mi = oi; }
+                }
+                if (lane == 0) { mx_s[sp] = m; arg_s[sp] = (mi < Dm) ? mi : 0; }
             }
+            __syncthreads();
+            // ---- phase V: V[s] = max_{s' != s} fl(Mx[s'] + logA[s'][s]) with its first arg-max: 32 / VL states per warp, VL lanes each ----
+            const int VL = (K <= 4) ? 4 : ((K <= 8) ? 8 : ((K <= 16) ? 16 : 32));
+            for (int s0 = warp * (32 / VL); s0 < K; s0 += nwarps * (32 / VL)) {
+                const int s = s0 + lane / VL, l = lane % VL;
+                float v = -INFINITY;
+                int vi = K;
+                if (s < K) {
+                    for (int sp = l; sp < K; sp += VL) {
+                        if (sp == s) continue;
+                        const float u = __fadd_rn(mx_s[sp], A_s[sp * K + s]);
+                        if (u > v) { v = u; vi = sp; }
+                    }
+                }
+                for (int o = VL / 2; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(FULL_MASK, v, o);
+                    const int oi = __shfl_xor_sync(FULL_MASK, vi, o);
+                    if (ov > v || (ov == v && oi < vi)) { v = ov; vi = oi; }
+                }
+                if (s < K && l == 0) { V_s[s] = v; varg_s[s] = (vi < K) ? vi : -1; }
+            }
+            __syncthreads();
+        } else {
+            __syncthreads();                                             // (step 0 has no phases A / V: order the window slide before the table build)
         }
-        __syncthreads();
+        // ---- the table of step t+1 (threads without a cell), beside phase B ----
+        if (t + 1 < T) build_tab((t & 1) ? tab : tab2, (head + 1 == WR) ? 0 : head + 1);
         // ---- phase B: one thread per cell (s, d) ----
         for (int pr = tid; pr < KD; pr += blockDim.x) {
             const int s = pr / Dm, d = pr % Dm + 1;
@@ -187,7 +208,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
             if (te < T) {
                 float osum;
                 {
-                    const float *tb = tab + s * TABW;
+                    const float *tb = tabc + s * TABW;
                     if (p.sum_order == 0) {
                         const int q = d >> 2;
                         float p0 = tb[q * 4];
@@ -216,7 +237,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                         int bsp = sp_last;
                         for (int sp = 0; sp < sp_last; ++sp) {
                             if (sp == s) continue;
-                            if (__fadd_rn(__fadd_rn(U_s[sp * K + s], oseg), dsc) == best) { bsp = sp; break; }
+                            if (__fadd_rn(__fadd_rn(__fadd_rn(mx_s[sp], A_s[sp * K + s]), oseg), dsc) == best) { bsp = sp; break; }
                         }
                         const float a = A_s[bsp * K + s];
                         const float *pv = prev + bsp * Dm;
@@ -239,13 +260,6 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                 if (sc < 0) sc += R;
                 ring[(size_t)sc * KD + pr] = -INFINITY;
             }
-        }
-        // slide the frame window: frame t + Dm goes into the spare row (the one that held frame t - 1), which no thread reads during
-        // this step; the barrier below orders it before the next step's prefix table.  (Round 1 slid the window AFTER the barrier
-        // into a row the next step reads at once: a race that showed up as wrong paths at B = 128.)
-        {
-            const int spare = (head == 0) ? WR - 1 : head - 1;
-            for (int s = tid; s < K; s += blockDim.x) win[spare * K + s] = (t + Dm < T) ? f[(size_t)(t + Dm) * K + s] : 0.f;
         }
         __syncthreads();
         if (++head == WR) head = 0;
@@ -275,6 +289,269 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
                 t = st0 - 1; cs = ns; cd = nd;
             } else break;
         }
+    }
+}
+
+// Second form of the same recursion: ONE block barrier per frame instead of four.
+//   * Mx[s'] = max_d' delta[t-1][s'][d'] (and its first arg-max) is not reduced from the ring at step t: the cell (s, d) of step t'
+//     writes its value into slot te = t' + d - 1 AND folds it into a running maximum of (te, s).  The candidates of a (te, s) arrive in
+//     the order d = Dmax .. 1, one per step, from one thread each, so "replace when >=" leaves the maximum with the smallest d.
+//   * V[s] = max_{s' != s} fl(Mx[s'] + logA[s'][s]) is recomputed by every cell of the state (K adds) instead of a phase of its own.
+//   * the prefix table of step t+1 and the incoming frame of the window are prepared during step t by threads that own no cell.
+// Same additions in the same order as hsmm_viterbi_kernel: scores and backpointers are bit-identical.
+// KT / DT: compile-time K and max_duration for the shape worth specialising (0 = run-time).  The cell's searches -- V[s], then the FIRST s'
+// and the FIRST d' whose own total rounds to the cell's value -- are then straight-line code over registers (all candidates evaluated
+// with independent loads and adds, the first match picked by a descending select chain) instead of data-dependent loops of
+// load -> add -> add -> add -> compare round trips, which were nine tenths of a step.
+constexpr int HS_TB_W = 64;                     // frames of backpointer rows staged per traceback round
+template <int KT, int DT>
+__global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
+    extern __shared__ __align__(16) float smem_h[];
+    const int K = KT > 0 ? KT : p.K, Dm = DT > 0 ? DT : p.Dm, T = p.T;
+    const int KD = K * Dm, R = Dm + 2;          // slots t-2 (being cleared), t-1 (read) and t .. t+Dm-1 (written) are distinct
+    const int NQ = Dm / 4 + 1;
+    const int TABW = (p.sum_order == 0) ? NQ * 4 : Dm + 1;
+    const int WR = Dm + 2;                      // window rows: frames t .. t+Dm are live at step t, frame t+Dm+1 lands in the free row
+    float *ring = smem_h;                       // [R][K][Dm]   delta for segments ending at te, slot te % R
+    float *mr = ring + (size_t)R * KD;          // [R][K]       running max_d' of the slot
+    int *ar = reinterpret_cast<int *>(mr + R * K);          // [R][K]  its first arg-max d' (0-based)
+    float *A_s = reinterpret_cast<float *>(ar + R * K);     // [K][K]
+    float *dur_s = A_s + K * K;                 // [K][Dm]
+    float *win = dur_s + KD;                    // [WR][K]      frames of f (ring, row `head` = frame t)
+    float *tab = win + (size_t)WR * K;          // [2][K][TABW] prefix sums of the frame window in the reference's order
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float *f = p.f + (size_t)b * T * K;
+    uint8_t *ps = p.psi_s + (size_t)b * T * KD;
+    uint8_t *pd = p.psi_d + (size_t)b * T * KD;
+
+    for (int i = tid; i < R * KD; i += blockDim.x) ring[i] = -INFINITY;
+    for (int i = tid; i < R * K; i += blockDim.x) { mr[i] = -INFINITY; ar[i] = 0; }
+    for (int i = tid; i < K * K; i += blockDim.x) A_s[i] = p.logA[i];
+    for (int i = tid; i < KD; i += blockDim.x) dur_s[i] = p.logdur[i];
+    for (int i = tid; i < WR * K; i += blockDim.x) {                    // frames 0 .. Dm (the free row is filled during step 0)
+        const int fr = i / K, s = i % K;
+        win[i] = (fr <= Dm && fr < T) ? f[(size_t)fr * K + s] : 0.f;
+    }
+    __syncthreads();
+    auto build_tab = [&](float *tbuf, int first_row) {                  // window rows first_row .. first_row + Dm - 1
+        for (int s = blockDim.x - 1 - tid; s < K; s += blockDim.x) {   // the LAST threads of the block
+            int r = first_row;
+            float *tb = tbuf + s * TABW;
+            if (p.sum_order == 0) {
+                float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+                tb[0] = 0.f; tb[1] = 0.f; tb[2] = 0.f; tb[3] = 0.f;
+                for (int q = 1; q < NQ; ++q) {
+                    float x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { x[j] = win[r * K + s]; if (++r == WR) r = 0; }
+                    p0 = __fadd_rn(p0, x[0]); p1 = __fadd_rn(p1, x[1]); p2 = __fadd_rn(p2, x[2]); p3 = __fadd_rn(p3, x[3]);
+                    tb[q * 4 + 0] = p0; tb[q * 4 + 1] = p1; tb[q * 4 + 2] = p2; tb[q * 4 + 3] = p3;
+                }
+            } else {
+                float a = 0.f;
+                tb[0] = 0.f;
+                for (int d = 1; d <= Dm; ++d) { a = __fadd_rn(a, win[r * K + s]); if (++r == WR) r = 0; tb[d] = a; }
+            }
+        }
+    };
+    float *tab2 = tab + (size_t)K * TABW;
+    build_tab(tab, 0);
+    // the frame that enters the window at step t (frame t + Dm + 1) is loaded one step ahead into a register, so that the load is in
+    // flight across the barrier instead of being waited for before it
+    const int fs = blockDim.x - 1 - tid - K;                            // the K threads below the table builders
+    float incoming = (fs >= 0 && fs < K && Dm + 1 < T) ? f[(size_t)(Dm + 1) * K + fs] : 0.f;
+    __syncthreads();
+
+    int head = 0, slot_prev = R - 1, slot_t = 0;
+    for (int t = 0; t < T; ++t) {
+        const float *prev = ring + (size_t)slot_prev * KD;              // segments ending at t-1
+        const float *mxp = mr + slot_prev * K;
+        const int *agp = ar + slot_prev * K;
+        const float *tabc = (t & 1) ? tab2 : tab;
+        if (fs >= 0 && fs < K) {                                        // window: frame t + Dm + 1 into the row that held frame t - 1
+            int row = head + Dm + 1;
+            if (row >= WR) row -= WR;
+            win[row * K + fs] = incoming;
+            incoming = (t + Dm + 2 < T) ? f[(size_t)(t + Dm + 2) * K + fs] : 0.f;
+        }
+        if (t + 1 < T) build_tab((t & 1) ? tab : tab2, (head + 1 == WR) ? 0 : head + 1);
+        for (int pr = tid; pr < KD; pr += blockDim.x) {
+            const int s = pr / Dm, d = pr % Dm + 1;
+            const int te = t + d - 1;
+            if (te < T) {
+                float osum;
+                {
+                    const float *tb = tabc + s * TABW;
+                    if (p.sum_order == 0) {
+                        const int q = d >> 2;
+                        float p0 = tb[q * 4];
+                        int r = head + 4 * q;
+                        if (r >= WR) r -= WR;
+                        for (int i = 4 * q; i < d; ++i) { p0 = __fadd_rn(p0, win[r * K + s]); if (++r == WR) r = 0; }
+                        p0 = __fadd_rn(p0, tb[q * 4 + 1]);
+                        p0 = __fadd_rn(p0, tb[q * 4 + 2]);
+                        osum = __fadd_rn(p0, tb[q * 4 + 3]);
+                    } else {
+                        osum = tb[d];
+                    }
+                }
+                const float oseg = p.segc ? __fadd_rn(p.segc[s], osum) : osum;
+                const float dsc = dur_s[s * Dm + d - 1];
+                float best;
+                int bs = 0, bd = 1;
+                if (t == 0) {
+                    best = p.logpi ? __fadd_rn(__fadd_rn(p.logpi[s], oseg), dsc) : __fadd_rn(oseg, dsc);
+                } else {
+                    // V[s] = max_{s' != s} fl(Mx[s'] + logA[s'][s]); fp32 rounding is monotone, so the maximum over all (s', d') is the
+                    // cell's map applied to V[s].  The reference's winner is the FIRST (s', d') in lexicographic order whose own total
+                    // equals that value: the first s' whose Mx does, and within it the first d' (Mx[s'] itself certainly does).
+                    if constexpr (KT > 0 && DT > 0 && DT % 4 == 0) {
+                        float u[KT];
+#pragma unroll
+                        for (int sp = 0; sp < KT; ++sp) u[sp] = (sp == s) ? -INFINITY : __fadd_rn(mxp[sp], A_s[sp * KT + s]);
+                        float v = u[0];
+#pragma unroll
+                        for (int sp = 1; sp < KT; ++sp) v = fmaxf(v, u[sp]);
+                        best = __fadd_rn(__fadd_rn(v, oseg), dsc);
+                        if (best > -INFINITY) {
+                            int bsp = 0;
+#pragma unroll
+                            for (int sp = KT - 1; sp >= 0; --sp)
+                                if (__fadd_rn(__fadd_rn(u[sp], oseg), dsc) == best) bsp = sp;
+                            const float a = A_s[bsp * KT + s];
+                            const float4 *pv4 = reinterpret_cast<const float4 *>(prev + bsp * DT);
+                            float pvv[DT];
+#pragma unroll
+                            for (int i4 = 0; i4 < DT / 4; ++i4) {
+                                const float4 q4 = pv4[i4];
+                                pvv[4 * i4] = q4.x; pvv[4 * i4 + 1] = q4.y; pvv[4 * i4 + 2] = q4.z; pvv[4 * i4 + 3] = q4.w;
+                            }
+                            int bdp = 0;
+#pragma unroll
+                            for (int dp = DT - 1; dp >= 0; --dp)
+                                if (__fadd_rn(__fadd_rn(__fadd_rn(pvv[dp], a), oseg), dsc) == best) bdp = dp;
+                            bs = bsp; bd = bdp + 1;
+                        }
+                    } else {
+                        float v = -INFINITY;
+                        int vi = -1;
+                        for (int sp = 0; sp < K; ++sp) {
+                            if (sp == s) continue;
+                            const float u = __fadd_rn(mxp[sp], A_s[sp * K + s]);
+                            if (u > v) { v = u; vi = sp; }
+                        }
+                        best = __fadd_rn(__fadd_rn(v, oseg), dsc);
+                        if (best > -INFINITY) {
+                            int bsp = vi;
+                            for (int sp = 0; sp < vi; ++sp) {
+                                if (sp == s) continue;
+                                if (__fadd_rn(__fadd_rn(__fadd_rn(mxp[sp], A_s[sp * K + s]), oseg), dsc) == best) { bsp = sp; break; }
+                            }
+                            const float a = A_s[bsp * K + s];
+                            const float *pv = prev + bsp * Dm;
+                            const int last = agp[bsp];
+                            int dp = 0;
+                            for (; dp < last; ++dp)
+                                if (__fadd_rn(__fadd_rn(__fadd_rn(pv[dp], a), oseg), dsc) == best) break;
+                            bs = bsp; bd = dp + 1;
+                        }
+                    }
+                }
+                int slot = slot_t + d - 1;
+                if (slot >= R) slot -= R;
+                ring[(size_t)slot * KD + s * Dm + d - 1] = best;
+                // running maximum of (te, s): this step's only candidate for it; ">=" so that the smallest d wins ties
+                if (best >= mr[slot * K + s]) { mr[slot * K + s] = best; ar[slot * K + s] = d - 1; }
+                ps[(size_t)t * KD + pr] = (uint8_t)bs;
+                pd[(size_t)t * KD + pr] = (uint8_t)bd;
+            }
+            if (t >= 2) {                                                // slot t-2 has been fully consumed by the previous step
+                int sc = slot_t - 2;
+                if (sc < 0) sc += R;
+                ring[(size_t)sc * KD + pr] = -INFINITY;
+                if (pr < K) { mr[sc * K + pr] = -INFINITY; ar[sc * K + pr] = 0; }
+            }
+        }
+        __syncthreads();
+        if (++head == WR) head = 0;
+        slot_prev = slot_t;
+        if (++slot_t == R) slot_t = 0;
+    }
+
+    // ---- traceback.  The chain of backpointers is serial (one hop per segment) and every hop used to be a dependent global load
+    // (~0.8 us: 1.5 ms for 2000 one-frame segments).  The hops move monotonically back in time, so the backpointer rows are staged
+    // HS_TB_W frames at a time in shared memory by the whole block (one contiguous copy) and one thread walks inside the staged
+    // rows; the path is collected in shared memory and written out by all threads.
+    __shared__ int tb_state[4];                                         // t, state, duration, final-score bits
+    const int tb_al = 16 / ((KD % 16 == 0) ? 16 : ((KD % 8 == 0) ? 8 : ((KD % 4 == 0) ? 4 : ((KD % 2 == 0) ? 2 : 1))));
+    const size_t stage_rows = (size_t)((HS_TB_W + 16) * KD + 15) & ~(size_t)15;
+    uint8_t *stage_s = reinterpret_cast<uint8_t *>(smem_h);             // [HS_TB_W + 16][KD]  predecessor states   (the DP tables are dead)
+    uint8_t *stage_d = stage_s + stage_rows;                            // [HS_TB_W + 16][KD]  predecessor durations
+    uint8_t *path = stage_d + stage_rows;                               // [T]
+    if (tid < 32) {
+        const float *last = ring + (size_t)((T - 1) % R) * KD;
+        float best = -INFINITY;
+        int bi = KD;                                                    // first cell (s-major, then d) attaining the maximum
+        for (int i = tid; i < KD; i += 32) { const float v = last[i]; if (v > best) { best = v; bi = i; } }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(FULL_MASK, best, o);
+            const int oi = __shfl_xor_sync(FULL_MASK, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (tid == 0) {
+            if (bi >= KD) bi = 0;                                       // everything -inf: the reference's (state 0, duration 1)
+            tb_state[0] = T - 1; tb_state[1] = bi / Dm; tb_state[2] = bi % Dm + 1;
+            if (p.score) p.score[b] = best;
+        }
+    }
+    __syncthreads();                                                    // (also: every thread is done with the ring before it is overwritten)
+    while (true) {
+        const int t = tb_state[0];
+        if (t < 0) break;
+        // the next backpointer row to be read is the start frame of the current segment; stage rows [lo, hi] = the HS_TB_W rows up to it
+        const int cd0 = tb_state[2];
+        const int hi = max(t - cd0 + 1, 0);
+        int lo = max(hi - HS_TB_W + 1, 0);
+        lo -= lo % tb_al;                                               // row lo starts on a 16-byte boundary (vector copies)
+        {
+            const size_t nbytes = (size_t)(hi - lo + 1) * KD;
+            const uint8_t *gs = ps + (size_t)lo * KD, *gd = pd + (size_t)lo * KD;
+            if ((((uintptr_t)gs | (uintptr_t)gd) & 15) == 0) {
+                const size_t n16 = nbytes / 16;
+                for (size_t i = tid; i < n16; i += blockDim.x) {
+                    reinterpret_cast<uint4 *>(stage_s)[i] = reinterpret_cast<const uint4 *>(gs)[i];
+                    reinterpret_cast<uint4 *>(stage_d)[i] = reinterpret_cast<const uint4 *>(gd)[i];
+                }
+                for (size_t i = n16 * 16 + tid; i < nbytes; i += blockDim.x) { stage_s[i] = gs[i]; stage_d[i] = gd[i]; }
+            } else {
+                for (size_t i = tid; i < nbytes; i += blockDim.x) { stage_s[i] = gs[i]; stage_d[i] = gd[i]; }
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tt = t, cs = tb_state[1], cd = cd0;
+            while (tt >= 0) {
+                int st0 = tt - cd + 1;
+                if (st0 < 0) st0 = 0;
+                if (st0 > 0 && st0 < lo) break;                         // its backpointer row is not staged: next round
+                for (int u = st0; u <= tt; ++u) path[u] = (uint8_t)cs;
+                if (st0 > 0) {
+                    const size_t o = (size_t)(st0 - lo) * KD + cs * Dm + cd - 1;
+                    const int ns = stage_s[o], nd = stage_d[o];
+                    tt = st0 - 1; cs = ns; cd = nd;
+                } else {
+                    tt = -1;
+                }
+            }
+            tb_state[0] = tt; tb_state[1] = cs; tb_state[2] = cd;
+        }
+        __syncthreads();
+    }
+    {
+        int64_t *st = p.states + (size_t)b * T;
+        for (int u = tid; u < T; u += blockDim.x) st[u] = (int64_t)path[u];
     }
 }
 
@@ -631,7 +908,7 @@ HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float
     const size_t need = hmmb200_hsmm_viterbi_workspace_bytes(B, T, K, Dm);
     if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "hsmm_viterbi: workspace %zu < %zu", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
-    const size_t smem = ((size_t)(Dm + 2) * K * Dm + 2 * (size_t)K * K + (size_t)2 * K * Dm + 5 * (size_t)K + (size_t)K * (Dm + 8)) * sizeof(float);
+    const size_t smem = ((size_t)(Dm + 2) * K * Dm + 2 * (size_t)K * K + (size_t)2 * K * Dm + 5 * (size_t)K + 2 * (size_t)K * (Dm + 8)) * sizeof(float);
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "hsmm_viterbi: K=%d, max_duration=%d need %zu bytes of shared memory", K, Dm, smem);
     cudaError_t e = cudaFuncSetAttribute(hsmm_viterbi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_viterbi smem opt-in: %s", cudaGetErrorString(e));
@@ -641,6 +918,25 @@ HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float
     p.psi_s = (uint8_t *)workspace; p.psi_d = (uint8_t *)workspace + (size_t)B * T * K * Dm;
     int threads = ((K * Dm + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
+    // one-barrier form: needs 2 K threads beside the cells (table builders, window feeders) and its own shared-memory layout
+    const int R = Dm + 2;
+    size_t smem2 = ((size_t)R * K * Dm + 2 * (size_t)R * K + (size_t)K * K + (size_t)K * Dm + (size_t)(Dm + 2) * K + 2 * (size_t)K * (Dm + 8)) * sizeof(float);
+    const size_t smem_tb = 2 * ((size_t)(HS_TB_W + 16) * K * Dm + 16) + (size_t)T + 64;       // traceback staging (reuses the DP tables' space)
+    if (smem_tb > smem2) smem2 = smem_tb;
+    int threads2 = ((K * Dm + 2 * K + 31) / 32) * 32;
+    bool v1 = threads2 > 1024 || smem2 > 200 * 1024;
+#ifdef HMMB200_DEBUG_HOOKS
+    if (getenv("HMMB200_HSMM_VIT_V1")) v1 = true;
+#endif
+    if (!v1) {
+        const bool spec = (K == 10 && Dm == 20);                // BASELINE config 4 (the reference factory's HSMM defaults)
+        e = spec ? cudaFuncSetAttribute(hsmm_viterbi2_kernel<10, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2)
+                 : cudaFuncSetAttribute(hsmm_viterbi2_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+        if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "hsmm_viterbi smem opt-in: %s", cudaGetErrorString(e));
+        if (spec) hsmm_viterbi2_kernel<10, 20><<<B, threads2, smem2, (cudaStream_t)stream>>>(p);
+        else hsmm_viterbi2_kernel<0, 0><<<B, threads2, smem2, (cudaStream_t)stream>>>(p);
+        return check_launch("hsmm_viterbi2_kernel");
+    }
     hsmm_viterbi_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(p);
     return check_launch("hsmm_viterbi_kernel");
 }
