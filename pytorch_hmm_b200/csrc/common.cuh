@@ -52,4 +52,9 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
 int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
                    int B, int T, int K, float *delta, void *psi, int64_t *states, float *score, void *workspace, cudaStream_t s);
 
+int largek_fb_viterbi(const float *emis, int fb_mode, int vit_mode, float floor_eps, int add_rowmax, const float *trans_prob,
+                      const float *init_prob, const float *log_trans, const float *log_init, int B, int T, int K,
+                      float *gamma, float *fwd_prob, float *bwd_prob, float *log_alpha, float *log_beta, float *loglik,
+                      float *delta, void *psi, int64_t *states, float *score, void *fb_workspace, void *vit_workspace, cudaStream_t s);
+
 }  // namespace hmmb200

@@ -192,7 +192,13 @@ HMMB200_EXPORT int hmmb200_fb_viterbi_f32(const float *emis, int fb_mode, int vi
             return HMMB200_OK;
         }
     }
-    // shapes the fused kernel does not take (K > 32, or backpointers that do not fit beside the sweeps): the two stand-alone passes
+    if (K > 32) {
+        if (!largek_shape_ok(K)) return set_error(HMMB200_EUNSUPPORTED, "fb_viterbi: K <= 512 states supported (got %d)", K);
+        return largek_fb_viterbi(emis, fb_mode, vit_mode, floor_eps, add_rowmax, trans_prob, init_prob, log_trans, log_init, B, T, K,
+                                 gamma, fwd_prob, bwd_prob, log_alpha, log_beta, loglik, delta, psi, states, score,
+                                 w, w + align256(fb_bytes), s);
+    }
+    // shapes the fused kernel does not take (backpointers that do not fit beside the sweeps): the two stand-alone passes
     if (int rc = hmmb200_forward_backward_f32(emis, fb_mode, floor_eps, add_rowmax, trans_prob, init_prob, B, T, K, gamma, fwd_prob,
                                               bwd_prob, log_alpha, log_beta, loglik, w, fb_bytes, stream)) return rc;
     return hmmb200_viterbi_f32(emis, vit_mode, floor_eps, log_trans, log_init, B, T, K, delta, psi, states, score,

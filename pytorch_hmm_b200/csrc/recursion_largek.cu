@@ -38,7 +38,7 @@ namespace cg = cooperative_groups;
 namespace hmmb200 {
 
 constexpr int LK_NSQ_MAX = 4;                   // sequences per group: 4, or 3 when that spreads one wave of clusters over more SMs
-constexpr int LK_NG = 2;                        // independent sequence groups per cluster (software-pipelined)
+constexpr int LK_NG = 4;                        // independent sequence groups per cluster at most (software-pipelined); LkParams::ngr are used
 constexpr int LK_NC = 64;                       // output states per CTA
 constexpr int LK_KS = 64;                       // source states per compute warp (k-slice) = one CTA's block of the vector
 constexpr int LK_NWC = 8;                       // compute warps per CTA (warps 0-7); warps 8-15 are the final warps
@@ -67,6 +67,7 @@ struct LkParams {
     const float *init;     // [K]    fb: probabilities; viterbi: log
     const float *rowmax;   // [B,T] per-frame max of the log-emissions (LOG emission modes) or null
     int B, T, K, CS;
+    int ngr;               // sequence groups per cluster in this launch (2 for a sweep on its own; more when several sweeps share the GPU)
     float *ws_a, *ws_b;    // [B,T,K] scaled alpha / beta (fb)
     float *ws_la, *ws_lb;  // [B,T]
     float *loglik;         // [B] or null
@@ -164,7 +165,7 @@ __device__ __forceinline__ void lk_bar_sync(int id, int n) { asm volatile("bar.s
 __device__ __forceinline__ void lk_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <int MODE, int NSQ>
-__global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
+__device__ __forceinline__ void lk_sweep_body(const LkParams &p, const int cluster_id) {
     extern __shared__ __align__(16) uint8_t lk_smem_raw[];
     LkSmem<NSQ> &sm = *reinterpret_cast<LkSmem<NSQ> *>(lk_smem_raw);
     constexpr bool VIT = (MODE == LK_VIT);
@@ -173,11 +174,10 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     const int K = p.K, T = p.T, B = p.B, CS = p.CS;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int cluster_id = blockIdx.x / CS;
-    const int seq0 = cluster_id * (NSQ * LK_NG);
+    const int seq0 = cluster_id * (NSQ * p.ngr);
     const int col0 = rank * LK_NC;
     const float PADV = VIT ? -INFINITY : 0.f;
-    const int n_groups = min(LK_NG, (B - seq0 + NSQ - 1) / NSQ);   // groups of this cluster that hold sequences
+    const int n_groups = min(p.ngr, (B - seq0 + NSQ - 1) / NSQ);   // groups of this cluster that hold sequences
 
     for (int i = tid; i < LK_NG * 2 * LK_CSMAX * NSQ * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
     for (int i = tid; i < LK_NG * 2 * NSQ * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
@@ -223,9 +223,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
         const bool active = warp < CS;                       // source states 64w.. exist
         for (int t = 0; t < T; ++t) {
             const int cur = t & 1, prv = cur ^ 1;
-#pragma unroll
-            for (int g = 0; g < LK_NG; ++g) {
-                if (g >= n_groups) continue;
+#pragma unroll 1                                             // (one copy of the product code: the groups differ by shared-memory offsets only)
+            for (int g = 0; g < n_groups; ++g) {
                 LK_TRACE(0);
                 if (t == 0) continue;                        // step 0 has no product (and was armed at set-up)
                 if (tid == 0) lk_mbar_expect_tx(&sm.bar[g][cur], tx_bytes);
@@ -310,7 +309,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
             lk_cp_commit();
         };
         for (int t = 0; t < LK_PF - 1; ++t) prefetch(t);
-        int ksum_g[LK_NG] = {0, 0};                          // running power-of-two exponent per group
+        int ks0 = 0, ks1 = 0, ks2 = 0, ks3 = 0;              // running power-of-two exponent per group (scalars: the group loop is rolled)
+        static_assert(LK_NG == 4, "four exponent scalars");
         float *ws_l = (DIR == 0) ? p.ws_la : p.ws_lb;
 
         for (int t = 0; t < T; ++t) {
@@ -318,9 +318,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
             prefetch(t + LK_PF - 1);
             lk_cp_wait<LK_PF - 1>();                         // this step's emissions have landed (own slots only)
             const int f = frame_of(t);
-#pragma unroll
-            for (int g = 0; g < LK_NG; ++g) {
-                if (g >= n_groups) continue;
+#pragma unroll 1
+            for (int g = 0; g < n_groups; ++g) {
                 const int fseq = seq0 + g * NSQ + fs;
                 const bool f_ok = valid && fseq < B && gcol < K;
                 const float raw = sm.eraw[g][t % LK_PF][ft];
@@ -363,7 +362,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                             m = lk_fmax3(m, y.x, y.y);
                         }
                         const unsigned eb = __float_as_uint(m) >> 23;
-                        ksum_g[g] += (int)eb - 127;
+                        const int de = (int)eb - 127;
+                        if (g == 0) ks0 += de; else if (g == 1) ks1 += de; else if (g == 2) ks2 += de; else ks3 += de;
                         r = __uint_as_float((254u - eb) << 23);
                     }
                     pre = acc * r;                           // beta_t (scaled) for the backward sweep
@@ -406,7 +406,8 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
                     else if (DIR == 0) p.ws_a[o] = wv;
                     else p.ws_b[o] = pre;
                 }
-                if (!VIT && rank == 0 && fc == 0 && valid && fseq < B) ws_l[(size_t)fseq * T + f] = __int_as_float(ksum_g[g]);
+                if (!VIT && rank == 0 && fc == 0 && valid && fseq < B)
+                    ws_l[(size_t)fseq * T + f] = __int_as_float((g == 0) ? ks0 : ((g == 1) ? ks1 : ((g == 2) ? ks2 : ks3)));
             }
         }
     }
@@ -416,7 +417,7 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     for (int g = 0; g < LK_NG; ++g)
         if (g < n_groups && ok) ok = lk_mbar_wait(&sm.bar[g][(T - 1) & 1], ((T - 1) >> 1) & 1);
     __syncthreads();
-    if (MODE == LK_FWD && p.loglik != nullptr && rank == 0 && warp < LK_NG * NSQ) {
+    if (MODE == LK_FWD && p.loglik != nullptr && rank == 0 && warp < n_groups * NSQ) {
         const int g = warp / NSQ, s = warp % NSQ, sq = seq0 + warp;
         if (sq < B) {
             float tot = 0.f;
@@ -428,6 +429,24 @@ __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
     }
     if (!ok && p.err != nullptr) atomicExch(p.err, 1);
     cluster.sync();
+}
+
+template <int MODE, int NSQ>
+__global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
+    lk_sweep_body<MODE, NSQ>(p, (int)blockIdx.x / p.CS);
+}
+
+// Several sweeps of the same batch in ONE launch (forward + backward, or forward + backward + Viterbi): clusters [0, ncl) run the
+// forward sweep, [ncl, 2 ncl) the backward sweep, [2 ncl, 3 ncl) the Viterbi recursion.  A B200 holds 15 clusters of 8 CTAs; on its
+// own a sweep of B = 64 sequences takes 11 of them, so the sweeps of one call used to run one after another.  With more sequence
+// groups per cluster (LkParams::ngr) the sweeps fit side by side, and the FMA pipes the lone sweep left idle between exchanges are
+// used by the other groups.
+template <int NSQ>
+__global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_multi_kernel(LkParams pf, LkParams pb, LkParams pv, int ncl) {
+    const int c = (int)blockIdx.x / pf.CS;
+    if (c < ncl) lk_sweep_body<LK_FWD, NSQ>(pf, c);
+    else if (c < 2 * ncl) lk_sweep_body<LK_BWD, NSQ>(pb, c - ncl);
+    else lk_sweep_body<LK_VIT, NSQ>(pv, c - 2 * ncl);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -643,7 +662,7 @@ static int lk_max_clusters(int cs) {
     auto kern = lk_sweep_kernel<MODE, NSQ>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem<NSQ>));
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cs * 64), 1, 1);
+    cfg.gridDim = dim3((unsigned)(cs * 32), 1, 1);
     cfg.blockDim = dim3(LK_THREADS, 1, 1);
     cfg.dynamicSmemBytes = sizeof(LkSmem<NSQ>);
     cudaLaunchAttribute attr[1];
@@ -661,7 +680,7 @@ static int lk_launch_nsq(const LkParams &p, cudaStream_t s) {
     const size_t smem = sizeof(LkSmem<NSQ>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K smem opt-in: %s", cudaGetErrorString(e));
-    const int n_clusters = (p.B + NSQ * LK_NG - 1) / (NSQ * LK_NG);
+    const int n_clusters = (p.B + NSQ * p.ngr - 1) / (NSQ * p.ngr);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_clusters * p.CS), 1, 1);
     cfg.blockDim = dim3(LK_THREADS, 1, 1);
@@ -691,9 +710,51 @@ __global__ void lk_poison_kernel(const int *err, int B, int T, float *loglik, fl
     }
 }
 
+template <int NSQ>
+static int lk_launch_multi_nsq(const LkParams &pf, const LkParams &pb, const LkParams &pv, int n_modes, cudaStream_t s) {
+    auto kern = lk_sweep_multi_kernel<NSQ>;
+    const size_t smem = sizeof(LkSmem<NSQ>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K smem opt-in: %s", cudaGetErrorString(e));
+    const int ncl = (pf.B + NSQ * pf.ngr - 1) / (NSQ * pf.ngr);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_modes * ncl * pf.CS), 1, 1);
+    cfg.blockDim = dim3(LK_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)pf.CS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, pf, pb, pv, ncl);
+    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K multi-sweep launch: %s", cudaGetErrorString(e));
+    return check_launch("lk_sweep_multi_kernel");
+}
+
+// n_modes sweeps side by side: the smallest number of groups per cluster (then 3 sequences per group before 4) for which all their
+// clusters are co-resident.  Returns 1 when they do not fit (the caller launches the sweeps one after another).
+static int lk_launch_multi(LkParams pf, LkParams pb, LkParams pv, int n_modes, cudaStream_t s) {
+    const int maxc = lk_max_clusters<LK_FWD, 4>(pf.CS);
+#ifdef HMMB200_DEBUG_HOOKS
+    if (getenv("HMMB200_LK_NO_MULTI")) return 1;
+#endif
+    for (int ngr = 2; ngr <= LK_NG; ++ngr)
+        for (int nsq = 3; nsq <= 4; ++nsq) {
+            const int ncl = (pf.B + nsq * ngr - 1) / (nsq * ngr);
+            if (n_modes * ncl > maxc) continue;
+            pf.ngr = pb.ngr = pv.ngr = ngr;
+            return (nsq == 3) ? lk_launch_multi_nsq<3>(pf, pb, pv, n_modes, s) : lk_launch_multi_nsq<4>(pf, pb, pv, n_modes, s);
+        }
+    return 1;
+}
+
 template <int MODE>
-static int lk_launch(const LkParams &p, cudaStream_t s) {
-    const int clusters3 = (p.B + 3 * LK_NG - 1) / (3 * LK_NG);
+static int lk_launch(LkParams p, cudaStream_t s) {
+    p.ngr = 2;
+    const int clusters3 = (p.B + 3 * p.ngr - 1) / (3 * p.ngr);
     bool three = clusters3 <= lk_max_clusters<MODE, 3>(p.CS);
 #ifdef HMMB200_DEBUG_HOOKS
     if (const char *f = getenv("HMMB200_LK_NSQ")) three = (f[0] == '3');   // debug builds can force either variant
@@ -702,19 +763,30 @@ static int lk_launch(const LkParams &p, cudaStream_t s) {
     return lk_launch_nsq<MODE, 4>(p, s);
 }
 
-int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, int add_rowmax, const float *trans_prob,
-                            const float *init_prob, int B, int T, int K, float *gamma, float *fwd_prob, float *bwd_prob,
-                            float *log_alpha, float *log_beta, float *loglik, void *workspace, cudaStream_t s) {
+// The two halves of a large-K call, split so that the sweeps of a forward-backward pass and of a Viterbi pass can share one launch:
+// *_prepare fills the sweep parameters and runs the small preparation kernels, *_finish turns the sweeps' raw outputs into results.
+struct LkFbCall {
+    LkParams p;            // forward sweep (the backward sweep is the same with loglik = null)
+    float *rowmax;
+    int add_m;
+    bool both;             // posteriors / backward values wanted: the backward sweep runs too
+    float *gamma, *fwd_prob, *bwd_prob, *log_alpha, *log_beta, *loglik;
+};
+
+static int lk_fb_prepare(LkFbCall &c, const float *emis, int emis_mode, float floor_eps, int add_rowmax, const float *trans_prob,
+                         const float *init_prob, int B, int T, int K, float *gamma, float *fwd_prob, float *bwd_prob,
+                         float *log_alpha, float *log_beta, float *loglik, void *workspace, cudaStream_t s) {
     const size_t n = (size_t)B * T;
     uint8_t *w = (uint8_t *)workspace;
-    LkParams p = {};
+    LkParams &p = c.p;
+    p = LkParams{};
     p.emis = emis; p.mode = emis_mode; p.eps = floor_eps; p.add_rowmax = add_rowmax;
-    p.trans = trans_prob; p.init = init_prob; p.B = B; p.T = T; p.K = K; p.CS = lk_cluster_size(K);
+    p.trans = trans_prob; p.init = init_prob; p.B = B; p.T = T; p.K = K; p.CS = lk_cluster_size(K); p.ngr = 2;
     p.ws_a = (float *)w;  w += lk_align256(n * K * sizeof(float));
     p.ws_b = (float *)w;  w += lk_align256(n * K * sizeof(float));
     p.ws_la = (float *)w; w += lk_align256(n * sizeof(float));
     p.ws_lb = (float *)w; w += lk_align256(n * sizeof(float));
-    float *rowmax = (float *)w; w += lk_align256(n * sizeof(float));
+    c.rowmax = (float *)w; w += lk_align256(n * sizeof(float));
     p.err = (int *)w;
     cudaMemsetAsync(p.err, 0, sizeof(int), s);
 #ifdef HMMB200_DEBUG_HOOKS
@@ -722,43 +794,57 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
 #endif
     p.loglik = loglik;
     if (emis_mode == HMMB200_EMIS_LOG || emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR) {
-        lk_rowmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(emis, (int64_t)n, K, rowmax);
+        lk_rowmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(emis, (int64_t)n, K, c.rowmax);
         if (int rc = check_launch("lk_rowmax_kernel")) return rc;
-        p.rowmax = rowmax;
+        p.rowmax = c.rowmax;
     }
-    const int add_m = (emis_mode == HMMB200_EMIS_LOG) || (emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR && add_rowmax);
-    if (int rc = lk_launch<LK_FWD>(p, s)) return rc;
-    lk_logscale_kernel<<<(unsigned)B, 32, 0, s>>>(p.ws_la, rowmax, T, 0, add_m, loglik);
+    c.add_m = (emis_mode == HMMB200_EMIS_LOG) || (emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR && add_rowmax);
+    c.both = gamma || fwd_prob || bwd_prob || log_alpha || log_beta;
+    c.gamma = gamma; c.fwd_prob = fwd_prob; c.bwd_prob = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta; c.loglik = loglik;
+    return HMMB200_OK;
+}
+
+static int lk_fb_finish(const LkFbCall &c, cudaStream_t s) {
+    const LkParams &p = c.p;
+    const size_t n = (size_t)p.B * p.T;
+    lk_logscale_kernel<<<(unsigned)p.B, 32, 0, s>>>(p.ws_la, c.rowmax, p.T, 0, c.add_m, c.loglik);
     if (int rc = check_launch("lk_logscale_kernel")) return rc;
-    if (gamma || fwd_prob || bwd_prob || log_alpha || log_beta) {
-        LkParams q = p;
-        q.loglik = nullptr;
-        if (int rc = lk_launch<LK_BWD>(q, s)) return rc;
-        lk_logscale_kernel<<<(unsigned)B, 32, 0, s>>>(p.ws_lb, rowmax, T, 1, add_m, nullptr);
+    if (c.both) {
+        lk_logscale_kernel<<<(unsigned)p.B, 32, 0, s>>>(p.ws_lb, c.rowmax, p.T, 1, c.add_m, nullptr);
         if (int rc = check_launch("lk_logscale_kernel")) return rc;
-        LkCombineParams c;
-        c.ws_a = p.ws_a; c.ws_b = p.ws_b; c.ws_la = p.ws_la; c.ws_lb = p.ws_lb; c.n_frames = (int64_t)n; c.K = K;
-        c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
-        lk_combine_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(c);
+        LkCombineParams cc;
+        cc.ws_a = p.ws_a; cc.ws_b = p.ws_b; cc.ws_la = p.ws_la; cc.ws_lb = p.ws_lb; cc.n_frames = (int64_t)n; cc.K = p.K;
+        cc.gamma = c.gamma; cc.fwd = c.fwd_prob; cc.bwd = c.bwd_prob; cc.log_alpha = c.log_alpha; cc.log_beta = c.log_beta;
+        lk_combine_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(cc);
         if (int rc = check_launch("lk_combine_kernel")) return rc;
     }
-    if (loglik != nullptr) {
-        lk_poison_kernel<<<1, 256, 0, s>>>(p.err, B, T, loglik, nullptr, nullptr);
+    if (c.loglik != nullptr) {
+        lk_poison_kernel<<<1, 256, 0, s>>>(p.err, p.B, p.T, c.loglik, nullptr, nullptr);
         if (int rc = check_launch("lk_poison_kernel")) return rc;
     }
     return HMMB200_OK;
 }
 
-int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
-                   int B, int T, int K, float *delta, void *psi, int64_t *states, float *score, void *workspace, cudaStream_t s) {
+struct LkVitCall {
+    LkParams p;
+    float *logPT;
+    const float *log_trans;
+    void *psi;
+    int64_t *states;
+    float *score;
+};
+
+static int lk_vit_prepare(LkVitCall &c, const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
+                          int B, int T, int K, float *delta, void *psi, int64_t *states, float *score, void *workspace, cudaStream_t s) {
     const size_t n = (size_t)B * T;
     uint8_t *w = (uint8_t *)workspace;
     float *ws_delta = (float *)w; w += lk_align256(n * K * sizeof(float));
-    float *logPT = (float *)w;    w += lk_align256((size_t)K * K * sizeof(float));
+    c.logPT = (float *)w;         w += lk_align256((size_t)K * K * sizeof(float));
     float *rowmax = (float *)w;   w += lk_align256(n * sizeof(float));
-    LkParams p = {};
+    LkParams &p = c.p;
+    p = LkParams{};
     p.emis = emis; p.mode = emis_mode; p.eps = floor_eps; p.trans = log_trans; p.init = log_init;
-    p.B = B; p.T = T; p.K = K; p.CS = lk_cluster_size(K);
+    p.B = B; p.T = T; p.K = K; p.CS = lk_cluster_size(K); p.ngr = 2;
     p.delta = delta ? delta : ws_delta;
     p.err = (int *)w;
     cudaMemsetAsync(p.err, 0, sizeof(int), s);
@@ -767,20 +853,80 @@ int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const floa
         if (int rc = check_launch("lk_rowmax_kernel")) return rc;
         p.rowmax = rowmax;
     }
-    lk_transpose_kernel<<<(K * K + 255) / 256, 256, 0, s>>>(log_trans, K, logPT);
+    lk_transpose_kernel<<<(K * K + 255) / 256, 256, 0, s>>>(log_trans, K, c.logPT);
     if (int rc = check_launch("lk_transpose_kernel")) return rc;
-    if (int rc = lk_launch<LK_VIT>(p, s)) return rc;
-    lk_traceback_kernel<<<(B + 3) / 4, 128, 0, s>>>(p.delta, logPT, B, T, K, states, score);
+    c.log_trans = log_trans; c.psi = psi; c.states = states; c.score = score;
+    return HMMB200_OK;
+}
+
+static int lk_vit_finish(const LkVitCall &c, cudaStream_t s) {
+    const LkParams &p = c.p;
+    const size_t n = (size_t)p.B * p.T;
+    const int B = p.B, T = p.T, K = p.K;
+    lk_traceback_kernel<<<(B + 3) / 4, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
     if (int rc = check_launch("lk_traceback_kernel")) return rc;
-    if (psi != nullptr) {
+    if (c.psi != nullptr) {
         const int64_t n_warps = (int64_t)n * ((K + 31) / 32);
         const unsigned blocks = (unsigned)((n_warps + 7) / 8);
-        if (K <= 256) lk_psi_kernel<uint8_t><<<blocks, 256, 0, s>>>(p.delta, log_trans, B, T, K, (uint8_t *)psi);
-        else lk_psi_kernel<uint16_t><<<blocks, 256, 0, s>>>(p.delta, log_trans, B, T, K, (uint16_t *)psi);
+        if (K <= 256) lk_psi_kernel<uint8_t><<<blocks, 256, 0, s>>>(p.delta, c.log_trans, B, T, K, (uint8_t *)c.psi);
+        else lk_psi_kernel<uint16_t><<<blocks, 256, 0, s>>>(p.delta, c.log_trans, B, T, K, (uint16_t *)c.psi);
         if (int rc = check_launch("lk_psi_kernel")) return rc;
     }
-    lk_poison_kernel<<<1, 256, 0, s>>>(p.err, B, T, nullptr, score, states);
+    lk_poison_kernel<<<1, 256, 0, s>>>(p.err, B, T, nullptr, c.score, c.states);
     return check_launch("lk_poison_kernel");
+}
+
+int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, int add_rowmax, const float *trans_prob,
+                            const float *init_prob, int B, int T, int K, float *gamma, float *fwd_prob, float *bwd_prob,
+                            float *log_alpha, float *log_beta, float *loglik, void *workspace, cudaStream_t s) {
+    LkFbCall c;
+    if (int rc = lk_fb_prepare(c, emis, emis_mode, floor_eps, add_rowmax, trans_prob, init_prob, B, T, K, gamma, fwd_prob, bwd_prob,
+                               log_alpha, log_beta, loglik, workspace, s)) return rc;
+    LkParams q = c.p;
+    q.loglik = nullptr;
+    int rc = c.both ? lk_launch_multi(c.p, q, q, 2, s) : 1;    // forward and backward side by side when their clusters fit
+    if (rc < 0) return rc;
+    if (rc == 1) {
+        if (int r2 = lk_launch<LK_FWD>(c.p, s)) return r2;
+        if (c.both) if (int r2 = lk_launch<LK_BWD>(q, s)) return r2;
+    }
+    return lk_fb_finish(c, s);
+}
+
+int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const float *log_trans, const float *log_init,
+                   int B, int T, int K, float *delta, void *psi, int64_t *states, float *score, void *workspace, cudaStream_t s) {
+    LkVitCall c;
+    if (int rc = lk_vit_prepare(c, emis, emis_mode, floor_eps, log_trans, log_init, B, T, K, delta, psi, states, score, workspace, s)) return rc;
+    if (int rc = lk_launch<LK_VIT>(c.p, s)) return rc;
+    return lk_vit_finish(c, s);
+}
+
+// forward + backward + Viterbi of the same batch: the three sweeps in one launch when their clusters are co-resident
+// (fb_workspace / vit_workspace: the two calls' own workspaces)
+int largek_fb_viterbi(const float *emis, int fb_mode, int vit_mode, float floor_eps, int add_rowmax, const float *trans_prob,
+                      const float *init_prob, const float *log_trans, const float *log_init, int B, int T, int K,
+                      float *gamma, float *fwd_prob, float *bwd_prob, float *log_alpha, float *log_beta, float *loglik,
+                      float *delta, void *psi, int64_t *states, float *score, void *fb_workspace, void *vit_workspace, cudaStream_t s) {
+    LkFbCall f;
+    LkVitCall v;
+    if (int rc = lk_fb_prepare(f, emis, fb_mode, floor_eps, add_rowmax, trans_prob, init_prob, B, T, K, gamma, fwd_prob, bwd_prob,
+                               log_alpha, log_beta, loglik, fb_workspace, s)) return rc;
+    if (int rc = lk_vit_prepare(v, emis, vit_mode, floor_eps, log_trans, log_init, B, T, K, delta, psi, states, score, vit_workspace, s)) return rc;
+    LkParams q = f.p;
+    q.loglik = nullptr;
+    int rc = f.both ? lk_launch_multi(f.p, q, v.p, 3, s) : 1;
+    if (rc < 0) return rc;
+    if (rc == 1) {                                               // not co-resident: forward + backward together if possible, then Viterbi
+        int r2 = f.both ? lk_launch_multi(f.p, q, q, 2, s) : 1;
+        if (r2 < 0) return r2;
+        if (r2 == 1) {
+            if (int r3 = lk_launch<LK_FWD>(f.p, s)) return r3;
+            if (f.both) if (int r3 = lk_launch<LK_BWD>(q, s)) return r3;
+        }
+        if (int r3 = lk_launch<LK_VIT>(v.p, s)) return r3;
+    }
+    if (int r4 = lk_fb_finish(f, s)) return r4;
+    return lk_vit_finish(v, s);
 }
 
 }  // namespace hmmb200

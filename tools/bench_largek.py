@@ -43,8 +43,20 @@ def main():
         e.record(); e.synchronize()
         return s.elapsed_time(e) / a.iters
 
-    res = {"K": a.K, "B": a.B, "T": a.T, "forward_only_ms": ms(lambda: fb(())), "forward_backward_ms": ms(fb), "viterbi_ms": ms(vit)}
-    res["frames_per_s_fb_plus_viterbi"] = a.B * a.T / ((res["forward_backward_ms"] + res["viterbi_ms"]) * 1e-3)
+    fused_out = dict(fb_out); fused_out.update(v_out)
+    fused_ws = torch.empty(hm._lib.load().hmmb200_fb_viterbi_workspace_bytes(a.B, a.T, a.K), dtype=torch.uint8, device=dev)
+
+    def fused():                                                  # the three sweeps in one launch (csrc/recursion_largek.cu)
+        hm.ops.forward_backward_viterbi(obs, hm.ops.EMIS_PROB_FLOOR, hm.ops.EMIS_PROB_FLOOR, trans, init, logP, logp0, out=fused_out,
+                                        workspace=fused_ws)
+
+    res = {"K": a.K, "B": a.B, "T": a.T, "forward_only_ms": ms(lambda: fb(())), "forward_backward_ms": ms(fb), "viterbi_ms": ms(vit),
+           "fused_fb_viterbi_ms": ms(fused)}
+    fb(); vit(); torch.cuda.synchronize()
+    ref = {k: fb_out[k].clone() for k in ("gamma", "loglik")}; ref["states"] = v_out["states"].clone(); ref["delta"] = v_out["delta"].clone()
+    fused(); torch.cuda.synchronize()
+    res["fused_matches_separate"] = bool(all(torch.equal(ref[k], fused_out[k]) for k in ref))
+    res["frames_per_s_fb_plus_viterbi"] = a.B * a.T / (min(res["forward_backward_ms"] + res["viterbi_ms"], res["fused_fb_viterbi_ms"]) * 1e-3)
     res["exchange_ok"] = bool(int(fb_ws[-256:].view(torch.int32)[0]) == 0 and int(v_ws[-256:].view(torch.int32)[0]) == 0)
     import subprocess
     try:
