@@ -328,12 +328,42 @@ def alignment(ref):
     np.savez_compressed(os.path.join(OUT, "alignment.npz"), **out)
 
 
+def covariance(ref):
+    """the other covariance types of MixtureGaussianHMMLayer -- tied, spherical (mixture_gaussian.py:242-269) and
+    full (Cholesky parameters, :216-240, :271-288): emission log-likelihoods and the layer's Viterbi on them."""
+    out = {}
+    for tag, seed in (("tied", 7001), ("spherical", 7002), ("full", 7003)):
+        torch.manual_seed(seed)
+        K, C, D = 6, 3, 16
+        m = ref.MixtureGaussianHMMLayer(K, D, num_components=C, covariance_type=tag)
+        with torch.no_grad():
+            m.means.mul_(3.0)
+            if tag == "full":
+                m.cholesky_params.add_(0.15 * torch.randn_like(m.cholesky_params))
+            else:
+                m.log_vars.copy_(0.3 * torch.randn_like(m.log_vars))
+            m.mixture_weights_logits.copy_(torch.randn_like(m.mixture_weights_logits))
+        B, T = 2, 30
+        s = torch.randint(0, K, (B, T)); c = torch.randint(0, C, (B, T))
+        x = m.means.detach()[s, c] + 0.8 * torch.randn(B, T, D)
+        m.eval()
+        with torch.no_grad():
+            logb = m.get_observation_log_probs(x)
+            states, scores = m(x, return_log_probs=True)
+            log_trans = m._safe_log(m.get_transition_matrix())
+        for name, par in m.state_dict().items():
+            out[f"{tag}_sd_{name}"] = _np(par)
+        out.update({f"{tag}_x": _np(x), f"{tag}_logb": _np(logb), f"{tag}_log_trans": _np(log_trans),
+                    f"{tag}_states": _np(states), f"{tag}_scores": _np(scores)})
+    np.savez_compressed(os.path.join(OUT, "covariance.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = _import_reference()
     torch.set_num_threads(1)
     sections = {"core": core, "gaussian": gaussian, "mixture": mixture, "hsmm": hsmm, "semimarkov": semimarkov,
-                "streaming": streaming, "largek": largek, "neural": neural, "alignment": alignment}
+                "streaming": streaming, "largek": largek, "neural": neural, "alignment": alignment, "covariance": covariance}
     only = [a for a in sys.argv[1:] if a in sections or a == "segsum"]        # e.g. `make_golden.py largek`
     for name, fn in sections.items():
         if not only or name in only:

@@ -409,3 +409,55 @@ def test_fused_fb_viterbi_mixed_modes_and_optional_outputs(hm):
     v = hm.ops.viterbi(e, hm.ops.EMIS_PROB_FLOOR, _dev(logP), _dev(logp0), want_delta=False, want_score=False)
     assert torch.equal(r["gamma"], f["gamma"]) and torch.equal(r["loglik"], f["loglik"]) and torch.equal(r["states"], v["states"])
     assert "delta" not in r and "score" not in r
+
+
+# ------------------------------------------------------------------------------------------------------
+# tied / spherical / full covariance against the real reference (tests/golden/covariance.npz)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["tied", "spherical", "full"])
+def test_mixture_layer_other_covariance_types_vs_golden(hm, golden, tag):
+    g = golden("covariance")
+    K, C, D = 6, 3, 16
+    m = hm.MixtureGaussianHMMLayer(K, D, num_components=C, covariance_type=tag).cuda()
+    sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(f"{tag}_sd_")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)       # the reference's own parameter names and shapes
+    assert not unexpected and all("transition_matrix" in k for k in missing), (missing, unexpected)
+    m.eval()
+    x = torch.from_numpy(g[f"{tag}_x"]).cuda()
+    with torch.no_grad():
+        logb = m.get_observation_log_probs(x)
+        states, scores = m(x, return_log_probs=True)
+    # 1e-4 relative is the north star's bar for log-likelihoods; the kernels are well inside it
+    np.testing.assert_allclose(logb.cpu().numpy(), g[f"{tag}_logb"], rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(scores.cpu().numpy(), g[f"{tag}_scores"], rtol=2e-5)
+    ours, ref = states.cpu().numpy(), g[f"{tag}_states"]
+    if not np.array_equal(ours, ref):                               # a differing path must be a near-tie of the emissions' last bits
+        st2, _, _, _ = ref_port.mixture_viterbi(logb.cpu(), torch.from_numpy(g[f"{tag}_log_trans"]))
+        assert np.array_equal(ours, st2.numpy())
+    # bit-exact once the reference's own log-emissions are fed to the Viterbi kernel
+    st, sc = m._viterbi_decode(torch.from_numpy(g[f"{tag}_logb"]).cuda(), torch.from_numpy(g[f"{tag}_log_trans"]).cuda())
+    assert np.array_equal(st.cpu().numpy(), ref)
+    assert np.array_equal(sc.cpu().numpy(), g[f"{tag}_scores"])
+
+
+def test_full_covariance_emission_larger_shape_vs_float64(hm):
+    """K=12, C=4, D=80 (the headline shape) with random Cholesky factors against a float64 evaluation of the reference's formula
+    (mixture_gaussian.py:216-240): solve L y = x - mu, -0.5 (|y|^2 + 2 sum log diag L + D log 2 pi), private log-sum-exp."""
+    torch.manual_seed(11)
+    K, C, D, N = 12, 4, 80, 700
+    m = hm.MixtureGaussianHMMLayer(K, D, num_components=C, covariance_type="full").cuda()
+    with torch.no_grad():
+        m.means.mul_(2.0)
+        m.cholesky_params.add_(0.05 * torch.randn_like(m.cholesky_params))
+    x = (m.means.detach()[torch.randint(0, K, (N,)), torch.randint(0, C, (N,))] + torch.randn(N, D, device="cuda")).view(1, N, D)
+    with torch.no_grad():
+        logb = m.get_observation_log_probs(x)[0].double().cpu()
+        L = m._get_cholesky_factors().double().cpu()                                     # [K,C,D,D]
+        mu = m.means.double().cpu()
+        logw = torch.log(torch.softmax(m.mixture_weights_logits.double().cpu(), -1).clamp_min(1e-8))
+        diff = x[0].double().cpu()[:, None, None, :] - mu[None]                          # [N,K,C,D]
+        y = torch.linalg.solve_triangular(L[None].expand(N, K, C, D, D), diff.unsqueeze(-1), upper=False).squeeze(-1)
+        log_det = 2.0 * torch.log(torch.diagonal(L, dim1=-2, dim2=-1) + 1e-8).sum(-1)
+        comp = logw[None] - 0.5 * ((y ** 2).sum(-1) + log_det[None] + D * np.log(2 * np.pi))
+        ref = torch.logsumexp(comp, dim=-1)
+    np.testing.assert_allclose(logb.numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
