@@ -9,7 +9,7 @@ from .gmm import MixtureGaussianHMMLayer
 from .hsmm_layer import HSMMLayer, SemiMarkovHMM, DurationModel
 from .stream import StreamingHMMProcessor, StreamingResult
 from .neural import NeuralHMMRecursion
-from .transitions import create_transition_matrix, create_left_to_right_matrix
+from .transitions import create_transition_matrix, create_left_to_right_matrix, compute_state_durations
 from . import ops
 
 __version__ = "0.1.0"
@@ -56,4 +56,4 @@ class ModelFactory:
 
 __all__ = ["HMM", "HMMPyTorch", "HMMLayer", "GaussianHMMLayer", "MixtureGaussianHMMLayer", "HSMMLayer", "SemiMarkovHMM",
            "DurationModel", "StreamingHMMProcessor", "StreamingResult", "NeuralHMMRecursion", "create_speech_hmm", "ModelFactory",
-           "create_transition_matrix", "create_left_to_right_matrix", "ops"]
+           "create_transition_matrix", "create_left_to_right_matrix", "compute_state_durations", "ops"]

@@ -151,6 +151,37 @@ class HSMMLayer(nn.Module):
             return F.softplus(self.duration_scale) * torch.exp(torch.lgamma(1 + 1 / conc))
         return self.duration_means
 
+    def generate_sequence(self, length: int, initial_state: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Samples (states [length], observations [length, D]) from the model: a duration from the state's duration pmf, Gaussian
+        frames for the whole segment at once, then a successor other than the current state (hsmm.py:356-423).  Host-side helper."""
+        dev = self.observation_means.device
+        states = torch.zeros(length, dtype=torch.long, device=dev)
+        observations = torch.zeros(length, self.feature_dim, device=dev)
+        with torch.no_grad():
+            trans = self.get_transition_matrix()
+            dur = self.get_duration_probabilities()
+            std = torch.exp(0.5 * self.observation_log_vars)
+            cur, t, it = int(initial_state), 0, 0
+            while t < length and it < 2 * length:
+                it += 1
+                d = int(torch.multinomial(dur[cur], 1)) + self.min_duration
+                end = min(t + d, length)
+                states[t:end] = cur
+                observations[t:end] = self.observation_means[cur] + std[cur] * torch.randn(end - t, self.feature_dim, device=dev)
+                t = end
+                if t < length:
+                    w = trans[cur].clone()
+                    w[cur] = 0
+                    if w.sum() < 1e-8:
+                        w = torch.ones_like(w)
+                        w[cur] = 0
+                        if w.sum() < 1e-8:
+                            break
+                    cur = int(torch.multinomial(w / w.sum(), 1))
+            if it >= 2 * length and t < length:
+                warnings.warn(f"generate_sequence reached maximum iterations ({2 * length}). Generated {t}/{length} timesteps.")
+        return states, observations
+
     def get_model_info(self) -> dict:
         total = sum(p.numel() for p in self.parameters())
         return {"model_type": "HSMM", "num_states": self.num_states, "feature_dim": self.feature_dim,

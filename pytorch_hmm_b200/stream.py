@@ -14,6 +14,7 @@ Out of scope: beam search, the async worker thread, the ada
 from __future__ import annotations
 
 import time
+import warnings
 from collections import deque
 from dataclasses import dataclass
 from typing import Any, Dict, Optional, Tuple
@@ -139,8 +140,31 @@ class StreamingHMMProcessor(nn.Module):
         t0 = time.time()
         states, confidence = self._greedy_decode(torch.stack(frames))
         self.last_output_frame = len(self.feature_buffer) - 1
+        self.chunk_counter += 1                                           # (streaming.py:397)
         return StreamingResult(states, confidence.mean().item(), (time.time() - t0) * 1000, len(self.feature_buffer),
-                               self.chunk_counter, "flushed", {"frames_processed": len(frames)})
+                               self.chunk_counter, "flushed", {"final_chunk": True, "frames_processed": len(frames)})
+
+    def optimize_for_latency(self, target_latency_ms: float = 50.0):
+        """Parameter adjustment of the reference (streaming.py:444-488): trade beam width / chunk size against the measured latency.
+        Host-side bookkeeping only; decoding here is the greedy kernel whatever `use_beam_search` says."""
+        stats = self.get_performance_stats()
+        if "avg_processing_time_ms" not in stats:
+            warnings.warn("No performance data available for optimization")
+            return
+        cur = stats["avg_processing_time_ms"]
+        if cur > target_latency_ms:
+            if self.use_beam_search and self.beam_width > 2:
+                self.beam_width = max(2, self.beam_width - 1)
+            elif self.use_beam_search:
+                self.use_beam_search = False
+            elif self.chunk_size > 80:
+                self.chunk_size = max(80, int(self.chunk_size * 0.8))
+        elif cur < target_latency_ms * 0.5:
+            if not self.use_beam_search:
+                self.use_beam_search = True
+                self.beam_width = 2
+            elif self.beam_width < 8:
+                self.beam_width += 1
 
     def get_performance_stats(self) -> Dict[str, float]:
         if not self.processing_times:

@@ -32,3 +32,26 @@ def create_transition_matrix(num_states: int, transition_type: str = "ergodic", 
 def create_left_to_right_matrix(num_states: int, self_loop_prob: float = 0.7, device: str = "cpu") -> torch.Tensor:
     return create_transition_matrix(num_states, "left_to_right", self_loop_prob=self_loop_prob,
                                     forward_prob=1.0 - self_loop_prob, device=device)
+
+
+def compute_state_durations(state_sequence: torch.Tensor) -> torch.Tensor:
+    """Run lengths of a state path [T] -> [n_runs] (utils.py:447-476), as one vectorised pass instead of a Python loop over frames."""
+    n = len(state_sequence)
+    if n == 0:
+        return torch.tensor([])
+    s = state_sequence.reshape(-1)
+    change = torch.ones(n, dtype=torch.bool, device=s.device)
+    change[1:] = s[1:] != s[:-1]
+    starts = change.nonzero().flatten()
+    ends = torch.cat([starts[1:], torch.tensor([n], device=s.device)])
+    return (ends - starts).to(torch.long)
+
+
+def validate_transition_matrix(P: torch.Tensor, tolerance: float = 1e-6) -> dict:
+    """Checks of a transition matrix with the reference's result keys (utils.py: validate_transition_matrix)."""
+    row_sums = P.sum(dim=1)
+    return {"row_sums_valid": bool(torch.allclose(row_sums, torch.ones_like(row_sums), atol=tolerance)),
+            "non_negative": bool((P >= 0).all()), "finite": bool(torch.isfinite(P).all()),
+            "shape_valid": P.dim() == 2 and P.shape[0] == P.shape[1],
+            "min_value": float(P.min()), "max_value": float(P.max()),
+            "max_row_sum_error": float((row_sums - 1).abs().max())}
