@@ -7,7 +7,7 @@ torch.set_grad_enabled(False)
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-which = sys.argv[1:] or ["smallk", "largek", "scan", "hsmm", "emission", "bw"]
+which = sys.argv[1:] or ["smallk", "fused", "largek", "scan", "hsmm", "emission", "bw", "alignment"]
 if "emission" in which or "smallk" in which:
     m = hm.MixtureGaussianHMMLayer(12, 80, num_components=4).to(dev).eval()
     x = torch.randn(3, 200, 80, device=dev)
@@ -18,6 +18,12 @@ if "emission" in which or "smallk" in which:
     h = hm.HMMPyTorch(P, None, device="cuda")
     tr, ini = h._effective_probs(dev)
     hm.ops.forward_backward(logb, hm.ops.EMIS_LOG_NORM_FLOOR, tr, ini, want=("gamma", "fwd", "bwd"), method="sweep")
+if "fused" in which:
+    K = 12
+    P = torch.softmax(torch.randn(K, K), -1).to(dev) + 1e-8
+    p0 = torch.full((K,), 1.0 / K, device=dev)
+    lb = torch.randn(5, 300, K, device=dev) - 20
+    hm.ops.forward_backward_viterbi(lb, hm.ops.EMIS_LOG_NORM_FLOOR, hm.ops.EMIS_LOG, P, p0, torch.log(P), torch.log(p0))
 if "largek" in which:
     K = 96
     h = hm.HMMPyTorch(hm.create_transition_matrix(K, "ergodic"), None, device="cuda")
@@ -32,6 +38,17 @@ if "hsmm" in which:
     s = hm.HSMMLayer(5, 12, max_duration=7).to(dev).eval()
     x = torch.randn(2, 40, 12, device=dev)
     s(x); s.forward_backward(x)
+if "hsmm" in which:
+    s2 = hm.HSMMLayer(10, 16, max_duration=20).to(dev).eval()       # the specialised K = 10, Dmax = 20 kernels
+    x2 = torch.randn(2, 90, 16, device=dev)
+    s2(x2); s2.forward_backward(x2)
+if "alignment" in which:
+    import pytorch_hmm_b200.alignment as al
+    lp = torch.log_softmax(torch.randn(30, 3, 9, device=dev), -1)
+    tg = torch.randint(1, 9, (3, 6), device=dev)
+    il, tl = torch.tensor([30, 22, 30], device=dev), torch.tensor([6, 4, 0], device=dev)
+    al.ctc_forward_algorithm(lp, tg, il, tl); al.ctc_backward_algorithm(lp, tg, il, tl)
+    al.compute_dtw_path(torch.rand(40, 55, device=dev), "rabiner_juang")
 if "bw" in which:
     from pytorch_hmm_b200.baum_welch import BaumWelch
     m = hm.MixtureGaussianHMMLayer(4, 8, num_components=2).to(dev)
