@@ -372,6 +372,26 @@ def extra_config4(dev):
             "viterbi_ms": v_ms, "frames_per_s_fb_plus_viterbi": B * T / ((e_ms + fb_ms + v_ms) * 1e-3)}
 
 
+def extra_bf16_outputs(dev, he):
+    """The headline recursions + posteriors with bfloat16 posterior / forward / backward outputs (north star: bf16/fp32 outputs):
+    same kernels, the posterior kernel writes half the bytes."""
+    import pytorch_hmm_b200 as hm
+    e = he.eng
+    o = e.out
+    out16 = {"loglik": o["loglik"], "states": o["states"], "delta": o["log_delta"], "score": o["score"],
+             "gamma": torch.empty(BATCH, SEQ, K_STATES, dtype=torch.bfloat16, device=dev),
+             "fwd": torch.empty(BATCH, SEQ, K_STATES, dtype=torch.bfloat16, device=dev),
+             "bwd": torch.empty(BATCH, SEQ, K_STATES, dtype=torch.bfloat16, device=dev)}
+
+    def run16():
+        hm.ops.forward_backward_viterbi(he.logb, hm.ops.EMIS_LOG_NORM_FLOOR, hm.ops.EMIS_LOG, e.trans, e.init, e.log_trans, e.prior,
+                                        out=out16, workspace=e.slots[0].fused_ws, out_dtype=torch.bfloat16)
+    ms16 = _ms(run16, it=20, warm=3)
+    ms32 = _ms(he.fused, it=20, warm=3)
+    return {"what": "fused recursions + posterior kernel on resident log b, B=256, T=2000, K=12", "fp32_outputs_ms": ms32,
+            "bf16_outputs_ms": ms16, "output_bytes_fp32": 3 * BATCH * SEQ * K_STATES * 4, "output_bytes_bf16": 3 * BATCH * SEQ * K_STATES * 2}
+
+
 def extra_config5(dev):
     """configs[4]: K=512 ergodic, B=64, T=4000: forward_backward + viterbi_decode on softmax(randn) observations."""
     import pytorch_hmm_b200 as hm
@@ -639,6 +659,10 @@ def run_gpu_arm(args, rank, world, local_rank):
             extra["baum_welch"] = {"error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
         if rank == 0:
+            try:
+                extra["bf16_outputs"] = extra_bf16_outputs(dev, h)
+            except Exception as exc:                              # noqa: BLE001
+                extra["bf16_outputs"] = {"error": f"{type(exc).__name__}: {exc}"}
             for name, fn in (("config1", extra_config1), ("config4", extra_config4), ("config5", extra_config5)):
                 try:
                     extra[name] = fn(dev)

@@ -150,6 +150,8 @@ int    hmmb200_viterbi_f32(const float *emis, int emis_mode, float floor_eps,
  *   workspace: hmmb200_fb_viterbi_workspace_bytes(B, T, K) bytes.
  * --------------------------------------------------------------------------------------------------------- */
 #define HMMB200_FUSED_PDL 1
+#define HMMB200_FUSED_BF16_OUT 2   /* gamma / fwd_prob / bwd_prob point to bfloat16 arrays (K <= 32; log_alpha / log_beta must be NULL):   */
+                                   /* the posterior kernel is a pure streaming write -- half the bytes (north star: bf16/fp32 outputs)     */
 size_t hmmb200_fb_viterbi_workspace_bytes(int B, int T, int K);
 int    hmmb200_fb_viterbi_f32(const float *emis, int fb_mode, int vit_mode, float floor_eps, int add_rowmax,
                               const float *trans_prob, const float *init_prob,

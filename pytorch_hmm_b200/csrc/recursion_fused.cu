@@ -158,6 +158,10 @@ HMMB200_EXPORT int hmmb200_fb_viterbi_f32(const float *emis, int fb_mode, int vi
     if (B == 0 || T == 0) return HMMB200_OK;
     if (!emis || !trans_prob || !init_prob || !log_trans || !log_init || !states) return set_error(HMMB200_EINVAL, "fb_viterbi: null argument");
     if (fb_mode < 0 || fb_mode > 3 || vit_mode < 0 || vit_mode > 3) return set_error(HMMB200_EINVAL, "fb_viterbi: bad emission mode");
+    if (flags & HMMB200_FUSED_BF16_OUT) {
+        if (K > 32) return set_error(HMMB200_EUNSUPPORTED, "fb_viterbi: bfloat16 outputs are available for K <= 32");
+        if (log_alpha || log_beta) return set_error(HMMB200_EINVAL, "fb_viterbi: log_alpha / log_beta have no bfloat16 form");
+    }
     const size_t fb_bytes = hmmb200_fb_workspace_bytes(B, T, K);
     const size_t need = hmmb200_fb_viterbi_workspace_bytes(B, T, K);
     if (fb_bytes == 0) return set_error(HMMB200_EUNSUPPORTED, "fb_viterbi: K <= 512 states supported (got %d)", K);
@@ -187,6 +191,7 @@ HMMB200_EXPORT int hmmb200_fb_viterbi_f32(const float *emis, int fb_mode, int vi
                 c.ws_a = p.fb.ws_a; c.ws_b = p.fb.ws_b; c.ws_la = p.fb.ws_la; c.ws_lb = p.fb.ws_lb;
                 c.n_frames = (int64_t)n; c.K = K;
                 c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
+                c.bf16 = (flags & HMMB200_FUSED_BF16_OUT) ? 1 : 0;
                 return launch_combine(c, s);
             }
             return HMMB200_OK;

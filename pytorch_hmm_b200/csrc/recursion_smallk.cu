@@ -116,7 +116,7 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
         CombineParams c;
         c.ws_a = p.ws_a; c.ws_b = p.ws_b; c.ws_la = p.ws_la; c.ws_lb = p.ws_lb;
         c.n_frames = (int64_t)n; c.K = K;
-        c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta;
+        c.gamma = gamma; c.fwd = fwd_prob; c.bwd = bwd_prob; c.log_alpha = log_alpha; c.log_beta = log_beta; c.bf16 = 0;
         if (int rc = launch_combine(c, s)) return rc;
     }
     return HMMB200_OK;

@@ -656,7 +656,15 @@ struct CombineParams {
     int64_t n_frames;
     int K;
     float *gamma, *fwd, *bwd, *log_alpha, *log_beta;
+    int bf16;             // gamma / fwd / bwd are bfloat16 arrays (round to nearest even); log_alpha / log_beta must then be null
 };
+
+// two floats -> packed bf16 pair (first argument in the low half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
 
 // Scalar form (K not a multiple of 4, or unaligned outputs): one thread per frame, COMBINE_FPT frames per thread.
 // Explicit fused / rounded operations in a fixed order: a frame's result must not depend on how the batch was sharded.
@@ -677,6 +685,14 @@ static __global__ void __launch_bounds__(256) fb_combine_kernel(CombineParams p)
         const float inv = __fdiv_rn(1.f, Z);
         for (int k = 0; k < K; ++k) {
             float x = a[k], y = b[k];
+            if (p.bf16) {
+                unsigned short *g16 = reinterpret_cast<unsigned short *>(p.gamma), *f16 = reinterpret_cast<unsigned short *>(p.fwd);
+                unsigned short *b16 = reinterpret_cast<unsigned short *>(p.bwd);
+                if (g16) g16[idx * K + k] = (unsigned short)(pack_bf16x2(__fmul_rn(__fmul_rn(x, y), inv), 0.f) & 0xffffu);
+                if (f16) f16[idx * K + k] = (unsigned short)(pack_bf16x2(x * ea, 0.f) & 0xffffu);
+                if (b16) b16[idx * K + k] = (unsigned short)(pack_bf16x2(y * eb, 0.f) & 0xffffu);
+                continue;
+            }
             if (p.gamma) p.gamma[idx * K + k] = __fmul_rn(__fmul_rn(x, y), inv);
             if (p.fwd) p.fwd[idx * K + k] = x * ea;
             if (p.bwd) p.bwd[idx * K + k] = y * eb;
@@ -738,6 +754,12 @@ __global__ void __launch_bounds__(256) fb_combine_warp_kernel(CombineParams p) {
             const float4 x = xa[j], y = xb[j];
             const int64_t o = f0 * KV + idx;
             auto g = [&](float u, float v) { return __fmul_rn(__fmul_rn(u, v), inv); };
+            if (p.bf16) {                                    // 8-byte pieces: half the bytes of the fp32 outputs
+                if (p.gamma) __stcs(reinterpret_cast<uint2 *>(p.gamma) + o, make_uint2(pack_bf16x2(g(x.x, y.x), g(x.y, y.y)), pack_bf16x2(g(x.z, y.z), g(x.w, y.w))));
+                if (p.fwd) __stcs(reinterpret_cast<uint2 *>(p.fwd) + o, make_uint2(pack_bf16x2(x.x * ea, x.y * ea), pack_bf16x2(x.z * ea, x.w * ea)));
+                if (p.bwd) __stcs(reinterpret_cast<uint2 *>(p.bwd) + o, make_uint2(pack_bf16x2(y.x * eb, y.y * eb), pack_bf16x2(y.z * eb, y.w * eb)));
+                continue;
+            }
             if (p.gamma) __stcs(reinterpret_cast<float4 *>(p.gamma) + o, make_float4(g(x.x, y.x), g(x.y, y.y), g(x.z, y.z), g(x.w, y.w)));
             if (p.fwd) __stcs(reinterpret_cast<float4 *>(p.fwd) + o, make_float4(x.x * ea, x.y * ea, x.z * ea, x.w * ea));
             if (p.bwd) __stcs(reinterpret_cast<float4 *>(p.bwd) + o, make_float4(y.x * eb, y.y * eb, y.z * eb, y.w * eb));

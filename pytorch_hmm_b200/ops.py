@@ -289,6 +289,7 @@ def tv_viterbi(log_emis: torch.Tensor, log_trans: torch.Tensor, log_init: torch.
 
 
 FUSED_PDL = 1
+FUSED_BF16_OUT = 2
 
 
 def fb_viterbi_workspace(B: int, T: int, K: int, dev) -> torch.Tensor:
@@ -299,7 +300,8 @@ def fb_viterbi_workspace(B: int, T: int, K: int, dev) -> torch.Tensor:
 def forward_backward_viterbi(emis: torch.Tensor, fb_mode: int, vit_mode: int, trans_prob: torch.Tensor, init_prob: torch.Tensor,
                              log_trans: torch.Tensor, log_init: torch.Tensor, eps: float = EPS, add_rowmax: bool = False,
                              want=("gamma", "fwd", "bwd"), want_delta: bool = True, want_psi: bool = False, want_score: bool = True,
-                             out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None, pdl: bool = False) -> dict:
+                             out: Optional[dict] = None, workspace: Optional[torch.Tensor] = None, pdl: bool = False,
+                             out_dtype: torch.dtype = torch.float32) -> dict:
     """Forward-backward and Viterbi on the same emissions in one pass (hmmb200_fb_viterbi_f32: one launch for K <= 32).
     Returns the union of forward_backward()'s and viterbi()'s dicts.  pdl: the kernel may overlap the tail of the previous
     kernel on the stream (the emission kernel that writes `emis`); only pass True when that kernel writes none of the tables."""
@@ -310,9 +312,14 @@ def forward_backward_viterbi(emis: torch.Tensor, fb_mode: int, vit_mode: int, tr
     log_trans, log_init = _f32c(log_trans, dev), _f32c(log_init, dev)
     lib = _lib.load()
     res = {} if out is None else out
+    bf16 = out_dtype == torch.bfloat16                           # posteriors / forward / backward as bfloat16 (K <= 32)
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("out_dtype must be torch.float32 or torch.bfloat16")
     for name in ("gamma", "fwd", "bwd", "log_alpha", "log_beta"):
         if name in want and name not in res:
-            res[name] = torch.empty(B, T, K, dtype=torch.float32, device=dev)
+            res[name] = torch.empty(B, T, K, dtype=out_dtype if name in ("gamma", "fwd", "bwd") else torch.float32, device=dev)
+    if bf16 and any(res[n].dtype != torch.bfloat16 for n in ("gamma", "fwd", "bwd") if n in res):
+        raise ValueError("out_dtype=bfloat16 needs bfloat16 output tensors")
     if "loglik" not in res:
         res["loglik"] = torch.empty(B, dtype=torch.float32, device=dev)
     if "states" not in res:
@@ -331,7 +338,7 @@ def forward_backward_viterbi(emis: torch.Tensor, fb_mode: int, vit_mode: int, tr
             _p(log_trans), _p(log_init), B, T, K,
             _p(res.get("gamma")), _p(res.get("fwd")), _p(res.get("bwd")), _p(res.get("log_alpha")), _p(res.get("log_beta")),
             _p(res["loglik"]), _p(res.get("delta")), _p(res.get("psi")), _p(res["states"]), _p(res.get("score")),
-            _p(ws), ws_bytes, FUSED_PDL if pdl else 0, _stream(dev)), "hmmb200_fb_viterbi_f32")
+            _p(ws), ws_bytes, (FUSED_PDL if pdl else 0) | (FUSED_BF16_OUT if bf16 else 0), _stream(dev)), "hmmb200_fb_viterbi_f32")
     return res
 
 

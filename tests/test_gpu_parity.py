@@ -461,3 +461,21 @@ def test_full_covariance_emission_larger_shape_vs_float64(hm):
         comp = logw[None] - 0.5 * ((y ** 2).sum(-1) + log_det[None] + D * np.log(2 * np.pi))
         ref = torch.logsumexp(comp, dim=-1)
     np.testing.assert_allclose(logb.numpy(), ref.numpy(), rtol=1e-5, atol=1e-4)
+
+
+def test_fused_pass_bf16_outputs_are_the_rounded_fp32_outputs(hm):
+    """North star: 'coalesced, vectorised bf16/fp32 outputs'.  With HMMB200_FUSED_BF16_OUT the posterior kernel writes gamma / forward /
+    backward as bfloat16: bit-identical to rounding the fp32 outputs (round to nearest even); everything else is unchanged."""
+    torch.manual_seed(21)
+    for K, B, T in ((12, 5, 333), (7, 3, 65)):                   # vector form (K % 4 == 0) and scalar form
+        P = torch.softmax(torch.randn(K, K), -1).cuda() + 1e-8
+        p0 = torch.full((K,), 1.0 / K, device="cuda")
+        lb = (3.0 * torch.randn(B, T, K, device="cuda") - 40.0)
+        args = (lb, hm.ops.EMIS_LOG_NORM_FLOOR, hm.ops.EMIS_LOG, P, p0, torch.log(P), torch.log(p0))
+        r32 = hm.ops.forward_backward_viterbi(*args)
+        r16 = hm.ops.forward_backward_viterbi(*args, out_dtype=torch.bfloat16)
+        for name in ("gamma", "fwd", "bwd"):
+            assert r16[name].dtype == torch.bfloat16
+            assert torch.equal(r16[name], r32[name].to(torch.bfloat16)), name
+        assert torch.equal(r16["states"], r32["states"]) and torch.equal(r16["delta"], r32["delta"])
+        assert torch.equal(r16["loglik"], r32["loglik"])
