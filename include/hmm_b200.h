@@ -82,7 +82,7 @@ int    hmmb200_gmm_emission_full_f32(const float *x, const float *W, const float
                                      int K, int C, int D, float *logb, float *comp, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------------
- * Forward-backward (K <= 32: warp-per-sequence sweeps; 32 < K <= 512: cluster kernels, BASELINE config 5).
+ * Forward-backward (K <= 32: warp-per-sequence sweeps; 32 < K <= 512: cluster kernels, BASELINE config 5; 512 < K <= 2048: one launch per frame).
  *   replaces  HMMPyTorch.forward_backward / compute_likelihood    pytorch_hmm/hmm.py:66-130, :186-211
  *
  *   emis [B,T,K] read according to emis_mode / floor_eps (see HMMB200_EMIS_*).

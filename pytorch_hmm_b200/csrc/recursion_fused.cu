@@ -164,7 +164,7 @@ HMMB200_EXPORT int hmmb200_fb_viterbi_f32(const float *emis, int fb_mode, int vi
     }
     const size_t fb_bytes = hmmb200_fb_workspace_bytes(B, T, K);
     const size_t need = hmmb200_fb_viterbi_workspace_bytes(B, T, K);
-    if (fb_bytes == 0) return set_error(HMMB200_EUNSUPPORTED, "fb_viterbi: K <= 512 states supported (got %d)", K);
+    if (fb_bytes == 0) return set_error(HMMB200_EUNSUPPORTED, "fb_viterbi: K <= 2048 states supported (got %d)", K);
     if (!workspace || workspace_bytes < need) return set_error(HMMB200_EWORKSPACE, "fb_viterbi: workspace %zu < %zu bytes", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -198,7 +198,7 @@ HMMB200_EXPORT int hmmb200_fb_viterbi_f32(const float *emis, int fb_mode, int vi
         }
     }
     if (K > 32) {
-        if (!largek_shape_ok(K)) return set_error(HMMB200_EUNSUPPORTED, "fb_viterbi: K <= 512 states supported (got %d)", K);
+        if (!largek_shape_ok(K)) return set_error(HMMB200_EUNSUPPORTED, "fb_viterbi: K <= 2048 states supported (got %d)", K);
         return largek_fb_viterbi(emis, fb_mode, vit_mode, floor_eps, add_rowmax, trans_prob, init_prob, log_trans, log_init, B, T, K,
                                  gamma, fwd_prob, bwd_prob, log_alpha, log_beta, loglik, delta, psi, states, score,
                                  w, w + align256(fb_bytes), s);

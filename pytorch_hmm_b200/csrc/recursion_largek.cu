@@ -547,13 +547,13 @@ __device__ __forceinline__ void lk_warp_argmax(float &v, int &i) {
     }
 }
 
+template <int MAXR>                                          // delta-row registers per lane: K <= 32 MAXR
 __global__ void __launch_bounds__(128) lk_traceback_kernel(const float *delta, const float *logPT, int B, int T, int K,
                                                            int64_t *states, float *score) {
     const int sq = blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (sq >= B) return;
     const float *d = delta + (size_t)sq * T * K;
-    constexpr int MAXR = LK_KMAX / 32;
     float bv = -INFINITY;
     int bi = K;
     for (int k = lane; k < K; k += 32) {
@@ -633,17 +633,23 @@ __global__ void __launch_bounds__(256) lk_psi_kernel(const float *delta, const f
 // ----------------------------------------------------------------------------------------------------------------------
 static size_t lk_align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-bool largek_shape_ok(int K) { return K > 32 && K <= LK_KMAX; }
+constexpr int XL_KMAX = 2048;                   // above LK_KMAX: one launch per time step (recursion_xlk.cu)
+size_t xlk_extra_bytes(int B, int K);
+int xlk_sweep(int mode3, const float *emis, int emis_mode, float eps, const float *M, const float *init, const float *rowmax,
+              int B, int T, int K, float *ws_out, float *ws_l, void *extra, float *loglik, cudaStream_t s);
+
+bool largek_shape_ok(int K) { return K > 32 && K <= XL_KMAX; }
 
 // fb workspace: ws_a, ws_b [B,T,K]; la, lb, rowmax [B,T]; err flag
 size_t largek_fb_workspace_bytes(int B, int T, int K) {
     const size_t n = (size_t)B * T;
-    return 2 * lk_align256(n * K * sizeof(float)) + 3 * lk_align256(n * sizeof(float)) + 256;
+    return 2 * lk_align256(n * K * sizeof(float)) + 3 * lk_align256(n * sizeof(float)) + 256 + (K > LK_KMAX ? xlk_extra_bytes(B, K) : 0);
 }
 // viterbi workspace: delta [B,T,K] (used when the caller does not want delta), logPT [K,K], rowmax [B,T], err flag
 size_t largek_viterbi_workspace_bytes(int B, int T, int K) {
     const size_t n = (size_t)B * T;
-    return lk_align256(n * K * sizeof(float)) + lk_align256((size_t)K * K * sizeof(float)) + lk_align256(n * sizeof(float)) + 256;
+    return lk_align256(n * K * sizeof(float)) + lk_align256((size_t)K * K * sizeof(float)) + lk_align256(n * sizeof(float)) + 256 +
+           (K > LK_KMAX ? xlk_extra_bytes(B, K) : 0);
 }
 
 static int lk_cluster_size(int K) {
@@ -768,6 +774,7 @@ static int lk_launch(LkParams p, cudaStream_t s) {
 struct LkFbCall {
     LkParams p;            // forward sweep (the backward sweep is the same with loglik = null)
     float *rowmax;
+    void *xl_extra;        // K > 512: scratch of the step-per-launch path
     int add_m;
     bool both;             // posteriors / backward values wanted: the backward sweep runs too
     float *gamma, *fwd_prob, *bwd_prob, *log_alpha, *log_beta, *loglik;
@@ -788,6 +795,7 @@ static int lk_fb_prepare(LkFbCall &c, const float *emis, int emis_mode, float fl
     p.ws_lb = (float *)w; w += lk_align256(n * sizeof(float));
     c.rowmax = (float *)w; w += lk_align256(n * sizeof(float));
     p.err = (int *)w;
+    c.xl_extra = w + 256;
     cudaMemsetAsync(p.err, 0, sizeof(int), s);
 #ifdef HMMB200_DEBUG_HOOKS
     p.trace = getenv("HMMB200_LK_TRACE") != nullptr;
@@ -828,6 +836,7 @@ static int lk_fb_finish(const LkFbCall &c, cudaStream_t s) {
 struct LkVitCall {
     LkParams p;
     float *logPT;
+    void *xl_extra;
     const float *log_trans;
     void *psi;
     int64_t *states;
@@ -847,6 +856,7 @@ static int lk_vit_prepare(LkVitCall &c, const float *emis, int emis_mode, float 
     p.B = B; p.T = T; p.K = K; p.CS = lk_cluster_size(K); p.ngr = 2;
     p.delta = delta ? delta : ws_delta;
     p.err = (int *)w;
+    c.xl_extra = w + 256;
     cudaMemsetAsync(p.err, 0, sizeof(int), s);
     if (emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR) {
         lk_rowmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(emis, (int64_t)n, K, rowmax);
@@ -863,7 +873,8 @@ static int lk_vit_finish(const LkVitCall &c, cudaStream_t s) {
     const LkParams &p = c.p;
     const size_t n = (size_t)p.B * p.T;
     const int B = p.B, T = p.T, K = p.K;
-    lk_traceback_kernel<<<(B + 3) / 4, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
+    if (K <= LK_KMAX) lk_traceback_kernel<LK_KMAX / 32><<<(B + 3) / 4, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
+    else lk_traceback_kernel<XL_KMAX / 32><<<(B + 3) / 4, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
     if (int rc = check_launch("lk_traceback_kernel")) return rc;
     if (c.psi != nullptr) {
         const int64_t n_warps = (int64_t)n * ((K + 31) / 32);
@@ -882,6 +893,18 @@ int largek_forward_backward(const float *emis, int emis_mode, float floor_eps, i
     LkFbCall c;
     if (int rc = lk_fb_prepare(c, emis, emis_mode, floor_eps, add_rowmax, trans_prob, init_prob, B, T, K, gamma, fwd_prob, bwd_prob,
                                log_alpha, log_beta, loglik, workspace, s)) return rc;
+    if (K > LK_KMAX) {                                          // step-per-launch path (recursion_xlk.cu)
+        const LkParams &p = c.p;
+        if (int r = xlk_sweep(0, emis, emis_mode, floor_eps, trans_prob, init_prob, p.rowmax, B, T, K, p.ws_a, p.ws_la, c.xl_extra, loglik, s)) return r;
+        if (c.both) {
+            auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+            float *PT = (float *)((uint8_t *)c.xl_extra + 2 * al((size_t)B * K * sizeof(float)));
+            lk_transpose_kernel<<<(K * K + 255) / 256, 256, 0, s>>>(trans_prob, K, PT);
+            if (int r = check_launch("lk_transpose_kernel")) return r;
+            if (int r = xlk_sweep(1, emis, emis_mode, floor_eps, PT, init_prob, p.rowmax, B, T, K, p.ws_b, p.ws_lb, c.xl_extra, nullptr, s)) return r;
+        }
+        return lk_fb_finish(c, s);
+    }
     LkParams q = c.p;
     q.loglik = nullptr;
     int rc = c.both ? lk_launch_multi(c.p, q, q, 2, s) : 1;    // forward and backward side by side when their clusters fit
@@ -897,6 +920,10 @@ int largek_viterbi(const float *emis, int emis_mode, float floor_eps, const floa
                    int B, int T, int K, float *delta, void *psi, int64_t *states, float *score, void *workspace, cudaStream_t s) {
     LkVitCall c;
     if (int rc = lk_vit_prepare(c, emis, emis_mode, floor_eps, log_trans, log_init, B, T, K, delta, psi, states, score, workspace, s)) return rc;
+    if (K > LK_KMAX) {
+        if (int r = xlk_sweep(2, emis, emis_mode, floor_eps, log_trans, log_init, c.p.rowmax, B, T, K, c.p.delta, nullptr, c.xl_extra, nullptr, s)) return r;
+        return lk_vit_finish(c, s);
+    }
     if (int rc = lk_launch<LK_VIT>(c.p, s)) return rc;
     return lk_vit_finish(c, s);
 }
@@ -907,6 +934,11 @@ int largek_fb_viterbi(const float *emis, int fb_mode, int vit_mode, float floor_
                       const float *init_prob, const float *log_trans, const float *log_init, int B, int T, int K,
                       float *gamma, float *fwd_prob, float *bwd_prob, float *log_alpha, float *log_beta, float *loglik,
                       float *delta, void *psi, int64_t *states, float *score, void *fb_workspace, void *vit_workspace, cudaStream_t s) {
+    if (K > LK_KMAX) {
+        if (int rc = largek_forward_backward(emis, fb_mode, floor_eps, add_rowmax, trans_prob, init_prob, B, T, K, gamma, fwd_prob, bwd_prob,
+                                             log_alpha, log_beta, loglik, fb_workspace, s)) return rc;
+        return largek_viterbi(emis, vit_mode, floor_eps, log_trans, log_init, B, T, K, delta, psi, states, score, vit_workspace, s);
+    }
     LkFbCall f;
     LkVitCall v;
     if (int rc = lk_fb_prepare(f, emis, fb_mode, floor_eps, add_rowmax, trans_prob, init_prob, B, T, K, gamma, fwd_prob, bwd_prob,

@@ -90,7 +90,7 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
     if (B < 0 || T < 0 || K <= 0) return set_error(HMMB200_EINVAL, "forward_backward: bad shape B=%d T=%d K=%d", B, T, K);
     if (B == 0 || T == 0) return HMMB200_OK;
     if (K > 32 && !largek_shape_ok(K))
-        return set_error(HMMB200_EUNSUPPORTED, "forward_backward: K <= 512 states supported (got %d)", K);
+        return set_error(HMMB200_EUNSUPPORTED, "forward_backward: K <= 2048 states supported (got %d)", K);
     if (!emis || !trans_prob || !init_prob) return set_error(HMMB200_EINVAL, "forward_backward: null input");
     if (emis_mode < 0 || emis_mode > 3) return set_error(HMMB200_EINVAL, "forward_backward: bad emis_mode %d", emis_mode);
     if (!workspace || workspace_bytes < hmmb200_fb_workspace_bytes(B, T, K))
@@ -138,7 +138,7 @@ HMMB200_EXPORT int hmmb200_viterbi_f32(const float *emis, int emis_mode, float f
     uint8_t *psi = (uint8_t *)psi_out;
     if (B < 0 || T < 0 || K <= 0) return set_error(HMMB200_EINVAL, "viterbi: bad shape B=%d T=%d K=%d", B, T, K);
     if (B == 0 || T == 0) return HMMB200_OK;
-    if (K > 32 && !largek_shape_ok(K)) return set_error(HMMB200_EUNSUPPORTED, "viterbi: K <= 512 states supported (got %d)", K);
+    if (K > 32 && !largek_shape_ok(K)) return set_error(HMMB200_EUNSUPPORTED, "viterbi: K <= 2048 states supported (got %d)", K);
     if (!emis || !log_trans || !log_init || !states) return set_error(HMMB200_EINVAL, "viterbi: null argument");
     if (emis_mode < 0 || emis_mode > 3) return set_error(HMMB200_EINVAL, "viterbi: bad emis_mode %d", emis_mode);
     size_t need = hmmb200_viterbi_workspace_bytes(B, T, K);

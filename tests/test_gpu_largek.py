@@ -34,7 +34,8 @@ def _exchange_ok(ws):
 
 @pytest.mark.parametrize("K,T,B", [(33, 7, 1), (40, 50, 3), (64, 64, 4), (65, 30, 5), (100, 45, 2), (128, 33, 9),
                                    (129, 20, 4), (200, 25, 3), (256, 40, 2), (257, 12, 1), (384, 18, 6), (500, 16, 2),
-                                   (512, 30, 5), (512, 1, 2), (48, 2, 1), (512, 10, 130), (64, 20, 150)])
+                                   (512, 30, 5), (512, 1, 2), (48, 2, 1), (512, 10, 130), (64, 20, 150),
+                                   (513, 12, 3), (600, 25, 9), (1024, 9, 2), (2048, 4, 1)])   # > 512: one launch per frame (recursion_xlk.cu)
 def test_largek_viterbi_bit_exact(hm, K, T, B):
     rng = np.random.default_rng(7000 + K + T)
     logb = (rng.standard_normal((B, T, K)) * 3.0).astype(np.float32)
@@ -48,7 +49,7 @@ def test_largek_viterbi_bit_exact(hm, K, T, B):
     ws = hm.ops.viterbi_workspace(B, T, K, "cuda")
     r = hm.ops.viterbi(_dev(logb), hm.ops.EMIS_LOG, _dev(logP), _dev(logp0), want_delta=True, want_psi=True, workspace=ws)
     torch.cuda.synchronize()
-    assert _exchange_ok(ws)
+    assert K > 512 or _exchange_ok(ws)
     assert np.array_equal(r["delta"].cpu().numpy(), delta)
     # packed backpointers: uint8 up to K = 256, uint16 above (int16 storage; K <= 512 so no sign issue)
     assert r["psi"].dtype == (torch.uint8 if K <= 256 else torch.int16)
@@ -61,7 +62,7 @@ def test_largek_viterbi_bit_exact(hm, K, T, B):
 
 
 @pytest.mark.parametrize("K,T,B", [(33, 9, 2), (50, 60, 3), (64, 100, 4), (96, 40, 5), (130, 50, 2), (256, 64, 3),
-                                   (300, 30, 1), (512, 80, 6), (512, 1, 1), (512, 8, 130)])
+                                   (300, 30, 1), (512, 80, 6), (512, 1, 1), (512, 8, 130), (520, 40, 3), (1000, 16, 10)])
 @pytest.mark.parametrize("mode", ["prob", "log", "norm_floor"])
 def test_largek_forward_backward_vs_float64(hm, K, T, B, mode):
     rng = np.random.default_rng(8000 + K + T)
@@ -88,7 +89,7 @@ def test_largek_forward_backward_vs_float64(hm, K, T, B, mode):
     r = hm.ops.forward_backward(_dev(e), emode, _dev(Pe), _dev(p0e), want=("gamma", "fwd", "bwd", "log_alpha", "log_beta"),
                                 workspace=ws)
     torch.cuda.synchronize()
-    assert _exchange_ok(ws)
+    assert K > 512 or _exchange_ok(ws)
     # 1e-4 relative on posteriors (atol 1e-7 for numerically-zero entries) and on the log-likelihood
     np.testing.assert_allclose(r["gamma"].cpu().numpy(), gam, rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(r["loglik"].cpu().numpy(), ll, rtol=RTOL, atol=1e-4)
@@ -166,7 +167,7 @@ def test_largek_both_group_sizes(hm, K, T, B):
     ws = hm.ops.viterbi_workspace(B, T, K, "cuda")
     r = hm.ops.viterbi(_dev(logb), hm.ops.EMIS_LOG, _dev(logP), _dev(np.log(p0)), want_delta=True, workspace=ws)
     torch.cuda.synchronize()
-    assert _exchange_ok(ws)
+    assert K > 512 or _exchange_ok(ws)
     assert np.array_equal(r["delta"].cpu().numpy(), delta)
     assert np.array_equal(r["states"].cpu().numpy(), st)
     assert np.array_equal(r["score"].cpu().numpy(), score)

@@ -347,9 +347,9 @@ def test_errors_and_edges(hm):
         hmm.forward_backward(torch.rand(2, 5, 4).cuda())
     with pytest.raises(ValueError):
         hm.HMM(torch.ones(3, 4))
-    e = torch.rand(2, 5, 600).cuda()
-    with pytest.raises(RuntimeError, match="K <= 512"):
-        hm.ops.viterbi(e, hm.ops.EMIS_LOG, torch.zeros(600, 600).cuda(), torch.zeros(600).cuda())
+    e = torch.rand(2, 5, 2100).cuda()                             # K <= 2048 (recursion_xlk.cu); beyond that the call is refused
+    with pytest.raises(RuntimeError, match="K <= 2048"):
+        hm.ops.viterbi(e, hm.ops.EMIS_LOG, torch.zeros(2100, 2100).cuda(), torch.zeros(2100).cuda())
     # empty batch is a no-op
     r = hm.ops.viterbi(torch.empty(0, 5, 3).cuda(), hm.ops.EMIS_LOG, torch.zeros(3, 3).cuda(), torch.zeros(3).cuda())
     assert r["states"].shape == (0, 5)
