@@ -60,10 +60,16 @@ __global__ void __launch_bounds__(XL_THREADS) xl_step_kernel(XlParams p) {
             }
             __syncthreads();
             // this thread's quarter of the 64 source states
-#pragma unroll 4
-            for (int ii = kq; ii < 64; ii += XL_KQ) {
-                const int i = i0 + ii;
-                const float m = (i < K && j < K) ? __ldg(p.M + (size_t)i * K + j) : NEUTRAL;
+            float mv[64 / XL_KQ];                            // all of the thread's matrix elements of this slice in flight at once
+#pragma unroll
+            for (int q = 0; q < 64 / XL_KQ; ++q) {
+                const int i = i0 + kq + XL_KQ * q;
+                mv[q] = (i < K && j < K) ? __ldg(p.M + (size_t)i * K + j) : NEUTRAL;
+            }
+#pragma unroll
+            for (int q = 0; q < 64 / XL_KQ; ++q) {
+                const int ii = kq + XL_KQ * q;
+                const float m = mv[q];
                 const float4 va = *reinterpret_cast<const float4 *>(&v_s[ii][0]), vb = *reinterpret_cast<const float4 *>(&v_s[ii][4]);
                 const float vv[XL_NS] = {va.x, va.y, va.z, va.w, vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
@@ -111,8 +117,11 @@ __global__ void __launch_bounds__(XL_THREADS) xl_step_kernel(XlParams p) {
             if (ok) {
                 p.v_cur[(size_t)b * K + j] = wv;
                 p.ws_out[((size_t)b * T + f) * K + j] = (p.dir == 0) ? wv : pre;
-                atomicMax(p.mx + (t % 3) * B + b, __float_as_uint(wv));
             }
+            // the 32 lanes of a warp finish the same sequence: one atomic per warp (a per-thread atomic put 1024 same-address
+            // atomics per sequence and step through the L2)
+            const unsigned wmax = __reduce_max_sync(FULL_MASK, __float_as_uint(wv));      // wv >= 0
+            if ((threadIdx.x & 31) == 0 && b < B) atomicMax(p.mx + (t % 3) * B + b, wmax);
             if (blockIdx.x == 0 && jl == 0 && b < B) {       // one thread per sequence keeps the running exponent
                 const int ks = ((t == 0) ? 0 : p.ksum[b]) + de;
                 p.ksum[b] = ks;
