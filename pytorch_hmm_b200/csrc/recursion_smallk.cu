@@ -122,9 +122,20 @@ HMMB200_EXPORT int hmmb200_forward_backward_f32(const float *emis, int emis_mode
     return HMMB200_OK;
 }
 
+// K <= 32: do the decoded path and the traceback tables of a group of sequences fit one CTA's shared memory?  (NS T bytes of path:
+// T up to ~24 k at K <= 4, ~48 k at K <= 8, ~95 k at K <= 16, ~190 k above.)  Longer sequences take the cluster kernel's sweep
+// (one CTA per group, trellis in HBM) and its path-only traceback: same arithmetic, same results, no length limit.
+static bool vit_smallk_fits(int T, int K) {
+    int G = group_lanes(K), L, nC; bool in_smem; size_t smem;
+    const size_t budget = 200 * 1024 - raw_stage_bytes(K, 32 / G);
+    vit_plan(T, G, L, nC, in_smem, smem, budget);
+    return smem <= budget;
+}
+
 HMMB200_EXPORT size_t hmmb200_viterbi_workspace_bytes(int B, int T, int K) {
     if (B <= 0 || T <= 0 || K <= 0) return 0;
     if (K > 32) return largek_shape_ok(K) ? largek_viterbi_workspace_bytes(B, T, K) : 0;
+    if (!vit_smallk_fits(T, K)) return largek_viterbi_workspace_bytes(B, T, K);
     int G = group_lanes(K), L, nC; bool in_smem; size_t smem;
     // (the launch may also carve the raw emission stage out of the same budget: plan with it, so that the query never under-reports)
     vit_plan(T, G, L, nC, in_smem, smem, 200 * 1024 - raw_stage_bytes(K, 32 / G));
@@ -145,7 +156,7 @@ HMMB200_EXPORT int hmmb200_viterbi_f32(const float *emis, int emis_mode, float f
     if (need && (!workspace || workspace_bytes < need))
         return set_error(HMMB200_EWORKSPACE, "viterbi: workspace %zu < %zu bytes", workspace_bytes, need);
     if (int rc = require_sm100()) return rc;
-    if (K > 32)
+    if (K > 32 || !vit_smallk_fits(T, K))
         return largek_viterbi(emis, emis_mode, floor_eps, log_trans, log_init, B, T, K, delta, psi, states, score, workspace,
                               (cudaStream_t)stream);
     VitParams p;

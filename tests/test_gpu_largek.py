@@ -178,3 +178,19 @@ def test_largek_both_group_sizes(hm, K, T, B):
     assert _exchange_ok(ws)
     np.testing.assert_allclose(f["gamma"].cpu().numpy(), gam, rtol=RTOL, atol=1e-7)
     np.testing.assert_allclose(f["loglik"].cpu().numpy(), ll, rtol=RTOL, atol=1e-4)
+
+
+@pytest.mark.parametrize("K,T,B", [(5, 120_000, 1), (12, 100_000, 2), (3, 30_000, 3)])
+def test_smallk_viterbi_has_no_length_limit(hm, K, T, B):
+    """Past the length whose traceback tables fit one CTA's shared memory (~24 k frames at K <= 4, ~95 k at K <= 16)
+    the small-K Viterbi call takes the cluster kernel's sweep and path-only traceback: bit-exact all the same."""
+    rng = np.random.default_rng(K + T)
+    logb = (rng.standard_normal((B, T, K)) * 2.0).astype(np.float32)
+    P = rng.random((K, K)).astype(np.float32) + 0.05
+    logP = np.log(P / P.sum(1, keepdims=True)).astype(np.float32)
+    logp0 = np.log(np.full(K, 1.0 / K)).astype(np.float32)
+    st, delta, psi, score = c_oracle.viterbi_f32(logb, logP, logp0)
+    r = hm.ops.viterbi(_dev(logb), hm.ops.EMIS_LOG, _dev(logP), _dev(logp0), want_delta=True)
+    assert np.array_equal(r["states"].cpu().numpy(), st)
+    assert np.array_equal(r["delta"].cpu().numpy(), delta)
+    assert np.array_equal(r["score"].cpu().numpy(), score)
