@@ -4,7 +4,8 @@ The reference gets its gradients from autograd through the per-time-step ATen op
 forward pass is one kernel launch, so the backward pass is written out: for L = log p(o_1..T),
     dL / d log b_t(k) = gamma_t(k),    dL / d log P(i,j) = sum_t xi_t(i,j),    dL / d log p0(k) = gamma_0(k)
 (docs/01_hmm_theory.md:196-227).  gamma comes from the forward-backward kernels, the xi sums from `hmmb200_xi_sum_f32`
-(weighted by the incoming gradient per sequence).  Small-K path only (K <= 32).
+(weighted by the incoming gradient per sequence); for K > 32 the same sums are one library GEMM per sequence over the scaled vectors
+the large-K sweeps leave in the workspace.
 """
 from __future__ import annotations
 
@@ -21,8 +22,6 @@ class _HMMLogLikelihood(torch.autograd.Function):
         dev = ops.require_cuda(emis.device if emis.is_cuda else None)
         e = ops._f32c(emis.detach(), dev)
         B, T, K = e.shape
-        if K > 32:
-            raise NotImplementedError("gradients of the log-likelihood are implemented for K <= 32")
         trans = torch.exp(ops._f32c(log_P.detach(), dev))
         init = torch.exp(ops._f32c(log_p0.detach(), dev))
         ws = ops.fb_workspace(B, T, K, dev)
@@ -50,14 +49,44 @@ class _HMMLogLikelihood(torch.autograd.Function):
                 grad_e = grad_e * p / (p + ctx.eps)
             grad_e = grad_e.to(ctx.devs[0])
         if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            xi = torch.zeros(K, K, dtype=torch.float64, device=dev)
-            g1 = torch.zeros(K, dtype=torch.float64, device=dev)
-            with torch.cuda.device(dev):
-                ops._check(_lib.load().hmmb200_xi_sum_f32(ops._p(e), int(ctx.mode), float(ctx.eps), ops._p(trans), ops._p(ws), ops._p(g),
-                                                          B, T, K, ops._p(xi), ops._p(g1), ops._stream(dev)), "hmmb200_xi_sum_f32")
+            if K > 32:
+                xi, g1 = _xi_sum_large_k(e, ctx.mode, ctx.eps, trans, ws, g)
+            else:
+                xi = torch.zeros(K, K, dtype=torch.float64, device=dev)
+                g1 = torch.zeros(K, dtype=torch.float64, device=dev)
+                with torch.cuda.device(dev):
+                    ops._check(_lib.load().hmmb200_xi_sum_f32(ops._p(e), int(ctx.mode), float(ctx.eps), ops._p(trans), ops._p(ws), ops._p(g),
+                                                              B, T, K, ops._p(xi), ops._p(g1), ops._stream(dev)), "hmmb200_xi_sum_f32")
             grad_P = xi.float().to(ctx.devs[1]) if ctx.needs_input_grad[1] else None
             grad_p0 = g1.float().to(ctx.devs[2]) if ctx.needs_input_grad[2] else None
         return grad_e, grad_P, grad_p0, None, None
+
+
+def _xi_sum_large_k(e, mode, eps, trans, ws, g):
+    """sum_b g_b sum_t xi_t(i,j) and sum_b g_b gamma_0 for K > 32, from the scaled alpha / beta vectors the large-K sweeps leave in the
+    forward-backward workspace:  xi_t = a_t(i) P(i,j) u_{t+1}(j) / Z_t with u = b~ .* beta, i.e.  P .* (A^T U)  -- a [K,T] x [T,K]
+    product per sequence, which is plain library GEMM work (torch.bmm), not a kernel of this package."""
+    B, T, K = e.shape
+    n = B * T
+    stride = (n * K * 4 + 255) & ~255
+    a = ws[: n * K * 4].view(torch.float32).view(B, T, K)
+    b = ws[stride: stride + n * K * 4].view(torch.float32).view(B, T, K)
+    if mode == ops.EMIS_PROB_FLOOR:
+        bt = e + eps
+    elif mode == ops.EMIS_LOG_EXP_FLOOR:
+        bt = torch.exp(e) + eps
+    else:
+        bt = torch.exp(e - e.max(-1, keepdim=True)[0]) + (eps if mode == ops.EMIS_LOG_NORM_FLOOR else 0.0)
+    g0 = a[:, 0] * b[:, 0]
+    g1 = ((g0 / g0.sum(-1, keepdim=True)).double() * g.double().view(B, 1)).sum(0)
+    if T < 2:
+        return torch.zeros(K, K, dtype=torch.float64, device=e.device), g1
+    U = bt[:, 1:] * b[:, 1:]                                               # [B,T-1,K]
+    A = a[:, :-1]
+    Z = (A * (U @ trans.t())).sum(-1, keepdim=True)                        # a_t . (P u_{t+1})
+    An = A / Z * g.view(B, 1, 1)
+    xi = trans.double() * torch.bmm(An.transpose(1, 2), U).double().sum(0)
+    return xi, g1
 
 
 def hmm_log_likelihood(emis: torch.Tensor, log_P: torch.Tensor, log_p0: torch.Tensor, mode: int = ops.EMIS_LOG,

@@ -115,7 +115,7 @@ class HMMPyTorch(HMM):
         last = r["fwd"][:, -1]
         ll = torch.logsumexp(torch.log(last + EPS), dim=-1)
         from . import autograd as ag
-        if ag.needs_grad(observations, self.log_P, self.log_p0) and self.K <= 32:
+        if ag.needs_grad(observations, self.log_P, self.log_p0):
             # Training callers (HMMLayer.compute_loss, hmm_layer.py:144-173).  The VALUE is the reference's saturating
             # formula; the gradient is that of the true log-likelihood damped by the saturation factor
             # sum_k alpha_k / sum_k (alpha_k + 1e-8) (equal to the reference's own gradient when no state is floored).

@@ -26,7 +26,7 @@ def _ref_loglik(log_b, log_P, log_p0):
     return la
 
 
-@pytest.mark.parametrize("K,T,B", [(3, 12, 2), (5, 40, 3), (12, 130, 4), (17, 33, 2), (32, 20, 1)])
+@pytest.mark.parametrize("K,T,B", [(3, 12, 2), (5, 40, 3), (12, 130, 4), (17, 33, 2), (32, 20, 1), (40, 25, 3), (130, 18, 2), (600, 9, 2)])
 def test_loglik_gradients_vs_float64_autograd(hm, K, T, B):
     from pytorch_hmm_b200.autograd import hmm_log_likelihood
     g = torch.Generator().manual_seed(K * 100 + T)
