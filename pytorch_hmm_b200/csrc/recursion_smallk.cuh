@@ -57,7 +57,6 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 // latency-critical consumer warps' shared-memory round trips queue in.  One cp.async.bulk per (sequence, chunk) moves the same
 // bytes without occupying that FIFO at all; its arrival is counted on an mbarrier (transaction bytes); NR chunks are in flight.
 constexpr int NR = 2;
-constexpr int RAW_REL_DEFAULT = 1;   // see loader_loop_bulk: how a reader warp releases a raw buffer
 __device__ __forceinline__ uint32_t sk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void sk_mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sk_smem_u32(bar)), "r"(count) : "memory");
@@ -91,14 +90,8 @@ struct RawStage {
     uint64_t *full, *empty;   // [NR] each: bytes of the chunk have landed / every reader warp has copied its frames out
     float *buf;               // [NR][NS][raw_seq_floats(K)]
     int seq_floats;
-    int rel;                  // how a reader warp releases a buffer (debug builds try the alternatives: p.bulk = 1 + 16 * rel)
-    __device__ RawStage() : full(nullptr), empty(nullptr), buf(nullptr), seq_floats(0), rel(1) {}
-    __device__ RawStage(uint8_t *smem, int K, int bulk) {
-#ifdef HMMB200_DEBUG_HOOKS
-        rel = bulk >> 4;
-#else
-        rel = RAW_REL_DEFAULT;
-#endif
+    __device__ RawStage() : full(nullptr), empty(nullptr), buf(nullptr), seq_floats(0) {}
+    __device__ RawStage(uint8_t *smem, int K, int /*bulk*/) {
         full = reinterpret_cast<uint64_t *>(smem);
         empty = full + NR;
         buf = reinterpret_cast<float *>(smem + 64);
@@ -191,6 +184,36 @@ __device__ __forceinline__ void row_to_log(int mode, float eps, int K, float (&e
     }
 }
 
+// scaled-probability form with the hardware exponential (ex2.approx, relative error 2^-22: far inside the 1e-4 contract of the
+// posteriors, and a fifth of the instructions of expf -- the helper warps' instruction footprint is what the consumers' instruction
+// fetches compete with, see the bulk loader below)
+__device__ __forceinline__ float fast_exp(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
+    return y;
+}
+template <int KP>
+__device__ __forceinline__ void row_to_scaled_fast(int mode, float eps, int K, float (&e)[KP], float &m) {
+    m = 0.f;
+    if (mode == HMMB200_EMIS_PROB_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = e[k] + eps;
+    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = fast_exp(e[k]) + eps;
+    } else {
+        float t[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) t[k] = (k < K) ? e[k] : -INFINITY;
+        float mx = max_tree<KP>(t);
+        if (!(mx > -INFINITY)) mx = 0.f;                     // all states impossible: keep the frame finite
+        const float add = (mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; ++k) e[k] = fast_exp(e[k] - mx) + add;
+        m = mx;
+    }
+}
+
 // Loader-warp loop: stream this CTA's NS sequences from HBM one chunk (CH frames) ahead of the consumer, transform each
 // frame (scaled-probability form for forward/backward, log form for Viterbi) and publish the per-lane values in bt[b]
 // (and the per-frame log-scale in mraw[b]).  NL loader warps split the frames; lane (sub, q) of loader `lw` handles
@@ -232,7 +255,7 @@ __device__ __forceinline__ void loader_loop(const float *emis, int mode, float e
             const int u = u_base + i;
             const bool ok = seq_ok && (c * CH + u) < T;
             float m = 0.f;
-            if (SCALED) row_to_scaled<KP>(mode, eps, K, cur[i], m);
+            if (SCALED) row_to_scaled_fast<KP>(mode, eps, K, cur[i], m);   // (the same arithmetic as the bulk-copy feed: results do not depend on the tensor's alignment)
             else row_to_log<KP>(mode, eps, K, cur[i]);
             float *dst = btb + u * BT_PITCH + sub * G;
 #pragma unroll
@@ -250,36 +273,6 @@ __device__ __forceinline__ void loader_loop(const float *emis, int mode, float e
             for (int k = 0; k < KP; ++k) cur[i][k] = nxt[i][k];
     }
     for (int c = max(0, nch - NB); c < nch; ++c) bar_sync(pb.done0 + (c % NB), pb.n);
-}
-
-// scaled-probability form with the hardware exponential (ex2.approx, relative error 2^-22: far inside the 1e-4 contract of the
-// posteriors, and a fifth of the instructions of expf -- the helper warps' instruction footprint is what the consumers' instruction
-// fetches compete with, see the bulk loader below)
-__device__ __forceinline__ float fast_exp(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));
-    return y;
-}
-template <int KP>
-__device__ __forceinline__ void row_to_scaled_fast(int mode, float eps, int K, float (&e)[KP], float &m) {
-    m = 0.f;
-    if (mode == HMMB200_EMIS_PROB_FLOOR) {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = e[k] + eps;
-    } else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) {
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = fast_exp(e[k]) + eps;
-    } else {
-        float t[KP];
-#pragma unroll
-        for (int k = 0; k < KP; ++k) t[k] = (k < K) ? e[k] : -INFINITY;
-        float mx = max_tree<KP>(t);
-        if (!(mx > -INFINITY)) mx = 0.f;                     // all states impossible: keep the frame finite
-        const float add = (mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f;
-#pragma unroll
-        for (int k = 0; k < KP; ++k) e[k] = fast_exp(e[k] - mx) + add;
-        m = mx;
-    }
 }
 
 // Same role with the chunks arriving in the raw stage by bulk copies (lane 0 of loader 0 issues them NR chunks ahead; needs every
@@ -1119,15 +1112,8 @@ inline void vit_plan(int T, int G, int &L, int &nC, bool &psi_in_smem, size_t &s
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 // every chunk of every sequence starts and ends on a 16-byte boundary: the bulk-copy feed applies
 inline bool bulk_feed_ok(const float *emis, int T, int K) { return (((uintptr_t)emis) & 15) == 0 && ((size_t)T * K) % 4 == 0; }
-// value of the kernels' `bulk` parameter: 0 per-lane loads, else 1 + 16 * (release variant; only debug builds look at it)
-inline int bulk_feed_param(const float *emis, int T, int K) {
-    if (!bulk_feed_ok(emis, T, K)) return 0;
-    int rel = RAW_REL_DEFAULT;
-#ifdef HMMB200_DEBUG_HOOKS
-    if (const char *e = getenv("HMMB200_RAW_REL")) rel = atoi(e);
-#endif
-    return 1 + 16 * rel;
-}
+// value of the kernels' `bulk` parameter: 1 bulk-copy feed, 0 per-lane loads
+inline int bulk_feed_param(const float *emis, int T, int K) { return bulk_feed_ok(emis, T, K) ? 1 : 0; }
 
 // posterior / exp(log alpha) / exp(log beta) from the scaled sweeps left in the workspace
 inline int launch_combine(const CombineParams &c, cudaStream_t s) {

@@ -479,3 +479,37 @@ def test_fused_pass_bf16_outputs_are_the_rounded_fp32_outputs(hm):
             assert torch.equal(r16[name], r32[name].to(torch.bfloat16)), name
         assert torch.equal(r16["states"], r32["states"]) and torch.equal(r16["delta"], r32["delta"])
         assert torch.equal(r16["loglik"], r32["loglik"])
+
+
+def test_recursion_kernels_side_by_side_are_deterministic(hm):
+    """Regression for the race found in round 2: a loader warp released its raw emission buffer before its shared-memory
+    loads had been performed, so the refill could overwrite rows still to be read -- visible only when another kernel shared the SM
+    (wrong Viterbi paths / forward values in 20-60 % of runs).  Viterbi on one stream, forward-backward on another, the full headline
+    batch so that the CTAs are co-resident; every repetition must reproduce the results of the kernels run alone, bit for bit."""
+    torch.manual_seed(33)
+    K, B, T = 12, 256, 2000
+    P = torch.softmax(torch.randn(K, K), -1).cuda() + 1e-8
+    p0 = torch.full((K,), 1.0 / K, device="cuda")
+    lb = 4.0 * torch.randn(B, T, K, device="cuda") - 60.0
+    logP, logp0 = torch.log(P), torch.log(p0)
+    ref_v = hm.ops.viterbi(lb, hm.ops.EMIS_LOG, logP, logp0, want_delta=True)
+    ref_f = hm.ops.forward_backward(lb, hm.ops.EMIS_LOG_NORM_FLOOR, P, p0, want=("gamma", "fwd"), method="sweep")
+    torch.cuda.synchronize()
+    ref = {k: v.clone() for k, v in (("states", ref_v["states"]), ("delta", ref_v["delta"]), ("gamma", ref_f["gamma"]), ("fwd", ref_f["fwd"]))}
+    aux = torch.cuda.Stream()
+    out_v = {"states": torch.empty_like(ref["states"]), "delta": torch.empty_like(ref["delta"]), "score": torch.empty(B, device="cuda")}
+    out_f = {"gamma": torch.empty_like(ref["gamma"]), "fwd": torch.empty_like(ref["fwd"]), "loglik": torch.empty(B, device="cuda")}
+    ws_f = hm.ops.fb_workspace(B, T, K, "cuda")
+    bad = 0
+    for _ in range(30):
+        out_v["delta"].zero_(); out_f["gamma"].zero_()
+        aux.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(aux):
+            hm.ops.forward_backward(lb, hm.ops.EMIS_LOG_NORM_FLOOR, P, p0, want=("gamma", "fwd"), out=out_f, workspace=ws_f, method="sweep")
+        hm.ops.viterbi(lb, hm.ops.EMIS_LOG, logP, logp0, out=out_v)
+        torch.cuda.current_stream().wait_stream(aux)
+        torch.cuda.synchronize()
+        same = (torch.equal(out_v["states"], ref["states"]) and torch.equal(out_v["delta"], ref["delta"])
+                and torch.equal(out_f["gamma"], ref["gamma"]) and torch.equal(out_f["fwd"], ref["fwd"]))
+        bad += 0 if same else 1
+    assert bad == 0, f"{bad} of 30 concurrent runs differ from the kernels run alone"

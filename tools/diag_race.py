@@ -1,6 +1,6 @@
-"""Isolate run-to-run differences of the small-K kernels when they run next to each other (debug build: per-kernel feed switches,
-HMMB200_RAW_REL = how a loader warp releases a raw-stage buffer: 0 syncwarp + arrive, 1 data-dependent vote + arrive, 2 syncwarp +
-fence.proxy.async + arrive)."""
+"""Run-to-run differences of the small-K kernels when they run next to each other (debug build: per-kernel feed switches).
+Round 2 found a write-after-read race on the raw emission stage with this script (a reader warp released a buffer before its
+shared-memory loads had been performed); it is kept as the regression check: every line must report 0 differences."""
 import os, sys
 os.environ["HMMB200_DEBUG_BUILD"] = "1"
 import torch
@@ -15,7 +15,7 @@ h.emission(x)
 torch.cuda.synchronize()
 e, o = h.eng, h.eng.out
 aux = torch.cuda.Stream(dev)
-ENV = ("HMMB200_NO_BULK", "HMMB200_NO_BULK_FB", "HMMB200_NO_BULK_VIT", "HMMB200_RAW_REL")
+ENV = ("HMMB200_NO_BULK", "HMMB200_NO_BULK_FB", "HMMB200_NO_BULK_VIT")
 
 
 def setenv(env):
@@ -24,7 +24,7 @@ def setenv(env):
     os.environ.update(env)
 
 
-# references from the per-lane feed, each kernel alone
+# references: each kernel alone (per-lane feed; the two feeds compute the same numbers)
 setenv({"HMMB200_NO_BULK": "1"})
 h.vit(); h.fb(); torch.cuda.synchronize()
 ref_v = (o["log_delta"].clone(), o["states"].clone())
@@ -77,14 +77,8 @@ def run_fused(tag, env, reps=60):
 
 
 run("viterbi per-lane beside fb per-lane", True, {"HMMB200_NO_BULK": "1"})
-for rel in ("0", "1", "2"):
-    run(f"rel={rel} viterbi bulk, alone", False, {"HMMB200_RAW_REL": rel})
-    run(f"rel={rel} viterbi bulk beside fb bulk", True, {"HMMB200_RAW_REL": rel})
-    run(f"rel={rel} viterbi bulk beside fb per-lane", True, {"HMMB200_RAW_REL": rel, "HMMB200_NO_BULK_FB": "1"})
-    run(f"rel={rel} viterbi per-lane beside fb bulk", True, {"HMMB200_RAW_REL": rel, "HMMB200_NO_BULK_VIT": "1"})
-    run_fused(f"rel={rel} fused kernel", {"HMMB200_RAW_REL": rel})
-
-# cost of the release variants (fused kernel, no posterior pass)
-for rel in ("1", "2", "1", "2"):
-    setenv({"HMMB200_RAW_REL": rel})
-    print(f"rel={rel} fused kernel {bench.event_ms(lambda: h.fused(want=()), 40):.4f} ms", flush=True)
+run("viterbi bulk, alone", False, {})
+run("viterbi bulk beside fb bulk", True, {})
+run("viterbi bulk beside fb per-lane", True, {"HMMB200_NO_BULK_FB": "1"})
+run("viterbi per-lane beside fb bulk", True, {"HMMB200_NO_BULK_VIT": "1"})
+run_fused("fused kernel", {})
