@@ -3,6 +3,11 @@
     python tools/run_ref_suite.py --vendor     # build container: copies /root/reference/tests/test_*.py into ref_suite/_vendored/
                                                # (git-ignored -- reference sources are never committed -- but it travels with gpurun)
     python tools/run_ref_suite.py --run        # GPU box: pytest over the vendored files, `import pytorch_hmm` aliased by ref_suite/alias.py
+    python tools/run_ref_suite.py --clean      # remove the vendored copies again (do this after the run: they are reference sources)
+
+Typical use from the build container:
+    python tools/run_ref_suite.py --vendor && gpurun -- 'python tools/run_ref_suite.py --run > gpurun_out/ref_suite.log 2>&1' ; python tools/run_ref_suite.py --clean
+The last result is kept in profiles/r02_reference_suite.txt.
 """
 import argparse
 import os
@@ -25,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--vendor", action="store_true")
     ap.add_argument("--run", action="store_true")
+    ap.add_argument("--clean", action="store_true")
     ap.add_argument("--ref", default="/root/reference")
     a = ap.parse_args()
     if a.vendor:
@@ -34,6 +40,9 @@ def main():
         with open(os.path.join(VENDOR, "conftest.py"), "w") as fh:
             fh.write(CONFTEST)
         print("vendored", FILES, "->", VENDOR)
+    if a.clean:
+        shutil.rmtree(VENDOR, ignore_errors=True)
+        print("removed", VENDOR)
     if a.run:
         if not os.path.isdir(VENDOR):
             raise SystemExit("ref_suite/_vendored is missing: run with --vendor in the build container first")
