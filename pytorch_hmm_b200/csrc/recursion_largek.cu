@@ -31,6 +31,7 @@
 #include "common.cuh"
 
 #include <cooperative_groups.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace cg = cooperative_groups;
@@ -129,14 +130,17 @@ __device__ __forceinline__ void lk_cp_commit() { asm volatile("cp.async.commit_g
 template <int N>
 __device__ __forceinline__ void lk_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NSQ>
+// A group holds NSQ x NP sequences: the product and the finals take them in NP passes of NSQ (the register accumulators of a pass
+// are the limit), the exchange moves the whole group at once.  With NP = 2 there are half as many groups (same footprint).
+template <int NSQ, int NP>
 struct LkSmem {
-    float vec[LK_NG][2][LK_CSMAX][NSQ][LK_BLK];   // the exchanged state vector: one block per source CTA, double-buffered
-    float part[LK_NG][LK_NSL][NSQ][LK_NC];        // per-k-slice partial sums, one buffer per group
-    float stage[LK_NG][2][NSQ][LK_BLK];           // this CTA's new block before it is pushed (double-buffered)
-    float eraw[LK_NG][LK_PF][LK_FINAL];              // prefetched emissions, one slot per final thread
-    float mraw[LK_NG][LK_PF][LK_FINAL];              // prefetched per-frame max
-    uint64_t bar[LK_NG][2];
+    static constexpr int NSQT = NSQ * NP, NGM = LK_NG / NP;
+    float vec[NGM][2][LK_CSMAX][NSQT][LK_BLK];    // the exchanged state vector: one block per source CTA, double-buffered
+    float part[NGM][LK_NSL][NSQT][LK_NC];         // per-k-slice partial sums, one buffer per group
+    float stage[NGM][2][NSQT][LK_BLK];            // this CTA's new block before it is pushed (double-buffered)
+    float eraw[NGM][LK_PF][NP][LK_FINAL];         // prefetched emissions, one slot per (pass, final thread)
+    float mraw[NGM][LK_PF][NP][LK_FINAL];         // prefetched per-frame max
+    uint64_t bar[NGM][2];
 };
 
 // timing trace (debug builds only, -DHMMB200_DEBUG_HOOKS; tools/lk_trace.py): clock64 at the phase boundaries of steps 64..71 of
@@ -164,35 +168,38 @@ __device__ long long lk_trace_buf[8 * 8];
 __device__ __forceinline__ void lk_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void lk_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <int MODE, int NSQ>
+template <int MODE, int NSQ, int NP>
 __device__ __forceinline__ void lk_sweep_body(const LkParams &p, const int cluster_id) {
     extern __shared__ __align__(16) uint8_t lk_smem_raw[];
-    LkSmem<NSQ> &sm = *reinterpret_cast<LkSmem<NSQ> *>(lk_smem_raw);
+    using Smem = LkSmem<NSQ, NP>;
+    constexpr int NSQT = Smem::NSQT, NGM = Smem::NGM;
+    Smem &sm = *reinterpret_cast<Smem *>(lk_smem_raw);
     constexpr bool VIT = (MODE == LK_VIT);
     constexpr int DIR = (MODE == LK_BWD) ? 1 : 0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int K = p.K, T = p.T, B = p.B, CS = p.CS;
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
-    const int seq0 = cluster_id * (NSQ * p.ngr);
+    const int seq0 = cluster_id * (NSQT * p.ngr);
     const int col0 = rank * LK_NC;
     const float PADV = VIT ? -INFINITY : 0.f;
-    const int n_groups = min(p.ngr, (B - seq0 + NSQ - 1) / NSQ);   // groups of this cluster that hold sequences
+    const int n_groups = min(min(p.ngr, NGM), (B - seq0 + NSQT - 1) / NSQT);   // groups of this cluster that hold sequences
 
-    for (int i = tid; i < LK_NG * 2 * LK_CSMAX * NSQ * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
-    for (int i = tid; i < LK_NG * 2 * NSQ * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
-    for (int i = tid; i < LK_NG * LK_NSL * NSQ * LK_NC; i += LK_THREADS) (&sm.part[0][0][0][0])[i] = PADV;   // idle k-slices: neutral element
+    for (int i = tid; i < NGM * 2 * LK_CSMAX * NSQT * LK_BLK; i += LK_THREADS) (&sm.vec[0][0][0][0][0])[i] = 0.f;   // unused blocks stay 0
+    for (int i = tid; i < NGM * 2 * NSQT * LK_BLK; i += LK_THREADS) (&sm.stage[0][0][0][0])[i] = 0.f;
+    for (int i = tid; i < NGM * LK_NSL * NSQT * LK_NC; i += LK_THREADS) (&sm.part[0][0][0][0])[i] = PADV;   // idle k-slices: neutral element
     // bytes every receiver gets per step and group: one [NSQ][BLK] block from each of the CS CTAs
-    constexpr uint32_t BLOCK_BYTES = NSQ * LK_BLK * sizeof(float);
-    const uint32_t tx_bytes = (uint32_t)CS * BLOCK_BYTES;
+    constexpr uint32_t BLOCK_BYTES = NSQT * LK_BLK * sizeof(float);
+    const uint32_t tx_bytes = (uint32_t)(CS - 1) * BLOCK_BYTES;   // (the CTA's own block is written in place by its final warps)
     if (tid == 0) {
 #pragma unroll
-        for (int g = 0; g < LK_NG; ++g) { lk_mbar_init(&sm.bar[g][0], 1); lk_mbar_init(&sm.bar[g][1], 1); }
+        // a phase = the arming thread's expect_tx + the 8 final warps of this CTA (own block) + the bytes of the other CTAs' blocks
+        for (int g = 0; g < NGM; ++g) { lk_mbar_init(&sm.bar[g][0], 1 + LK_NWC); lk_mbar_init(&sm.bar[g][1], 1 + LK_NWC); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // step 0 is armed here: the final warps push it without waiting for the compute warps (no product at t = 0),
         // so nothing else orders this expect_tx before their complete_tx
 #pragma unroll
-        for (int g = 0; g < LK_NG; ++g)
+        for (int g = 0; g < NGM; ++g)
             if (g < n_groups) lk_mbar_expect_tx(&sm.bar[g][0], tx_bytes);
     }
     cluster.sync();                                          // every CTA's mbarriers exist (and are armed) before anyone pushes
@@ -232,8 +239,10 @@ __device__ __forceinline__ void lk_sweep_body(const LkParams &p, const int clust
                 if (ok) ok = lk_mbar_wait(&sm.bar[g][prv], ((t - 1) >> 1) & 1);   // after a time-out: drain without waiting
                 LK_TRACE(1);
                 if (active) {
-                    const float *v = &sm.vec[g][prv][warp][0][hw * LK_KH];             // states 64w.. = CTA w's block
-                    float *po = &sm.part[g][2 * warp + hw][0][c4];
+#pragma unroll 1                                             // (one copy of the product code: the passes differ by shared-memory offsets only)
+                  for (int h = 0; h < NP; ++h) {
+                    const float *v = &sm.vec[g][prv][warp][h * NSQ][hw * LK_KH];       // states 64w.. = CTA w's block
+                    float *po = &sm.part[g][2 * warp + hw][h * NSQ][c4];
                     if (!VIT) {
                         float2 acc[NSQ][4];
 #pragma unroll
@@ -279,6 +288,7 @@ __device__ __forceinline__ void lk_sweep_body(const LkParams &p, const int clust
                         for (int s = 0; s < NSQ; ++s)
                             *reinterpret_cast<float4 *>(po + s * LK_NC) = make_float4(m[s][0], m[s][1], m[s][2], m[s][3]);
                     }
+                  }
                     LK_TRACE(2);
                 }
                 // (part[g] is free again by then: group g's next exchange, which the wait above needs, is pushed after its finals)
@@ -298,18 +308,21 @@ __device__ __forceinline__ void lk_sweep_body(const LkParams &p, const int clust
             if (t < T && valid) {
                 const int f = frame_of(t);
 #pragma unroll
-                for (int g = 0; g < LK_NG; ++g) {
+                for (int g = 0; g < NGM; ++g) {
                     if (g >= n_groups) continue;
-                    const int sq = seq0 + g * NSQ + fs;
-                    const bool okk = sq < B && gcol < K;
-                    lk_cp_async4(&sm.eraw[g][t % LK_PF][ft], p.emis + ((size_t)(okk ? sq : 0) * T + f) * K + (okk ? gcol : 0));
-                    if (need_m) lk_cp_async4(&sm.mraw[g][t % LK_PF][ft], p.rowmax + (size_t)(sq < B ? sq : 0) * T + f);
+#pragma unroll
+                    for (int h = 0; h < NP; ++h) {
+                        const int sq = seq0 + g * NSQT + h * NSQ + fs;
+                        const bool okk = sq < B && gcol < K;
+                        lk_cp_async4(&sm.eraw[g][t % LK_PF][h][ft], p.emis + ((size_t)(okk ? sq : 0) * T + f) * K + (okk ? gcol : 0));
+                        if (need_m) lk_cp_async4(&sm.mraw[g][t % LK_PF][h][ft], p.rowmax + (size_t)(sq < B ? sq : 0) * T + f);
+                    }
                 }
             }
             lk_cp_commit();
         };
         for (int t = 0; t < LK_PF - 1; ++t) prefetch(t);
-        int ks0 = 0, ks1 = 0, ks2 = 0, ks3 = 0;              // running power-of-two exponent per group (scalars: the group loop is rolled)
+        int ks0 = 0, ks1 = 0, ks2 = 0, ks3 = 0;              // running power-of-two exponent per (group, pass) (scalars: the loops are rolled)
         static_assert(LK_NG == 4, "four exponent scalars");
         float *ws_l = (DIR == 0) ? p.ws_la : p.ws_lb;
 
@@ -320,105 +333,126 @@ __device__ __forceinline__ void lk_sweep_body(const LkParams &p, const int clust
             const int f = frame_of(t);
 #pragma unroll 1
             for (int g = 0; g < n_groups; ++g) {
-                const int fseq = seq0 + g * NSQ + fs;
-                const bool f_ok = valid && fseq < B && gcol < K;
-                const float raw = sm.eraw[g][t % LK_PF][ft];
-                const float mf = need_m ? sm.mraw[g][t % LK_PF][ft] : 0.f;
-                float bq = 0.f, lb = 0.f;                    // emission: probability form (fb) / log form (viterbi)
-                if (!VIT) {
-                    if (p.mode == HMMB200_EMIS_PROB_FLOOR) bq = raw + p.eps;
-                    else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) bq = expf(raw) + p.eps;
-                    else bq = expf(raw - mf) + ((p.mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? p.eps : 0.f);
-                    if (!f_ok) bq = 0.f;
-                } else {                                     // the reference's formula per input kind
-                    if (p.mode == HMMB200_EMIS_LOG) lb = raw;
-                    else if (p.mode == HMMB200_EMIS_PROB_FLOOR) lb = logf(raw + p.eps);
-                    else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) lb = logf(expf(raw) + p.eps);
-                    else lb = logf(expf(raw - mf) + p.eps);
-                }
                 if (t > 0) {
                     lk_bar_sync(LK_BAR_PART + g, LK_THREADS);                           // all k-slice partials are in part[g]
                     if (ok) ok = lk_mbar_wait(&sm.bar[g][prv], ((t - 1) >> 1) & 1);     // the previous vector (its maxima) is visible
                 }
                 LK_TRACE(4);
-                float wv, pre = 0.f;                         // wv: the value pushed to the cluster
-                if (!VIT) {
-                    float acc, r = 1.f;
-                    if (t == 0) {
-                        acc = (DIR == 0) ? (f_ok ? __ldg(p.init + gcol) : 0.f) : (f_ok ? 1.f : 0.f);
-                    } else {
-                        float a4[4];                         // fixed summation order: deterministic
+                float wv_h[NP], pre_h[NP];                   // wv: the value pushed to the cluster
 #pragma unroll
-                        for (int w = 0; w < LK_NSL; ++w) {
-                            const float x = sm.part[g][w][fs][fc];
-                            a4[w & 3] = (w < 4) ? x : a4[w & 3] + x;
-                        }
-                        acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
-                        // power-of-two normaliser from the largest entry of the previous vector (all CTAs' local maxima)
-                        float m = 0.f;
-#pragma unroll
-                        for (int q = 0; q < LK_CSMAX; ++q) {
-                            const float2 y = *reinterpret_cast<const float2 *>(&sm.vec[g][prv][q][fs][LK_NC]);
-                            m = lk_fmax3(m, y.x, y.y);
-                        }
-                        const unsigned eb = __float_as_uint(m) >> 23;
-                        const int de = (int)eb - 127;
-                        if (g == 0) ks0 += de; else if (g == 1) ks1 += de; else if (g == 2) ks2 += de; else ks3 += de;
-                        r = __uint_as_float((254u - eb) << 23);
+                for (int h = 0; h < NP; ++h) {
+                    const int gs = h * NSQ + fs;             // sequence within the group
+                    const int fseq = seq0 + g * NSQT + gs;
+                    const bool f_ok = valid && fseq < B && gcol < K;
+                    const float raw = sm.eraw[g][t % LK_PF][h][ft];
+                    const float mf = need_m ? sm.mraw[g][t % LK_PF][h][ft] : 0.f;
+                    float bq = 0.f, lb = 0.f;                // emission: probability form (fb) / log form (viterbi)
+                    if (!VIT) {
+                        if (p.mode == HMMB200_EMIS_PROB_FLOOR) bq = raw + p.eps;
+                        else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) bq = expf(raw) + p.eps;
+                        else bq = expf(raw - mf) + ((p.mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? p.eps : 0.f);
+                        if (!f_ok) bq = 0.f;
+                    } else {                                 // the reference's formula per input kind
+                        if (p.mode == HMMB200_EMIS_LOG) lb = raw;
+                        else if (p.mode == HMMB200_EMIS_PROB_FLOOR) lb = logf(raw + p.eps);
+                        else if (p.mode == HMMB200_EMIS_LOG_EXP_FLOOR) lb = logf(expf(raw) + p.eps);
+                        else lb = logf(expf(raw - mf) + p.eps);
                     }
-                    pre = acc * r;                           // beta_t (scaled) for the backward sweep
-                    wv = acc * (bq * r);
-                } else {
-                    float acc;
-                    if (t == 0) {
-                        acc = f_ok ? __ldg(p.init + gcol) : -INFINITY;
-                    } else {
-                        float a4[4];
+                    float wv, pre = 0.f;
+                    if (!VIT) {
+                        float acc, r = 1.f;
+                        if (t == 0) {
+                            acc = (DIR == 0) ? (f_ok ? __ldg(p.init + gcol) : 0.f) : (f_ok ? 1.f : 0.f);
+                        } else {
+                            float a4[4];                     // fixed summation order: deterministic
 #pragma unroll
-                        for (int w = 0; w < LK_NSL; ++w) {
-                            const float x = sm.part[g][w][fs][fc];
-                            a4[w & 3] = (w < 4) ? x : fmaxf(a4[w & 3], x);
+                            for (int w = 0; w < LK_NSL; ++w) {
+                                const float x = sm.part[g][w][gs][fc];
+                                a4[w & 3] = (w < 4) ? x : a4[w & 3] + x;
+                            }
+                            acc = (a4[0] + a4[1]) + (a4[2] + a4[3]);
+                            // power-of-two normaliser from the largest entry of the previous vector (all CTAs' local maxima)
+                            float m = 0.f;
+#pragma unroll
+                            for (int q = 0; q < LK_CSMAX; ++q) {
+                                const float2 y = *reinterpret_cast<const float2 *>(&sm.vec[g][prv][q][gs][LK_NC]);
+                                m = lk_fmax3(m, y.x, y.y);
+                            }
+                            const unsigned eb = __float_as_uint(m) >> 23;
+                            const int de = (int)eb - 127;
+                            const int ki = g * NP + h;
+                            if (ki == 0) ks0 += de; else if (ki == 1) ks1 += de; else if (ki == 2) ks2 += de; else ks3 += de;
+                            r = __uint_as_float((254u - eb) << 23);
                         }
-                        acc = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
+                        pre = acc * r;                       // beta_t (scaled) for the backward sweep
+                        wv = acc * (bq * r);
+                    } else {
+                        float acc;
+                        if (t == 0) {
+                            acc = f_ok ? __ldg(p.init + gcol) : -INFINITY;
+                        } else {
+                            float a4[4];
+#pragma unroll
+                            for (int w = 0; w < LK_NSL; ++w) {
+                                const float x = sm.part[g][w][gs][fc];
+                                a4[w & 3] = (w < 4) ? x : fmaxf(a4[w & 3], x);
+                            }
+                            acc = fmaxf(fmaxf(a4[0], a4[1]), fmaxf(a4[2], a4[3]));
+                        }
+                        wv = f_ok ? __fadd_rn(acc, lb) : -INFINITY;   // delta_t = max_i(..) + log b_t  (hmm.py:168)
                     }
-                    wv = f_ok ? __fadd_rn(acc, lb) : -INFINITY;   // delta_t = max_i(..) + log b_t  (hmm.py:168)
+                    wv_h[h] = wv; pre_h[h] = pre;
+                    // ---- stage the block in shared memory for the other CTAs; the CTA's own copy is written in place
+                    if (valid) { sm.stage[g][cur][gs][fc] = wv; sm.vec[g][cur][rank][gs][fc] = wv; }
+                    if (!VIT && valid) {
+                        const float lmax = __uint_as_float(__reduce_max_sync(FULL_MASK, __float_as_uint(wv)));   // wv >= 0
+                        if (lane == 0) { sm.stage[g][cur][gs][LK_NC + (fwarp & 1)] = lmax; sm.vec[g][cur][rank][gs][LK_NC + (fwarp & 1)] = lmax; }
+                    }
                 }
-                // ---- push the block: stage in shared memory, then ONE bulk DSMEM copy per CTA of the cluster --------
-                if (valid) sm.stage[g][cur][fs][fc] = wv;
-                if (!VIT && valid) {
-                    const float lmax = __uint_as_float(__reduce_max_sync(FULL_MASK, __float_as_uint(wv)));   // wv >= 0
-                    if (lane == 0) sm.stage[g][cur][fs][LK_NC + (fwarp & 1)] = lmax;
-                }
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(lk_smem_u32(&sm.bar[g][cur])) : "memory");
+                // ---- push: ONE bulk DSMEM copy per OTHER CTA of the cluster for the whole group.  These shared::cta -> shared::cluster
+                // copies are what a step costs: they move ~3 bytes per cycle per SM (~27 B/cycle for the whole cluster, all CTAs
+                // sending at once) -- 2 600 cycles per group of 4 sequences against 1 100 - 1 400 cycles of product, i.e. 5 400 /
+                // 7 900 / 10 100 cycles per step with 2 / 3 / 4 one-pass groups (tools/lk_trace.py).  Four other exchanges were
+                // measured and lost (profiles/r02_largek_exchange_experiments.txt).
                 LK_TRACE(5);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async-proxy reads
                 lk_bar_sync(LK_BAR_FINAL, LK_FINAL);
                 LK_TRACE(6);
                 // (the bulk copy is a per-warp uniform-datapath instruction: one destination per final warp)
-                if (lane == 0 && fwarp < CS)
+                if (lane == 0 && fwarp < CS && fwarp != rank)
                     lk_bulk_push(lk_mapa(lk_smem_u32(&sm.vec[g][cur][rank][0][0]), fwarp), lk_smem_u32(&sm.stage[g][cur][0][0]),
                                  BLOCK_BYTES, lk_mapa(lk_smem_u32(&sm.bar[g][cur]), fwarp));
                 LK_TRACE(7);
                 // ---- results to HBM: after the push, off the step's critical path.  The log scale goes out as the integer
                 // exponent; lk_logscale_kernel turns it into log units (and adds the per-frame maxima) in double afterwards.
-                if (f_ok) {
-                    const size_t o = ((size_t)fseq * T + f) * K + gcol;
-                    if (VIT) p.delta[o] = wv;
-                    else if (DIR == 0) p.ws_a[o] = wv;
-                    else p.ws_b[o] = pre;
+#pragma unroll
+                for (int h = 0; h < NP; ++h) {
+                    const int fseq = seq0 + g * NSQT + h * NSQ + fs;
+                    const bool f_ok = valid && fseq < B && gcol < K;
+                    if (f_ok) {
+                        const size_t o = ((size_t)fseq * T + f) * K + gcol;
+                        if (VIT) p.delta[o] = wv_h[h];
+                        else if (DIR == 0) p.ws_a[o] = wv_h[h];
+                        else p.ws_b[o] = pre_h[h];
+                    }
+                    if (!VIT && rank == 0 && fc == 0 && valid && fseq < B) {
+                        const int ki = g * NP + h;
+                        ws_l[(size_t)fseq * T + f] = __int_as_float((ki == 0) ? ks0 : ((ki == 1) ? ks1 : ((ki == 2) ? ks2 : ks3)));
+                    }
                 }
-                if (!VIT && rank == 0 && fc == 0 && valid && fseq < B)
-                    ws_l[(size_t)fseq * T + f] = __int_as_float((g == 0) ? ks0 : ((g == 1) ? ks1 : ((g == 2) ? ks2 : ks3)));
             }
         }
     }
 
     // ---- epilogue: everybody waits for the last vectors (no CTA may exit while blocks are still in flight to it) ------
 #pragma unroll
-    for (int g = 0; g < LK_NG; ++g)
+    for (int g = 0; g < NGM; ++g)
         if (g < n_groups && ok) ok = lk_mbar_wait(&sm.bar[g][(T - 1) & 1], ((T - 1) >> 1) & 1);
     __syncthreads();
-    if (MODE == LK_FWD && p.loglik != nullptr && rank == 0 && warp < n_groups * NSQ) {
-        const int g = warp / NSQ, s = warp % NSQ, sq = seq0 + warp;
+    if (MODE == LK_FWD && p.loglik != nullptr && rank == 0 && warp < n_groups * NSQT) {
+        const int g = warp / NSQT, s = warp % NSQT, sq = seq0 + warp;
         if (sq < B) {
             float tot = 0.f;
             for (int k = lane; k < K; k += 32) tot += sm.vec[g][(T - 1) & 1][k / LK_NC][s][k % LK_NC];
@@ -431,22 +465,21 @@ __device__ __forceinline__ void lk_sweep_body(const LkParams &p, const int clust
     cluster.sync();
 }
 
-template <int MODE, int NSQ>
+template <int MODE, int NSQ, int NP>
 __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_kernel(LkParams p) {
-    lk_sweep_body<MODE, NSQ>(p, (int)blockIdx.x / p.CS);
+    lk_sweep_body<MODE, NSQ, NP>(p, (int)blockIdx.x / p.CS);
 }
 
 // Several sweeps of the same batch in ONE launch (forward + backward, or forward + backward + Viterbi): clusters [0, ncl) run the
 // forward sweep, [ncl, 2 ncl) the backward sweep, [2 ncl, 3 ncl) the Viterbi recursion.  A B200 holds 15 clusters of 8 CTAs; on its
-// own a sweep of B = 64 sequences takes 11 of them, so the sweeps of one call used to run one after another.  With more sequence
-// groups per cluster (LkParams::ngr) the sweeps fit side by side, and the FMA pipes the lone sweep left idle between exchanges are
-// used by the other groups.
-template <int NSQ>
+// own a sweep of B = 64 sequences takes 11 of them, so the sweeps of one call used to run one after another.  With more sequences
+// per cluster (LkParams::ngr groups, NP passes per group) the sweeps fit side by side.
+template <int NSQ, int NP>
 __global__ void __launch_bounds__(LK_THREADS, 1) lk_sweep_multi_kernel(LkParams pf, LkParams pb, LkParams pv, int ncl) {
     const int c = (int)blockIdx.x / pf.CS;
-    if (c < ncl) lk_sweep_body<LK_FWD, NSQ>(pf, c);
-    else if (c < 2 * ncl) lk_sweep_body<LK_BWD, NSQ>(pb, c - ncl);
-    else lk_sweep_body<LK_VIT, NSQ>(pv, c - 2 * ncl);
+    if (c < ncl) lk_sweep_body<LK_FWD, NSQ, NP>(pf, c);
+    else if (c < 2 * ncl) lk_sweep_body<LK_BWD, NSQ, NP>(pb, c - ncl);
+    else lk_sweep_body<LK_VIT, NSQ, NP>(pv, c - 2 * ncl);
 }
 
 // ----------------------------------------------------------------------------------------------------------------------
@@ -538,13 +571,14 @@ __global__ void lk_transpose_kernel(const float *src, int K, float *dst) {
     if (i < K * K) dst[(size_t)(i % K) * K + i / K] = src[i];
 }
 
+// first arg-max over the warp of (v, i), v never NaN: two warp reductions (REDUX) on an order-preserving integer key instead of five
+// shuffle rounds -- the traceback's step is a dependency chain and this is a third of it
 __device__ __forceinline__ void lk_warp_argmax(float &v, int &i) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(FULL_MASK, v, o);
-        const int oi = __shfl_xor_sync(FULL_MASK, i, o);
-        if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
-    }
+    const unsigned u = __float_as_uint(v + 0.f);                       // (-0 -> +0: equal values must get equal keys)
+    const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    const unsigned mx = __reduce_max_sync(FULL_MASK, key);
+    i = (int)__reduce_min_sync(FULL_MASK, (key == mx) ? (unsigned)i : 0xffffffffu);
+    v = __uint_as_float((mx & 0x80000000u) ? (mx & 0x7fffffffu) : ~mx);
 }
 
 template <int MAXR>                                          // delta-row registers per lane: K <= 32 MAXR
@@ -659,18 +693,16 @@ static int lk_cluster_size(int K) {
     return cs;                                               // 1, 2, 4 or 8
 }
 
-// Sequences per group: 3 when one wave of clusters still covers the batch (more clusters = more SMs on a latency-bound
-// sweep: B = 64 runs on 11 clusters = 88 SMs instead of 8 = 64), otherwise 4 (fewer waves).
-template <int MODE, int NSQ>
+// Clusters of `cs` CTAs that are co-resident on the device (every variant of the sweep kernels takes one SM per CTA).
 static int lk_max_clusters(int cs) {
     static int cache[LK_CSMAX + 1] = {0};
     if (cache[cs] > 0) return cache[cs];
-    auto kern = lk_sweep_kernel<MODE, NSQ>;
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem<NSQ>));
+    auto kern = lk_sweep_kernel<LK_FWD, 4, 1>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LkSmem<4, 1>));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(cs * 32), 1, 1);
     cfg.blockDim = dim3(LK_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = sizeof(LkSmem<NSQ>);
+    cfg.dynamicSmemBytes = sizeof(LkSmem<4, 1>);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -678,30 +710,6 @@ static int lk_max_clusters(int cs) {
     int n = 0;
     if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = 1; }
     return cache[cs] = n;
-}
-
-template <int MODE, int NSQ>
-static int lk_launch_nsq(const LkParams &p, cudaStream_t s) {
-    auto kern = lk_sweep_kernel<MODE, NSQ>;
-    const size_t smem = sizeof(LkSmem<NSQ>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K smem opt-in: %s", cudaGetErrorString(e));
-    const int n_clusters = (p.B + NSQ * p.ngr - 1) / (NSQ * p.ngr);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(n_clusters * p.CS), 1, 1);
-    cfg.blockDim = dim3(LK_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p.CS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, p);
-    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K sweep launch: %s", cudaGetErrorString(e));
-    return check_launch("lk_sweep_kernel");
 }
 
 // An exchange wait that timed out (never in a correct run) leaves the sweep's outputs undefined: make that visible to a caller
@@ -716,13 +724,11 @@ __global__ void lk_poison_kernel(const int *err, int B, int T, float *loglik, fl
     }
 }
 
-template <int NSQ>
-static int lk_launch_multi_nsq(const LkParams &pf, const LkParams &pb, const LkParams &pv, int n_modes, cudaStream_t s) {
-    auto kern = lk_sweep_multi_kernel<NSQ>;
-    const size_t smem = sizeof(LkSmem<NSQ>);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K smem opt-in: %s", cudaGetErrorString(e));
-    const int ncl = (pf.B + NSQ * pf.ngr - 1) / (NSQ * pf.ngr);
+// n_modes sweeps (1: mode0; 2: forward + backward; 3: + Viterbi) in one launch with NSQ x NP sequences per group
+template <int NSQ, int NP>
+static int lk_launch_variant(int mode0, const LkParams &pf, const LkParams &pb, const LkParams &pv, int n_modes, cudaStream_t s) {
+    const size_t smem = sizeof(LkSmem<NSQ, NP>);
+    const int ncl = (pf.B + NSQ * NP * pf.ngr - 1) / (NSQ * NP * pf.ngr);
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(n_modes * ncl * pf.CS), 1, 1);
     cfg.blockDim = dim3(LK_THREADS, 1, 1);
@@ -735,39 +741,72 @@ static int lk_launch_multi_nsq(const LkParams &pf, const LkParams &pb, const LkP
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, pf, pb, pv, ncl);
-    if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K multi-sweep launch: %s", cudaGetErrorString(e));
-    return check_launch("lk_sweep_multi_kernel");
+    auto launch = [&](auto kern, auto... args) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K smem opt-in: %s", cudaGetErrorString(e));
+        e = cudaLaunchKernelEx(&cfg, kern, args...);
+        if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "large-K sweep launch: %s", cudaGetErrorString(e));
+        return check_launch("lk_sweep_kernel");
+    };
+    if (n_modes > 1) return launch(lk_sweep_multi_kernel<NSQ, NP>, pf, pb, pv, ncl);
+    if (mode0 == LK_FWD) return launch(lk_sweep_kernel<LK_FWD, NSQ, NP>, pf);
+    if (mode0 == LK_BWD) return launch(lk_sweep_kernel<LK_BWD, NSQ, NP>, pf);
+    return launch(lk_sweep_kernel<LK_VIT, NSQ, NP>, pf);
 }
 
-// n_modes sweeps side by side: the smallest number of groups per cluster (then 3 sequences per group before 4) for which all their
-// clusters are co-resident.  Returns 1 when they do not fit (the caller launches the sweeps one after another).
-static int lk_launch_multi(LkParams pf, LkParams pb, LkParams pv, int n_modes, cudaStream_t s) {
-    const int maxc = lk_max_clusters<LK_FWD, 4>(pf.CS);
+// How a sweep's batch is cut into clusters: `ngr` groups per cluster, NSQ sequences per register pass, NP passes per group.
+// A step of a cluster (tools/lk_trace.py, profiles/r02_largek_exchange_experiments.txt; cycles) is the longest of
+//   the products of all its sequences        ngr x NP x 370 NSQ                    (the compute warps do nothing else),
+//   one group's dependency chain             NP x (370 NSQ + 600) + its exchange + 300   (product, finals, exchange),
+//   the exchange of all its sequences        82 x CS per sequence                  (DSMEM bandwidth: what usually decides),
+// and the launch takes ceil(clusters / co-resident clusters) waves of T such steps.  The cheapest estimate wins: as many clusters
+// as are co-resident, and among equals the fewest groups (two-pass groups keep the finals and the barriers per sequence down).
+struct LkShape { int ngr, nsq, np; };
+
+static LkShape lk_choose_shape(int B, int cs, int n_modes) {
+    const int maxc = lk_max_clusters(cs);
+    LkShape best = {2, 4, 1};
+    double best_cost = 1e300;
+    for (int np = 1; np <= 2; ++np)
+        for (int ngr = 2; ngr <= LK_NG / np; ++ngr)
+            for (int nsq = 3; nsq <= 4; ++nsq) {
+                const int per = nsq * np * ngr;
+                const int ncl = (B + per - 1) / per;
+                const int waves = (n_modes * ncl + maxc - 1) / maxc;
+                const double prod = 370.0 * nsq, xchg = 82.0 * cs * nsq * np;
+                double step = ngr * np * prod;
+                const double chain = np * (prod + 600.0) + xchg + 300.0, queue = ngr * xchg + 150.0 * ngr;
+                if (chain > step) step = chain;
+                if (queue > step) step = queue;
+                const double cost = waves * step;
+                if (cost < best_cost) { best_cost = cost; best = {ngr, nsq, np}; }
+            }
+#ifdef HMMB200_DEBUG_HOOKS
+    if (const char *f = getenv("HMMB200_LK_SHAPE")) {            // "ngr,nsq,np": debug builds can force a shape
+        int a = 0, b = 0, c = 0;
+        if (sscanf(f, "%d,%d,%d", &a, &b, &c) == 3 && a >= 1 && a * c <= LK_NG && (b == 3 || b == 4) && (c == 1 || c == 2)) best = {a, b, c};
+    }
+#endif
+    return best;
+}
+
+static int lk_launch_shaped(int mode0, LkParams pf, LkParams pb, LkParams pv, int n_modes, cudaStream_t s) {
+    const LkShape sh = lk_choose_shape(pf.B, pf.CS, n_modes);
+    pf.ngr = pb.ngr = pv.ngr = sh.ngr;
+    if (sh.np == 1) return (sh.nsq == 3) ? lk_launch_variant<3, 1>(mode0, pf, pb, pv, n_modes, s) : lk_launch_variant<4, 1>(mode0, pf, pb, pv, n_modes, s);
+    return (sh.nsq == 3) ? lk_launch_variant<3, 2>(mode0, pf, pb, pv, n_modes, s) : lk_launch_variant<4, 2>(mode0, pf, pb, pv, n_modes, s);
+}
+
+// n_modes sweeps side by side in one launch
+static int lk_launch_multi(const LkParams &pf, const LkParams &pb, const LkParams &pv, int n_modes, cudaStream_t s) {
 #ifdef HMMB200_DEBUG_HOOKS
     if (getenv("HMMB200_LK_NO_MULTI")) return 1;
 #endif
-    for (int ngr = 2; ngr <= LK_NG; ++ngr)
-        for (int nsq = 3; nsq <= 4; ++nsq) {
-            const int ncl = (pf.B + nsq * ngr - 1) / (nsq * ngr);
-            if (n_modes * ncl > maxc) continue;
-            pf.ngr = pb.ngr = pv.ngr = ngr;
-            return (nsq == 3) ? lk_launch_multi_nsq<3>(pf, pb, pv, n_modes, s) : lk_launch_multi_nsq<4>(pf, pb, pv, n_modes, s);
-        }
-    return 1;
+    return lk_launch_shaped(LK_FWD, pf, pb, pv, n_modes, s);
 }
 
 template <int MODE>
-static int lk_launch(LkParams p, cudaStream_t s) {
-    p.ngr = 2;
-    const int clusters3 = (p.B + 3 * p.ngr - 1) / (3 * p.ngr);
-    bool three = clusters3 <= lk_max_clusters<MODE, 3>(p.CS);
-#ifdef HMMB200_DEBUG_HOOKS
-    if (const char *f = getenv("HMMB200_LK_NSQ")) three = (f[0] == '3');   // debug builds can force either variant
-#endif
-    if (three) return lk_launch_nsq<MODE, 3>(p, s);
-    return lk_launch_nsq<MODE, 4>(p, s);
-}
+static int lk_launch(const LkParams &p, cudaStream_t s) { return lk_launch_shaped(MODE, p, p, p, 1, s); }
 
 // The two halves of a large-K call, split so that the sweeps of a forward-backward pass and of a Viterbi pass can share one launch:
 // *_prepare fills the sweep parameters and runs the small preparation kernels, *_finish turns the sweeps' raw outputs into results.
@@ -858,6 +897,9 @@ static int lk_vit_prepare(LkVitCall &c, const float *emis, int emis_mode, float 
     p.err = (int *)w;
     c.xl_extra = w + 256;
     cudaMemsetAsync(p.err, 0, sizeof(int), s);
+#ifdef HMMB200_DEBUG_HOOKS
+    p.trace = getenv("HMMB200_LK_TRACE") != nullptr;
+#endif
     if (emis_mode == HMMB200_EMIS_LOG_NORM_FLOOR) {
         lk_rowmax_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(emis, (int64_t)n, K, rowmax);
         if (int rc = check_launch("lk_rowmax_kernel")) return rc;
@@ -966,7 +1008,7 @@ int largek_fb_viterbi(const float *emis, int fb_mode, int vit_mode, float floor_
 #ifdef HMMB200_DEBUG_HOOKS
 HMMB200_EXPORT int hmmb200_debug_lk_max_clusters(int cs) {
     if (cs < 1 || cs > hmmb200::LK_CSMAX) return -1;
-    return hmmb200::lk_max_clusters<hmmb200::LK_FWD, 4>(cs);
+    return hmmb200::lk_max_clusters(cs);
 }
 
 HMMB200_EXPORT int hmmb200_debug_lk_trace(long long *host64) {

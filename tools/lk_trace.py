@@ -11,13 +11,21 @@ dev = torch.device("cuda", 0)
 hmm = hm.HMMPyTorch(hm.create_transition_matrix(K, "ergodic"), None, device="cuda")
 obs = torch.softmax(torch.randn(B, T, K, device=dev), -1)
 trans, init = hmm._effective_probs(dev)
+MODE = os.environ.get("MODE", "fwd")            # fwd | fb | vit | all
 for _ in range(2):
-    hm.ops.forward_backward(obs, hm.ops.EMIS_PROB_FLOOR, trans, init, want=())
+    if MODE == "all":     # the three sweeps in one launch (cluster 0 = the forward sweep)
+        hm.ops.forward_backward_viterbi(torch.log(obs), hm.ops.EMIS_LOG, hm.ops.EMIS_LOG, trans, init, torch.log(trans), torch.log(init))
+    elif MODE == "fb":
+        hm.ops.forward_backward(obs, hm.ops.EMIS_PROB_FLOOR, trans, init)
+    elif MODE == "vit":
+        hm.ops.viterbi(torch.log(obs), hm.ops.EMIS_LOG, torch.log(trans), torch.log(init))
+    else:
+        hm.ops.forward_backward(obs, hm.ops.EMIS_PROB_FLOOR, trans, init, want=())
 torch.cuda.synchronize()
 buf = np.zeros(64, np.int64)
 ctypes.CDLL(_lib.lib_path()).hmmb200_debug_lk_trace(buf.ctypes.data_as(ctypes.c_void_p))
 buf = buf.reshape(8, 8)
-names = ["top", "waited", "computed", "-", "synced", "staged", "final_bar", "pushed"]
+names = ["top", "waited", "computed", "-", "synced", "stored", "arrived", "pushed"]
 buf[:, 3] = buf[:, 2]      # slot 3 unused
 for i in range(8):
     base = buf[i, 0]

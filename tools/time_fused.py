@@ -10,3 +10,5 @@ h = bench.Headline(model, dev)
 h.emission(x); torch.cuda.synchronize()
 for _ in range(3):
     print("fused", round(bench.event_ms(lambda: h.fused(want=()), 40), 4), "fb", round(bench.event_ms(lambda: h.fb(want=()), 40), 4), "vit", round(bench.event_ms(h.vit, 40), 4))
+for _ in range(3):
+    print("fused+posteriors", round(bench.event_ms(lambda: h.fused(), 40), 4), "step", round(bench.event_ms(lambda: h.step(x), 40), 4))
