@@ -581,7 +581,10 @@ __device__ __forceinline__ void lk_warp_argmax(float &v, int &i) {
     v = __uint_as_float((mx & 0x80000000u) ? (mx & 0x7fffffffu) : ~mx);
 }
 
-template <int MAXR>                                          // delta-row registers per lane: K <= 32 MAXR
+constexpr int LK_TB_PF = 6;                                  // delta rows prefetched into L2 ahead of the traceback
+// MAXR: delta-row registers per lane (K <= 32 MAXR); ALIGNED: K is a multiple of 32, so a 32-state slice is either whole or absent
+// (uniform predicates instead of per-lane index clamps: the step is a dependency chain and its instruction count is its time)
+template <int MAXR, bool ALIGNED>
 __global__ void __launch_bounds__(128) lk_traceback_kernel(const float *delta, const float *logPT, int B, int T, int K,
                                                            int64_t *states, float *score) {
     const int sq = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -601,32 +604,52 @@ __global__ void __launch_bounds__(128) lk_traceback_kernel(const float *delta, c
         states[(size_t)sq * T + (T - 1)] = s;
         if (score) score[sq] = bv;
     }
-    float nxt[MAXR];
+    const int mk = K >> 5;                                   // whole slices
+    auto have = [&](int m) { return ALIGNED ? (m < mk) : (lane + 32 * m < K); };
+    auto at = [&](int m) { return ALIGNED ? lane + 32 * m : min(lane + 32 * m, K - 1); };
+    float nxt[MAXR];                                         // delta row of the next step; -inf where the lane has no state
+    const float *dn = d + (size_t)(T >= 2 ? T - 2 : 0) * K;
 #pragma unroll
-    for (int m = 0; m < MAXR; ++m) nxt[m] = (T >= 2 && lane + 32 * m < K) ? d[(size_t)(T - 2) * K + lane + 32 * m] : -INFINITY;
+    for (int m = 0; m < MAXR; ++m) nxt[m] = (T >= 2 && have(m)) ? dn[at(m)] : -INFINITY;
+    int64_t *st = states + (size_t)sq * T;
     for (int t = T - 1; t >= 1; --t) {
+        const float *col = logPT + (size_t)s * K;
+        // The loads of the logPT row first -- they are the step's critical path -- and none inside a per-lane branch: with the load
+        // under `if (i < K)` the compiler issued them one by one, each behind the previous compare -- 16 L2 round trips per step
+        // instead of one (ncu source page: 4.4 ms for T = 4000, 90 % of it on the 16 dependent FADDs; 2.3 ms with the loads batched)
+        float cv[MAXR];
+#pragma unroll
+        for (int m = 0; m < MAXR; ++m) cv[m] = (!ALIGNED || m < mk) ? __ldg(col + at(m)) : 0.f;
         float cur[MAXR];
 #pragma unroll
         for (int m = 0; m < MAXR; ++m) cur[m] = nxt[m];
-        if (t >= 2) {                                        // the next delta row does not depend on s: fetch it now
+        dn -= K;
+        if (t >= 2) {                                        // the next delta row does not depend on s: fetch it behind them
 #pragma unroll
-            for (int m = 0; m < MAXR; ++m) nxt[m] = (lane + 32 * m < K) ? d[(size_t)(t - 2) * K + lane + 32 * m] : -INFINITY;
+            for (int m = 0; m < MAXR; ++m) nxt[m] = have(m) ? __ldcs(dn + at(m)) : -INFINITY;
         }
-        const float *col = logPT + (size_t)s * K;
-        float v = -INFINITY;
-        int vi = K;
+        // ... and pull the rows after it from HBM into L2 ahead of time (a step is shorter than an HBM round trip)
+        if (t >= 2 + LK_TB_PF && lane * 32 < K) asm volatile("prefetch.global.L2 [%0];" ::"l"(dn - (size_t)LK_TB_PF * K + lane * 32));
+        // the lane's first arg-max over its MAXR candidates as a tree over the slice number (ties keep the lower index; a NaN
+        // candidate never wins, as in a sequential `c > v` scan; absent states are -inf through `cur`)
+        float cc[MAXR];
+        int cm[MAXR];
 #pragma unroll
         for (int m = 0; m < MAXR; ++m) {
-            const int i = lane + 32 * m;
-            if (i < K) {
-                const float c = __fadd_rn(cur[m], __ldg(col + i));
-                if (c > v) { v = c; vi = i; }
-            }
+            const float c = __fadd_rn(cur[m], cv[m]);
+            cc[m] = (c > -INFINITY) ? c : -INFINITY;
+            cm[m] = m;
         }
-        if (vi == K) vi = lane < K ? lane : 0;
+#pragma unroll
+        for (int w = 1; w < MAXR; w <<= 1)
+#pragma unroll
+            for (int m = 0; m + w < MAXR; m += 2 * w)
+                if (cc[m + w] > cc[m]) { cc[m] = cc[m + w]; cm[m] = cm[m + w]; }
+        float v = cc[0];
+        int vi = (v > -INFINITY) ? lane + 32 * cm[0] : (lane < K ? lane : 0);
         lk_warp_argmax(v, vi);
         s = vi;
-        if (lane == 0) states[(size_t)sq * T + (t - 1)] = s;
+        if (lane == 0) st[t - 1] = s;
     }
 }
 
@@ -915,8 +938,10 @@ static int lk_vit_finish(const LkVitCall &c, cudaStream_t s) {
     const LkParams &p = c.p;
     const size_t n = (size_t)p.B * p.T;
     const int B = p.B, T = p.T, K = p.K;
-    if (K <= LK_KMAX) lk_traceback_kernel<LK_KMAX / 32><<<(B + 3) / 4, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
-    else lk_traceback_kernel<XL_KMAX / 32><<<(B + 3) / 4, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
+    const dim3 tb_grid((B + 3) / 4);
+    if (K <= LK_KMAX && K % 32 == 0) lk_traceback_kernel<LK_KMAX / 32, true><<<tb_grid, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
+    else if (K <= LK_KMAX) lk_traceback_kernel<LK_KMAX / 32, false><<<tb_grid, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
+    else lk_traceback_kernel<XL_KMAX / 32, false><<<tb_grid, 128, 0, s>>>(p.delta, c.logPT, B, T, K, c.states, c.score);
     if (int rc = check_launch("lk_traceback_kernel")) return rc;
     if (c.psi != nullptr) {
         const int64_t n_warps = (int64_t)n * ((K + 31) / 32);
