@@ -303,6 +303,11 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi_kernel(HsmmVitParams p) {
 // and the FIRST d' whose own total rounds to the cell's value -- are then straight-line code over registers (all candidates evaluated
 // with independent loads and adds, the first match picked by a descending select chain) instead of data-dependent loops of
 // load -> add -> add -> add -> compare round trips, which were nine tenths of a step.
+__device__ __forceinline__ float2 hs_fadd2(float2 a, float2 b) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b), rd;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    return *reinterpret_cast<float2 *>(&rd);
+}
 constexpr int HS_TB_W = 64;                     // frames of backpointer rows staged per traceback round
 template <int KT, int DT>
 __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
@@ -364,6 +369,116 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
     __syncthreads();
 
     int head = 0, slot_prev = R - 1, slot_t = 0;
+    // Specialised shape: one cell per thread for the whole sweep, so everything that depends on the cell only -- its state and
+    // duration, its column of logA, its duration score, its table offsets, its backpointer addresses -- is set up once, and the
+    // searches are straight-line packed adds (add.rn.f32x2 rounds each half like add.rn.f32: same bits).  The frame loop below this
+    // block is the general form of the same step; it spent half of its ~430 instructions per cell and frame on that bookkeeping.
+    if constexpr (KT > 0 && DT > 0 && DT % 4 == 0) {
+        const bool is_cell = tid < KT * DT;
+        const int s = is_cell ? tid / DT : 0, dd = is_cell ? tid % DT : 0, d = dd + 1;
+        const int q4 = (d >> 2) * 4, rem = d & 3;
+        float acol[KT];                                                 // logA[s'][s]; -inf at s' = s (no self transition)
+#pragma unroll
+        for (int sp = 0; sp < KT; ++sp) acol[sp] = (sp == s) ? -INFINITY : A_s[sp * KT + s];
+        const float a_first = A_s[s];                                   // logA[0][s]
+        const float dsc = dur_s[s * DT + dd];
+        const bool has_seg = p.segc != nullptr;
+        const float segv = has_seg ? p.segc[s] : 0.f;
+        const float pi0 = p.logpi ? p.logpi[s] : 0.f;
+        uint8_t *psp = ps + tid, *pdp = pd + tid;
+        const int tab_off = s * TABW + q4;
+        for (int t = 0; t < T; ++t) {
+            const float *prev = ring + (size_t)slot_prev * (KT * DT);
+            const float *mxp = mr + slot_prev * KT;
+            const float *tabc = (t & 1) ? tab2 : tab;
+            if (fs >= 0 && fs < K) {                                    // window: frame t + Dm + 1 into the row that held frame t - 1
+                int row = head + Dm + 1;
+                if (row >= WR) row -= WR;
+                win[row * K + fs] = incoming;
+                incoming = (t + Dm + 2 < T) ? f[(size_t)(t + Dm + 2) * K + fs] : 0.f;
+            }
+            if (t + 1 < T) build_tab((t & 1) ? tab : tab2, (head + 1 == WR) ? 0 : head + 1);
+            if (is_cell) {
+                if (t + dd < T) {
+                    float osum;
+                    if (p.sum_order == 0) {
+                        const float *tb = tabc + tab_off;
+                        float p0 = tb[0];
+                        int r = head + q4;
+                        if (r >= WR) r -= WR;
+                        if (rem > 0) { p0 = __fadd_rn(p0, win[r * KT + s]); if (++r == WR) r = 0; }
+                        if (rem > 1) { p0 = __fadd_rn(p0, win[r * KT + s]); if (++r == WR) r = 0; }
+                        if (rem > 2) { p0 = __fadd_rn(p0, win[r * KT + s]); }
+                        p0 = __fadd_rn(p0, tb[1]);
+                        p0 = __fadd_rn(p0, tb[2]);
+                        osum = __fadd_rn(p0, tb[3]);
+                    } else {
+                        osum = tabc[s * TABW + d];
+                    }
+                    const float oseg = has_seg ? __fadd_rn(segv, osum) : osum;
+                    const float2 oseg2 = make_float2(oseg, oseg), dsc2 = make_float2(dsc, dsc);
+                    float best;
+                    int bs = 0, bd = 1;
+                    if (t == 0) {
+                        best = p.logpi ? __fadd_rn(__fadd_rn(pi0, oseg), dsc) : __fadd_rn(oseg, dsc);
+                    } else {
+                        static_assert(KT % 2 == 0, "pairs of predecessor states");
+                        float2 u2[KT / 2], w2[KT / 2];                  // u = Mx[s'] + logA[s'][s];  w = its total with this cell's terms
+#pragma unroll
+                        for (int i = 0; i < KT / 2; ++i) {
+                            const float2 m2 = *reinterpret_cast<const float2 *>(mxp + 2 * i);
+                            u2[i] = hs_fadd2(m2, make_float2(acol[2 * i], acol[2 * i + 1]));
+                            w2[i] = hs_fadd2(hs_fadd2(u2[i], oseg2), dsc2);
+                        }
+                        float v = fmaxf(u2[0].x, u2[0].y);
+#pragma unroll
+                        for (int i = 1; i < KT / 2; ++i) v = fmaxf(v, fmaxf(u2[i].x, u2[i].y));
+                        best = __fadd_rn(__fadd_rn(v, oseg), dsc);
+                        if (best > -INFINITY) {
+                            int bsp = 0;
+                            float a = a_first;
+#pragma unroll
+                            for (int sp = KT - 1; sp >= 0; --sp) {
+                                const float w = (sp & 1) ? w2[sp / 2].y : w2[sp / 2].x;
+                                if (w == best) { bsp = sp; a = acol[sp]; }
+                            }
+                            const float4 *pv4 = reinterpret_cast<const float4 *>(prev + bsp * DT);
+                            const float2 a2 = make_float2(a, a);
+                            int bdp = 0;
+#pragma unroll
+                            for (int i4 = DT / 4 - 1; i4 >= 0; --i4) {
+                                const float4 q = pv4[i4];
+                                const float2 hi = hs_fadd2(hs_fadd2(hs_fadd2(make_float2(q.z, q.w), a2), oseg2), dsc2);
+                                const float2 lo = hs_fadd2(hs_fadd2(hs_fadd2(make_float2(q.x, q.y), a2), oseg2), dsc2);
+                                if (hi.y == best) bdp = 4 * i4 + 3;
+                                if (hi.x == best) bdp = 4 * i4 + 2;
+                                if (lo.y == best) bdp = 4 * i4 + 1;
+                                if (lo.x == best) bdp = 4 * i4;
+                            }
+                            bs = bsp; bd = bdp + 1;
+                        }
+                    }
+                    int slot = slot_t + dd;
+                    if (slot >= R) slot -= R;
+                    ring[(size_t)slot * (KT * DT) + tid] = best;
+                    // running maximum of (te, s): this step's only candidate for it; ">=" so that the smallest d wins ties
+                    if (best >= mr[slot * KT + s]) { mr[slot * KT + s] = best; ar[slot * KT + s] = dd; }
+                    psp[(size_t)t * (KT * DT)] = (uint8_t)bs;
+                    pdp[(size_t)t * (KT * DT)] = (uint8_t)bd;
+                }
+                if (t >= 2) {                                            // slot t-2 has been fully consumed by the previous step
+                    int sc = slot_t - 2;
+                    if (sc < 0) sc += R;
+                    ring[(size_t)sc * (KT * DT) + tid] = -INFINITY;
+                    if (tid < KT) { mr[sc * KT + tid] = -INFINITY; ar[sc * KT + tid] = 0; }
+                }
+            }
+            __syncthreads();
+            if (++head == WR) head = 0;
+            slot_prev = slot_t;
+            if (++slot_t == R) slot_t = 0;
+        }
+    } else
     for (int t = 0; t < T; ++t) {
         const float *prev = ring + (size_t)slot_prev * KD;              // segments ending at t-1
         const float *mxp = mr + slot_prev * K;
@@ -923,7 +1038,9 @@ HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float
     size_t smem2 = ((size_t)R * K * Dm + 2 * (size_t)R * K + (size_t)K * K + (size_t)K * Dm + (size_t)(Dm + 2) * K + 2 * (size_t)K * (Dm + 8)) * sizeof(float);
     const size_t smem_tb = 2 * ((size_t)(HS_TB_W + 16) * K * Dm + 16) + (size_t)T + 64;       // traceback staging (reuses the DP tables' space)
     if (smem_tb > smem2) smem2 = smem_tb;
-    int threads2 = ((K * Dm + 2 * K + 31) / 32) * 32;
+    // (the helpers get warps of their own: sharing a warp with cells, that warp ran the cell code AND the table builder one after the
+    // other and the frame barrier waited for it)
+    int threads2 = ((K * Dm + 31) / 32) * 32 + ((2 * K + 31) / 32) * 32;
     bool v1 = threads2 > 1024 || smem2 > 200 * 1024;
 #ifdef HMMB200_DEBUG_HOOKS
     if (getenv("HMMB200_HSMM_VIT_V1")) v1 = true;
