@@ -33,6 +33,7 @@ struct HsmmVitParams {
     int64_t *states;       // [B,T]
     float *score;          // [B]
     uint8_t *psi_s, *psi_d;  // [B,T,K*Dm] workspace: predecessor (state, duration) of the segment (s,d) STARTING at frame t
+    int dbg;               // debug builds only: 1 = stop after the recursion (timing experiments)
 };
 
 // sum of d values col[0], col[stride], ... in the order torch.sum uses on a strided fp32 slice
@@ -308,7 +309,7 @@ __device__ __forceinline__ float2 hs_fadd2(float2 a, float2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
     return *reinterpret_cast<float2 *>(&rd);
 }
-constexpr int HS_TB_W = 64;                     // frames of backpointer rows staged per traceback round
+constexpr int HS_TB_W = 128;                    // frames of backpointer rows staged per traceback round
 template <int KT, int DT>
 __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
     extern __shared__ __align__(16) float smem_h[];
@@ -327,8 +328,9 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const float *f = p.f + (size_t)b * T * K;
-    uint8_t *ps = p.psi_s + (size_t)b * T * KD;
-    uint8_t *pd = p.psi_d + (size_t)b * T * KD;
+    // backpointers of this kernel: ONE 16-bit entry per cell (predecessor state | predecessor duration << 8) in the space of the two
+    // byte tables -- one store per cell and frame, one load per hop of the traceback
+    uint16_t *psd = reinterpret_cast<uint16_t *>(p.psi_s) + (size_t)b * T * KD;
 
     for (int i = tid; i < R * KD; i += blockDim.x) ring[i] = -INFINITY;
     for (int i = tid; i < R * K; i += blockDim.x) { mr[i] = -INFINITY; ar[i] = 0; }
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
         const bool has_seg = p.segc != nullptr;
         const float segv = has_seg ? p.segc[s] : 0.f;
         const float pi0 = p.logpi ? p.logpi[s] : 0.f;
-        uint8_t *psp = ps + tid, *pdp = pd + tid;
+        uint16_t *psp = psd + tid;
         const int tab_off = s * TABW + q4;
         for (int t = 0; t < T; ++t) {
             const float *prev = ring + (size_t)slot_prev * (KT * DT);
@@ -402,16 +404,19 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
                 if (t + dd < T) {
                     float osum;
                     if (p.sum_order == 0) {
-                        const float *tb = tabc + tab_off;
-                        float p0 = tb[0];
-                        int r = head + q4;
-                        if (r >= WR) r -= WR;
-                        if (rem > 0) { p0 = __fadd_rn(p0, win[r * KT + s]); if (++r == WR) r = 0; }
-                        if (rem > 1) { p0 = __fadd_rn(p0, win[r * KT + s]); if (++r == WR) r = 0; }
-                        if (rem > 2) { p0 = __fadd_rn(p0, win[r * KT + s]); }
-                        p0 = __fadd_rn(p0, tb[1]);
-                        p0 = __fadd_rn(p0, tb[2]);
-                        osum = __fadd_rn(p0, tb[3]);
+                        // (all loads first, none under a branch: the adds are the only chain)
+                        const float4 tb = *reinterpret_cast<const float4 *>(tabc + tab_off);
+                        int r0 = head + q4;
+                        if (r0 >= WR) r0 -= WR;
+                        const int r1 = (r0 + 1 == WR) ? 0 : r0 + 1, r2 = (r1 + 1 == WR) ? 0 : r1 + 1;
+                        const float w0 = win[r0 * KT + s], w1 = win[r1 * KT + s], w2 = win[r2 * KT + s];
+                        float p0 = tb.x;
+                        p0 = (rem > 0) ? __fadd_rn(p0, w0) : p0;
+                        p0 = (rem > 1) ? __fadd_rn(p0, w1) : p0;
+                        p0 = (rem > 2) ? __fadd_rn(p0, w2) : p0;
+                        p0 = __fadd_rn(p0, tb.y);
+                        p0 = __fadd_rn(p0, tb.z);
+                        osum = __fadd_rn(p0, tb.w);
                     } else {
                         osum = tabc[s * TABW + d];
                     }
@@ -463,8 +468,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
                     ring[(size_t)slot * (KT * DT) + tid] = best;
                     // running maximum of (te, s): this step's only candidate for it; ">=" so that the smallest d wins ties
                     if (best >= mr[slot * KT + s]) { mr[slot * KT + s] = best; ar[slot * KT + s] = dd; }
-                    psp[(size_t)t * (KT * DT)] = (uint8_t)bs;
-                    pdp[(size_t)t * (KT * DT)] = (uint8_t)bd;
+                    psp[(size_t)t * (KT * DT)] = (uint16_t)(bs | (bd << 8));
                 }
                 if (t >= 2) {                                            // slot t-2 has been fully consumed by the previous step
                     int sc = slot_t - 2;
@@ -578,8 +582,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
                 ring[(size_t)slot * KD + s * Dm + d - 1] = best;
                 // running maximum of (te, s): this step's only candidate for it; ">=" so that the smallest d wins ties
                 if (best >= mr[slot * K + s]) { mr[slot * K + s] = best; ar[slot * K + s] = d - 1; }
-                ps[(size_t)t * KD + pr] = (uint8_t)bs;
-                pd[(size_t)t * KD + pr] = (uint8_t)bd;
+                psd[(size_t)t * KD + pr] = (uint16_t)(bs | (bd << 8));
             }
             if (t >= 2) {                                                // slot t-2 has been fully consumed by the previous step
                 int sc = slot_t - 2;
@@ -598,12 +601,14 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
     // (~0.8 us: 1.5 ms for 2000 one-frame segments).  The hops move monotonically back in time, so the backpointer rows are staged
     // HS_TB_W frames at a time in shared memory by the whole block (one contiguous copy) and one thread walks inside the staged
     // rows; the path is collected in shared memory and written out by all threads.
+#ifdef HMMB200_DEBUG_HOOKS
+    if (p.dbg & 1) return;
+#endif
     __shared__ int tb_state[4];                                         // t, state, duration, final-score bits
-    const int tb_al = 16 / ((KD % 16 == 0) ? 16 : ((KD % 8 == 0) ? 8 : ((KD % 4 == 0) ? 4 : ((KD % 2 == 0) ? 2 : 1))));
-    const size_t stage_rows = (size_t)((HS_TB_W + 16) * KD + 15) & ~(size_t)15;
-    uint8_t *stage_s = reinterpret_cast<uint8_t *>(smem_h);             // [HS_TB_W + 16][KD]  predecessor states   (the DP tables are dead)
-    uint8_t *stage_d = stage_s + stage_rows;                            // [HS_TB_W + 16][KD]  predecessor durations
-    uint8_t *path = stage_d + stage_rows;                               // [T]
+    const int tb_al = 8 / ((KD % 8 == 0) ? 8 : ((KD % 4 == 0) ? 4 : ((KD % 2 == 0) ? 2 : 1)));   // rows per 16-byte boundary
+    const size_t stage_elems = (size_t)((HS_TB_W + 8) * KD + 7) & ~(size_t)7;
+    uint16_t *stage = reinterpret_cast<uint16_t *>(smem_h);             // [HS_TB_W + 8][KD]  (the DP tables are dead)
+    uint8_t *path = reinterpret_cast<uint8_t *>(stage + stage_elems);   // [T]
     if (tid < 32) {
         const float *last = ring + (size_t)((T - 1) % R) * KD;
         float best = -INFINITY;
@@ -631,34 +636,48 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
         int lo = max(hi - HS_TB_W + 1, 0);
         lo -= lo % tb_al;                                               // row lo starts on a 16-byte boundary (vector copies)
         {
-            const size_t nbytes = (size_t)(hi - lo + 1) * KD;
-            const uint8_t *gs = ps + (size_t)lo * KD, *gd = pd + (size_t)lo * KD;
-            if ((((uintptr_t)gs | (uintptr_t)gd) & 15) == 0) {
+            const size_t nbytes = (size_t)(hi - lo + 1) * KD * 2;
+            const uint8_t *gs = reinterpret_cast<const uint8_t *>(psd + (size_t)lo * KD);
+            uint8_t *ss = reinterpret_cast<uint8_t *>(stage);
+            if (((uintptr_t)gs & 15) == 0) {
+                // all of a thread's loads before its stores (as load -> store pairs the compiler keeps them in order)
                 const size_t n16 = nbytes / 16;
-                for (size_t i = tid; i < n16; i += blockDim.x) {
-                    reinterpret_cast<uint4 *>(stage_s)[i] = reinterpret_cast<const uint4 *>(gs)[i];
-                    reinterpret_cast<uint4 *>(stage_d)[i] = reinterpret_cast<const uint4 *>(gd)[i];
+                constexpr int NPT = 4;
+                for (size_t i0 = 0; i0 < n16; i0 += (size_t)NPT * blockDim.x) {
+                    uint4 vs[NPT];
+#pragma unroll
+                    for (int j = 0; j < NPT; ++j) {
+                        const size_t i = i0 + (size_t)j * blockDim.x + tid;
+                        if (i < n16) vs[j] = __ldcs(reinterpret_cast<const uint4 *>(gs) + i);
+                    }
+#pragma unroll
+                    for (int j = 0; j < NPT; ++j) {
+                        const size_t i = i0 + (size_t)j * blockDim.x + tid;
+                        if (i < n16) reinterpret_cast<uint4 *>(ss)[i] = vs[j];
+                    }
                 }
-                for (size_t i = n16 * 16 + tid; i < nbytes; i += blockDim.x) { stage_s[i] = gs[i]; stage_d[i] = gd[i]; }
+                for (size_t i = n16 * 16 + tid; i < nbytes; i += blockDim.x) ss[i] = gs[i];
             } else {
-                for (size_t i = tid; i < nbytes; i += blockDim.x) { stage_s[i] = gs[i]; stage_d[i] = gd[i]; }
+                for (size_t i = tid; i < nbytes; i += blockDim.x) ss[i] = gs[i];
             }
         }
         __syncthreads();
         if (tid == 0) {
+            // The walk is a chain of dependent hops (with one-frame segments: T of them), so a hop is kept to a handful of
+            // instructions: one 16-bit load, and a path fill that is a plain rolled loop (unrolled by 16 with its remainder ladders it
+            // was 60 instructions per hop, a fifth of the kernel's time).
             int tt = t, cs = tb_state[1], cd = cd0;
+#ifdef HMMB200_DEBUG_HOOKS
+            if (p.dbg & 2) tt = -1;
+#endif
             while (tt >= 0) {
-                int st0 = tt - cd + 1;
-                if (st0 < 0) st0 = 0;
+                const int st0 = max(tt - cd + 1, 0);
                 if (st0 > 0 && st0 < lo) break;                         // its backpointer row is not staged: next round
-                for (int u = st0; u <= tt; ++u) path[u] = (uint8_t)cs;
-                if (st0 > 0) {
-                    const size_t o = (size_t)(st0 - lo) * KD + cs * Dm + cd - 1;
-                    const int ns = stage_s[o], nd = stage_d[o];
-                    tt = st0 - 1; cs = ns; cd = nd;
-                } else {
-                    tt = -1;
-                }
+#pragma unroll 1
+                for (int u = tt; u >= st0; --u) path[u] = (uint8_t)cs;
+                if (st0 == 0) { tt = -1; break; }
+                const unsigned e = stage[(size_t)(st0 - lo) * KD + cs * Dm + cd - 1];
+                tt = st0 - 1; cs = (int)(e & 255u); cd = (int)(e >> 8);
             }
             tb_state[0] = tt; tb_state[1] = cs; tb_state[2] = cd;
         }
@@ -666,6 +685,9 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
     }
     {
         int64_t *st = p.states + (size_t)b * T;
+#ifdef HMMB200_DEBUG_HOOKS
+        if (p.dbg & 4) return;
+#endif
         for (int u = tid; u < T; u += blockDim.x) st[u] = (int64_t)path[u];
     }
 }
@@ -1031,12 +1053,16 @@ HMMB200_EXPORT int hmmb200_hsmm_viterbi_f32(const float *frame_logp, const float
     p.f = frame_logp; p.segc = seg_const; p.logdur = log_dur; p.logA = log_trans; p.logpi = log_init;
     p.B = B; p.T = T; p.K = K; p.Dm = Dm; p.sum_order = sum_order; p.states = states; p.score = score;
     p.psi_s = (uint8_t *)workspace; p.psi_d = (uint8_t *)workspace + (size_t)B * T * K * Dm;
+    p.dbg = 0;
+#ifdef HMMB200_DEBUG_HOOKS
+    if (const char *e = getenv("HMMB200_HSMM_VIT_DBG")) p.dbg = atoi(e);
+#endif
     int threads = ((K * Dm + 31) / 32) * 32;
     if (threads > 1024) threads = 1024;
     // one-barrier form: needs 2 K threads beside the cells (table builders, window feeders) and its own shared-memory layout
     const int R = Dm + 2;
     size_t smem2 = ((size_t)R * K * Dm + 2 * (size_t)R * K + (size_t)K * K + (size_t)K * Dm + (size_t)(Dm + 2) * K + 2 * (size_t)K * (Dm + 8)) * sizeof(float);
-    const size_t smem_tb = 2 * ((size_t)(HS_TB_W + 16) * K * Dm + 16) + (size_t)T + 64;       // traceback staging (reuses the DP tables' space)
+    const size_t smem_tb = 2 * ((size_t)(HS_TB_W + 8) * K * Dm + 8) + (size_t)T + 64;         // traceback staging (reuses the DP tables' space)
     if (smem_tb > smem2) smem2 = smem_tb;
     // (the helpers get warps of their own: sharing a warp with cells, that warp ran the cell code AND the table builder one after the
     // other and the frame barrier waited for it)
