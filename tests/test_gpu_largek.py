@@ -180,6 +180,33 @@ def test_largek_both_group_sizes(hm, K, T, B):
     np.testing.assert_allclose(f["loglik"].cpu().numpy(), ll, rtol=RTOL, atol=1e-4)
 
 
+# (K, T, B): the launch shape (groups per cluster x sequences per register pass x passes per group) is chosen from the batch size, the
+# cluster size and the number of sweeps in the launch (recursion_largek.cu lk_choose_shape): batches on either side of its switches
+@pytest.mark.parametrize("K,T,B", [(512, 10, 24), (512, 8, 64), (512, 6, 100), (512, 5, 200), (130, 20, 50), (300, 12, 31), (64, 9, 150)])
+def test_largek_fused_launch_equals_the_separate_passes(hm, K, T, B):
+    """forward + backward + Viterbi in ONE launch (two-pass groups) against the stand-alone calls (one-pass groups): bit for bit --
+    a sequence's arithmetic must not depend on how the batch was cut into clusters, groups and passes."""
+    rng = np.random.default_rng(9300 + K + B)
+    logb = (rng.standard_normal((B, T, K)) * 3.0 - 20.0).astype(np.float32)
+    P = rng.random((K, K)).astype(np.float32) ** 3 + 0.01
+    P /= P.sum(1, keepdims=True)
+    logP = np.log(P).astype(np.float32)
+    p0 = np.full(K, 1.0 / K, np.float32)
+    e = _dev(logb)
+    sep_f = hm.ops.forward_backward(e, hm.ops.EMIS_LOG, _dev(P), _dev(p0), want=("gamma", "fwd", "bwd"))
+    sep_v = hm.ops.viterbi(e, hm.ops.EMIS_LOG, _dev(logP), _dev(np.log(p0)), want_delta=True)
+    fwd_only = hm.ops.forward_backward(e, hm.ops.EMIS_LOG, _dev(P), _dev(p0), want=())
+    r = hm.ops.forward_backward_viterbi(e, hm.ops.EMIS_LOG, hm.ops.EMIS_LOG, _dev(P), _dev(p0), _dev(logP), _dev(np.log(p0)))
+    torch.cuda.synchronize()
+    for k in ("gamma", "fwd", "bwd", "loglik"):
+        assert torch.equal(r[k], sep_f[k]), k
+    assert torch.equal(fwd_only["loglik"], sep_f["loglik"])
+    for k in ("states", "delta", "score"):
+        assert torch.equal(r[k], sep_v[k]), k
+    st, delta, _, score = c_oracle.viterbi_f32(logb, logP, np.log(p0))
+    assert np.array_equal(r["states"].cpu().numpy(), st) and np.array_equal(r["delta"].cpu().numpy(), delta)
+
+
 @pytest.mark.parametrize("K,T,B", [(5, 120_000, 1), (12, 100_000, 2), (3, 30_000, 3)])
 def test_smallk_viterbi_has_no_length_limit(hm, K, T, B):
     """Past the length whose traceback tables fit one CTA's shared memory (~24 k frames at K <= 4, ~95 k at K <= 16)
