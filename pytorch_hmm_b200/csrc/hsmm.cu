@@ -392,6 +392,7 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
         for (int t = 0; t < T; ++t) {
             const float *prev = ring + (size_t)slot_prev * (KT * DT);
             const float *mxp = mr + slot_prev * KT;
+            const int *agp = ar + slot_prev * KT;
             const float *tabc = (t & 1) ? tab2 : tab;
             if (fs >= 0 && fs < K) {                                    // window: frame t + Dm + 1 into the row that held frame t - 1
                 int row = head + Dm + 1;
@@ -447,18 +448,26 @@ __global__ void __launch_bounds__(1024) hsmm_viterbi2_kernel(HsmmVitParams p) {
                                 const float w = (sp & 1) ? w2[sp / 2].y : w2[sp / 2].x;
                                 if (w == best) { bsp = sp; a = acol[sp]; }
                             }
+                            // The first d' whose total equals best is at or before the first arg-max of the row (that one's total IS
+                            // best, and only an earlier, smaller entry can round to the same total): candidates are d' < agp[bsp]
+                            // only.  The bound is made uniform over the warp so that the loop does not diverge; when the winners
+                            // are short segments it is zero or one group of four instead of all twenty candidates.
                             const float4 *pv4 = reinterpret_cast<const float4 *>(prev + bsp * DT);
                             const float2 a2 = make_float2(a, a);
-                            int bdp = 0;
-#pragma unroll
-                            for (int i4 = DT / 4 - 1; i4 >= 0; --i4) {
+                            const int last = agp[bsp];
+                            const int wmax = (int)__reduce_max_sync(__activemask(), (unsigned)last);
+                            int bdp = last;
+#pragma unroll 1
+                            for (int i4 = 0; 4 * i4 < wmax; ++i4) {
                                 const float4 q = pv4[i4];
                                 const float2 hi = hs_fadd2(hs_fadd2(hs_fadd2(make_float2(q.z, q.w), a2), oseg2), dsc2);
                                 const float2 lo = hs_fadd2(hs_fadd2(hs_fadd2(make_float2(q.x, q.y), a2), oseg2), dsc2);
-                                if (hi.y == best) bdp = 4 * i4 + 3;
-                                if (hi.x == best) bdp = 4 * i4 + 2;
-                                if (lo.y == best) bdp = 4 * i4 + 1;
-                                if (lo.x == best) bdp = 4 * i4;
+                                int m = DT;
+                                if (hi.y == best) m = 4 * i4 + 3;
+                                if (hi.x == best) m = 4 * i4 + 2;
+                                if (lo.y == best) m = 4 * i4 + 1;
+                                if (lo.x == best) m = 4 * i4;
+                                bdp = min(bdp, m);
                             }
                             bs = bsp; bd = bdp + 1;
                         }
