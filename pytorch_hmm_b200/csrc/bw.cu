@@ -588,10 +588,155 @@ __global__ void __launch_bounds__(512, 1) bw_gmm_stats_mma_kernel(const float *x
     }
 }
 
+// The same statistics with the rows staged by bulk copies.  bw_xi_kernel loads a frame's 27 values with scalar loads and waits for
+// them before it computes -- 12 warps per SM with nothing in flight while they compute: 1.3 TB/s of HBM (ncu: a third of the samples
+// on the first use of the loaded data).  Here a warp's NEXT task (32 frames x three arrays, 4.6 KB) travels as three cp.async.bulk
+// copies into the warp's other staging buffer while the current one is consumed from shared memory.  Needs K % 4 == 0 (16-byte rows),
+// K == KP and T > 1; same arithmetic per frame, same order of the frames within a warp's accumulators.
+constexpr int XI_FPW = 32;
+template <int KP, int LPF>
+__global__ void __launch_bounds__(384) bw_xi_bulk_kernel(const float *emis, int mode, float eps, const float *trans,
+                                                         const float *ws_a, const float *ws_b, const float *wseq, int B, int T,
+                                                         double *xi, double *gamma1) {
+    extern __shared__ __align__(16) uint8_t xi_raw[];
+    constexpr int K = KP, R = (KP + LPF - 1) / LPF, FPI = 32 / LPF, KV = KP / 4;
+    constexpr int BUF = XI_FPW * KP;                           // floats per staged array
+    const int nw = blockDim.x >> 5;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(xi_raw);     // [nw][2]
+    double *xi_s = reinterpret_cast<double *>(xi_raw + (((size_t)nw * 2 * sizeof(uint64_t) + 15) & ~(size_t)15));
+    double *g1_s = xi_s + K * K;
+    float *stg_all = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(xi_s) + (((size_t)(K * K + K) * sizeof(double) + 15) & ~(size_t)15));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int fr = lane / LPF, part = lane % LPF;
+    float *stg = stg_all + (size_t)warp * 2 * 3 * BUF;
+    uint64_t *bar = bars + warp * 2;
+    for (int i = threadIdx.x; i < K * K + K; i += blockDim.x) xi_s[i] = 0.0;
+    if (lane == 0) { bw_mbar_init(bar, 1); bw_mbar_init(bar + 1, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncthreads();
+    const int bps = (T - 1 + XI_FPW - 1) / XI_FPW;
+    const int64_t n_tasks = (int64_t)B * bps, n_warps = (int64_t)gridDim.x * nw;
+    float Prow[R][KP], acc[R][KP];
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            const int i = part * R + r;
+            Prow[r][j] = (i < K) ? trans[i * K + j] : 0.f;
+            acc[r][j] = 0.f;
+        }
+    auto issue = [&](int64_t task, int buf) {                  // lane 0: the three arrays of a task into staging buffer `buf`
+        const int b = (int)(task / bps), blk = (int)(task % bps);
+        const int t0 = blk * XI_FPW, n = min(T - 1, t0 + XI_FPW) - t0;
+        const uint32_t bytes = (uint32_t)n * K * sizeof(float);
+        float *dst = stg + (size_t)buf * 3 * BUF;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the buffer's earlier generic reads come first
+        bw_mbar_expect_tx(bar + buf, 3 * bytes);
+        bw_bulk_g2s(dst, emis + ((size_t)b * T + t0 + 1) * K, bytes, bar + buf);
+        bw_bulk_g2s(dst + BUF, ws_b + ((size_t)b * T + t0 + 1) * K, bytes, bar + buf);
+        bw_bulk_g2s(dst + 2 * BUF, ws_a + ((size_t)b * T + t0) * K, bytes, bar + buf);
+    };
+    int64_t task = (int64_t)blockIdx.x * nw + warp;
+    if (task < n_tasks && lane == 0) issue(task, 0);
+    for (int it = 0; task < n_tasks; ++it, task += n_warps) {
+        const int buf = it & 1;
+        if (task + n_warps < n_tasks && lane == 0) issue(task + n_warps, buf ^ 1);
+        const int b = (int)(task / bps), blk = (int)(task % bps);
+        const float wb = wseq ? wseq[b] : 1.f;                 // per-sequence weight (autograd: d loss / d loglik_b)
+        const int n = min(T - 1, blk * XI_FPW + XI_FPW) - blk * XI_FPW;
+        bw_mbar_wait(bar + buf, (uint32_t)((it >> 1) & 1));
+        const float *es = stg + (size_t)buf * 3 * BUF, *bs = es + BUF, *as = es + 2 * BUF;
+        for (int tb = 0; tb < n; tb += FPI) {
+            const bool live = tb + fr < n;
+            const int row = live ? tb + fr : 0;
+            float u[KP], bb[KP];
+#pragma unroll
+            for (int q = 0; q < KV; ++q) {
+                const float4 e4 = reinterpret_cast<const float4 *>(es + row * KP)[q], b4 = reinterpret_cast<const float4 *>(bs + row * KP)[q];
+                u[4 * q] = e4.x; u[4 * q + 1] = e4.y; u[4 * q + 2] = e4.z; u[4 * q + 3] = e4.w;
+                bb[4 * q] = b4.x; bb[4 * q + 1] = b4.y; bb[4 * q + 2] = b4.z; bb[4 * q + 3] = b4.w;
+            }
+            float a[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { const int i = part * R + r; a[r] = (i < K) ? as[row * KP + i] : 0.f; }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) mx = fmaxf(mx, u[j]);
+            if (!(mx > -INFINITY)) mx = 0.f;
+#pragma unroll
+            for (int j = 0; j < KP; ++j) {
+                float bt;
+                if (mode == HMMB200_EMIS_PROB_FLOOR) bt = u[j] + eps;
+                else if (mode == HMMB200_EMIS_LOG_EXP_FLOOR) bt = expf(u[j]) + eps;
+                else bt = expf(u[j] - mx) + ((mode == HMMB200_EMIS_LOG_NORM_FLOOR) ? eps : 0.f);
+                u[j] = bt * bb[j];
+            }
+            float pu[R][KP], z = 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                float rs = 0.f;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) { pu[r][j] = Prow[r][j] * u[j]; rs += pu[r][j]; }
+                z = fmaf(a[r], rs, z);
+            }
+#pragma unroll
+            for (int o = LPF / 2; o > 0; o >>= 1) z += __shfl_xor_sync(FULL_MASK, z, o);
+            const float inv = (live && z > 0.f) ? wb / z : 0.f;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float sc = a[r] * inv;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) acc[r][j] = fmaf(sc, pu[r][j], acc[r][j]);
+            }
+        }
+        if (blk == 0 && gamma1 != nullptr) {               // gamma_0 = a_0 .* b_0 / sum
+            const bool ok = lane < K;
+            const float g = ok ? ws_a[(size_t)b * T * K + lane] * ws_b[(size_t)b * T * K + lane] : 0.f;
+            float Z = g;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) Z += __shfl_xor_sync(FULL_MASK, Z, o);
+            if (ok && Z > 0.f) atomicAdd(g1_s + lane, (double)(wb * g / Z));
+        }
+        __syncwarp();                                          // every lane is done with this buffer before it is refilled
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < KP; ++j) {
+            float v = acc[r][j];
+#pragma unroll
+            for (int o = LPF; o < 32; o <<= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+            const int i = part * R + r;
+            if (fr == 0 && i < K && v != 0.f) atomicAdd(&xi_s[i * K + j], (double)v);
+        }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * K; i += blockDim.x) if (xi_s[i] != 0.0) atomicAdd(xi + i, xi_s[i]);
+    if (gamma1 != nullptr)
+        for (int i = threadIdx.x; i < K; i += blockDim.x) if (g1_s[i] != 0.0) atomicAdd(gamma1 + i, g1_s[i]);
+}
+
 template <int KP, int LPF>
 static int launch_xi_kp(const float *emis, int mode, float eps, const float *trans, const float *ws_a, const float *ws_b,
                         const float *wseq, int B, int T, int K, double *xi, double *gamma1, cudaStream_t s) {
     const int fpw = 64, warps = 12;
+    int dev0 = 0, sms0 = 148;
+    cudaGetDevice(&dev0);
+    cudaDeviceGetAttribute(&sms0, cudaDevAttrMultiProcessorCount, dev0);
+    bool bulk = (K == KP) && T > 1 && ((((uintptr_t)emis | (uintptr_t)ws_a | (uintptr_t)ws_b) & 15) == 0);
+#ifdef HMMB200_DEBUG_HOOKS
+    if (getenv("HMMB200_XI_NO_BULK")) bulk = false;
+#endif
+    if (bulk) {
+        const size_t smem = (((size_t)warps * 2 * sizeof(uint64_t) + 15) & ~(size_t)15) + (((size_t)(K * K + K) * sizeof(double) + 15) & ~(size_t)15) +
+                            (size_t)warps * 2 * 3 * XI_FPW * KP * sizeof(float);
+        if (smem <= 200 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(bw_xi_bulk_kernel<KP, LPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "bw_xi smem opt-in: %s", cudaGetErrorString(e));
+            const int64_t nt = (int64_t)B * ((T - 1 + XI_FPW - 1) / XI_FPW);
+            const int64_t nc = min((nt + warps - 1) / warps, (int64_t)sms0);
+            bw_xi_bulk_kernel<KP, LPF><<<(unsigned)nc, warps * 32, smem, s>>>(emis, mode, eps, trans, ws_a, ws_b, wseq, B, T, xi, gamma1);
+            return check_launch("bw_xi_bulk_kernel");
+        }
+    }
     const int blocks_per_seq = T > 1 ? (T - 1 + fpw - 1) / fpw : 1;
     const int64_t n_tasks = (int64_t)B * blocks_per_seq;
     int dev = 0, sms = 148;
