@@ -28,7 +28,11 @@ def _problem(seed, B, T, K, C, D):
     return x, means, var, w, P, p0
 
 
-@pytest.mark.parametrize("B,T,K,C,D", [(3, 40, 4, 2, 8), (2, 257, 12, 4, 80), (5, 1, 3, 1, 5), (2, 65, 7, 3, 33)])
+# (the second row of shapes: K a multiple of 4 takes the bulk-staged xi kernel -- tasks of 32 frames, so T around its multiples,
+# batches that give a warp several tasks, and every lanes-per-frame variant)
+@pytest.mark.parametrize("B,T,K,C,D", [(3, 40, 4, 2, 8), (2, 257, 12, 4, 80), (5, 1, 3, 1, 5), (2, 65, 7, 3, 33),
+                                       (1, 2, 8, 1, 4), (40, 34, 16, 1, 4), (3, 97, 20, 2, 8), (2, 33, 24, 1, 8), (2, 66, 28, 1, 4),
+                                       (1, 129, 32, 1, 4), (300, 130, 12, 2, 8)])
 def test_e_step_statistics_vs_float64_oracle(hm, B, T, K, C, D):
     from pytorch_hmm_b200 import baum_welch as bw
     x, means, var, w, P, p0 = _problem(B * 7 + K, B, T, K, C, D)
