@@ -71,6 +71,34 @@ def test_hsmm_viterbi_vs_c_oracle(hm, K, Dm, T, B):
     assert np.array_equal(states.cpu().numpy(), st)
 
 
+@pytest.mark.parametrize("K,Dm", [(10, 20), (6, 10)])
+@pytest.mark.parametrize("kind", ["integers", "merging", "flat"])
+def test_hsmm_viterbi_exact_ties_and_roundings(hm, K, Dm, kind):
+    """The winner of a cell is the FIRST (state, duration) whose own fp32 total equals the maximum (hsmm.py:283-300): inputs built so
+    that many candidates tie exactly (small integers), or differ by less than an ulp of the total (so that distinct candidates round to
+    the same total and an EARLIER, smaller one must win), or are all equal.  K = 10, Dmax = 20 is the specialised kernel (searches
+    bounded by the row's first arg-max); the other shape runs the general one."""
+    rng = np.random.default_rng(77 + K + len(kind))
+    B, T = 3, 150
+    if kind == "integers":
+        logb = -rng.integers(1, 4, (B, T, K)).astype(np.float32)
+        logdur = -rng.integers(1, 3, (K, Dm)).astype(np.float32)
+        logA = np.full((K, K), -2.0, np.float32)
+    elif kind == "merging":
+        logb = (-rng.integers(1, 3, (B, T, K)) * 64.0).astype(np.float32)                      # totals around -1e4: ulp ~ 1e-3
+        logdur = (-1.0 - rng.random((K, Dm)) * 1e-4).astype(np.float32)                        # differences far below that ulp
+        logA = (-2.0 - rng.random((K, K)) * 1e-4).astype(np.float32)
+    else:
+        logb = np.full((B, T, K), -1.5, np.float32)
+        logdur = np.full((K, Dm), -0.75, np.float32)
+        logA = np.full((K, K), -2.25, np.float32)
+    np.fill_diagonal(logA, np.float32(np.log(1e-8)))
+    st, sc = c_oracle.hsmm_viterbi_f32(logb, logdur, logA)
+    states, scores = hm.ops.hsmm_viterbi(_dev(logb), _dev(logdur), _dev(logA), sum_order=0)
+    assert np.array_equal(scores.cpu().numpy(), sc)
+    assert np.array_equal(states.cpu().numpy(), st)
+
+
 def _semimarkov(hm, g):
     K, D = g["observation_means"].shape
     Dm = g["forward_variables"].shape[2]

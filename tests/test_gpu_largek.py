@@ -180,6 +180,29 @@ def test_largek_both_group_sizes(hm, K, T, B):
     np.testing.assert_allclose(f["loglik"].cpu().numpy(), ll, rtol=RTOL, atol=1e-4)
 
 
+@pytest.mark.parametrize("K,T,B", [(512, 40, 5), (130, 60, 3), (96, 33, 2)])
+@pytest.mark.parametrize("kind", ["integers", "flat", "zeros"])
+def test_largek_viterbi_exact_ties(hm, K, T, B, kind):
+    """Ties everywhere: torch.max / argmax return the FIRST maximum (hmm.py:167, :174), so must the sweep's maxima and the
+    traceback's warp-wide arg-max (two integer-key reductions; +0 and -0 are equal)."""
+    rng = np.random.default_rng(500 + K + len(kind))
+    if kind == "integers":
+        logb = -rng.integers(0, 3, (B, T, K)).astype(np.float32)
+        logP = -rng.integers(1, 3, (K, K)).astype(np.float32)
+        logp0 = -rng.integers(1, 3, K).astype(np.float32)
+    elif kind == "flat":
+        logb = np.full((B, T, K), -1.25, np.float32); logP = np.full((K, K), -3.5, np.float32); logp0 = np.full(K, -2.0, np.float32)
+    else:
+        logb = np.zeros((B, T, K), np.float32); logb[:, ::2] = -0.0
+        logP = np.zeros((K, K), np.float32); logp0 = np.zeros(K, np.float32)
+    st, delta, _, score = c_oracle.viterbi_f32(logb, logP, logp0)
+    r = hm.ops.viterbi(_dev(logb), hm.ops.EMIS_LOG, _dev(logP), _dev(logp0), want_delta=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(r["delta"].cpu().numpy(), delta)
+    assert np.array_equal(r["states"].cpu().numpy(), st)
+    assert np.array_equal(r["score"].cpu().numpy(), score)
+
+
 # (K, T, B): the launch shape (groups per cluster x sequences per register pass x passes per group) is chosen from the batch size, the
 # cluster size and the number of sweeps in the launch (recursion_largek.cu lk_choose_shape): batches on either side of its switches
 @pytest.mark.parametrize("K,T,B", [(512, 10, 24), (512, 8, 64), (512, 6, 100), (512, 5, 200), (130, 20, 50), (300, 12, 31), (64, 9, 150)])
