@@ -34,6 +34,15 @@ __device__ __forceinline__ float lse_cands(const float *c, int n) {
     for (int i = 0; i < n; ++i) s += expf(c[i] - m);
     return logf(s) + m;
 }
+// The same log-sum-exp over three candidates of which some may be -inf (= dropped by the reference): the terms are added in the same
+// order and a dropped one contributes exp(-inf) = +0, which changes no partial sum -- the same fp32 result without the candidate list
+// (a dynamically indexed local array lives in local memory, and its round trips were most of a frame's time).  -inf if all three are.
+__device__ __forceinline__ float lse3(float a, float b, float c) {
+    const float m = fmaxf(fmaxf(a, b), c);
+    if (!(m > -INFINITY)) return -INFINITY;
+    const float s = (expf(a - m) + expf(b - m)) + expf(c - m);
+    return logf(s) + m;
+}
 
 template <int DIR>
 __global__ void __launch_bounds__(1024) ctc_trellis_kernel(CtcParams p) {
@@ -73,13 +82,11 @@ __global__ void __launch_bounds__(1024) ctc_trellis_kernel(CtcParams p) {
             for (int s = threadIdx.x; s < S; s += blockDim.x) {
                 float v = NEG;
                 if (live && s < E) {
-                    float c[3];
-                    int n = 0;
                     const float a0 = prev[s];
-                    if (a0 > NEG) c[n++] = a0;
-                    if (s > 0) { const float a1 = prev[s - 1]; if (a1 > NEG) c[n++] = a1; }
-                    if (s > 1 && ext[s] != ext[s - 2]) { const float a2 = prev[s - 2]; if (a2 > NEG) c[n++] = a2; }
-                    if (n) v = ((s == s0) ? e_own : emit(t, s)) + lse_cands(c, n);
+                    const float a1 = (s > 0) ? prev[s - 1] : NEG;
+                    const float a2 = (s > 1 && ext[s] != ext[s - 2]) ? prev[s - 2] : NEG;
+                    const float l = lse3(a0, a1, a2);
+                    if (l > NEG) v = ((s == s0) ? e_own : emit(t, s)) + l;
                 }
                 // (rows at or after the utterance's length stay -inf in the table but do not advance the recursion: ctc.py:75-76)
                 if (live) cur[s] = v;
@@ -119,13 +126,10 @@ __global__ void __launch_bounds__(1024) ctc_trellis_kernel(CtcParams p) {
                 if (t == Tb - 1) {
                     if (s == E - 1 || s == E - 2) v = 0.f;
                 } else if (t < Tb - 1 && s < E) {
-                    float c[3];
-                    int n = 0;
                     const float b0 = next[s];
-                    if (b0 > NEG) c[n++] = b0;
-                    if (s + 1 < E) { const float b1 = next[s + 1]; if (b1 > NEG) c[n++] = b1; }
-                    if (s + 2 < E && ext[s] != ext[s + 2]) { const float b2 = next[s + 2]; if (b2 > NEG) c[n++] = b2; }
-                    if (n) v = lse_cands(c, n);
+                    const float b1 = (s + 1 < E) ? next[s + 1] : NEG;
+                    const float b2 = (s + 2 < E && ext[s] != ext[s + 2]) ? next[s + 2] : NEG;
+                    v = lse3(b0, b1, b2);
                 }
                 float hat = NEG;
                 if (v > NEG) hat = v + ((s == s0) ? e_own : emit(t, s));
@@ -173,11 +177,21 @@ __global__ void __launch_bounds__(1024) dtw_kernel(DtwParams p) {
     const float *dist = p.dist + (size_t)pr * N * M;
     float *cost = p.cost + (size_t)pr * N * M;
     uint8_t *dir = p.dir + (size_t)pr * N * M;
+    // A thread's own row i0 = threadIdx.x walks j = k - i0 = 0, 1, 2, ... as k grows: its local distances are consecutive floats, loaded
+    // one diagonal ahead (issued before the barrier, used after it) so that the load's latency is not part of a diagonal's time.
+    const int i0 = threadIdx.x;
+    float d_own = (i0 < N) ? dist[(size_t)i0 * M] : 0.f;               // (i0, 0): first used at k = i0
+    const bool vec4 = (M % 4 == 0) && ((((uintptr_t)cost) & 15) == 0) && ((((uintptr_t)dir) & 3) == 0);
+    float cb0 = 0.f, cb1 = 0.f, cb2 = 0.f;
+    unsigned db = 0u;
     for (int k = 0; k <= N + M - 2; ++k) {
         const int i_lo = max(0, k - (M - 1)), i_hi = min(N - 1, k);
-        for (int i = i_lo + threadIdx.x; i <= i_hi; i += blockDim.x) {
+        const float d_cur = d_own;
+        if (i0 < N && k + 1 >= i0 && k + 1 - i0 < M && k >= i0) d_own = dist[(size_t)i0 * M + (k + 1 - i0)];
+        for (int i = threadIdx.x; i <= i_hi; i += blockDim.x) {            // (fixed rows per thread: the first one is i0)
+            if (i < i_lo) continue;
             const int j = k - i;
-            const float d = dist[(size_t)i * M + j];
+            const float d = (i == i0) ? d_cur : dist[(size_t)i * M + j];
             float c;
             uint8_t bp = 0;
             if (k == 0) {
@@ -202,31 +216,50 @@ __global__ void __launch_bounds__(1024) dtw_kernel(DtwParams p) {
                 }
             }
             d0[i] = c;
-            cost[(size_t)i * M + j] = c;
-            dir[(size_t)i * M + j] = bp;
+            if (i == i0 && vec4) {
+                // the thread's own row is written left to right, one cell per diagonal: four cells at a time as one 16-byte and one
+                // 4-byte store (cell-by-cell stores along an anti-diagonal touch a different sector per thread -- 64 store
+                // transactions per warp and diagonal, which was the time of a diagonal)
+                const int q = j & 3;                                         // (selects, not an indexed array: that would live in local memory)
+                cb0 = (q == 0) ? c : cb0; cb1 = (q == 1) ? c : cb1; cb2 = (q == 2) ? c : cb2;
+                db |= (unsigned)bp << (8 * q);
+                if (q == 3) {
+                    *reinterpret_cast<float4 *>(cost + (size_t)i * M + j - 3) = make_float4(cb0, cb1, cb2, c);
+                    *reinterpret_cast<unsigned *>(dir + (size_t)i * M + j - 3) = db;
+                    db = 0u;
+                }
+            } else {
+                cost[(size_t)i * M + j] = c;
+                dir[(size_t)i * M + j] = bp;
+            }
         }
         __syncthreads();
         float *tmp = d2; d2 = d1; d1 = d0; d0 = tmp;
     }
     // traceback (dtw.py:124-151): the step is chosen on the COST of the three predecessors, which is what `dir` recorded
+    // One walk (each hop is a dependent load of a direction byte), recorded backwards in shared memory; all threads then write the path
+    // out in forward order.  [It was walked twice -- once for the length, once to fill -- by one thread with 64-bit global stores.]
+    __shared__ int path_n;
+    int *pbuf = reinterpret_cast<int *>(smem_w + 3 * N);               // [N + M - 1] packed (i << 16) | j   (N, M <= 65535)
     if (threadIdx.x == 0) {
-        int64_t *pi = p.path_i + (size_t)pr * (N + M - 1), *pj = p.path_j + (size_t)pr * (N + M - 1);
         int i = N - 1, j = M - 1, len = 0;
         while (i > 0 || j > 0) {
-            ++len;
+            pbuf[len++] = (i << 16) | j;
             const uint8_t bp = dir[(size_t)i * M + j];
             if (bp == 0) { --i; --j; } else if (bp == 1) --i; else --j;
         }
-        ++len;
+        pbuf[len++] = 0;
+        path_n = len;
         p.path_len[pr] = len;
-        i = N - 1; j = M - 1;
-        int pos = len - 1;
-        while (i > 0 || j > 0) {
-            pi[pos] = i; pj[pos] = j; --pos;
-            const uint8_t bp = dir[(size_t)i * M + j];
-            if (bp == 0) { --i; --j; } else if (bp == 1) --i; else --j;
+    }
+    __syncthreads();
+    {
+        int64_t *pi = p.path_i + (size_t)pr * (N + M - 1), *pj = p.path_j + (size_t)pr * (N + M - 1);
+        const int len = path_n;
+        for (int q = threadIdx.x; q < len; q += blockDim.x) {
+            const int e = pbuf[len - 1 - q];
+            pi[q] = e >> 16; pj[q] = e & 0xffff;
         }
-        pi[0] = 0; pj[0] = 0;
     }
 }
 
@@ -256,8 +289,9 @@ HMMB200_EXPORT int hmmb200_dtw_f32(const float *dist, int n_pairs, int N, int M,
     if (n_pairs == 0) return HMMB200_OK;
     if (!dist || !cost || !dir_ws || !path_i || !path_j || !path_len) return set_error(HMMB200_EINVAL, "dtw: null argument");
     if (int rc = require_sm100()) return rc;
-    const size_t smem = 3 * (size_t)N * sizeof(float);
-    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "dtw: N=%d rows exceed one CTA's shared memory (pass the shorter sequence first)", N);
+    if (N > 65535 || M > 65535) return set_error(HMMB200_EUNSUPPORTED, "dtw: sequences of at most 65535 frames (got %d x %d)", N, M);
+    const size_t smem = 3 * (size_t)N * sizeof(float) + ((size_t)N + M) * sizeof(int);     // three anti-diagonals + the path
+    if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "dtw: N=%d, M=%d exceed one CTA's shared memory (pass the shorter sequence first)", N, M);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(dtw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(HMMB200_ELAUNCH, "dtw smem opt-in: %s", cudaGetErrorString(e));
