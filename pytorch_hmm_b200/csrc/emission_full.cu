@@ -32,32 +32,50 @@ __device__ __forceinline__ void ef_cp16(void *dst, const void *src) {
 
 // rows [16 BAND, 16 BAND + 16) of the lower-triangular factor only reach columns < 16 (BAND + 1): the column loop of a band is a
 // compile-time bound, so the x row stays in registers and at most 15 of every 16 (BAND + 1) products are above the diagonal
-template <int DT, int BAND>
-__device__ __forceinline__ void ef_band_rows(const float *Wb, int D, const float (&xr)[DT], float &q) {
+__device__ __forceinline__ float2 ef_ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long *>(&a), rb = *reinterpret_cast<unsigned long long *>(&b);
+    unsigned long long rc = *reinterpret_cast<unsigned long long *>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2 *>(&rd);
+}
+
+// The two running sums of a row (even and odd columns) are the halves of ONE packed accumulator: a 16-byte load of the row feeds two
+// fma.rn.f32x2 instead of four FFMA -- same products, same order, same bits, 3 instead of 5 instructions per four FMAs (the kernel was
+// issue-bound: 71 % of its instructions FFMA at 54 % issue utilisation).
+// NF frames per thread: every 16-byte load of a row of W (a broadcast: the same address in all lanes, but 512 bytes on the return path
+// per warp) feeds 4 NF FMAs -- with one frame per thread the kernel sat on the shared-memory return path at a third of the FMA rate.
+template <int DT, int BAND, int NF>
+__device__ __forceinline__ void ef_band_rows(const float *Wb, int D, const float2 (&xr)[NF][DT / 2], float (&q)[NF]) {
     constexpr int NB4 = (4 * (BAND + 1) < DT / 4) ? 4 * (BAND + 1) : DT / 4;
     const int r_hi = min(D, 16 * BAND + 16);
     for (int r = 16 * BAND; r < r_hi; ++r) {
         const float4 *wr = reinterpret_cast<const float4 *>(Wb + r * DT);
-        float y0 = Wb[D * DT + r], y1 = 0.f;
+        const float c0 = Wb[D * DT + r];
+        float2 y2[NF];
+#pragma unroll
+        for (int f = 0; f < NF; ++f) y2[f] = make_float2(c0, 0.f);
 #pragma unroll
         for (int d4 = 0; d4 < NB4; ++d4) {
             const float4 w = wr[d4];
-            y0 = fmaf(w.x, xr[4 * d4], y0); y1 = fmaf(w.y, xr[4 * d4 + 1], y1);
-            y0 = fmaf(w.z, xr[4 * d4 + 2], y0); y1 = fmaf(w.w, xr[4 * d4 + 3], y1);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                y2[f] = ef_ffma2(make_float2(w.x, w.y), xr[f][2 * d4], y2[f]);
+                y2[f] = ef_ffma2(make_float2(w.z, w.w), xr[f][2 * d4 + 1], y2[f]);
+            }
         }
-        const float y = y0 + y1;
-        q = fmaf(y, y, q);
+#pragma unroll
+        for (int f = 0; f < NF; ++f) { const float y = y2[f].x + y2[f].y; q[f] = fmaf(y, y, q[f]); }
     }
-    if constexpr (16 * (BAND + 1) < DT) ef_band_rows<DT, BAND + 1>(Wb, D, xr, q);
+    if constexpr (16 * (BAND + 1) < DT) ef_band_rows<DT, BAND + 1, NF>(Wb, D, xr, q);
 }
 
-template <int DT>            // DT = D padded to a multiple of 4 (compile-time: the x row and the inner loops live in registers)
+template <int DT, int NF>    // DT = D padded to a multiple of 4 (compile-time: the x rows and the inner loops live in registers); NF frames per thread
 __global__ void __launch_bounds__(EF_THREADS) gmm_emission_full_kernel(FullParams p) {
     extern __shared__ __align__(16) float ef_smem[];
     const int D = p.D, DP = DT, KC = p.K * p.C, C = p.C;
     const int wfloats = D * DP + DP;                       // one component: W rows + c (padded)
     float *const wbuf0 = ef_smem, *const wbuf1 = ef_smem + wfloats;
-    float *lrow = ef_smem + 2 * wfloats;                   // [EF_THREADS][C] per-thread component values of the current state
+    float *lrow = ef_smem + 2 * wfloats;                   // [NF][EF_THREADS][C] per-frame component values of the current state
     const int tid = threadIdx.x;
     auto stage = [&](int kc, int b) {                      // W_kc (D x DP) and c_kc into buffer b
         const float4 *src = reinterpret_cast<const float4 *>(p.W + (size_t)kc * D * DP);
@@ -67,23 +85,29 @@ __global__ void __launch_bounds__(EF_THREADS) gmm_emission_full_kernel(FullParam
         for (int i = tid; i < DP; i += EF_THREADS) wb[D * DP + i] = (i < D) ? p.cvec[(size_t)kc * D + i] : 0.f;
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    const int64_t n_tiles = (p.n + EF_THREADS - 1) / EF_THREADS;
+    constexpr int TILE = EF_THREADS * NF;
+    const int64_t n_tiles = (p.n + TILE - 1) / TILE;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t fr = tile * EF_THREADS + tid;
-        const bool live = fr < p.n;
-        float xr[DT];
+        int64_t fr[NF];
+        bool live[NF];
+        float2 xr[NF][DT / 2];
 #pragma unroll
-        for (int d = 0; d < DT; d += 4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && d < D) {
-                if ((D & 3) == 0 && ((((uintptr_t)p.x) & 15) == 0)) v = *reinterpret_cast<const float4 *>(p.x + fr * D + d);
-                else { v.x = p.x[fr * D + d]; if (d + 1 < D) v.y = p.x[fr * D + d + 1]; if (d + 2 < D) v.z = p.x[fr * D + d + 2]; if (d + 3 < D) v.w = p.x[fr * D + d + 3]; }
+        for (int f = 0; f < NF; ++f) {
+            fr[f] = tile * TILE + f * EF_THREADS + tid;    // (consecutive threads take consecutive frames)
+            live[f] = fr[f] < p.n;
+#pragma unroll
+            for (int d = 0; d < DT; d += 4) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live[f] && d < D) {
+                    const float *xp = p.x + fr[f] * D + d;
+                    if ((D & 3) == 0 && ((((uintptr_t)p.x) & 15) == 0)) v = *reinterpret_cast<const float4 *>(xp);
+                    else { v.x = xp[0]; if (d + 1 < D) v.y = xp[1]; if (d + 2 < D) v.z = xp[2]; if (d + 3 < D) v.w = xp[3]; }
+                }
+                xr[f][d / 2] = make_float2(v.x, v.y); xr[f][d / 2 + 1] = make_float2(v.z, v.w);
             }
-            xr[d] = v.x; xr[d + 1] = v.y; xr[d + 2] = v.z; xr[d + 3] = v.w;
         }
         __syncthreads();                                   // previous tile done with the W buffers
         stage(0, 0);
-        float *mine = lrow + tid * C;
         for (int kc = 0; kc < KC; ++kc) {
             const int b = kc & 1;
             if (kc + 1 < KC) stage(kc + 1, b ^ 1);
@@ -91,23 +115,30 @@ __global__ void __launch_bounds__(EF_THREADS) gmm_emission_full_kernel(FullParam
             else asm volatile("cp.async.wait_group 0;" ::: "memory");
             __syncthreads();
             const float *Wb = b ? wbuf1 : wbuf0;
-            float q = 0.f;
-            ef_band_rows<DT, 0>(Wb, D, xr, q);
-            const float l = fmaf(-0.5f, q, __ldg(p.cst + kc));
-            if (p.comp && live) p.comp[fr * KC + kc] = l;
-            mine[kc % C] = l;
-            if (kc % C == C - 1) {                         // the state's C components are in: the reference's private log-sum-exp
-                float out;
-                if (C == 1) out = l;
-                else {
-                    float m = mine[0];
-                    for (int c = 1; c < C; ++c) m = fmaxf(m, mine[c]);
-                    if (isinf(m)) m = 0.f;
-                    float s = 0.f;
-                    for (int c = 0; c < C; ++c) s += expf(mine[c] - m);
-                    out = logf(fmaxf(s, 1e-8f)) + m;
+            float q[NF];
+#pragma unroll
+            for (int f = 0; f < NF; ++f) q[f] = 0.f;
+            ef_band_rows<DT, 0, NF>(Wb, D, xr, q);
+            const float cstv = __ldg(p.cst + kc);
+#pragma unroll
+            for (int f = 0; f < NF; ++f) {
+                float *mine = lrow + ((size_t)f * EF_THREADS + tid) * C;
+                const float l = fmaf(-0.5f, q[f], cstv);
+                if (p.comp && live[f]) p.comp[fr[f] * KC + kc] = l;
+                mine[kc % C] = l;
+                if (kc % C == C - 1) {                     // the state's C components are in: the reference's private log-sum-exp
+                    float out;
+                    if (C == 1) out = l;
+                    else {
+                        float m = mine[0];
+                        for (int c = 1; c < C; ++c) m = fmaxf(m, mine[c]);
+                        if (isinf(m)) m = 0.f;
+                        float sm = 0.f;
+                        for (int c = 0; c < C; ++c) sm += expf(mine[c] - m);
+                        out = logf(fmaxf(sm, 1e-8f)) + m;
+                    }
+                    if (live[f]) p.logb[fr[f] * p.K + kc / C] = out;
                 }
-                if (live) p.logb[fr * p.K + kc / C] = out;
             }
             __syncthreads();                               // buffer b may be refilled by the next-but-one component
         }
@@ -133,16 +164,25 @@ HMMB200_EXPORT int hmmb200_gmm_emission_full_f32(const float *x, const float *W,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int64_t n_tiles = (n_frames + EF_THREADS - 1) / EF_THREADS;
+    // two frames per thread when their x rows fit the register file (D <= 80: 2 x 80 of the 255 registers)
+    const int NF = (p.DP <= 80) ? 2 : 1;
+    const int64_t n_tiles = (n_frames + EF_THREADS * NF - 1) / (EF_THREADS * NF);
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = (2 * ((size_t)D * p.DP + p.DP) + (size_t)EF_THREADS * C) * sizeof(float);
+    const size_t smem = (2 * ((size_t)D * p.DP + p.DP) + (size_t)NF * EF_THREADS * C) * sizeof(float);
     if (smem > 200 * 1024) return set_error(HMMB200_EUNSUPPORTED, "gmm_emission_full: D = %d, C = %d need %zu bytes of shared memory", D, C, smem);
-    const int grid = (int)min((int64_t)sms * 2, n_tiles);
+    // persistent CTAs, as many per SM as fit (the kernel waits on shared-memory loads between its FFMA runs: with two 4-warp CTAs per
+    // SM the schedulers issued 54 % of the time)
+    int grid = 0;
 #define EF_LAUNCH(N)                                                                                                            \
-    case N:                                                                                                                     \
-        if (smem > 48 * 1024) cudaFuncSetAttribute(gmm_emission_full_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        gmm_emission_full_kernel<N><<<grid, EF_THREADS, smem, s>>>(p);                                                          \
-        break;
+    case N: {                                                                                                                   \
+        auto kern = (N <= 80) ? gmm_emission_full_kernel<N, (N <= 80 ? 2 : 1)> : gmm_emission_full_kernel<N, 1>;                \
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+        int occ = 2;                                                                                                            \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, EF_THREADS, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 2; } \
+        grid = (int)min((int64_t)sms * occ, n_tiles);                                                                           \
+        kern<<<grid, EF_THREADS, smem, s>>>(p);                                                                                 \
+        break;                                                                                                                  \
+    }
     switch (p.DP) {
         EF_LAUNCH(4) EF_LAUNCH(8) EF_LAUNCH(12) EF_LAUNCH(16) EF_LAUNCH(20) EF_LAUNCH(24) EF_LAUNCH(28) EF_LAUNCH(32)
         EF_LAUNCH(40) EF_LAUNCH(48) EF_LAUNCH(64) EF_LAUNCH(80) EF_LAUNCH(96)
