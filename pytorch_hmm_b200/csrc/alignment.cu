@@ -40,8 +40,8 @@ __device__ __forceinline__ float lse_cands(const float *c, int n) {
 __device__ __forceinline__ float lse3(float a, float b, float c) {
     const float m = fmaxf(fmaxf(a, b), c);
     if (!(m > -INFINITY)) return -INFINITY;
-    const float s = (expf(a - m) + expf(b - m)) + expf(c - m);
-    return logf(s) + m;
+    const float s = (__expf(a - m) + __expf(b - m)) + __expf(c - m);      // (arguments <= 0, sum in [1, 3]: the fast forms are ~1e-7 here)
+    return __logf(s) + m;
 }
 
 template <int DIR>
