@@ -112,7 +112,12 @@ __device__ __forceinline__ void hsmm_sweep(const HsmmFb2Params &p, float *sm, in
     __syncwarp();
     // the lane's slots: ring_l[j * LPS * KS]; their duration weights: dp[-j * LPS * KS] with dp = durc2 + (a0 + Dm) * KS + sc,
     // a0 = (position - r) mod Dm.  Slot j is a real slot when r + LPS j < Dm (always, except possibly for the last j).
-    float *ring_l = ring + r * KS + sc;
+    // The lane's slots are its own (no other lane reads them) and every one of them is rewritten every step, so they live in REGISTERS:
+    // as a shared-memory ring they cost seven loads and seven stores per step whose latencies a single in-order warp cannot hide,
+    // and the stores kept the compiler from hoisting the step's other loads.
+    float rg[NSLOT];
+#pragma unroll
+    for (int j = 0; j < NSLOT; ++j) rg[j] = 0.f;
     int a0 = (Dm - r % Dm) % Dm;
     const float *dp = durc2 + (a0 + Dm) * KS + sc;
     // slot j of this lane exists when r + LPS j < Dm; with a compile-time Dmax that is a run-time question for the last j only
@@ -130,7 +135,7 @@ __device__ __forceinline__ void hsmm_sweep(const HsmmFb2Params &p, float *sm, in
 #pragma unroll
         for (int j = 0; j < NSLOT; ++j) {
             const bool vj = slot_ok(j);
-            const float old = ring_l[j * LPS * KS];             // (rows past Dm exist and stay zero)
+            const float old = rg[j];                            // (slots past Dm exist and stay zero)
             // a slot whose duration index is 0 opens NOW: its old content (duration Dm + 1) expires
             x[j] = (a0 == LPS * j || !vj) ? 0.f : old * bq;
             pp = fmaf(x[j], vj ? dp[-j * LPS * KS] : 0.f, pp);
@@ -166,14 +171,14 @@ __device__ __forceinline__ void hsmm_sweep(const HsmmFb2Params &p, float *sm, in
             fresh_v = g * bq;
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j)
-                if (slot_ok(j)) ring_l[j * LPS * KS] = (a0 == LPS * j) ? fresh_v : x[j] * rho;
+                if (slot_ok(j)) rg[j] = (a0 == LPS * j) ? fresh_v : x[j] * rho;
         } else {
             g = acc;
             e = fmaf(g, bq * durc1, pp);
             fresh_v = g * bq;
 #pragma unroll
             for (int j = 0; j < NSLOT; ++j)
-                if (slot_ok(j)) ring_l[j * LPS * KS] = (a0 == LPS * j) ? fresh_v : x[j];
+                if (slot_ok(j)) rg[j] = (a0 == LPS * j) ? fresh_v : x[j];
         }
         if (r == 0) vec[(n & 1) * KP + s] = e;                  // (lanes without a state write the padding of the vector: Am = 0 there)
         if (writer) { *ws_v = e; *ws_g = g; }
