@@ -124,11 +124,14 @@ __device__ __forceinline__ void tv_sweep(const TvParams &p, float *stage_sm, uin
         r_cur = __uint_as_float((254u - eb) << 23);
         if (eb == 0u || eb >= 254u) { k_cur = 0; r_cur = 1.f; }      // all-zero (impossible frame) or non-finite vector: leave it alone
     };
+    // maximum over the warp with ONE integer reduction on an order-preserving key instead of five dependent shuffle rounds (a single warp
+    // issues in order: the rounds' latencies were step time)
     auto row_max = [&](float e) {
-        float m = ok ? e : -INFINITY;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL_MASK, m, o));
-        return (m > -INFINITY) ? m : 0.f;
+        const unsigned u = __float_as_uint(e);
+        const unsigned key = ok ? ((u & 0x80000000u) ? ~u : (u | 0x80000000u)) : 0u;      // NaN-free inputs; absent lanes lowest
+        const unsigned mx = __reduce_max_sync(FULL_MASK, key);
+        const float m = __uint_as_float((mx & 0x80000000u) ? (mx & 0x7fffffffu) : ~mx);
+        return (mx != 0u && m > -INFINITY) ? m : 0.f;
     };
     float w;                            // DIR 0: scaled alpha_t(j);  DIR 1: scaled beta_t(j) * b~_t(j)
     {
