@@ -203,6 +203,26 @@ def semimarkov(ref):
     np.savez_compressed(os.path.join(OUT, "semimarkov.npz"), **out)
 
 
+def semimarkov_supervised(ref):
+    """A13, alignment given: SemiMarkovHMM._supervised_forward (semi_markov.py:280-305) with its three terms
+    (:385-453, :100-153).  Three sequences: segments that tile T exactly, segments that stop short of T, and segments that overrun T
+    (the reference stops adding observation terms at the first segment that does not fit, :404-411)."""
+    torch.manual_seed(4201)
+    K, D, Dm, T = 4, 5, 8, 20
+    out = {}
+    for dist in ("gamma", "poisson", "gaussian"):
+        m = ref.SemiMarkovHMM(K, D, max_duration=Dm, duration_distribution=dist, min_duration=2 if dist == "gaussian" else 1)
+        x = torch.randn(3, T, D)
+        states = torch.tensor([[0, 2, 1, 3, 0], [3, 1, 0, 2, 1], [1, 0, 3, 2, 0]])
+        durs = torch.tensor([[4, 6, 3, 5, 2], [2, 3, 4, 1, 2], [7, 6, 5, 4, 3]])
+        with torch.no_grad():
+            res = m(x, states, durs)
+        out.update({f"{dist}_{n}": _np(p) for n, p in m.named_parameters()})
+        out.update({f"{dist}_x": _np(x), f"{dist}_states": states.numpy(), f"{dist}_durs": durs.numpy()})
+        out.update({f"{dist}_{k}": _np(v) for k, v in res.items()})
+    np.savez_compressed(os.path.join(OUT, "semimarkov_sup.npz"), **out)
+
+
 def streaming(ref):
     """A14: StreamingHMMProcessor greedy path (streaming.py:183-320), two consecutive chunks."""
     torch.manual_seed(5101)
@@ -362,7 +382,7 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     ref = _import_reference()
     torch.set_num_threads(1)
-    sections = {"core": core, "gaussian": gaussian, "mixture": mixture, "hsmm": hsmm, "semimarkov": semimarkov,
+    sections = {"core": core, "gaussian": gaussian, "mixture": mixture, "hsmm": hsmm, "semimarkov": semimarkov, "semimarkov_sup": semimarkov_supervised,
                 "streaming": streaming, "largek": largek, "neural": neural, "alignment": alignment, "covariance": covariance}
     only = [a for a in sys.argv[1:] if a in sections or a == "segsum"]        # e.g. `make_golden.py largek`
     for name, fn in sections.items():

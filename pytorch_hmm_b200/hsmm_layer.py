@@ -21,7 +21,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import ops
+from . import autograd, ops
 from ._cache import DerivedCache
 
 
@@ -210,23 +210,38 @@ class DurationModel(nn.Module):
         else:
             raise ValueError(f"Unknown distribution_type: {distribution_type}")
 
-    def log_table(self) -> torch.Tensor:
-        """[K, Dmax] log p_s(d), d = 1..Dmax, exactly the per-state formulas of semi_markov.py:122-153 (no floor)."""
-        d = torch.arange(1, self.max_duration + 1, device=next(self.parameters()).device).float().unsqueeze(0)
+    def _log_density(self, d: torch.Tensor, idx=None) -> torch.Tensor:
+        """log p_s(d) by the per-state formulas of semi_markov.py:122-153 (no floor).  idx None: d is [1, N] and the result [K, N]
+        (every state against every duration); idx [N]: d is [N] and the result [N] (state idx[i] against d[i])."""
+        par = (lambda p: p.unsqueeze(1)) if idx is None else (lambda p: p[idx])
         if self.distribution_type == "gamma":
-            a = (F.softplus(self.alpha_params) + 1e-6).unsqueeze(1)
-            b = (F.softplus(self.beta_params) + 1e-6).unsqueeze(1)
+            a = par(F.softplus(self.alpha_params) + 1e-6)
+            b = par(F.softplus(self.beta_params) + 1e-6)
             logp = (a - 1) * torch.log(d + 1e-8) - b * d
             logp = logp - (torch.lgamma(a) - a * torch.log(b))
         elif self.distribution_type == "poisson":
-            lam = (F.softplus(self.lambda_params) + 1e-6).unsqueeze(1)
+            lam = par(F.softplus(self.lambda_params) + 1e-6)
             logp = d * torch.log(lam + 1e-8) - lam
             logp = logp - torch.lgamma(d + 1)
         else:
-            mean = (F.softplus(self.mean_params) + self.min_duration).unsqueeze(1)
-            std = (F.softplus(self.std_params) + 1e-6).unsqueeze(1)
+            mean = par(F.softplus(self.mean_params) + self.min_duration)
+            std = par(F.softplus(self.std_params) + 1e-6)
             logp = -0.5 * torch.log(2 * math.pi * std ** 2) - 0.5 * ((d - mean) / std) ** 2
         return torch.where(d >= self.min_duration, logp, torch.full_like(logp, float("-inf")))
+
+    def log_table(self) -> torch.Tensor:
+        """[K, Dmax] log p_s(d), d = 1..Dmax."""
+        d = torch.arange(1, self.max_duration + 1, device=next(self.parameters()).device).float().unsqueeze(0)
+        return self._log_density(d)
+
+    def forward(self, state_indices: torch.Tensor, durations=None) -> torch.Tensor:
+        """semi_markov.py:63-119: durations None -> [N, Dmax] rows of the table for the given states; else log p_{s_i}(d_i), [N]
+        (the parametric formulas are evaluated at the given duration, also beyond max_duration, as the reference does)."""
+        dev = next(self.parameters()).device
+        idx = state_indices.to(dev).long()
+        if durations is None:
+            return self.log_table()[idx]
+        return self._log_density(durations.to(dev).float(), idx)
 
 
 class SemiMarkovHMM(nn.Module):
@@ -263,9 +278,41 @@ class SemiMarkovHMM(nn.Module):
         return self.duration_model.log_table().detach().to(dev), log_trans.to(dev), log_init.to(dev)
 
     def forward(self, observations: torch.Tensor, state_sequence=None, duration_sequence=None) -> Dict[str, torch.Tensor]:
-        if state_sequence is not None or duration_sequence is not None:
-            raise NotImplementedError("the supervised segment likelihood is outside the B200 hot path")
+        if state_sequence is not None and duration_sequence is not None:
+            return self._supervised_forward(observations, state_sequence, duration_sequence)
         return self._unsupervised_forward(observations)
+
+    def _supervised_forward(self, observations: torch.Tensor, state_sequence: torch.Tensor,
+                            duration_sequence: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Log-probability of a GIVEN segmentation (semi_markov.py:280-305): observation term per segment = the per-segment
+        constant + the frame terms of the emission kernel summed over the segment (:385-411, :413-432; segments are taken in
+        order until the first one that would end beyond T, the rest contribute no observation term), duration term (:100-119),
+        transition term (:434-453).  The frame terms come from the CUDA emission kernel; the three sums are gathers over a
+        handful of segments per sequence and stay on the device as tensor operations."""
+        dev = ops.require_cuda(self.observation_means.device if self.observation_means.is_cuda else None)
+        train = autograd.needs_grad(observations, *self.parameters())                # supervised training: keep the graph
+        if train:
+            const = (-0.5 * self.observation_logvars.sum(-1) - 0.5 * self.observation_dim * math.log(2 * math.pi)).to(dev)
+            q = autograd.gmm_log_probs(observations.to(dev), self.observation_means, self.observation_logvars, None, 1.0) - const
+        else:
+            q, const = self._frame_terms(observations, dev)                          # [B, T, K], [K]
+        B, T, K = q.shape
+        st = state_sequence.to(dev).long()
+        du = duration_sequence.to(dev).long()
+        start = torch.cumsum(du, 1) - du
+        fits = torch.cumprod((start + du <= T).long(), 1).bool()                     # the reference breaks at the first misfit
+        csum = torch.cat([q.new_zeros(B, 1, K, dtype=torch.float64), torch.cumsum(q.double(), 1)], 1)    # [B, T+1, K]
+        pick = lambda pos: csum.gather(1, pos.clamp(0, T).unsqueeze(-1).expand(-1, -1, K)).gather(2, st.unsqueeze(-1)).squeeze(-1)
+        seg = (pick(start + du) - pick(start)).float() + const[st]
+        log_obs = torch.where(fits, seg, torch.zeros_like(seg)).sum(1)
+        log_dur = self.duration_model(st.flatten(), du.flatten()).to(dev).view(B, -1).sum(1)
+        log_trans_m = torch.log(F.softmax(self.transition_logits, dim=1) + 1e-8).to(dev)
+        if not train:
+            log_dur, log_trans_m = log_dur.detach(), log_trans_m.detach()
+        log_tr = log_trans_m[st[:, :-1], st[:, 1:]].sum(1) if st.shape[1] > 1 else q.new_zeros(B)
+        back = (lambda t: t) if observations.device == dev else (lambda t: t.to(observations.device))
+        return {"log_probability": back(log_obs + log_dur + log_tr), "log_observation": back(log_obs),
+                "log_duration": back(log_dur), "log_transition": back(log_tr)}
 
     def _unsupervised_forward(self, observations: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Marginal log-probability over all segmentations (semi_markov.py:308-383).  Like the reference it reports batch

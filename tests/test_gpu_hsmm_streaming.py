@@ -133,6 +133,65 @@ def test_semimarkov_viterbi_vs_reference_golden(hm, golden):
     np.testing.assert_allclose(lp.item(), float(g["vit_logprob"]), rtol=1e-5)
 
 
+def _semimarkov_sup(hm, g, dist):
+    K, D = g[f"{dist}_observation_means"].shape
+    m = hm.SemiMarkovHMM(K, D, max_duration=8, duration_distribution=dist, min_duration=2 if dist == "gaussian" else 1).cuda()
+    m.load_state_dict({k: torch.from_numpy(g[f"{dist}_{k}"]) for k in m.state_dict()})
+    return m
+
+
+@pytest.mark.parametrize("dist", ["gamma", "poisson", "gaussian"])
+def test_semimarkov_supervised_forward_vs_reference_golden(hm, golden, dist):
+    """SemiMarkovHMM.forward(x, state_sequence, duration_sequence) (semi_markov.py:280-305): segments that tile T, stop short of T,
+    and overrun T; one duration below min_duration (-inf) in the gaussian case.  1e-5 relative: fp32 sums of a few dozen terms."""
+    g = golden("semimarkov_sup")
+    m = _semimarkov_sup(hm, g, dist)
+    with torch.no_grad():
+        res = m(_dev(g[f"{dist}_x"]), _dev(g[f"{dist}_states"]), _dev(g[f"{dist}_durs"]))
+    for k in ("log_observation", "log_duration", "log_transition", "log_probability"):
+        ref = g[f"{dist}_{k}"]; ours = res[k].cpu().numpy()
+        assert not res[k].requires_grad
+        assert np.array_equal(np.isfinite(ours), np.isfinite(ref)), k
+        np.testing.assert_allclose(ours[np.isfinite(ref)], ref[np.isfinite(ref)], rtol=1e-5, atol=1e-5, err_msg=k)
+
+
+def test_semimarkov_supervised_forward_gradients(hm, golden):
+    """Supervised training through the given segmentation: gradients w.r.t. every parameter against float64 autograd of the
+    reference's formulas restated with tensor operations (same three terms)."""
+    g = golden("semimarkov_sup")
+    m = _semimarkov_sup(hm, g, "gamma")
+    x, st, du = _dev(g["gamma_x"]), _dev(g["gamma_states"]), _dev(g["gamma_durs"])
+    res = m(x, st, du)
+    np.testing.assert_allclose(res["log_probability"].detach().cpu().numpy(), g["gamma_log_probability"], rtol=1e-5)
+    res["log_probability"].sum().backward()
+    ours = {n: p.grad.detach().double().cpu() for n, p in m.named_parameters() if p.grad is not None}
+    P = {n: p.detach().double().cpu().requires_grad_(True) for n, p in m.named_parameters()}
+    xd, T = x.double().cpu(), x.shape[1]
+    F = torch.nn.functional
+    total = 0.0
+    for b in range(xd.shape[0]):
+        t = 0
+        for j in range(st.shape[1]):
+            s_, d_ = int(st[b, j]), int(du[b, j])
+            a = F.softplus(P["duration_model.alpha_params"][s_]) + 1e-6
+            be = F.softplus(P["duration_model.beta_params"][s_]) + 1e-6
+            total = total + (a - 1) * np.log(d_ + 1e-8) - be * d_ - (torch.lgamma(a) - a * torch.log(be))
+            if j > 0:
+                total = total + torch.log(F.softmax(P["transition_logits"], 1) + 1e-8)[int(st[b, j - 1]), s_]
+        for j in range(st.shape[1]):
+            s_, d_ = int(st[b, j]), int(du[b, j])
+            if t + d_ > T:
+                break
+            lv = P["observation_logvars"][s_]
+            total = total - 0.5 * lv.sum() - 0.5 * xd.shape[2] * np.log(2 * np.pi) \
+                - 0.5 * (((xd[b, t:t + d_] - P["observation_means"][s_]) ** 2) / torch.exp(lv)).sum()
+            t += d_
+    total.backward()
+    for n in ("observation_means", "observation_logvars", "transition_logits", "duration_model.alpha_params",
+              "duration_model.beta_params"):
+        np.testing.assert_allclose(ours[n].numpy(), P[n].grad.numpy(), rtol=2e-4, atol=2e-4, err_msg=n)
+
+
 def test_hsmm_forward_vs_float64_oracle(hm):
     rng = np.random.default_rng(12)
     K, Dm, T = 5, 7, 60
