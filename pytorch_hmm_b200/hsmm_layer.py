@@ -90,9 +90,8 @@ class HSMMLayer(nn.Module):
     def get_observation_log_probs(self, observations: torch.Tensor) -> torch.Tensor:
         """(B,T,D) -> (B,T,S) single diagonal Gaussian per state (hsmm.py:181-206) on the emission kernel."""
         dev = self._cuda()
-        from . import autograd as ag
-        if ag.needs_grad(observations, self.observation_means, self.observation_log_vars):
-            return ag.gmm_log_probs(observations, self.observation_means, self.observation_log_vars, None, 1.0)
+        if autograd.needs_grad(observations, self.observation_means, self.observation_log_vars):
+            return autograd.gmm_log_probs(observations, self.observation_means, self.observation_log_vars, None, 1.0)
         packed = self._derived.get("packed", (self.observation_means, self.observation_log_vars),
                                    lambda: ops.gmm_pack(self.observation_means, self.observation_log_vars, 1.0, None))
         out = ops.gmm_emission(observations.detach().to(dev), packed, self.num_states, 1, self.feature_dim)
