@@ -8,11 +8,16 @@ launch of `hmmb200_greedy_decode_f32`, continuing from the previous chunk's last
 New (north star): `forward_chunk()` runs the forward recursion over a chunk with the filtered state vector carried between
 calls (`hmmb200_forward_chunk_f32`); chunked calls equal one unchunked pass.
 
-Out of scope: beam search, the async worker thread, the adaptive latency controller.  With
+The asynchronous front end (streaming.py:123-181: start / stop, add_audio_chunk_async, get_result_async) is one worker thread
+feeding process_chunk from a bounded queue, chunks decoded in arrival order.
+
+Out of scope: beam search, the adaptive latency controller.  With
 `use_beam_search=True` (the reference's default) decoding uses the greedy kernel and says so in the result metadata.
 """
 from __future__ import annotations
 
+import queue
+import threading
 import time
 import warnings
 from collections import deque
@@ -50,6 +55,9 @@ class StreamingHMMProcessor(nn.Module):
         self.emission_net = nn.Sequential(nn.Linear(feature_dim, 128), nn.ReLU(), nn.Dropout(0.1),
                                           nn.Linear(128, num_states), nn.LogSoftmax(dim=-1))
         self.processing_times = deque(maxlen=1000)
+        self.processing_queue: "queue.Queue" = queue.Queue(maxsize=buffer_size)
+        self.result_queue: "queue.Queue" = queue.Queue(maxsize=buffer_size)
+        self.is_processing, self.processing_thread = False, None
         self.reset_streaming_state()
 
     def reset_streaming_state(self):
@@ -66,6 +74,50 @@ class StreamingHMMProcessor(nn.Module):
 
     def _cuda(self) -> torch.device:
         return ops.require_cuda(self.transition_logits.device if self.transition_logits.is_cuda else None)
+
+    # -- asynchronous front end (streaming.py:123-181) ----------------------------------------------------------
+    def start_async_processing(self):
+        if self.is_processing:
+            return
+        self.is_processing = True
+        self.processing_thread = threading.Thread(target=self._worker, name="hmm-stream", daemon=True)
+        self.processing_thread.start()
+
+    def stop_async_processing(self):
+        self.is_processing = False
+        t, self.processing_thread = self.processing_thread, None
+        if t is not None:
+            t.join(timeout=1.0)
+
+    def _worker(self):
+        while self.is_processing:
+            try:
+                chunk = self.processing_queue.get(timeout=0.1)
+            except queue.Empty:
+                continue
+            try:
+                with torch.no_grad():
+                    result = self.process_chunk(chunk)
+                if not self.result_queue.full():                 # a full result queue drops the newest result, as the reference does
+                    self.result_queue.put(result)
+            except Exception as exc:                            # the worker must survive a bad chunk
+                warnings.warn(f"Error in async processing: {exc}")
+            finally:
+                self.processing_queue.task_done()
+
+    def add_audio_chunk_async(self, audio_chunk: torch.Tensor) -> bool:
+        """False when the input queue is full (the chunk is not taken)."""
+        try:
+            self.processing_queue.put_nowait(audio_chunk)
+            return True
+        except queue.Full:
+            return False
+
+    def get_result_async(self) -> Optional[StreamingResult]:
+        try:
+            return self.result_queue.get_nowait()
+        except queue.Empty:
+            return None
 
     # -- reference API -------------------------------------------------------------------------------------
     def process_chunk(self, audio_chunk: torch.Tensor) -> StreamingResult:

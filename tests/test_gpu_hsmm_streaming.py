@@ -341,3 +341,36 @@ def test_factories(hm):
     assert isinstance(hm.ModelFactory.create_realtime_model(4, 8), hm.StreamingHMMProcessor)
     with pytest.raises(ValueError):
         hm.create_speech_hmm(3, 4, "nope")
+
+
+def test_streaming_async_front_end_equals_synchronous_calls(hm):
+    """start_async_processing / add_audio_chunk_async / get_result_async (streaming.py:123-181): the worker thread decodes the
+    chunks in arrival order, so the results equal those of process_chunk called directly on a second processor with the same
+    parameters."""
+    import time
+    torch.manual_seed(77)
+    a = hm.StreamingHMMProcessor(5, 25, chunk_size=40, use_beam_search=False).cuda().eval()
+    b = hm.StreamingHMMProcessor(5, 25, chunk_size=40, use_beam_search=False).cuda().eval()
+    b.load_state_dict(a.state_dict())
+    chunks = [torch.randn(40, 25) for _ in range(6)]
+    with torch.no_grad():
+        want = [b.process_chunk(c) for c in chunks]
+    a.start_async_processing()
+    try:
+        assert all(a.add_audio_chunk_async(c) for c in chunks)
+        got, deadline = [], time.time() + 20.0
+        while len(got) < len(chunks) and time.time() < deadline:
+            r = a.get_result_async()
+            if r is None:
+                time.sleep(0.005)
+            else:
+                got.append(r)
+    finally:
+        a.stop_async_processing()
+    assert len(got) == len(chunks) and a.get_result_async() is None
+    for g, w in zip(got, want):
+        assert isinstance(g, hm.StreamingResult) and g.status == w.status and g.chunk_id == w.chunk_id
+        if w.decoded_states is None:
+            assert g.decoded_states is None
+        else:
+            assert torch.equal(g.decoded_states.cpu(), w.decoded_states.cpu())
