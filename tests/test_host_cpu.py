@@ -120,3 +120,43 @@ def test_hsmm_posterior_oracle_vs_brute_force():
         np.testing.assert_allclose(t1, t2, rtol=1e-12)
         np.testing.assert_allclose(g1, g2, rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(g1.sum(-1), 1.0, rtol=1e-9)
+
+
+def test_baum_welch_oracle_vs_brute_force():
+    """Baum-Welch (A9) has formulas only in the reference (docs/01_hmm_theory.md:196-227): pin the float64 E-step oracle
+    (oracle/hmm_oracle.c::orc_bw_stats_f64) by first principles -- enumerate every state path of a tiny GMM-HMM, weight it by its
+    joint probability with the observations, and count: first-frame posteriors, transition counts, component occupancies and the
+    occupancy-weighted first / second moments."""
+    import itertools
+    import numpy as np
+    from oracle import c_oracle
+    rng = np.random.default_rng(97)
+    for B, T, K, Cn, D in ((2, 4, 3, 2, 2), (1, 5, 2, 3, 1), (3, 1, 3, 1, 2), (1, 6, 3, 1, 3)):
+        x = rng.standard_normal((B, T, D)).astype(np.float32)
+        means = rng.standard_normal((K, Cn, D)); var = np.exp(0.3 * rng.standard_normal((K, Cn, D)))
+        w = rng.dirichlet(np.ones(Cn) * 3, size=K); P = rng.dirichlet(np.ones(K) * 2, size=K); p0 = rng.dirichlet(np.ones(K) * 2)
+        xd = x.astype(np.float64)
+        comp = np.log(w)[None, None] - 0.5 * (((xd[:, :, None, None, :] - means[None, None]) ** 2 / var[None, None]).sum(-1)
+                                              + np.log(var).sum(-1)[None, None] + D * np.log(2 * np.pi))          # [B,T,K,C]
+        got = c_oracle.bw_stats_f64(x, comp, np.log(P), np.log(p0))
+        dens = np.exp(comp)                                      # joint density of (x_t, component c) given state k
+        b = dens.sum(-1)                                         # [B,T,K]
+        resp = dens / b[..., None]
+        g1 = np.zeros(K); xi = np.zeros((K, K)); occ = np.zeros((K, Cn)); sx = np.zeros((K, Cn, D)); sxx = np.zeros((K, Cn, D)); ll = 0.0
+        for u in range(B):
+            paths = list(itertools.product(range(K), repeat=T))
+            wts = np.array([p0[s[0]] * np.prod([P[s[t - 1], s[t]] for t in range(1, T)]) * np.prod([b[u, t, s[t]] for t in range(T)])
+                            for s in paths])
+            Z = wts.sum(); ll += np.log(Z)
+            for s, wt in zip(paths, wts / Z):
+                g1[s[0]] += wt
+                for t in range(T):
+                    if t:
+                        xi[s[t - 1], s[t]] += wt
+                    o = wt * resp[u, t, s[t]]                    # [C]
+                    occ[s[t]] += o
+                    sx[s[t]] += o[:, None] * xd[u, t][None]
+                    sxx[s[t]] += o[:, None] * (xd[u, t] ** 2)[None]
+        np.testing.assert_allclose(got["loglik"], ll, rtol=1e-12)
+        for name, want in (("gamma1", g1), ("xi", xi), ("occ", occ), ("sx", sx), ("sxx", sxx)):
+            np.testing.assert_allclose(got[name], want, rtol=1e-9, atol=1e-12, err_msg=f"{name} B={B} T={T} K={K} C={Cn}")
