@@ -353,8 +353,25 @@ def extra_config1(dev):
         hm.ops.forward_backward_viterbi(logb, hm.ops.EMIS_LOG_NORM_FLOOR, hm.ops.EMIS_LOG_NORM_FLOOR, trans, init, logP, logp0,
                                         want=("gamma", "fwd", "bwd"), out=out, workspace=ws)
     ms = _ms(step, it=20, warm=3)
-    return {"config": "configs[0]: K=10 left-to-right, D=80 diag-Gaussian, B=32, T=1000 (emission + forward_backward + viterbi_decode)",
-            "ms_per_step": ms, "frames_per_s": B * T / (ms * 1e-3)}
+    res = {"config": "configs[0]: K=10 left-to-right, D=80 diag-Gaussian, B=32, T=1000 (emission + forward_backward + viterbi_decode)",
+           "ms_per_step": ms, "frames_per_s": B * T / (ms * 1e-3), "launch": "one call per kernel from Python"}
+    # the same step replayed from a CUDA graph, as the headline step is: at B = 32 the three kernels are short enough for the
+    # per-call host time to show
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            step()
+        gms = _ms(gr.replay, it=20, warm=3)
+        res.update({"graph_ms_per_step": gms, "graph_frames_per_s": B * T / (gms * 1e-3)})
+    except Exception as exc:                                                         # reported, never fatal for the bench line
+        res["graph_error"] = str(exc)[:200]
+    return res
 
 
 def extra_config4(dev):
