@@ -160,3 +160,24 @@ def test_baum_welch_oracle_vs_brute_force():
         np.testing.assert_allclose(got["loglik"], ll, rtol=1e-12)
         for name, want in (("gamma1", g1), ("xi", xi), ("occ", occ), ("sx", sx), ("sxx", sxx)):
             np.testing.assert_allclose(got[name], want, rtol=1e-9, atol=1e-12, err_msg=f"{name} B={B} T={T} K={K} C={Cn}")
+
+
+def test_duration_model_forward_matches_reference(golden):
+    """DurationModel.forward (semi_markov.py:63-153), host side: log p_{s_i}(d_i) summed per sequence against the reference's
+    'log_duration' of the supervised SemiMarkovHMM fixture (a duration below min_duration gives -inf), and the no-durations form
+    against the rows of the table."""
+    import numpy as np
+    import pytorch_hmm_b200 as hm
+    g = golden("semimarkov_sup")
+    for dist in ("gamma", "poisson", "gaussian"):
+        dm = hm.DurationModel(4, 8, dist, min_duration=2 if dist == "gaussian" else 1)
+        dm.load_state_dict({k[len("duration_model."):]: torch.from_numpy(g[f"{dist}_{k}"])
+                            for k in (f[len(dist) + 1:] for f in g.files if f.startswith(f"{dist}_duration_model."))})
+        st, du = torch.from_numpy(g[f"{dist}_states"]), torch.from_numpy(g[f"{dist}_durs"])
+        with torch.no_grad():
+            got = dm(st.flatten(), du.flatten()).view(st.shape).sum(1).numpy()
+            rows = dm(st[0])
+        ref = g[f"{dist}_log_duration"]
+        assert np.array_equal(np.isfinite(got), np.isfinite(ref))
+        np.testing.assert_allclose(got[np.isfinite(ref)], ref[np.isfinite(ref)], rtol=1e-5)
+        assert torch.equal(rows, dm.log_table()[st[0]])
